@@ -1,0 +1,183 @@
+/*
+ * vt_b200.h — C ABI of the B200 (sm_100a) video-transformer hot-path kernels.
+ *
+ * Drop-in boundary: the reference has no FFI layer of its own — its hot path is the
+ * forward/backward of the nn.Modules in transformer.py / video_transformer.py, executed by stock
+ * ATen/cuBLAS/cuDNN calls.  This library is what a maintainer binds *underneath* those modules
+ * (ctypes stub in INTEGRATION.md); each entry point names the reference call site it replaces
+ * (paths relative to the reference repo root).
+ *
+ * Conventions
+ *  - every function: int fn(const <params>*, void* cuda_stream); 0 = ok, non-zero = error
+ *    (message via vt_last_error).  No exceptions, no abort, no fallback: unsupported shapes are errors.
+ *  - all pointers are device pointers owned by the caller (PyTorch caching allocator); kernels are
+ *    enqueued on `cuda_stream` and never allocate, free, synchronise or retain pointers.
+ *  - bf16 = raw uint16 storage of __nv_bfloat16; "rows" are contiguous along the last dimension.
+ *  - re-entrant: callable from the Python main thread (forward) and the autograd thread (backward).
+ */
+#ifndef VT_B200_H
+#define VT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VT_ABI_VERSION 1
+
+int vt_version(void);
+/* copies the calling thread's last error message (NUL terminated) into buf; returns its length */
+int vt_last_error(char* buf, size_t buf_bytes);
+/* number of SMs of the current device (grid sizing is done inside the library) */
+int vt_sm_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * GEMM on tcgen05 tensor cores:  acc[M,N] = sum_k A[m,k] * B[n,k]   (bf16 x bf16 -> fp32 in TMEM)
+ * Operands are fed by TMA into 128B-swizzled shared memory.
+ *   a_mn_major = 0 : A stored row-major [M, K] (leading dim lda)      "K-major"
+ *   a_mn_major = 1 : A stored row-major [K, M] (leading dim lda)      "MN-major" (no transpose copy)
+ *   b_mn_major = 0 : B stored row-major [N, K] (leading dim ldb)      (nn.Linear weight layout)
+ *   b_mn_major = 1 : B stored row-major [K, N]
+ * Replaces: nn.Linear forward (F.linear -> cuBLASLt addmm) at transformer.py:167 (qkv), :175 (proj),
+ *   :267 (temporal_fc), :501-505 (FFN), the Conv2d/Conv3d patch projection :116-126 after im2col,
+ *   and autograd's dgrad / wgrad GEMMs of the same layers.
+ *
+ * Epilogues (thread = accumulator row, fused in the TMEM->register drain):
+ *   VT_EPI_BF16  : out_bf16[orow(m), n]  = s(m) * (acc + bias[n])
+ *   VT_EPI_F32   : out_f32 [orow(m), n]  = s(m) * (acc + bias[n]) + (aux ? aux_f32[arow(m), n] : 0)
+ *                  (residual add / pos+time-embed add / fp32 gradients)
+ *   VT_EPI_GELU  : out_bf16[m,n] = z = acc + bias[n];  out2_bf16[m,n] = gelu_erf(z)     (transformer.py:501-503)
+ *   VT_EPI_DGELU : out_bf16[m,n] = acc * gelu_erf'(aux_bf16[m,n])                        (autograd of nn.GELU)
+ * orow(m) = out_row ? out_row[m] : m  (negative => row skipped);  arow likewise (negative => no addend);  s(m) = row_scale ? row_scale[m] : 1
+ * (row_scale carries DropPath's per-row mask/keep factor, transformer.py:34-42, and the 1/T of the cls mean :371-373).
+ *
+ * Split-K: when `workspace` is given and the tile count under-fills the GPU (weight gradients:
+ * K = tokens), K is split; partial tiles go to the fp32 workspace and are summed by a second kernel.
+ * Only with VT_EPI_F32, no row maps.
+ * ------------------------------------------------------------------------------------------- */
+enum { VT_EPI_BF16 = 0, VT_EPI_F32 = 1, VT_EPI_GELU = 2, VT_EPI_DGELU = 3 };
+
+typedef struct {
+  const void* a;      /* bf16 */
+  const void* b;      /* bf16 */
+  int64_t lda, ldb;   /* leading dims in elements (multiples of 8) */
+  int32_t M, N, K;
+  int32_t a_mn_major, b_mn_major;
+  int32_t epilogue;
+  const float* bias;       /* [N] or NULL */
+  void* out;               /* bf16 or fp32 per epilogue */
+  void* out2;              /* VT_EPI_GELU only */
+  const void* aux;         /* fp32 (VT_EPI_F32) or bf16 (VT_EPI_DGELU) or NULL */
+  int64_t ldo, ldo2, ldaux;
+  const int32_t* out_row;  /* [M] or NULL */
+  const int32_t* aux_row;  /* [M] or NULL */
+  const float* row_scale;  /* [M] or NULL */
+  void* workspace;         /* fp32 scratch for split-K or NULL */
+  int64_t workspace_bytes;
+  int32_t force_splits;    /* 0 = heuristic, >0 = exactly this many K splits (tests) */
+  int32_t force_bn;        /* 0 = heuristic, 128 or 256 (tests) */
+} vt_gemm_params;
+
+int vt_gemm(const vt_gemm_params* p, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * LayerNorm over the last dim (biased variance), fp32 statistics, one warp per row.
+ * Replaces nn.LayerNorm at transformer.py:257 / :359 / :439 / :519 and video_transformer.py:251,
+ * fused with the einops regroupings around it (transformer.py:250, :352-356): row m of the output
+ * is the normalised row in_row[m] of x, so '(b t) p' / '(b p) t' orders and the per-frame cls copy
+ * cost no separate pass.
+ *   y_bf16[m,:] = (x[in_row ? in_row[m] : m, :] - mean) * rstd * gamma + beta ;  mean/rstd saved.
+ * D must be a multiple of 128 and <= 1024.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* x; int64_t ldx;
+  const int32_t* in_row;
+  const float* gamma; const float* beta;
+  void* y;            /* bf16 [rows, D] (or fp32 when y_fp32 != 0) */
+  float* mean; float* rstd;   /* [rows] */
+  int32_t rows, D;
+  float eps;
+  int32_t y_fp32;
+} vt_ln_fwd_params;
+int vt_layernorm_fwd(const vt_ln_fwd_params* p, void* stream);
+
+/* LayerNorm backward.  g = dy*gamma ; dx = rstd*(g - mean(g) - xhat*mean(g*xhat)).
+ * Scatter: t = out_row ? out_row[m] : m.
+ *   t >= 0 : dx[t,:]        = dx_row + (dres ? dres[t,:] : 0)      (adds the residual-path gradient)
+ *   t <  0 : dx_aux[-t-1,:] = dx_row                                (replicated cls rows, summed by caller)
+ * dgamma/dbeta: per-CTA partials into `partials` ([blocks, 2, D] fp32, blocks = vt_ln_bwd_blocks()),
+ * then reduce with vt_reduce_rows. */
+typedef struct {
+  const void* dy; int32_t dy_fp32;      /* bf16 [rows, D] (fp32 if dy_fp32) */
+  const float* x; int64_t ldx; const int32_t* in_row;
+  const float* mean; const float* rstd; const float* gamma;
+  const float* dres; float* dx; int64_t lddx;
+  float* dx_aux;
+  const int32_t* out_row;
+  float* partials;
+  int32_t rows, D;
+} vt_ln_bwd_params;
+int vt_ln_bwd_blocks(int32_t rows);
+int vt_layernorm_bwd(const vt_ln_bwd_params* p, void* stream);
+
+/* out[j] = (accumulate ? out[j] : 0) + scale * sum_{s<S} in[s*stride + j],  j < n (n % 4 == 0) */
+typedef struct { const float* in; float* out; int64_t stride; int32_t S; int64_t n; int32_t accumulate; float scale; } vt_reduce_params;
+int vt_reduce_rows(const vt_reduce_params* p, void* stream);
+
+/* Column sums of a bf16 [M,N] matrix (bias gradients): out_f32[n] = sum_m in[m,n].
+ * workspace: fp32 [vt_colsum_chunks(M), N]. */
+typedef struct { const void* in; int64_t ld; int32_t M, N; float* out; float* workspace; } vt_colsum_params;
+int vt_colsum_chunks(int32_t M);
+int vt_colsum_bf16(const vt_colsum_params* p, void* stream);
+
+/* fp32 -> bf16 casts.  vt_cast: flat.  vt_gather_cast: out[m,:] = bf16(src[in_row[m],:] * row_scale[m])
+ * (gradient of the residual scatter + DropPath scale; in_row < 0 => zeros). */
+typedef struct { const float* src; void* dst; int64_t n; } vt_cast_params;
+int vt_cast_f32_bf16(const vt_cast_params* p, void* stream);
+typedef struct { const float* src; int64_t lds; const int32_t* in_row; const float* row_scale; void* dst; int32_t rows, D; } vt_gather_cast_params;
+int vt_gather_cast_bf16(const vt_gather_cast_params* p, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Multi-head softmax attention core on a packed qkv tensor (no projection):
+ *   qkv bf16 [Bp, N, 3, H, hd] (the layout produced by transformer.py:167's reshape), hd = 64
+ *   ctx bf16 [Bp, N, H*hd] = softmax(q k^T * scale) v      (transformer.py:170-174)
+ *   lse fp32 [Bp, H, N]   (saved for backward);  probs fp32 [Bp,H,N,N] optional (Attention returns it, :177)
+ * vt_attn_fwd/bwd: generic warp-per-query kernels for any N <= 256 (temporal N=8, ViViT N=9, tests).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* qkv; void* ctx; float* lse; float* probs;
+  int32_t Bp, N, H, hd; float scale;
+} vt_attn_fwd_params;
+int vt_attn_fwd(const vt_attn_fwd_params* p, void* stream);
+typedef struct {
+  const void* qkv; const void* ctx; const void* dctx; const float* lse; void* dqkv;
+  int32_t Bp, N, H, hd; float scale;
+} vt_attn_bwd_params;
+int vt_attn_bwd(const vt_attn_bwd_params* p, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Patch / tubelet embedding operand: non-overlapping Conv2d k16 s16 (transformer.py:116-120,:145-147)
+ * or Conv3d k(tube,16,16) (:122-126,:141-143) == im2col + GEMM.
+ *   x fp32 [B, T, C, H, W] -> cols bf16 [B*(T/tube)*(H/ph)*(W/pw), C*tube*ph*pw], k = ((c*tube+dt)*ph+i)*pw+j
+ * vt_col2im is its adjoint (gradient w.r.t. the clip), fp32 out, from fp32 cols.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct { const float* x; void* cols; int32_t B, T, C, H, W, tube, ph, pw; } vt_im2col_params;
+int vt_im2col_bf16(const vt_im2col_params* p, void* stream);
+typedef struct { const float* cols; float* dx; int32_t B, T, C, H, W, tube, ph, pw; } vt_col2im_params;
+int vt_col2im_f32(const vt_col2im_params* p, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * MaskFeat HOG target (dataset.py:39-45 -> skimage.feature.hog x3 + 2x2 cell regroup).
+ *   frames u8 [F, H, W, 3] (H, W multiples of 16) -> feat fp32 [F, H/16, W/16, 108]
+ *   bins (optional) u8 [F, 3, H, W]: orientation bin 0..8 per pixel/channel, 9 = no bin
+ *   lut u8 [511*511]: bin of integer gradient (gy+255, gx+255), built on the host with numpy
+ * ------------------------------------------------------------------------------------------- */
+typedef struct { const uint8_t* frames; const uint8_t* lut; float* feat; uint8_t* bins; int32_t F, H, W; } vt_hog_params;
+int vt_hog(const vt_hog_params* p, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VT_B200_H */

@@ -1,0 +1,238 @@
+"""Generate the golden vectors in tests/golden from the REAL reference modules.
+
+Run in the build container only (needs /root/reference):
+
+    python oracle/make_golden.py
+
+The reference is imported unmodified with `sys.modules` stubs for its
+non-arithmetic top-level imports (matplotlib, pytorch_lightning.utilities.distributed,
+pytorchvideo.* — SURVEY.md §8c).  For every case the script also runs the oracle
+restatement (oracle/vt_oracle.py, oracle/mask_oracle.py) and asserts agreement,
+i.e. this script is what pins the oracle.  Outputs are small .npz files.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import random
+import sys
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+GOLD = os.path.join(ROOT, 'tests', 'golden')
+REF = '/root/reference'
+
+
+def import_reference():
+    def stub(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+
+    stub('matplotlib'); stub('matplotlib.pyplot')
+    stub('pytorch_lightning'); stub('pytorch_lightning.utilities')
+    stub('pytorch_lightning.utilities.distributed', rank_zero_only=lambda f: f)
+    stub('pytorchvideo')
+    stub('pytorchvideo.layers', MultiScaleBlock=None, SpatioTemporalClsPositionalEncoding=None)
+    stub('pytorchvideo.layers.utils', round_width=None, set_attributes=None)
+    stub('pytorchvideo.models')
+    stub('pytorchvideo.models.vision_transformers', MultiscaleVisionTransformers=None)
+    sys.path.insert(0, REF)
+    import transformer, video_transformer, mask_generator  # noqa
+    return transformer, video_transformer, mask_generator
+
+
+def randomize(model, seed):
+    """Reference init leaves temporal_fc at zero (transformer.py:228-232) and LN at
+    identity; perturb everything so no branch is silently a no-op."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if 'temporal_fc' in n or n.endswith('norm.bias') or n.endswith('.bias'):
+                p.add_(torch.randn(p.shape, generator=g, dtype=torch.float64).to(p.dtype) * 0.05)
+            elif n.endswith('norm.weight'):
+                p.add_(torch.randn(p.shape, generator=g, dtype=torch.float64).to(p.dtype) * 0.1)
+
+
+def pack_grads(save, grads):
+    """Small grads verbatim (fp32); large ones as 3 fp64 checksums
+    [sum, l2, <g, linspace(-1,1)>] to keep fixtures small."""
+    for n, g in grads.items():
+        if g.numel() <= 4096:
+            save['grad::' + n] = g.float().numpy()
+        else:
+            lin = torch.linspace(-1, 1, g.numel(), dtype=torch.float64)
+            save['gradsum::' + n] = np.array([g.sum().item(), g.norm().item(),
+                                              (g.reshape(-1) * lin).sum().item()])
+
+
+def rel(a, b):
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def timesformer_case(vt, name, cfg, B, seed):
+    from oracle import vt_oracle as O
+    torch.manual_seed(seed)
+    m = vt.TimeSformer(num_frames=cfg['num_frames'], img_size=cfg['img_size'], patch_size=cfg['patch_size'],
+                       embed_dims=cfg['embed_dims'], num_heads=cfg['num_heads'],
+                       num_transformer_layers=cfg['num_transformer_layers'],
+                       attention_type='divided_space_time')
+    randomize(m, seed + 1)
+    m = m.double()
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    x = torch.randn(B, cfg['num_frames'], 3, cfg['img_size'], cfg['img_size'], dtype=torch.float64)
+    # fp32-representable inputs/params so fp32 consumers see identical values
+    x = x.float().double()
+    for k in sd:
+        sd[k] = sd[k].float().double()
+    m.load_state_dict(sd)
+
+    out = {}
+    m.eval()
+    with torch.no_grad():
+        y_eval = m(x)
+        tok = m.prepare_tokens(x)[0]
+        attn = m.get_last_selfattention(x)
+    out['y_eval'] = y_eval
+    out['tokens'] = tok
+    out['last_attn'] = attn
+
+    # train mode: DropPath live, CPU generator seeded
+    m.train()
+    xg = x.clone().requires_grad_(True)
+    torch.manual_seed(1000 + seed)
+    y_tr = m(xg)
+    w = torch.linspace(-1, 1, y_tr.numel(), dtype=torch.float64).reshape(y_tr.shape)
+    (y_tr * w).sum().backward()
+    out['y_train'] = y_tr.detach()
+    out['loss_w'] = w
+    out['dx'] = xg.grad.float()
+    grads = {n: p.grad.detach().clone() for n, p in m.named_parameters()}
+
+    # ---- pin the oracle ----
+    with torch.no_grad():
+        assert rel(O.timesformer_forward(sd, x, cfg), y_eval) < 1e-12
+        assert rel(O.timesformer_tokens(sd, x, cfg), tok) < 1e-12
+        assert rel(O.timesformer_last_selfattention(sd, x, cfg), attn) < 1e-12
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    xo = x.clone().requires_grad_(True)
+    torch.manual_seed(1000 + seed)
+    yo = O.timesformer_forward(sdg, xo, cfg, training=True)
+    (yo * w).sum().backward()
+    assert rel(yo.detach(), y_tr.detach()) < 1e-12, rel(yo.detach(), y_tr.detach())
+    assert rel(xo.grad, xg.grad) < 1e-10
+    for n, g in grads.items():
+        assert rel(sdg[n].grad, g) < 1e-9, (n, rel(sdg[n].grad, g))
+    print(f'[{name}] oracle == reference (eval, tokens, last_attn, train fwd, all {len(grads)} grads)')
+
+    save = {'x': x.float().numpy(), 'train_seed': np.int64(1000 + seed), 'B': np.int64(B)}
+    for k, v in cfg.items():
+        if isinstance(v, int):
+            save['cfg_' + k] = np.int64(v)
+    for k, v in sd.items():
+        save['sd::' + k] = v.float().numpy()
+    for k, v in out.items():
+        save['out::' + k] = v.numpy()               # fp64
+    pack_grads(save, grads)
+    np.savez_compressed(os.path.join(GOLD, name + '.npz'), **save)
+
+
+def vivit_case(vt, name, cfg, B, seed):
+    from oracle import vt_oracle as O
+    torch.manual_seed(seed)
+    m = vt.ViViT(num_frames=cfg['num_frames_in'], img_size=cfg['img_size'], patch_size=cfg['patch_size'],
+                 embed_dims=cfg['embed_dims'], num_heads=cfg['num_heads'],
+                 num_transformer_layers=cfg['num_transformer_layers'], attention_type='fact_encoder')
+    randomize(m, seed + 1)
+    m = m.double()
+    sd = {k: v.detach().clone().float().double() for k, v in m.state_dict().items()}
+    m.load_state_dict(sd)
+    x = torch.randn(B, cfg['num_frames_in'], 3, cfg['img_size'], cfg['img_size'], dtype=torch.float64).float().double()
+    m.eval()
+    with torch.no_grad():
+        y_eval = m(x)
+        assert rel(O.vivit_forward(sd, x, cfg), y_eval) < 1e-12
+    m.train()
+    xg = x.clone().requires_grad_(True)
+    torch.manual_seed(2000 + seed)
+    y_tr = m(xg)
+    w = torch.linspace(-1, 1, y_tr.numel(), dtype=torch.float64).reshape(y_tr.shape)
+    (y_tr * w).sum().backward()
+    grads = {n: p.grad.detach().clone() for n, p in m.named_parameters()}
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    xo = x.clone().requires_grad_(True)
+    torch.manual_seed(2000 + seed)
+    yo = O.vivit_forward(sdg, xo, cfg, training=True)
+    (yo * w).sum().backward()
+    assert rel(yo.detach(), y_tr.detach()) < 1e-12
+    assert rel(xo.grad, xg.grad) < 1e-10
+    for n, g in grads.items():
+        assert rel(sdg[n].grad, g) < 1e-9, n
+    print(f'[{name}] oracle == reference (eval, train fwd, all {len(grads)} grads)')
+    save = {'x': x.float().numpy(), 'train_seed': np.int64(2000 + seed), 'B': np.int64(B)}
+    for k, v in cfg.items():
+        if isinstance(v, int):
+            save['cfg_' + k] = np.int64(v)
+    for k, v in sd.items():
+        save['sd::' + k] = v.float().numpy()
+    save['out::y_eval'] = y_eval.numpy()
+    save['out::y_train'] = y_tr.detach().numpy()
+    save['out::loss_w'] = w.numpy()
+    save['out::dx'] = xg.grad.float().numpy()
+    pack_grads(save, grads)
+    np.savez_compressed(os.path.join(GOLD, name + '.npz'), **save)
+
+
+def mask_cases(mg):
+    from oracle.mask_oracle import CubeMaskOracle
+    rows = {}
+    for seed in range(8):
+        random.seed(seed); np.random.seed(seed)
+        ref = mg.CubeMaskGenerator(input_size=(8, 14, 14), min_num_patches=16)
+        masks, markers = [], []
+        for _ in range(3):                       # three consecutive calls per seed
+            m, mk = ref()
+            masks.append(m); markers.append(mk)
+        random.seed(seed); np.random.seed(seed)
+        mine = CubeMaskOracle(input_size=(8, 14, 14), min_num_patches=16)
+        for i in range(3):
+            m2, mk2 = mine()
+            assert m2.dtype == masks[i].dtype and np.array_equal(m2, masks[i]), (seed, i)
+            assert mk2 == markers[i], (seed, i)
+        rows[f'mask_{seed}'] = np.stack(masks).astype(np.int32)
+        flat = []
+        for i, mk in enumerate(markers):
+            for s, n in mk:
+                flat.append([i, s, n])
+        rows[f'markers_{seed}'] = np.asarray(flat, dtype=np.int32)
+    # SURVEY Appendix D known answers (first call)
+    assert hashlib.sha256(rows['mask_0'][0].tobytes()).hexdigest()[:16] == 'c87b9c69a35b57eb'
+    assert hashlib.sha256(rows['mask_1'][0].tobytes()).hexdigest()[:16] == '88bae48972b63616'
+    assert hashlib.sha256(rows['mask_2'][0].tobytes()).hexdigest()[:16] == '150b214c947d31fd'
+    np.savez_compressed(os.path.join(GOLD, 'cube_mask.npz'), **rows)
+    print('[cube_mask] oracle == reference for seeds 0..7 x 3 calls; Appendix-D hashes ok')
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    tr, vt, mg = import_reference()
+    tiny = dict(num_frames=4, img_size=32, patch_size=16, embed_dims=32, num_heads=4,
+                num_transformer_layers=2)
+    timesformer_case(vt, 'timesformer_tiny', tiny, B=2, seed=0)
+    hd64 = dict(num_frames=4, img_size=48, patch_size=16, embed_dims=128, num_heads=2,
+                num_transformer_layers=1)
+    timesformer_case(vt, 'timesformer_hd64', hd64, B=2, seed=1)
+    vv = dict(num_frames_in=8, img_size=32, patch_size=16, embed_dims=32, num_heads=4,
+              num_transformer_layers=2)
+    vivit_case(vt, 'vivit_tiny_b1', vv, B=1, seed=2)
+    vivit_case(vt, 'vivit_tiny_b3', vv, B=3, seed=3)
+    mask_cases(mg)
+
+
+if __name__ == '__main__':
+    main()

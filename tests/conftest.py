@@ -1,0 +1,86 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLD = os.path.join(ROOT, 'tests', 'golden')
+
+
+def pytest_configure(config):
+    config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box: pytest -m gpu)')
+
+
+def pytest_collection_modifyitems(config, items):
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason='no CUDA device')
+    for it in items:
+        if 'gpu' in it.keywords:
+            it.add_marker(skip)
+
+
+class Golden:
+    """One reference-generated fixture (oracle/make_golden.py)."""
+
+    def __init__(self, name):
+        z = np.load(os.path.join(GOLD, name + '.npz'))
+        self.raw = z
+        self.x = torch.from_numpy(z['x'])
+        self.sd = {k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith('sd::')}
+        self.out = {k[5:]: torch.from_numpy(z[k]) for k in z.files if k.startswith('out::')}
+        self.grad = {k[6:]: torch.from_numpy(z[k]) for k in z.files if k.startswith('grad::')}
+        self.gradsum = {k[9:]: z[k] for k in z.files if k.startswith('gradsum::')}
+        self.cfg = {k[4:]: int(z[k]) for k in z.files if k.startswith('cfg_')}
+        self.train_seed = int(z['train_seed'])
+        self.B = int(z['B'])
+
+
+@pytest.fixture(scope='session')
+def golden():
+    cache = {}
+
+    def get(name):
+        if name not in cache:
+            cache[name] = Golden(name)
+        return cache[name]
+    return get
+
+
+def rel_err(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def check_grads(named_grads, g, tol):
+    """named_grads: dict name -> tensor; compares against verbatim grads and checksum triples."""
+    worst = 0.0
+    for n, ref in g.grad.items():
+        e = rel_err(named_grads[n].cpu(), ref)
+        worst = max(worst, e)
+        assert e < tol, (n, e)
+    for n, ref in g.gradsum.items():
+        t = named_grads[n].detach().cpu().double()
+        lin = torch.linspace(-1, 1, t.numel(), dtype=torch.float64)
+        mine = np.array([t.sum().item(), t.norm().item(), (t.reshape(-1) * lin).sum().item()])
+        # l2 norm is the scale; sums are compared relative to it
+        scale = ref[1] + 1e-30
+        assert abs(mine[1] - ref[1]) / scale < tol, (n, mine, ref)
+        assert abs(mine[0] - ref[0]) / (scale * np.sqrt(t.numel())) < tol, (n, mine, ref)
+        assert abs(mine[2] - ref[2]) / (scale * np.sqrt(t.numel())) < tol, (n, mine, ref)
+    return worst
+
+
+@pytest.fixture
+def emu():
+    """Swap the kernel table for the CPU emulation (host-logic tests only)."""
+    from tests.emu_kernels import EmuKernels
+    from videotransformer_pytorch_b200 import _lib
+    old = _lib.K
+    _lib.K = EmuKernels(exact=True)
+    yield _lib.K
+    _lib.K = old

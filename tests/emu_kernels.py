@@ -1,0 +1,174 @@
+"""CPU emulation of the C-ABI kernel table (videotransformer_pytorch_b200._lib.CudaKernels).
+
+TEST INFRASTRUCTURE ONLY — lives under tests/ and is installed by the `emu` fixture so that the
+host-side logic of ops.py / transformer.py / video_transformer.py (row maps, cls handling, DropPath
+bookkeeping, backward formulas, state-dict surface) can be checked against the reference-generated
+goldens on a box without a GPU.  It mirrors each kernel's *contract* (include/vt_b200.h) with plain torch
+ops; set `exact=True` to skip bf16 rounding (then results match the fp64 goldens to ~1e-6 in fp32 /
+1e-12 in fp64, which pins the host logic independent of kernel precision).
+The product package never imports this file.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+
+class EmuKernels:
+    name = 'emu'
+
+    def __init__(self, exact=False, dtype=torch.float32):
+        self.exact = exact
+        self.f = dtype          # "fp32" storage type of the emulation (float64 for exact host-logic checks)
+        self.calls = []
+
+    # storage type standing in for bf16
+    def _h(self, t):
+        if self.exact:
+            return t.to(self.f)
+        return t.to(torch.bfloat16)
+
+    def _up(self, t):
+        return t.to(self.f)
+
+    def _idx(self, t):
+        return t.to(torch.int64)
+
+    def gemm(self, a, b, M, N, Kdim, *, a_mn=False, b_mn=False, epi='bf16', bias=None, out=None, out2=None,
+             aux=None, out_row=None, aux_row=None, row_scale=None, out_rows=None, split_ok=False,
+             force_splits=0, force_bn=0):
+        self.calls.append(('gemm', M, N, Kdim, a_mn, b_mn, epi))
+        A = self._up(a).t() if a_mn else self._up(a)
+        Bm = self._up(b) if b_mn else self._up(b).t()
+        assert A.shape == (M, Kdim) and Bm.shape == (Kdim, N), (A.shape, Bm.shape, M, N, Kdim)
+        acc = A @ Bm
+        if bias is not None:
+            acc = acc + self._up(bias)
+        if epi == 'gelu':
+            z = acc
+            h = 0.5 * z * (1 + torch.erf(z / math.sqrt(2.0)))
+            return self._h(z), self._h(h)
+        if epi == 'dgelu':
+            z = self._up(aux)
+            cdf = 0.5 * (1 + torch.erf(z / math.sqrt(2.0)))
+            pdf = torch.exp(-0.5 * z * z) / math.sqrt(2 * math.pi)
+            return self._h(acc * (cdf + z * pdf))
+        if row_scale is not None:
+            acc = acc * self._up(row_scale)[:, None]
+        if epi == 'f32' and aux is not None:
+            if aux_row is not None:
+                ar = self._idx(aux_row)
+                add = torch.zeros_like(acc)
+                ok = ar >= 0
+                add[ok] = self._up(aux)[ar[ok]]
+                acc = acc + add
+            else:
+                acc = acc + self._up(aux)
+        val = acc.to(self.f) if epi == 'f32' else self._h(acc)
+        if out is None:
+            rows = out_rows if out_rows is not None else M
+            out = torch.empty((rows, N), dtype=val.dtype)
+        if out_row is not None:
+            orow = self._idx(out_row)
+            ok = orow >= 0
+            out[orow[ok]] = val[ok].to(out.dtype)
+        else:
+            out[:M] = val.to(out.dtype)
+        return out
+
+    def ln_fwd(self, x2d, gamma, beta, eps, in_row=None, rows=None, out_fp32=False):
+        x = self._up(x2d)
+        if in_row is not None:
+            x = x[self._idx(in_row)]
+        elif rows is not None:
+            x = x[:rows]
+        mu = x.mean(-1, keepdim=True)
+        var = ((x - mu) ** 2).mean(-1, keepdim=True)
+        rstd = torch.rsqrt(var + eps)
+        y = (x - mu) * rstd * self._up(gamma) + self._up(beta)
+        return (y.to(self.f) if out_fp32 else self._h(y)), mu[:, 0].to(self.f), rstd[:, 0].to(self.f)
+
+    def ln_bwd(self, dy, x2d, mean, rstd, gamma, in_row=None, out_row=None, dres=None, dx=None, n_aux=0):
+        x = self._up(x2d)
+        xs = x[self._idx(in_row)] if in_row is not None else x[:dy.shape[0]]
+        d = self._up(dy)
+        xh = (xs - self._up(mean)[:, None]) * self._up(rstd)[:, None]
+        g = d * self._up(gamma)
+        m1 = g.mean(-1, keepdim=True)
+        m2 = (g * xh).mean(-1, keepdim=True)
+        val = self._up(rstd)[:, None] * (g - m1 - xh * m2)
+        D = d.shape[1]
+        if dx is None:
+            dx = torch.empty((x2d.shape[0], D), dtype=self.f)
+        aux = torch.empty((n_aux, D), dtype=self.f) if n_aux else None
+        if out_row is not None:
+            t = self._idx(out_row)
+            pos = t >= 0
+            add = val[pos]
+            if dres is not None:
+                add = add + self._up(dres)[t[pos]]
+            dx[t[pos]] = add.to(dx.dtype)
+            if (~pos).any():
+                aux[(-t[~pos] - 1)] = val[~pos].to(aux.dtype)
+        else:
+            add = val
+            if dres is not None:
+                add = add + self._up(dres)[:val.shape[0]]
+            dx[:val.shape[0]] = add.to(dx.dtype)
+        return dx, aux, (d * xh).sum(0).to(self.f), d.sum(0).to(self.f)
+
+    def colsum(self, x):
+        return self._up(x).sum(0).to(self.f)
+
+    def cast_bf16(self, x):
+        return self._h(x)
+
+    def gather_cast(self, src2d, in_row=None, row_scale=None, rows=None):
+        s = self._up(src2d)
+        if in_row is not None:
+            ir = self._idx(in_row)
+            v = torch.zeros((ir.numel(), s.shape[1]), dtype=s.dtype)
+            ok = ir >= 0
+            v[ok] = s[ir[ok]]
+        else:
+            v = s if rows is None else s[:rows]
+        if row_scale is not None:
+            v = v * self._up(row_scale)[:, None]
+        return self._h(v)
+
+    def attn_fwd(self, qkv, Bp, N, H, hd, scale, want_probs=False):
+        q = self._up(qkv).reshape(Bp, N, 3, H, hd).permute(2, 0, 3, 1, 4)
+        s = (q[0] @ q[1].transpose(-1, -2)) * scale
+        lse = torch.logsumexp(s, dim=-1)
+        p = torch.exp(s - lse[..., None])
+        o = (p @ q[2]).transpose(1, 2).reshape(Bp * N, H * hd)
+        return self._h(o), lse.to(self.f), (p.to(self.f) if want_probs else None)
+
+    def attn_bwd(self, qkv, ctx, dctx, lse, Bp, N, H, hd, scale):
+        q = self._up(qkv).reshape(Bp, N, 3, H, hd).permute(2, 0, 3, 1, 4)
+        Q, Kk, V = q[0], q[1], q[2]
+        O = self._up(ctx).reshape(Bp, N, H, hd).transpose(1, 2)
+        dO = self._up(dctx).reshape(Bp, N, H, hd).transpose(1, 2)
+        s = (Q @ Kk.transpose(-1, -2)) * scale
+        p = torch.exp(s - self._up(lse)[..., None])
+        dV = p.transpose(-1, -2) @ dO
+        dP = dO @ V.transpose(-1, -2)
+        delta = (dO * O).sum(-1, keepdim=True)
+        dS = p * (dP - delta) * scale
+        dQ = dS @ Kk
+        dK = dS.transpose(-1, -2) @ Q
+        d = torch.stack((dQ, dK, dV), dim=0).permute(1, 3, 0, 2, 4).reshape(qkv.shape)
+        return self._h(d)
+
+    def im2col(self, x, tube, ph, pw):
+        B, T, C, H, W = x.shape
+        Tp, Hp, Wp = T // tube, H // ph, W // pw
+        xx = self._up(x).reshape(B, Tp, tube, C, Hp, ph, Wp, pw).permute(0, 1, 4, 6, 3, 2, 5, 7)
+        return self._h(xx.reshape(B * Tp * Hp * Wp, C * tube * ph * pw))
+
+    def col2im(self, cols, shape, tube, ph, pw):
+        B, T, C, H, W = shape
+        Tp, Hp, Wp = T // tube, H // ph, W // pw
+        xx = self._up(cols).reshape(B, Tp, Hp, Wp, C, tube, ph, pw).permute(0, 1, 5, 4, 2, 6, 3, 7)
+        return xx.reshape(shape).to(self.f)

@@ -1,0 +1,442 @@
+// Bandwidth-bound warp-primitive kernels: LayerNorm fwd/bwd (fused with the token regroupings),
+// fp32->bf16 casts (+row gather, +DropPath scale), bias-gradient column sums, im2col / col2im for the
+// non-overlapping patch / tubelet embedding.  All loads/stores are 16-byte vectors on contiguous rows.
+#include <stdarg.h>
+#include <string.h>
+
+#include "vt_common.cuh"
+
+namespace vt {
+
+// ------------------------------------------------------------------------------------------------
+// error slot + device info
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = {0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
+    return 2;
+  }
+  return 0;
+}
+
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm forward: one warp per row, D = 128*V floats, row held in registers (V float4 per lane).
+// ------------------------------------------------------------------------------------------------
+constexpr int LN_WARPS = 8;
+
+template <int V>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+ln_fwd_kernel(const float* __restrict__ x, long long ldx, const int* __restrict__ in_row,
+              const float* __restrict__ gamma, const float* __restrict__ beta, void* __restrict__ y,
+              float* __restrict__ mean, float* __restrict__ rstd, int rows, float eps, int y_fp32) {
+  constexpr int D = V * 128;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4 g[V], b[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    g[i] = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * i);
+    b[i] = __ldg(reinterpret_cast<const float4*>(beta) + lane + 32 * i);
+  }
+  for (int m = blockIdx.x * LN_WARPS + warp; m < rows; m += gridDim.x * LN_WARPS) {
+    const int src = in_row ? in_row[m] : m;
+    const float4* xr = reinterpret_cast<const float4*>(x + (long long)src * ldx);
+    float4 v[V];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      v[i] = xr[lane + 32 * i];
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mu = warp_sum(s) * (1.0f / D);
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float a = v[i].x - mu, bb = v[i].y - mu, c = v[i].z - mu, d = v[i].w - mu;
+      ss += (a * a + bb * bb) + (c * c + d * d);
+    }
+    const float rs = rsqrtf(warp_sum(ss) * (1.0f / D) + eps);
+    if (lane == 0) {
+      mean[m] = mu;
+      rstd[m] = rs;
+    }
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float o0 = (v[i].x - mu) * rs * g[i].x + b[i].x;
+      const float o1 = (v[i].y - mu) * rs * g[i].y + b[i].y;
+      const float o2 = (v[i].z - mu) * rs * g[i].z + b[i].z;
+      const float o3 = (v[i].w - mu) * rs * g[i].w + b[i].w;
+      if (y_fp32) {
+        reinterpret_cast<float4*>(static_cast<float*>(y) + (long long)m * D)[lane + 32 * i] = make_float4(o0, o1, o2, o3);
+      } else {
+        uint2 o;
+        o.x = pack_bf16x2(o0, o1);
+        o.y = pack_bf16x2(o2, o3);
+        reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(y) + (long long)m * D)[lane + 32 * i] = o;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm backward: one warp per row; per-lane dgamma/dbeta partial sums kept in registers across
+// the CTA's rows, reduced across warps through shared memory, one partial row per CTA.
+// ------------------------------------------------------------------------------------------------
+template <int V>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+ln_bwd_kernel(const void* __restrict__ dy, int dy_fp32, const float* __restrict__ x, long long ldx,
+              const int* __restrict__ in_row, const float* __restrict__ mean, const float* __restrict__ rstd,
+              const float* __restrict__ gamma, const float* __restrict__ dres, float* __restrict__ dx, long long lddx,
+              float* __restrict__ dx_aux, const int* __restrict__ out_row, float* __restrict__ partials, int rows) {
+  constexpr int D = V * 128;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4 g[V], dg[V], db[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    g[i] = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * i);
+    dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int m = blockIdx.x * LN_WARPS + warp; m < rows; m += gridDim.x * LN_WARPS) {
+    const int src = in_row ? in_row[m] : m;
+    const float4* xr = reinterpret_cast<const float4*>(x + (long long)src * ldx);
+    const float mu = mean[m], rs = rstd[m];
+    float4 xh[V], gy[V];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      float4 d;
+      if (dy_fp32) {
+        d = reinterpret_cast<const float4*>(static_cast<const float*>(dy) + (long long)m * D)[lane + 32 * i];
+      } else {
+        const uint2 u = reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(dy) + (long long)m * D)[lane + 32 * i];
+        const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+        d = make_float4(a.x, a.y, b.x, b.y);
+      }
+      const float4 xv = xr[lane + 32 * i];
+      xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+      dg[i].x += d.x * xh[i].x; dg[i].y += d.y * xh[i].y; dg[i].z += d.z * xh[i].z; dg[i].w += d.w * xh[i].w;
+      db[i].x += d.x; db[i].y += d.y; db[i].z += d.z; db[i].w += d.w;
+      gy[i] = make_float4(d.x * g[i].x, d.y * g[i].y, d.z * g[i].z, d.w * g[i].w);
+      s1 += (gy[i].x + gy[i].y) + (gy[i].z + gy[i].w);
+      s2 += (gy[i].x * xh[i].x + gy[i].y * xh[i].y) + (gy[i].z * xh[i].z + gy[i].w * xh[i].w);
+    }
+    const float m1 = warp_sum(s1) * (1.0f / D);
+    const float m2 = warp_sum(s2) * (1.0f / D);
+    const int t = out_row ? out_row[m] : m;
+    float* dst;
+    const float* res = nullptr;
+    if (t >= 0) {
+      dst = dx + (long long)t * lddx;
+      if (dres) res = dres + (long long)t * lddx;
+    } else {
+      dst = dx_aux + (long long)(-t - 1) * D;
+    }
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      float4 o;
+      o.x = rs * (gy[i].x - m1 - xh[i].x * m2);
+      o.y = rs * (gy[i].y - m1 - xh[i].y * m2);
+      o.z = rs * (gy[i].z - m1 - xh[i].z * m2);
+      o.w = rs * (gy[i].w - m1 - xh[i].w * m2);
+      if (res) {
+        const float4 r = reinterpret_cast<const float4*>(res)[lane + 32 * i];
+        o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+      }
+      reinterpret_cast<float4*>(dst)[lane + 32 * i] = o;
+    }
+  }
+  // cross-warp reduction of dgamma / dbeta
+  __shared__ float4 sh[LN_WARPS][32];
+  float* pg = partials + (long long)blockIdx.x * 2 * D;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    for (int pass = 0; pass < 2; ++pass) {
+      __syncthreads();
+      sh[warp][lane] = pass == 0 ? dg[i] : db[i];
+      __syncthreads();
+      if (warp == 0) {
+        float4 a = sh[0][lane];
+        for (int w = 1; w < LN_WARPS; ++w) {
+          const float4 c = sh[w][lane];
+          a.x += c.x; a.y += c.y; a.z += c.z; a.w += c.w;
+        }
+        reinterpret_cast<float4*>(pg + pass * D)[lane + 32 * i] = a;
+      }
+    }
+  }
+}
+
+static int ln_blocks(int rows) {
+  int blocks = (rows + LN_WARPS - 1) / LN_WARPS;
+  const int cap = sm_count() * 4;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return blocks;
+}
+
+// ------------------------------------------------------------------------------------------------
+// casts
+// ------------------------------------------------------------------------------------------------
+__global__ void cast_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n8) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const float4 a = reinterpret_cast<const float4*>(src)[2 * i];
+    const float4 b = reinterpret_cast<const float4*>(src)[2 * i + 1];
+    uint4 o;
+    o.x = pack_bf16x2(a.x, a.y); o.y = pack_bf16x2(a.z, a.w);
+    o.z = pack_bf16x2(b.x, b.y); o.w = pack_bf16x2(b.z, b.w);
+    reinterpret_cast<uint4*>(dst)[i] = o;
+  }
+}
+__global__ void cast_tail_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long start, long long n) {
+  const long long i = start + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = __float2bfloat16_rn(src[i]);
+}
+
+__global__ void gather_cast_kernel(const float* __restrict__ src, long long lds, const int* __restrict__ in_row,
+                                   const float* __restrict__ row_scale, __nv_bfloat16* __restrict__ dst, int rows, int D8) {
+  // one warp per row, 8 elements (32 B in, 16 B out) per lane per step
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int m = warp; m < rows; m += nwarps) {
+    const int s = in_row ? in_row[m] : m;
+    const float sc = row_scale ? row_scale[m] : 1.0f;
+    uint4* o = reinterpret_cast<uint4*>(dst + (long long)m * D8 * 8);
+    if (s < 0) {
+      for (int i = lane; i < D8; i += 32) o[i] = make_uint4(0, 0, 0, 0);
+      continue;
+    }
+    const float4* r = reinterpret_cast<const float4*>(src + (long long)s * lds);
+    for (int i = lane; i < D8; i += 32) {
+      const float4 a = r[2 * i], b = r[2 * i + 1];
+      uint4 v;
+      v.x = pack_bf16x2(sc * a.x, sc * a.y); v.y = pack_bf16x2(sc * a.z, sc * a.w);
+      v.z = pack_bf16x2(sc * b.x, sc * b.y); v.w = pack_bf16x2(sc * b.z, sc * b.w);
+      o[i] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// column sums of a bf16 matrix: CTA = 64 columns x one row chunk; 256 threads = 8 row lanes x 32 column pairs
+// ------------------------------------------------------------------------------------------------
+constexpr int COLSUM_ROWS = 512;  // rows per chunk
+
+__global__ void __launch_bounds__(256)
+colsum_kernel(const __nv_bfloat16* __restrict__ in, long long ld, int M, int N, float* __restrict__ ws) {
+  const int cp = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int col = blockIdx.x * 64 + cp * 2;
+  const int r0 = blockIdx.y * COLSUM_ROWS;
+  const int r1 = min(M, r0 + COLSUM_ROWS);
+  float a0 = 0.f, a1 = 0.f;
+  if (col < N) {
+    for (int r = r0 + rl; r < r1; r += 8) {
+      const uint32_t u = *reinterpret_cast<const uint32_t*>(in + (long long)r * ld + col);
+      const float2 f = unpack_bf16x2(u);
+      a0 += f.x;
+      a1 += f.y;
+    }
+  }
+  __shared__ float2 sh[8][32];
+  sh[rl][cp] = make_float2(a0, a1);
+  __syncthreads();
+  if (rl == 0 && col < N) {
+    float2 s = sh[0][cp];
+    for (int w = 1; w < 8; ++w) { s.x += sh[w][cp].x; s.y += sh[w][cp].y; }
+    *reinterpret_cast<float2*>(ws + (long long)blockIdx.y * N + col) = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// im2col for non-overlapping patches / tubelets, and its adjoint
+//   cols[(b,t',hp,wp), ((c*tube+dt)*ph+i)*pw+j] = x[b, t'*tube+dt, c, hp*ph+i, wp*pw+j]
+// one thread = 8 consecutive j (pw % 8 == 0)
+// ------------------------------------------------------------------------------------------------
+__global__ void im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ cols, int B, int T, int C, int H,
+                              int W, int tube, int ph, int pw, long long total8) {
+  const int Kc = C * tube * ph * pw;
+  const int Hp = H / ph, Wp = W / pw, Tp = T / tube;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total8; idx += (long long)gridDim.x * blockDim.x) {
+    const long long e = idx * 8;
+    const long long row = e / Kc;
+    int k = (int)(e - row * Kc);
+    const int j = k % pw; k /= pw;
+    const int i = k % ph; k /= ph;
+    const int dt = k % tube; const int c = k / tube;
+    long long rr = row;
+    const int wp = (int)(rr % Wp); rr /= Wp;
+    const int hp = (int)(rr % Hp); rr /= Hp;
+    const int tp = (int)(rr % Tp); const int b = (int)(rr / Tp);
+    const float* src = x + ((((long long)b * T + (tp * tube + dt)) * C + c) * H + (hp * ph + i)) * W + wp * pw + j;
+    const float4 a = *reinterpret_cast<const float4*>(src);
+    const float4 bq = *reinterpret_cast<const float4*>(src + 4);
+    uint4 o;
+    o.x = pack_bf16x2(a.x, a.y); o.y = pack_bf16x2(a.z, a.w);
+    o.z = pack_bf16x2(bq.x, bq.y); o.w = pack_bf16x2(bq.z, bq.w);
+    *reinterpret_cast<uint4*>(cols + e) = o;
+  }
+}
+
+__global__ void col2im_kernel(const float* __restrict__ cols, float* __restrict__ dx, int B, int T, int C, int H, int W,
+                              int tube, int ph, int pw, long long total4) {
+  const int Kc = C * tube * ph * pw;
+  const int Hp = H / ph, Wp = W / pw, Tp = T / tube;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total4; idx += (long long)gridDim.x * blockDim.x) {
+    const long long e = idx * 4;
+    const long long row = e / Kc;
+    int k = (int)(e - row * Kc);
+    const int j = k % pw; k /= pw;
+    const int i = k % ph; k /= ph;
+    const int dt = k % tube; const int c = k / tube;
+    long long rr = row;
+    const int wp = (int)(rr % Wp); rr /= Wp;
+    const int hp = (int)(rr % Hp); rr /= Hp;
+    const int tp = (int)(rr % Tp); const int b = (int)(rr / Tp);
+    float* dst = dx + ((((long long)b * T + (tp * tube + dt)) * C + c) * H + (hp * ph + i)) * W + wp * pw + j;
+    *reinterpret_cast<float4*>(dst) = *reinterpret_cast<const float4*>(cols + e);
+  }
+}
+
+static int grid_for(long long work, int threads) {
+  long long b = (work + threads - 1) / threads;
+  const long long cap = (long long)sm_count() * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace vt
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+using namespace vt;
+
+extern "C" int vt_version(void) { return VT_ABI_VERSION; }
+
+extern "C" int vt_last_error(char* buf, size_t n) {
+  if (!buf || n == 0) return 0;
+  strncpy(buf, g_err, n - 1);
+  buf[n - 1] = 0;
+  return (int)strlen(buf);
+}
+
+extern "C" int vt_sm_count(void) { return sm_count(); }
+
+extern "C" int vt_layernorm_fwd(const vt_ln_fwd_params* p, void* stream) {
+  VT_REQUIRE(p && p->x && p->gamma && p->beta && p->y && p->mean && p->rstd, "vt_layernorm_fwd: null pointer");
+  VT_REQUIRE(p->rows > 0, "vt_layernorm_fwd: rows=%d", p->rows);
+  VT_REQUIRE(p->D % 128 == 0 && p->D >= 128 && p->D <= 1024, "vt_layernorm_fwd: D=%d unsupported (multiple of 128, <=1024)", p->D);
+  VT_REQUIRE(p->ldx % 4 == 0, "vt_layernorm_fwd: ldx must be a multiple of 4");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int blocks = ln_blocks(p->rows);
+#define VT_LN_FWD(V)                                                                                                    \
+  case V:                                                                                                               \
+    ln_fwd_kernel<V><<<blocks, LN_WARPS * 32, 0, st>>>(p->x, p->ldx, p->in_row, p->gamma, p->beta, p->y, p->mean,       \
+                                                       p->rstd, p->rows, p->eps, p->y_fp32);                           \
+    break;
+  switch (p->D / 128) {
+    VT_LN_FWD(1) VT_LN_FWD(2) VT_LN_FWD(3) VT_LN_FWD(4) VT_LN_FWD(5) VT_LN_FWD(6) VT_LN_FWD(7) VT_LN_FWD(8)
+  }
+#undef VT_LN_FWD
+  return check_launch("ln_fwd_kernel");
+}
+
+extern "C" int vt_ln_bwd_blocks(int32_t rows) { return ln_blocks(rows); }
+
+extern "C" int vt_layernorm_bwd(const vt_ln_bwd_params* p, void* stream) {
+  VT_REQUIRE(p && p->dy && p->x && p->mean && p->rstd && p->gamma && p->dx && p->partials, "vt_layernorm_bwd: null pointer");
+  VT_REQUIRE(p->D % 128 == 0 && p->D >= 128 && p->D <= 1024, "vt_layernorm_bwd: D=%d unsupported", p->D);
+  VT_REQUIRE(p->rows > 0, "vt_layernorm_bwd: rows=%d", p->rows);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int blocks = ln_blocks(p->rows);
+#define VT_LN_BWD(V)                                                                                                    \
+  case V:                                                                                                               \
+    ln_bwd_kernel<V><<<blocks, LN_WARPS * 32, 0, st>>>(p->dy, p->dy_fp32, p->x, p->ldx, p->in_row, p->mean, p->rstd,    \
+                                                       p->gamma, p->dres, p->dx, p->lddx, p->dx_aux, p->out_row,        \
+                                                       p->partials, p->rows);                                           \
+    break;
+  switch (p->D / 128) {
+    VT_LN_BWD(1) VT_LN_BWD(2) VT_LN_BWD(3) VT_LN_BWD(4) VT_LN_BWD(5) VT_LN_BWD(6) VT_LN_BWD(7) VT_LN_BWD(8)
+  }
+#undef VT_LN_BWD
+  return check_launch("ln_bwd_kernel");
+}
+
+extern "C" int vt_cast_f32_bf16(const vt_cast_params* p, void* stream) {
+  VT_REQUIRE(p && p->src && p->dst && p->n > 0, "vt_cast_f32_bf16: bad params");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long n8 = p->n / 8;
+  if (n8 > 0) cast_kernel<<<grid_for(n8, 256), 256, 0, st>>>(p->src, static_cast<__nv_bfloat16*>(p->dst), n8);
+  if (p->n % 8) cast_tail_kernel<<<1, 32, 0, st>>>(p->src, static_cast<__nv_bfloat16*>(p->dst), n8 * 8, p->n);
+  return check_launch("cast_kernel");
+}
+
+extern "C" int vt_gather_cast_bf16(const vt_gather_cast_params* p, void* stream) {
+  VT_REQUIRE(p && p->src && p->dst && p->rows > 0, "vt_gather_cast_bf16: bad params");
+  VT_REQUIRE(p->D % 8 == 0 && p->lds % 4 == 0, "vt_gather_cast_bf16: D %% 8 and lds %% 4 required");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int blocks = grid_for((long long)p->rows * 32, 256);
+  gather_cast_kernel<<<blocks, 256, 0, st>>>(p->src, p->lds, p->in_row, p->row_scale, static_cast<__nv_bfloat16*>(p->dst),
+                                             p->rows, p->D / 8);
+  return check_launch("gather_cast_kernel");
+}
+
+extern "C" int vt_colsum_chunks(int32_t M) { return (M + COLSUM_ROWS - 1) / COLSUM_ROWS; }
+
+namespace vt { int launch_reduce_rows(const float*, float*, long long, int, long long, int, float, cudaStream_t); }
+
+extern "C" int vt_colsum_bf16(const vt_colsum_params* p, void* stream) {
+  VT_REQUIRE(p && p->in && p->out && p->workspace && p->M > 0 && p->N > 0, "vt_colsum_bf16: bad params");
+  VT_REQUIRE(p->N % 4 == 0 && p->ld % 2 == 0, "vt_colsum_bf16: N %% 4 and ld %% 2 required");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int chunks = vt_colsum_chunks(p->M);
+  dim3 grid((p->N + 63) / 64, chunks);
+  colsum_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(p->in), p->ld, p->M, p->N, p->workspace);
+  int rc = check_launch("colsum_kernel");
+  if (rc) return rc;
+  return launch_reduce_rows(p->workspace, p->out, p->N, chunks, p->N, 0, 1.0f, st);
+}
+
+extern "C" int vt_im2col_bf16(const vt_im2col_params* p, void* stream) {
+  VT_REQUIRE(p && p->x && p->cols, "vt_im2col_bf16: null pointer");
+  VT_REQUIRE(p->pw % 8 == 0 && p->W % p->pw == 0 && p->H % p->ph == 0 && p->T % p->tube == 0 && p->W % 4 == 0,
+             "vt_im2col_bf16: unsupported geometry");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long total8 = (long long)p->B * p->T * p->C * p->H * p->W / 8;
+  im2col_kernel<<<grid_for(total8, 256), 256, 0, st>>>(p->x, static_cast<__nv_bfloat16*>(p->cols), p->B, p->T, p->C, p->H,
+                                                       p->W, p->tube, p->ph, p->pw, total8);
+  return check_launch("im2col_kernel");
+}
+
+extern "C" int vt_col2im_f32(const vt_col2im_params* p, void* stream) {
+  VT_REQUIRE(p && p->cols && p->dx, "vt_col2im_f32: null pointer");
+  VT_REQUIRE(p->pw % 4 == 0 && p->W % p->pw == 0 && p->H % p->ph == 0 && p->T % p->tube == 0, "vt_col2im_f32: unsupported geometry");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long total4 = (long long)p->B * p->T * p->C * p->H * p->W / 4;
+  col2im_kernel<<<grid_for(total4, 256), 256, 0, st>>>(p->cols, p->dx, p->B, p->T, p->C, p->H, p->W, p->tube, p->ph, p->pw,
+                                                       total4);
+  return check_launch("col2im_kernel");
+}

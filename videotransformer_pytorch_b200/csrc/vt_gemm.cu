@@ -1,0 +1,411 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a:
+//   TMA (cp.async.bulk.tensor, 128B swizzle) -> shared-memory ring -> tcgen05.mma (fp32 accum in TMEM,
+//   two accumulator stages) -> tcgen05.ld epilogue fused with bias / GELU / dGELU / residual / row maps.
+// One CTA per SM, 256 threads: warp0 = TMA producer, warp1 = MMA issuer, warp2 = TMEM allocator,
+// warps4-7 = epilogue (warp w drains TMEM lanes 32*(w%4)..+31).
+// Tile: 128 x BN x 64, BN in {128, 256}.  Both operands may be K-major or MN-major (UMMA descriptors),
+// so forward (X W^T), dgrad (dY W) and wgrad (dY^T X) all run without transposed copies.
+#include "vt_common.cuh"
+#include "vt_umma.cuh"
+
+namespace vt {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int GEMM_THREADS = 256;
+constexpr int CHUNK_BYTES = 64 * BK * 2;  // one 64-wide MN chunk of an MN-major tile (8 KiB)
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int TMEM_COLS = 2 * BN;  // 512 or 256: two accumulator stages
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct GemmDev {
+  int M, N, K;
+  int num_m, num_n, splits, kblocks;
+  int a_mn, b_mn, epi;
+  const float* bias;
+  void* out;
+  void* out2;
+  const void* aux;
+  long long ldo, ldo2, ldaux;
+  const int* out_row;
+  const int* aux_row;
+  const float* row_scale;
+  long long split_stride;  // elements between split partials (EPI_F32 only)
+};
+
+template <int BN>
+__device__ __forceinline__ void epilogue_chunk(const GemmDev& p, int row, int n0, int split, const uint32_t (&r)[32]) {
+  // row < M guaranteed by caller; columns n0..n0+31 clipped to N in groups of 8.
+  const float s = p.row_scale ? p.row_scale[row] : 1.0f;
+  const int orow = p.out_row ? p.out_row[row] : row;
+  if (orow < 0) return;
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    const int n = n0 + j;
+    if (n >= p.N) break;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[j + i]);
+    if (p.bias) {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
+      v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+      v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+    }
+    if (p.epi == VT_EPI_BF16) {
+      uint4 o;
+      o.x = pack_bf16x2(s * v[0], s * v[1]);
+      o.y = pack_bf16x2(s * v[2], s * v[3]);
+      o.z = pack_bf16x2(s * v[4], s * v[5]);
+      o.w = pack_bf16x2(s * v[6], s * v[7]);
+      *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + (long long)orow * p.ldo + n) = o;
+    } else if (p.epi == VT_EPI_F32) {
+      float4 o0 = make_float4(s * v[0], s * v[1], s * v[2], s * v[3]);
+      float4 o1 = make_float4(s * v[4], s * v[5], s * v[6], s * v[7]);
+      if (p.aux) {
+        const int arow = p.aux_row ? p.aux_row[row] : row;
+        if (arow >= 0) {  // negative => no addend for this row
+          const float* ap = static_cast<const float*>(p.aux) + (long long)arow * p.ldaux + n;
+          const float4 a0 = *reinterpret_cast<const float4*>(ap);
+          const float4 a1 = *reinterpret_cast<const float4*>(ap + 4);
+          o0.x += a0.x; o0.y += a0.y; o0.z += a0.z; o0.w += a0.w;
+          o1.x += a1.x; o1.y += a1.y; o1.z += a1.z; o1.w += a1.w;
+        }
+      }
+      float* op = static_cast<float*>(p.out) + (long long)split * p.split_stride + (long long)orow * p.ldo + n;
+      *reinterpret_cast<float4*>(op) = o0;
+      *reinterpret_cast<float4*>(op + 4) = o1;
+    } else if (p.epi == VT_EPI_GELU) {
+      uint4 z, h;
+      z.x = pack_bf16x2(v[0], v[1]); z.y = pack_bf16x2(v[2], v[3]);
+      z.z = pack_bf16x2(v[4], v[5]); z.w = pack_bf16x2(v[6], v[7]);
+      h.x = pack_bf16x2(gelu_erf(v[0]), gelu_erf(v[1])); h.y = pack_bf16x2(gelu_erf(v[2]), gelu_erf(v[3]));
+      h.z = pack_bf16x2(gelu_erf(v[4]), gelu_erf(v[5])); h.w = pack_bf16x2(gelu_erf(v[6]), gelu_erf(v[7]));
+      *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + (long long)orow * p.ldo + n) = z;
+      *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out2) + (long long)orow * p.ldo2 + n) = h;
+    } else {  // VT_EPI_DGELU
+      const uint4 zz =
+          *reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.aux) + (long long)row * p.ldaux + n);
+      const float2 z0 = unpack_bf16x2(zz.x), z1 = unpack_bf16x2(zz.y), z2 = unpack_bf16x2(zz.z),
+                   z3 = unpack_bf16x2(zz.w);
+      uint4 o;
+      o.x = pack_bf16x2(v[0] * dgelu_erf(z0.x), v[1] * dgelu_erf(z0.y));
+      o.y = pack_bf16x2(v[2] * dgelu_erf(z1.x), v[3] * dgelu_erf(z1.y));
+      o.z = pack_bf16x2(v[4] * dgelu_erf(z2.x), v[5] * dgelu_erf(z2.y));
+      o.w = pack_bf16x2(v[6] * dgelu_erf(z3.x), v[7] * dgelu_erf(z3.y));
+      *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + (long long)orow * p.ldo + n) = o;
+    }
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const GemmDev p) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + Cfg::STAGES;
+  uint64_t* tfull_bar = empty_bar + Cfg::STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < Cfg::STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_units = p.num_m * p.num_n * p.splits;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0, phase = 0;
+      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+        const int tile = unit / p.splits, split = unit - tile * p.splits;
+        const int m_blk = tile % p.num_m, n_blk = tile / p.num_m;
+        const int kb0 = (int)(((long long)p.kblocks * split) / p.splits);
+        const int kb1 = (int)(((long long)p.kblocks * (split + 1)) / p.splits);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sB = sA + Cfg::A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          if (!p.a_mn) {
+            tma_load_2d(sA, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BM / 64; ++c)
+              tma_load_2d(sA + c * CHUNK_BYTES, &tmA, &full_bar[stage], m_blk * BM + c * 64, kb * BK);
+          }
+          if (!p.b_mn) {
+            tma_load_2d(sB, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c)
+              tma_load_2d(sB + c * CHUNK_BYTES, &tmB, &full_bar[stage], n_blk * BN + c * 64, kb * BK);
+          }
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(BM, BN, (uint32_t)p.a_mn, (uint32_t)p.b_mn);
+      int stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+        const int tile = unit / p.splits, split = unit - tile * p.splits;
+        const int kb0 = (int)(((long long)p.kblocks * split) / p.splits);
+        const int kb1 = (int)(((long long)p.kblocks * (split + 1)) / p.splits);
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t adesc = p.a_mn ? sdesc_mnmajor(a_addr + k * 2048, CHUNK_BYTES) : sdesc_kmajor(a_addr + k * 32);
+            const uint64_t bdesc = p.b_mn ? sdesc_mnmajor(b_addr + k * 2048, CHUNK_BYTES) : sdesc_kmajor(b_addr + k * 32);
+            umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    int acc = 0, acc_phase = 0;
+    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+      const int tile = unit / p.splits, split = unit - tile * p.splits;
+      const int m_blk = tile % p.num_m, n_blk = tile / p.num_m;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const int row = m_blk * BM + q * 32 + lane;
+      const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(t_base + c * 32, r);
+        tmem_ld_wait();
+        const int n0 = n_blk * BN + c * 32;
+        if (row < p.M && n0 < p.N) epilogue_chunk<BN>(p, row, n0, split, r);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !ptr) return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// 2-D bf16 row-major [rows, cols] (leading dim ld), box {64 cols, box_rows}, 128B swizzle, OOB -> 0.
+int make_tmap_bf16_2d(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  VT_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
+  VT_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base pointer must be 16-byte aligned");
+  VT_REQUIRE((ld * 2) % 16 == 0, "TMA leading dimension must be a multiple of 8 elements (got %lld)", ld);
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)(ld * 2)};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  VT_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld box_rows=%d", (int)r,
+             rows, cols, ld, box_rows);
+  return 0;
+}
+
+__global__ void reduce_rows_kernel(const float* __restrict__ in, float* __restrict__ out, long long stride, int S,
+                                   long long n4, int accumulate, float scale) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < S; ++s) {
+      const float4 v = *reinterpret_cast<const float4*>(in + (long long)s * stride + i * 4);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    acc.x *= scale; acc.y *= scale; acc.z *= scale; acc.w *= scale;
+    float4* o = reinterpret_cast<float4*>(out + i * 4);
+    if (accumulate) {
+      const float4 p = *o;
+      acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+    }
+    *o = acc;
+  }
+}
+
+int launch_reduce_rows(const float* in, float* out, long long stride, int S, long long n, int accumulate, float scale,
+                       cudaStream_t st) {
+  VT_REQUIRE(n % 4 == 0 && stride % 4 == 0, "vt_reduce_rows: n and stride must be multiples of 4");
+  const long long n4 = n / 4;
+  int blocks = (int)((n4 + 255) / 256);
+  const int cap = sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  reduce_rows_kernel<<<blocks, 256, 0, st>>>(in, out, stride, S, n4, accumulate, scale);
+  return check_launch("reduce_rows_kernel");
+}
+
+template <int BN>
+static int launch_gemm(const vt_gemm_params* q, GemmDev& d, cudaStream_t st) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;  // benign race: idempotent
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
+    VT_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (!q->a_mn_major) rc = make_tmap_bf16_2d(&tmA, q->a, q->M, q->K, q->lda, BM);
+  else rc = make_tmap_bf16_2d(&tmA, q->a, q->K, q->M, q->lda, BK);
+  if (rc) return rc;
+  if (!q->b_mn_major) rc = make_tmap_bf16_2d(&tmB, q->b, q->N, q->K, q->ldb, BN);
+  else rc = make_tmap_bf16_2d(&tmB, q->b, q->K, q->N, q->ldb, BK);
+  if (rc) return rc;
+
+  d.num_m = (q->M + BM - 1) / BM;
+  d.num_n = (q->N + BN - 1) / BN;
+  d.kblocks = (q->K + BK - 1) / BK;
+  const int tiles = d.num_m * d.num_n;
+  const int sms = sm_count();
+
+  int splits = 1;
+  const long long tile_out = (long long)q->M * q->N;
+  if (q->epilogue == VT_EPI_F32 && q->workspace && !q->out_row && !q->aux && !q->row_scale && !q->bias) {
+    if (q->force_splits > 0) splits = q->force_splits;
+    else if (tiles * 2 <= sms && d.kblocks >= 16) {
+      splits = (2 * sms) / tiles;                 // about two waves of work units
+      if (splits > d.kblocks / 4) splits = d.kblocks / 4;
+    }
+    const long long max_by_ws = q->workspace_bytes / (tile_out * 4);
+    if (splits > max_by_ws) splits = (int)max_by_ws;
+    if (splits > d.kblocks) splits = d.kblocks;
+    if (splits < 1) splits = 1;
+  }
+  d.splits = splits;
+  void* final_out = d.out;
+  if (splits > 1) {
+    d.out = q->workspace;
+    d.ldo = q->N;
+    d.split_stride = tile_out;
+  } else {
+    d.split_stride = 0;
+  }
+  const int units = tiles * splits;
+  const int grid = units < sms ? units : sms;
+  gemm_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, d);
+  rc = check_launch("gemm_tcgen05_kernel");
+  if (rc) return rc;
+  if (splits > 1) {
+    // partials [splits, M, N] -> out [M, ldo]
+    if (q->ldo == q->N) {
+      return launch_reduce_rows(static_cast<const float*>(q->workspace), static_cast<float*>(final_out), tile_out, splits,
+                                tile_out, 0, 1.0f, st);
+    }
+    set_error("vt_gemm: split-K requires ldo == N");
+    return 1;
+  }
+  return 0;
+}
+
+}  // namespace vt
+
+extern "C" int vt_gemm(const vt_gemm_params* q, void* stream) {
+  using namespace vt;
+  VT_REQUIRE(q != nullptr, "vt_gemm: null params");
+  VT_REQUIRE(q->M > 0 && q->N > 0 && q->K > 0, "vt_gemm: bad shape M=%d N=%d K=%d", q->M, q->N, q->K);
+  VT_REQUIRE(q->N % 8 == 0, "vt_gemm: N must be a multiple of 8 (got %d)", q->N);
+  VT_REQUIRE(q->a && q->b && q->out, "vt_gemm: null operand");
+  VT_REQUIRE(q->epilogue >= VT_EPI_BF16 && q->epilogue <= VT_EPI_DGELU, "vt_gemm: bad epilogue %d", q->epilogue);
+  if (q->epilogue == VT_EPI_GELU) VT_REQUIRE(q->out2 != nullptr, "vt_gemm: VT_EPI_GELU needs out2");
+  if (q->epilogue == VT_EPI_DGELU) VT_REQUIRE(q->aux != nullptr, "vt_gemm: VT_EPI_DGELU needs aux (z)");
+  const int esz = (q->epilogue == VT_EPI_F32) ? 4 : 2;
+  VT_REQUIRE((q->ldo * esz) % 16 == 0 && (reinterpret_cast<uintptr_t>(q->out) & 15) == 0,
+             "vt_gemm: out must be 16B aligned with 16B-multiple row pitch");
+  if (q->aux) VT_REQUIRE((reinterpret_cast<uintptr_t>(q->aux) & 15) == 0 && (q->ldaux * esz) % 16 == 0, "vt_gemm: aux misaligned");
+  if (q->bias) VT_REQUIRE((reinterpret_cast<uintptr_t>(q->bias) & 15) == 0, "vt_gemm: bias misaligned");
+
+  GemmDev d;
+  d.M = q->M; d.N = q->N; d.K = q->K;
+  d.a_mn = q->a_mn_major ? 1 : 0;
+  d.b_mn = q->b_mn_major ? 1 : 0;
+  d.epi = q->epilogue;
+  d.bias = q->bias;
+  d.out = q->out; d.out2 = q->out2; d.aux = q->aux;
+  d.ldo = q->ldo; d.ldo2 = q->ldo2; d.ldaux = q->ldaux;
+  d.out_row = q->out_row; d.aux_row = q->aux_row; d.row_scale = q->row_scale;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+  int bn = q->force_bn;
+  if (bn == 0) bn = (q->N % 256 == 0 || q->N > 512) ? 256 : 128;
+  VT_REQUIRE(bn == 128 || bn == 256, "vt_gemm: force_bn must be 128 or 256");
+  if (bn == 256) return launch_gemm<256>(q, d, st);
+  return launch_gemm<128>(q, d, st);
+}
+
+extern "C" int vt_reduce_rows(const vt_reduce_params* p, void* stream) {
+  using namespace vt;
+  VT_REQUIRE(p && p->in && p->out && p->S >= 1, "vt_reduce_rows: bad params");
+  return launch_reduce_rows(p->in, p->out, p->stride, p->S, p->n, p->accumulate, p->scale,
+                            static_cast<cudaStream_t>(stream));
+}

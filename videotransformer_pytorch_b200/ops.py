@@ -1,0 +1,441 @@
+"""Sub-block level autograd functions of the video-transformer hot path.
+
+Each Function is the forward+backward of one reference sub-block, expressed as a fixed sequence of
+C-ABI kernel launches (see _lib.K):
+
+  TemporalAttnFn  <- DividedTemporalAttentionWithPreNorm.forward   (reference transformer.py:234-282)
+  SpatialAttnFn   <- DividedSpatialAttentionWithPreNorm.forward    (transformer.py:336-382)
+  JointAttnFn     <- MultiheadAttentionWithPreNorm.forward         (transformer.py:428-456)
+  FFNFn           <- FFNWithPreNorm.forward                        (transformer.py:516-523)
+  PatchTokensFn   <- PatchEmbed.forward + TimeSformer/ViViT.prepare_tokens
+                     (transformer.py:138-151, video_transformer.py:193-240 / :455-475)
+  ClsNormFn       <- final nn.LayerNorm(eps=1e-6) + cls select     (video_transformer.py:251-254)
+  AttentionCoreFn <- Attention.forward (stand-alone use)            (transformer.py:165-177)
+
+Data layout: the residual stream stays fp32 `[B, 1+P*T, D]` exactly as in the reference (token
+n = 1 + p*T + t).  The einops regroupings ('b (p t) d -> (b p) t d', '-> (b t) p d', cls replication /
+mean) never materialise: LayerNorm reads rows through an index map and the last GEMM of each
+sub-block scatters rows back through the inverse map while adding the residual.  GEMM operands are
+bf16 (fp32 accumulation in TMEM); weights are bf16 shadows of the fp32 nn.Parameters.
+"""
+from __future__ import annotations
+
+import functools
+
+import torch
+
+from . import _lib
+
+
+def K():
+    return _lib.K
+
+
+# --------------------------------------------------------------------------------------------------
+# index maps (int32, cached per geometry/device)
+# --------------------------------------------------------------------------------------------------
+@functools.lru_cache(maxsize=64)
+def token_maps(B: int, T: int, P: int, device: str):
+    dev = torch.device(device)
+    S = 1 + P * T
+    R = B * S
+    ar = functools.partial(torch.arange, device=dev, dtype=torch.int64)
+    # temporal layout m = (b*P + p)*T + t  ==  patch rows of the residual stream in order
+    m = ar(B * P * T)
+    temporal = (m // (P * T)) * S + 1 + (m % (P * T))
+    # spatial layout m = (b*T + t)*(P+1) + n ; n = 0 -> cls of sample b, n >= 1 -> patch n-1 of frame t
+    m = ar(B * T * (P + 1))
+    bt, n = m // (P + 1), m % (P + 1)
+    b, t = bt // T, bt % T
+    is_cls = n == 0
+    src = torch.where(is_cls, b * S, b * S + 1 + (n - 1) * T + t)
+    sp_out = torch.where(is_cls, R + bt, src)                 # forward: cls outputs go to R + (b*T+t)
+    sp_aux = torch.where(is_cls, torch.full_like(src, -1), src)
+    sp_bwd = torch.where(is_cls, -(bt) - 1, src)              # LN backward: cls grads go to aux[b*T+t]
+    cls_scale = torch.where(is_cls, torch.full_like(src, 1.0, dtype=torch.float32) / T,
+                            torch.ones_like(src, dtype=torch.float32))
+    # patch-embed GEMM rows m = (b*T + t)*P + p
+    m = ar(B * T * P)
+    bt, p = m // P, m % P
+    b, t = bt // T, bt % T
+    emb_out = b * S + 1 + p * T + t
+    emb_aux = p * T + t
+    i32 = lambda v: v.to(torch.int32).contiguous()
+    return dict(temporal=i32(temporal), sp_in=i32(src), sp_out=i32(sp_out), sp_aux=i32(sp_aux), sp_bwd=i32(sp_bwd),
+                sp_cls_scale=cls_scale.contiguous(), emb_out=i32(emb_out), emb_aux=i32(emb_aux),
+                cls_rows=i32(ar(B) * S))
+
+
+@functools.lru_cache(maxsize=64)
+def frame_maps(BT: int, P: int, device: str):
+    """ViViT spatial encoder tokens: rows (bt, n); patch-embed GEMM rows (bt, p) -> bt*(P+1)+1+p."""
+    dev = torch.device(device)
+    m = torch.arange(BT * P, device=dev, dtype=torch.int64)
+    bt, p = m // P, m % P
+    out = bt * (P + 1) + 1 + p
+    aux = 1 + p
+    return dict(emb_out=out.to(torch.int32).contiguous(), emb_aux=aux.to(torch.int32).contiguous())
+
+
+def drop_path_scale(p: float, training: bool, n0: int, repeat: int, device):
+    """Per-row DropPath factor, reference transformer.py:34-42: mask = floor(keep + U[0,1)) drawn with
+    torch.rand on the CPU default generator (one value per dim-0 row of the sub-block's own layout),
+    output = x / keep * mask.  Returns fp32 [n0*repeat] on `device`, or None when DropPath is inactive."""
+    if p == 0.0 or not training:
+        return None
+    keep = 1.0 - p
+    r = (keep + torch.rand((n0, 1, 1))).floor_().reshape(n0) / keep
+    r = r.to(device=device, dtype=torch.float32, non_blocking=True)
+    return r.repeat_interleave(repeat).contiguous() if repeat > 1 else r.contiguous()
+
+
+def _wgrad(dout, act, n_out, k_in, m_tok):
+    """dW[n_out, k_in] = dout[m_tok, n_out]^T @ act[m_tok, k_in]  (both operands MN-major, split-K)."""
+    return K().gemm(dout, act, n_out, k_in, m_tok, a_mn=True, b_mn=True, epi='f32', split_ok=True)
+
+
+def _dgrad(dout, w, m_tok, k_in, n_out, **kw):
+    """dX[m_tok, k_in] = dout[m_tok, n_out] @ W[n_out, k_in]  (W read MN-major)."""
+    return K().gemm(dout, w, m_tok, k_in, n_out, b_mn=True, **kw)
+
+
+def _mul_opt(a, b):
+    if a is None:
+        return b
+    if b is None:
+        return a
+    return a * b
+
+
+# --------------------------------------------------------------------------------------------------
+class TemporalAttnFn(torch.autograd.Function):
+    """y = cat(cls, x_p + temporal_fc(DropPath(proj(attn_T(LN(x_p))))))."""
+
+    @staticmethod
+    def forward(ctx, x, ln_w, ln_b, qkv_w, qkv_b, proj_w, proj_b, fc_w, fc_b, qkv_wh, proj_wh, fc_wh, dp, T, H, eps=1e-5):
+        k = K()
+        B, S, D = x.shape
+        P = (S - 1) // T
+        maps = token_maps(B, T, P, str(x.device))
+        x2 = x.reshape(B * S, D)
+        Mt = B * P * T
+        xn, mean, rstd = k.ln_fwd(x2, ln_w, ln_b, eps, in_row=maps['temporal'], rows=Mt)
+        qkv = k.gemm(xn, qkv_wh, Mt, 3 * D, D, bias=qkv_b, epi='bf16')
+        hd = D // H
+        cx, lse, _ = k.attn_fwd(qkv, B * P, T, H, hd, hd ** -0.5)
+        a = k.gemm(cx, proj_wh, Mt, D, D, bias=proj_b, epi='bf16', row_scale=dp)
+        y = torch.empty_like(x)
+        y2 = y.view(B * S, D)
+        k.gemm(a, fc_wh, Mt, D, D, bias=fc_b, epi='f32', aux=x2, aux_row=maps['temporal'], out=y2,
+               out_row=maps['temporal'])
+        y[:, 0] = x[:, 0]
+        ctx.save_for_backward(x, ln_w, mean, rstd, xn, qkv, cx, lse, a, qkv_wh, proj_wh, fc_wh, dp)
+        ctx.geom = (B, S, D, T, H, P)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        k = K()
+        x, ln_w, mean, rstd, xn, qkv, cx, lse, a, qkv_wh, proj_wh, fc_wh, dp = ctx.saved_tensors
+        B, S, D, T, H, P = ctx.geom
+        maps = token_maps(B, T, P, str(x.device))
+        hd = D // H
+        Mt = B * P * T
+        dy = dy.contiguous()
+        dy2 = dy.view(B * S, D)
+        x2 = x.reshape(B * S, D)
+        g = k.gather_cast(dy2, in_row=maps['temporal'], rows=Mt)
+        d_fc_w = _wgrad(g, a, D, D, Mt)
+        d_fc_b = k.colsum(g)
+        da = _dgrad(g, fc_wh, Mt, D, D, epi='bf16', row_scale=dp)
+        d_proj_w = _wgrad(da, cx, D, D, Mt)
+        d_proj_b = k.colsum(da)
+        dcx = _dgrad(da, proj_wh, Mt, D, D, epi='bf16')
+        dqkv = k.attn_bwd(qkv, cx, dcx, lse, B * P, T, H, hd, hd ** -0.5)
+        d_qkv_w = _wgrad(dqkv, xn, 3 * D, D, Mt)
+        d_qkv_b = k.colsum(dqkv)
+        dxn = _dgrad(dqkv, qkv_wh, Mt, D, 3 * D, epi='bf16')
+        dx = torch.empty_like(x)
+        _, _, d_ln_w, d_ln_b = k.ln_bwd(dxn, x2, mean, rstd, ln_w, in_row=maps['temporal'], out_row=maps['temporal'],
+                                        dres=dy2, dx=dx.view(B * S, D))
+        dx[:, 0] = dy[:, 0]
+        return (dx, d_ln_w, d_ln_b, d_qkv_w, d_qkv_b, d_proj_w, d_proj_b, d_fc_w, d_fc_b,
+                None, None, None, None, None, None, None)
+
+
+# --------------------------------------------------------------------------------------------------
+class SpatialAttnFn(torch.autograd.Function):
+    """y = x + cat(mean_t(cls_out), patches_out), out = DropPath(proj(attn_{1+P}(LN(cat(cls, frame)))))."""
+
+    @staticmethod
+    def forward(ctx, x, ln_w, ln_b, qkv_w, qkv_b, proj_w, proj_b, qkv_wh, proj_wh, dp, T, H, eps=1e-5):
+        k = K()
+        B, S, D = x.shape
+        P = (S - 1) // T
+        maps = token_maps(B, T, P, str(x.device))
+        R, Ms = B * S, B * T * (P + 1)
+        x2 = x.reshape(R, D)
+        hd = D // H
+        xn, mean, rstd = k.ln_fwd(x2, ln_w, ln_b, eps, in_row=maps['sp_in'], rows=Ms)
+        qkv = k.gemm(xn, qkv_wh, Ms, 3 * D, D, bias=qkv_b, epi='bf16')
+        cx, lse, _ = k.attn_fwd(qkv, B * T, P + 1, H, hd, hd ** -0.5)
+        ybig = torch.empty((R + B * T, D), dtype=torch.float32, device=x.device)
+        k.gemm(cx, proj_wh, Ms, D, D, bias=proj_b, epi='f32', aux=x2, aux_row=maps['sp_aux'], out=ybig,
+               out_row=maps['sp_out'], row_scale=dp)
+        y = ybig[:R].view(B, S, D)
+        y[:, 0] = x[:, 0] + ybig[R:].view(B, T, D).mean(dim=1)
+        ctx.save_for_backward(x, ln_w, mean, rstd, xn, qkv, cx, lse, qkv_wh, proj_wh, dp)
+        ctx.geom = (B, S, D, T, H, P)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        k = K()
+        x, ln_w, mean, rstd, xn, qkv, cx, lse, qkv_wh, proj_wh, dp = ctx.saved_tensors
+        B, S, D, T, H, P = ctx.geom
+        maps = token_maps(B, T, P, str(x.device))
+        hd = D // H
+        R, Ms = B * S, B * T * (P + 1)
+        dy = dy.contiguous()
+        dy2 = dy.view(R, D)
+        x2 = x.reshape(R, D)
+        g = k.gather_cast(dy2, in_row=maps['sp_in'], row_scale=_mul_opt(dp, maps['sp_cls_scale']), rows=Ms)
+        d_proj_w = _wgrad(g, cx, D, D, Ms)
+        d_proj_b = k.colsum(g)
+        dcx = _dgrad(g, proj_wh, Ms, D, D, epi='bf16')
+        dqkv = k.attn_bwd(qkv, cx, dcx, lse, B * T, P + 1, H, hd, hd ** -0.5)
+        d_qkv_w = _wgrad(dqkv, xn, 3 * D, D, Ms)
+        d_qkv_b = k.colsum(dqkv)
+        dxn = _dgrad(dqkv, qkv_wh, Ms, D, 3 * D, epi='bf16')
+        dx = torch.empty_like(x)
+        _, aux, d_ln_w, d_ln_b = k.ln_bwd(dxn, x2, mean, rstd, ln_w, in_row=maps['sp_in'], out_row=maps['sp_bwd'],
+                                          dres=dy2, dx=dx.view(R, D), n_aux=B * T)
+        dx[:, 0] = dy[:, 0] + aux.view(B, T, D).sum(dim=1)
+        return dx, d_ln_w, d_ln_b, d_qkv_w, d_qkv_b, d_proj_w, d_proj_b, None, None, None, None, None, None
+
+
+# --------------------------------------------------------------------------------------------------
+class JointAttnFn(torch.autograd.Function):
+    """y = x + DropPath(proj(attn_N(LN(x)))) on [Bp, N, D]."""
+
+    @staticmethod
+    def forward(ctx, x, ln_w, ln_b, qkv_w, qkv_b, proj_w, proj_b, qkv_wh, proj_wh, dp, H, eps=1e-5):
+        k = K()
+        Bp, N, D = x.shape
+        M = Bp * N
+        x2 = x.reshape(M, D)
+        hd = D // H
+        xn, mean, rstd = k.ln_fwd(x2, ln_w, ln_b, eps)
+        qkv = k.gemm(xn, qkv_wh, M, 3 * D, D, bias=qkv_b, epi='bf16')
+        cx, lse, _ = k.attn_fwd(qkv, Bp, N, H, hd, hd ** -0.5)
+        y = torch.empty_like(x)
+        k.gemm(cx, proj_wh, M, D, D, bias=proj_b, epi='f32', aux=x2, out=y.view(M, D), row_scale=dp)
+        ctx.save_for_backward(x, ln_w, mean, rstd, xn, qkv, cx, lse, qkv_wh, proj_wh, dp)
+        ctx.geom = (Bp, N, D, H)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        k = K()
+        x, ln_w, mean, rstd, xn, qkv, cx, lse, qkv_wh, proj_wh, dp = ctx.saved_tensors
+        Bp, N, D, H = ctx.geom
+        hd = D // H
+        M = Bp * N
+        dy = dy.contiguous()
+        dy2 = dy.view(M, D)
+        x2 = x.reshape(M, D)
+        g = k.gather_cast(dy2, row_scale=dp)
+        d_proj_w = _wgrad(g, cx, D, D, M)
+        d_proj_b = k.colsum(g)
+        dcx = _dgrad(g, proj_wh, M, D, D, epi='bf16')
+        dqkv = k.attn_bwd(qkv, cx, dcx, lse, Bp, N, H, hd, hd ** -0.5)
+        d_qkv_w = _wgrad(dqkv, xn, 3 * D, D, M)
+        d_qkv_b = k.colsum(dqkv)
+        dxn = _dgrad(dqkv, qkv_wh, M, D, 3 * D, epi='bf16')
+        dx = torch.empty_like(x)
+        _, _, d_ln_w, d_ln_b = k.ln_bwd(dxn, x2, mean, rstd, ln_w, dres=dy2, dx=dx.view(M, D))
+        return dx, d_ln_w, d_ln_b, d_qkv_w, d_qkv_b, d_proj_w, d_proj_b, None, None, None, None, None
+
+
+# --------------------------------------------------------------------------------------------------
+class FFNFn(torch.autograd.Function):
+    """y = x + DropPath(W2 gelu(W1 LN(x) + b1) + b2) on [B, S, D]."""
+
+    @staticmethod
+    def forward(ctx, x, ln_w, ln_b, w1, b1, w2, b2, w1h, w2h, dp, eps=1e-5):
+        k = K()
+        D = x.shape[-1]
+        M = x.numel() // D
+        Dh = w1h.shape[0]
+        x2 = x.reshape(M, D)
+        xn, mean, rstd = k.ln_fwd(x2, ln_w, ln_b, eps)
+        z, h = k.gemm(xn, w1h, M, Dh, D, bias=b1, epi='gelu')
+        y = torch.empty_like(x)
+        k.gemm(h, w2h, M, D, Dh, bias=b2, epi='f32', aux=x2, out=y.view(M, D), row_scale=dp)
+        ctx.save_for_backward(x, ln_w, mean, rstd, xn, z, h, w1h, w2h, dp)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        k = K()
+        x, ln_w, mean, rstd, xn, z, h, w1h, w2h, dp = ctx.saved_tensors
+        D = x.shape[-1]
+        M = x.numel() // D
+        Dh = w1h.shape[0]
+        dy = dy.contiguous()
+        dy2 = dy.view(M, D)
+        x2 = x.reshape(M, D)
+        g = k.gather_cast(dy2, row_scale=dp)
+        d_w2 = _wgrad(g, h, D, Dh, M)
+        d_b2 = k.colsum(g)
+        dz = _dgrad(g, w2h, M, Dh, D, epi='dgelu', aux=z)
+        d_w1 = _wgrad(dz, xn, Dh, D, M)
+        d_b1 = k.colsum(dz)
+        dxn = _dgrad(dz, w1h, M, D, Dh, epi='bf16')
+        dx = torch.empty_like(x)
+        _, _, d_ln_w, d_ln_b = k.ln_bwd(dxn, x2, mean, rstd, ln_w, dres=dy2, dx=dx.view(M, D))
+        return dx, d_ln_w, d_ln_b, d_w1, d_b1, d_w2, d_b2, None, None, None, None
+
+
+# --------------------------------------------------------------------------------------------------
+class PatchTokensFn(torch.autograd.Function):
+    """Patch / tubelet projection fused with token assembly.
+
+    mode 'timesformer': out [B, 1+P*T, D], row 1+p*T+t = conv(x)[b,t,p] + pos[1+p] + time[t];
+                        row 0 = cls + pos[0]                     (video_transformer.py:199-237)
+    mode 'frames'     : out [B*T', 1+P, D], row 1+p = conv(x)[bt,p] + pos[1+p]; row 0 = cls + pos[0]
+                        (ViViT fact_encoder, video_transformer.py:461-471)
+    """
+
+    @staticmethod
+    def forward(ctx, x, w, b, cls_token, pos_embed, time_embed, wh, mode, tube):
+        k = K()
+        B, T, C, Himg, Wimg = x.shape
+        D = w.shape[0]
+        ph, pw = w.shape[-2], w.shape[-1]
+        Tp = T // tube
+        P = (Himg // ph) * (Wimg // pw)
+        Kc = C * tube * ph * pw
+        cols = k.im2col(x.float(), tube, ph, pw)
+        M = B * Tp * P
+        pos = pos_embed.reshape(-1, D).float()
+        if mode == 'timesformer':
+            maps = token_maps(B, Tp, P, str(x.device))
+            S = 1 + P * Tp
+            table = (pos[1:, None, :] + time_embed.reshape(-1, D).float()[None, :, :]).reshape(P * Tp, D).contiguous()
+            out = torch.empty((B, S, D), dtype=torch.float32, device=x.device)
+            out_row, aux_row = maps['emb_out'], maps['emb_aux']
+        else:
+            maps = frame_maps(B * Tp, P, str(x.device))
+            S = 1 + P
+            table = pos.contiguous()
+            out = torch.empty((B * Tp, S, D), dtype=torch.float32, device=x.device)
+            out_row, aux_row = maps['emb_out'], maps['emb_aux']
+        k.gemm(cols, wh.reshape(D, Kc), M, D, Kc, bias=b, epi='f32', aux=table, aux_row=aux_row,
+               out=out.view(-1, D), out_row=out_row)
+        out[:, 0] = cls_token.reshape(D).float() + pos[0]
+        ctx.save_for_backward(cols, wh)
+        ctx.meta = (mode, tube, tuple(x.shape), tuple(w.shape), tuple(cls_token.shape), tuple(pos_embed.shape),
+                    None if time_embed is None else tuple(time_embed.shape), P, Tp, ctx.needs_input_grad[0])
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        k = K()
+        cols, wh = ctx.saved_tensors
+        mode, tube, xshape, wshape, cshape, pshape, tshape, P, Tp, need_dx = ctx.meta
+        B = xshape[0]
+        D = wshape[0]
+        Kc = cols.shape[1]
+        M = cols.shape[0]
+        dout = dout.contiguous()
+        d2 = dout.view(-1, D)
+        if mode == 'timesformer':
+            maps = token_maps(B, Tp, P, str(dout.device))
+        else:
+            maps = frame_maps(B * Tp, P, str(dout.device))
+        g = k.gather_cast(d2, in_row=maps['emb_out'], rows=M)
+        dw = _wgrad(g, cols, D, Kc, M).view(wshape)
+        db = k.colsum(g)
+        dcls = dout[:, 0].sum(dim=0)
+        if mode == 'timesformer':
+            dtab = dout[:, 1:].sum(dim=0).view(P, Tp, D)
+            dpos = torch.cat((dcls[None], dtab.sum(dim=1)), dim=0).view(pshape)
+            dtime = dtab.sum(dim=0).view(tshape)
+        else:
+            dpos = torch.cat((dcls[None], dout[:, 1:].sum(dim=0)), dim=0).view(pshape)
+            dtime = None
+        dx = None
+        if need_dx:
+            dcols = _dgrad(g, wh.reshape(D, Kc), M, Kc, D, epi='f32')
+            dx = k.col2im(dcols, xshape, tube, wshape[-2], wshape[-1])
+        return dx, dw, db, dcls.view(cshape), dpos, dtime, None, None, None
+
+
+# --------------------------------------------------------------------------------------------------
+class RowsNormFn(torch.autograd.Function):
+    """fp32 LayerNorm of selected rows of x2d [R, D] -> [len(rows), D] (final norm on the rows that are
+    actually consumed, video_transformer.py:251-256; rows=None => all rows)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, eps, rows):
+        k = K()
+        D = x.shape[-1]
+        x2 = x.reshape(-1, D)
+        n = x2.shape[0] if rows is None else rows.numel()
+        y, mean, rstd = k.ln_fwd(x2, w, b, eps, in_row=rows, rows=n, out_fp32=True)
+        ctx.save_for_backward(x, w, mean, rstd, rows if rows is not None else torch.empty(0))
+        ctx.has_rows = rows is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        k = K()
+        x, w, mean, rstd, rows = ctx.saved_tensors
+        rows = rows if ctx.has_rows else None
+        D = x.shape[-1]
+        x2 = x.reshape(-1, D)
+        dx = torch.zeros_like(x) if rows is not None else torch.empty_like(x)
+        _, _, dw, db = k.ln_bwd(dy.contiguous().float(), x2, mean, rstd, w, in_row=rows, out_row=rows,
+                                dx=dx.view(-1, D))
+        return dx, dw, db, None, None
+
+
+# --------------------------------------------------------------------------------------------------
+class AttentionCoreFn(torch.autograd.Function):
+    """Stand-alone Attention.forward (transformer.py:165-177): qkv linear, softmax(qk^T*scale)v, proj.
+    Returns (out fp32 [Bp,N,C], probs fp32 [Bp,H,N,N]); probs is not differentiable."""
+
+    @staticmethod
+    def forward(ctx, x, qkv_w, qkv_b, proj_w, proj_b, qkv_wh, proj_wh, H, want_probs):
+        k = K()
+        Bp, N, C = x.shape
+        M = Bp * N
+        hd = C // H
+        xh = k.gather_cast(x.reshape(M, C).float().contiguous())
+        qkv = k.gemm(xh, qkv_wh, M, 3 * C, C, bias=qkv_b, epi='bf16')
+        cx, lse, probs = k.attn_fwd(qkv, Bp, N, H, hd, hd ** -0.5, want_probs=want_probs)
+        out = k.gemm(cx, proj_wh, M, C, C, bias=proj_b, epi='f32').view(Bp, N, C)
+        ctx.save_for_backward(xh, qkv, cx, lse, qkv_wh, proj_wh)
+        ctx.geom = (Bp, N, C, H)
+        if probs is None:
+            probs = torch.empty(0, device=x.device)
+        ctx.mark_non_differentiable(probs)
+        return out, probs
+
+    @staticmethod
+    def backward(ctx, dout, _dprobs):
+        k = K()
+        xh, qkv, cx, lse, qkv_wh, proj_wh = ctx.saved_tensors
+        Bp, N, C, H = ctx.geom
+        M = Bp * N
+        hd = C // H
+        g = k.gather_cast(dout.contiguous().view(M, C).float())
+        d_proj_w = _wgrad(g, cx, C, C, M)
+        d_proj_b = k.colsum(g)
+        dcx = _dgrad(g, proj_wh, M, C, C, epi='bf16')
+        dqkv = k.attn_bwd(qkv, cx, dcx, lse, Bp, N, H, hd, hd ** -0.5)
+        d_qkv_w = _wgrad(dqkv, xh, 3 * C, C, M)
+        d_qkv_b = k.colsum(dqkv)
+        dx = _dgrad(dqkv, qkv_wh, M, C, 3 * C, epi='f32').view(Bp, N, C)
+        return dx, d_qkv_w, d_qkv_b, d_proj_w, d_proj_b, None, None, None, None
