@@ -32,6 +32,8 @@ int vt_version(void);
 int vt_last_error(char* buf, size_t buf_bytes);
 /* number of SMs of the current device (grid sizing is done inside the library) */
 int vt_sm_count(void);
+/* number of kernels this library has launched in this process (mod 2^31); bench.py's gpu_launches */
+int vt_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------------
  * GEMM on tcgen05 tensor cores:  acc[M,N] = sum_k A[m,k] * B[n,k]   (bf16 x bf16 -> fp32 in TMEM)

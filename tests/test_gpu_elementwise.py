@@ -1,0 +1,81 @@
+"""Warp-primitive kernels vs torch.  -m gpu"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def K():
+    from videotransformer_pytorch_b200 import _lib
+    return _lib.K
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+
+
+@pytest.mark.parametrize('D', [128, 384, 768, 1024])
+@pytest.mark.parametrize('rows', [1, 37, 4096])
+def test_layernorm_fwd_bwd(D, rows):
+    torch.manual_seed(0)
+    R = rows + 11
+    x = (torch.randn(R, D) * 2 + 0.5).cuda()
+    g, b = (1 + 0.1 * torch.randn(D)).cuda(), (0.1 * torch.randn(D)).cuda()
+    in_row = torch.randperm(R)[:rows].to(torch.int32).cuda()
+    y, mean, rstd = K().ln_fwd(x, g, b, 1e-5, in_row=in_row, rows=rows, out_fp32=True)
+    xs = x[in_row.long()].clone().requires_grad_(True)
+    gr, br = g.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    yr = torch.nn.functional.layer_norm(xs, (D,), gr, br, 1e-5)
+    assert rel(y, yr) < 1e-5
+    yb, _, _ = K().ln_fwd(x, g, b, 1e-5, in_row=in_row, rows=rows)
+    assert yb.dtype == torch.bfloat16 and rel(yb, yr) < 4e-3
+    dy = torch.randn(rows, D).cuda()
+    yr.backward(dy)
+    dres = torch.randn(R, D).cuda()
+    dx = torch.full((R, D), 7.0, device='cuda')
+    _, _, dg, db = K().ln_bwd(dy, x, mean, rstd, g, in_row=in_row, out_row=in_row, dres=dres, dx=dx)
+    exp = torch.full((R, D), 7.0, device='cuda')
+    exp[in_row.long()] = xs.grad + dres[in_row.long()]
+    assert rel(dx, exp) < 1e-5
+    assert rel(dg, gr.grad) < 1e-4 and rel(db, br.grad) < 1e-4
+    # bf16 dy + aux rows (negative out_row)
+    out_row = in_row.clone()
+    n_aux = min(3, rows)
+    out_row[:n_aux] = -(torch.arange(n_aux, dtype=torch.int32, device='cuda')) - 1
+    dx2, aux, _, _ = K().ln_bwd(dy.bfloat16(), x, mean, rstd, g, in_row=in_row, out_row=out_row, n_aux=n_aux,
+                                dx=torch.zeros(R, D, device='cuda'))
+    xs2 = x[in_row.long()].clone().requires_grad_(True)
+    torch.nn.functional.layer_norm(xs2, (D,), g, b, 1e-5).backward(dy.bfloat16().float())
+    assert rel(aux, xs2.grad[:n_aux]) < 1e-5
+    assert rel(dx2[in_row[n_aux:].long()], xs2.grad[n_aux:]) < 1e-5 or rows == n_aux
+
+
+def test_casts_and_colsum():
+    torch.manual_seed(1)
+    x = torch.randn(1000, 768).cuda()
+    assert torch.equal(K().cast_bf16(x), x.bfloat16())
+    y = torch.randn(12345).cuda()
+    assert torch.equal(K().cast_bf16(y), y.bfloat16())
+    in_row = torch.randint(-1, 1000, (700,)).to(torch.int32).cuda()
+    rs = torch.rand(700).cuda()
+    g = K().gather_cast(x, in_row=in_row, row_scale=rs, rows=700)
+    exp = x[in_row.long().clamp(min=0)] * rs[:, None]
+    exp[in_row < 0] = 0
+    assert torch.equal(g, exp.bfloat16())
+    xb = torch.randn(12552, 3072).cuda().bfloat16()
+    assert rel(K().colsum(xb), xb.float().sum(0)) < 1e-5
+    xb = torch.randn(77, 136).cuda().bfloat16()
+    assert rel(K().colsum(xb), xb.float().sum(0)) < 1e-5
+
+
+@pytest.mark.parametrize('tube', [1, 2])
+def test_im2col_col2im(tube):
+    torch.manual_seed(2)
+    B, T, C, H, W = 2, 4, 3, 48, 32
+    x = torch.randn(B, T, C, H, W).cuda()
+    cols = K().im2col(x, tube, 16, 16)
+    Tp, Hp, Wp = T // tube, H // 16, W // 16
+    ref = x.reshape(B, Tp, tube, C, Hp, 16, Wp, 16).permute(0, 1, 4, 6, 3, 2, 5, 7).reshape(B * Tp * Hp * Wp, -1)
+    assert torch.equal(cols, ref.bfloat16())
+    back = K().col2im(ref.contiguous(), (B, T, C, H, W), tube, 16, 16)
+    assert torch.equal(back, x)

@@ -1,0 +1,118 @@
+"""tcgen05 GEMM (vt_gemm) vs torch fp32 matmul on the same bf16-rounded operands.  -m gpu"""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def K():
+    from videotransformer_pytorch_b200 import _lib
+    return _lib.K
+
+
+def mk(shape, seed, scale=1.0):
+    g = torch.Generator(device='cpu').manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).cuda()
+
+
+def ref_mm(a, b, a_mn, b_mn):
+    A = a.float().t() if a_mn else a.float()
+    B = b.float() if b_mn else b.float().t()
+    return A @ B
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+
+
+SHAPES = [(128, 128, 64), (128, 256, 64), (256, 256, 128), (384, 512, 192), (200, 136, 72), (1000, 768, 768),
+          (12544, 2304, 768)]
+
+
+@pytest.mark.parametrize('M,N,Kd', SHAPES)
+@pytest.mark.parametrize('a_mn,b_mn', [(False, False), (False, True), (True, True), (True, False)])
+def test_gemm_plain_f32(M, N, Kd, a_mn, b_mn):
+    if (a_mn and M % 8) or (b_mn and N % 8) or Kd % 8:
+        pytest.skip('leading dims must be multiples of 8')
+    a = mk((Kd, M) if a_mn else (M, Kd), 1).bfloat16()
+    b = mk((Kd, N) if b_mn else (N, Kd), 2).bfloat16()
+    out = K().gemm(a, b, M, N, Kd, a_mn=a_mn, b_mn=b_mn, epi='f32')
+    torch.cuda.synchronize()
+    r = ref_mm(a, b, a_mn, b_mn)
+    assert rel(out, r) < 1e-5, rel(out, r)
+
+
+@pytest.mark.parametrize('bn', [128, 256])
+def test_gemm_bf16_bias_rowscale(bn):
+    M, N, Kd = 640, 512, 256
+    a, b = mk((M, Kd), 3).bfloat16(), mk((N, Kd), 4).bfloat16()
+    bias, rs = mk((N,), 5), mk((M,), 6).abs()
+    out = K().gemm(a, b, M, N, Kd, epi='bf16', bias=bias, row_scale=rs, force_bn=bn)
+    r = (ref_mm(a, b, False, False) + bias) * rs[:, None]
+    assert out.dtype == torch.bfloat16
+    assert rel(out, r) < 4e-3
+
+
+def test_gemm_f32_residual_rowmaps():
+    M, N, Kd, R = 300, 256, 128, 400
+    a, b = mk((M, Kd), 7).bfloat16(), mk((N, Kd), 8).bfloat16()
+    bias, rs = mk((N,), 9), mk((M,), 10)
+    aux = mk((R, N), 11)
+    perm = torch.randperm(R, generator=torch.Generator().manual_seed(0))[:M]
+    out_row = perm.to(torch.int32).cuda()
+    out_row[5] = -1                      # skipped row
+    aux_row = torch.randint(0, R, (M,), generator=torch.Generator().manual_seed(1)).to(torch.int32).cuda()
+    aux_row[7] = -1                      # no addend
+    out = torch.full((R, N), 123.0, device='cuda')
+    K().gemm(a, b, M, N, Kd, epi='f32', bias=bias, row_scale=rs, aux=aux, aux_row=aux_row, out=out, out_row=out_row)
+    r = (ref_mm(a, b, False, False) + bias) * rs[:, None]
+    add = aux[aux_row.long().clamp(min=0)]
+    add[7] = 0
+    r = r + add
+    exp = torch.full((R, N), 123.0, device='cuda')
+    ok = out_row >= 0
+    exp[out_row[ok].long()] = r[ok]
+    assert rel(out, exp) < 1e-5
+
+
+def test_gemm_gelu_and_dgelu():
+    M, N, Kd = 256, 512, 128
+    a, b = mk((M, Kd), 12, 0.3).bfloat16(), mk((N, Kd), 13, 0.3).bfloat16()
+    bias = mk((N,), 14)
+    z, h = K().gemm(a, b, M, N, Kd, epi='gelu', bias=bias)
+    zr = ref_mm(a, b, False, False) + bias
+    assert rel(z, zr) < 4e-3
+    assert rel(h, torch.nn.functional.gelu(zr)) < 4e-3
+    # dgelu: out = acc * gelu'(z)
+    g = mk((M, Kd), 15, 0.3).bfloat16()
+    out = K().gemm(g, b, M, N, Kd, epi='dgelu', aux=z)
+    zz = z.float().requires_grad_(True)
+    torch.nn.functional.gelu(zz).sum().backward()
+    assert rel(out, ref_mm(g, b, False, False) * zz.grad) < 4e-3
+
+
+@pytest.mark.parametrize('splits', [2, 5, 16])
+def test_gemm_splitk_wgrad(splits):
+    Mtok, Nout, Kin = 2048 + 64, 384, 256
+    dy, x = mk((Mtok, Nout), 16).bfloat16(), mk((Mtok, Kin), 17).bfloat16()
+    out = K().gemm(dy, x, Nout, Kin, Mtok, a_mn=True, b_mn=True, epi='f32', split_ok=True, force_splits=splits)
+    r = dy.float().t() @ x.float()
+    assert rel(out, r) < 1e-5
+
+
+def test_gemm_wgrad_heuristic_split_big():
+    Mtok, Nout, Kin = 12552, 768, 3072
+    dy, x = mk((Mtok, Nout), 18, 0.1).bfloat16(), mk((Mtok, Kin), 19, 0.1).bfloat16()
+    out = K().gemm(dy, x, Nout, Kin, Mtok, a_mn=True, b_mn=True, epi='f32', split_ok=True)
+    r = dy.float().t() @ x.float()
+    assert rel(out, r) < 1e-5
+
+
+def test_gemm_rejects_bad_args():
+    a, b = mk((64, 64), 1).bfloat16(), mk((64, 64), 2).bfloat16()
+    with pytest.raises(RuntimeError):
+        K().gemm(a.float(), b, 64, 64, 64)
+    with pytest.raises(RuntimeError):
+        K().gemm(a, b, 64, 60, 64)        # N not a multiple of 8 / shape mismatch

@@ -82,7 +82,7 @@ class HogParams(C.Structure):
                 ('F', c_i32), ('H', c_i32), ('W', c_i32)]
 
 
-EXPORTS = ['vt_version', 'vt_last_error', 'vt_sm_count', 'vt_gemm', 'vt_layernorm_fwd', 'vt_ln_bwd_blocks',
+EXPORTS = ['vt_version', 'vt_last_error', 'vt_sm_count', 'vt_launch_count', 'vt_gemm', 'vt_layernorm_fwd', 'vt_ln_bwd_blocks',
            'vt_layernorm_bwd', 'vt_reduce_rows', 'vt_colsum_chunks', 'vt_colsum_bf16', 'vt_cast_f32_bf16',
            'vt_gather_cast_bf16', 'vt_attn_fwd', 'vt_attn_bwd', 'vt_im2col_bf16', 'vt_col2im_f32', 'vt_hog']
 
@@ -347,6 +347,11 @@ class CudaKernels:
         p.F, p.H, p.W = F, H, W
         _check(lib.vt_hog(C.byref(p), _stream()), 'vt_hog')
         return feat, bins
+
+
+def launch_count() -> int:
+    """Kernels launched by libvt_b200.so in this process so far."""
+    return int(load_library().vt_launch_count())
 
 
 K = CudaKernels()

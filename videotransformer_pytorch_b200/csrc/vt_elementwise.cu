@@ -20,7 +20,10 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static unsigned long long g_launches = 0;
+
 int check_launch(const char* what) {
+  __atomic_add_fetch(&g_launches, 1ull, __ATOMIC_RELAXED);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
@@ -344,6 +347,8 @@ extern "C" int vt_last_error(char* buf, size_t n) {
 }
 
 extern "C" int vt_sm_count(void) { return sm_count(); }
+
+extern "C" int vt_launch_count(void) { return (int)(__atomic_load_n(&g_launches, __ATOMIC_RELAXED) & 0x7fffffffull); }
 
 extern "C" int vt_layernorm_fwd(const vt_ln_fwd_params* p, void* stream) {
   VT_REQUIRE(p && p->x && p->gamma && p->beta && p->y && p->mean && p->rstd, "vt_layernorm_fwd: null pointer");

@@ -1,0 +1,110 @@
+"""Data-parallel gradient exchange: bucketed all-reduce (mean) of parameter gradients over NCCL,
+overlapped with the backward pass.
+
+Replaces what PyTorch-Lightning's DDPPlugin gives the reference (model_pretrain.py:200-204,
+SURVEY.md §2.2 C1): one process per GPU, full replica, one all-reduce of the gradients per step and
+nothing else on the data path.  Design for NVLink 5 / NVSwitch:
+
+  * parameters are grouped into flat fp32 buckets in *reverse registration order* (the order backward
+    produces them), one bucket ~= one transformer layer (default 32 MiB), and every `p.grad` is a view
+    into its bucket, so wgrad results land in the bucket without a gather copy;
+  * a post-accumulate-grad hook counts ready parameters; when a bucket is complete its all-reduce is
+    issued on a dedicated communication stream (ordered after the producing kernels by an event), so
+    NCCL (NVLS in-switch reduction when available) runs under the remaining backward compute;
+  * `finish()` makes the compute stream wait for the communication stream.
+
+`torch.nn.parallel.DistributedDataParallel` also works with these modules (all gradients flow through
+ordinary autograd); this class exists so the exchange is explicit, allocation-free per step and
+measurable.  Works with the `gloo` backend on CPU tensors (tests), where the overlap degenerates to
+synchronous calls.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+class GradientBuckets:
+    def __init__(self, module: torch.nn.Module, bucket_bytes: int = 32 << 20, process_group=None,
+                 broadcast_parameters: bool = True):
+        if not dist.is_initialized():
+            raise RuntimeError('GradientBuckets needs an initialised torch.distributed process group')
+        self.group = process_group
+        self.world = dist.get_world_size(process_group)
+        params = [p for p in module.parameters() if p.requires_grad]
+        if not params:
+            raise RuntimeError('module has no trainable parameters')
+        self.device = params[0].device
+        self.cuda = self.device.type == 'cuda'
+        if broadcast_parameters:                       # DDP constructor semantics
+            with torch.no_grad():
+                for p in module.parameters():
+                    dist.broadcast(p.data, src=0, group=process_group)
+                for b in module.buffers():
+                    dist.broadcast(b.data, src=0, group=process_group)
+        # bucket assignment in reverse order
+        self.buckets: List[torch.Tensor] = []
+        self._bucket_params: List[List[torch.nn.Parameter]] = []
+        cur, cur_bytes = [], 0
+        for p in reversed(params):
+            cur.append(p)
+            cur_bytes += p.numel() * 4
+            if cur_bytes >= bucket_bytes:
+                self._bucket_params.append(cur)
+                cur, cur_bytes = [], 0
+        if cur:
+            self._bucket_params.append(cur)
+        self._owner = {}
+        for bi, ps in enumerate(self._bucket_params):
+            n = sum(p.numel() for p in ps)
+            flat = torch.zeros(n, dtype=torch.float32, device=self.device)
+            off = 0
+            for p in ps:
+                p.grad = flat[off:off + p.numel()].view_as(p)
+                off += p.numel()
+                self._owner[p] = bi
+                p.register_post_accumulate_grad_hook(self._hook)
+            self.buckets.append(flat)
+        self._pending = [len(ps) for ps in self._bucket_params]
+        self._works = []
+        self.comm_stream = torch.cuda.Stream(device=self.device) if self.cuda else None
+        self.bytes_per_step = sum(b.numel() * 4 for b in self.buckets)
+
+    # -- per step -------------------------------------------------------------------------------
+    def zero_grad(self):
+        """Gradients live in the buckets: zero them in place (keeps the p.grad views valid)."""
+        for b in self.buckets:
+            b.zero_()
+        self._pending = [len(ps) for ps in self._bucket_params]
+
+    def _hook(self, p):
+        bi = self._owner[p]
+        self._pending[bi] -= 1
+        if self._pending[bi] == 0:
+            self._launch(bi)
+
+    def _launch(self, bi: int):
+        flat = self.buckets[bi]
+        if self.world == 1:
+            return
+        if self.cuda:
+            ready = torch.cuda.Event()
+            ready.record(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(self.comm_stream):
+                self.comm_stream.wait_event(ready)
+                dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group)
+        else:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+            flat.div_(self.world)
+
+    def finish(self):
+        """Call after backward(): the compute stream waits for all bucket reductions."""
+        missing = [i for i, n in enumerate(self._pending) if n != 0]
+        if missing:
+            raise RuntimeError(f'buckets {missing} did not receive all gradients this step '
+                               '(every parameter must get a gradient, as in the reference with '
+                               'find_unused_parameters=False)')
+        if self.cuda and self.world > 1:
+            torch.cuda.current_stream(self.device).wait_stream(self.comm_stream)
