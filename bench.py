@@ -68,7 +68,7 @@ def cpu_step_factory(batch):
         feat = O.timesformer_forward(sd, x, cfg, training=True)
         loss = torch.nn.functional.cross_entropy(feat @ head_w.t() + head_b, y)
         loss.backward()
-        return float(loss)
+        return float(loss.detach())
     return step
 
 

@@ -103,7 +103,7 @@ def test_layer_backward_at_timesformer_b_shape():
 
     def run(sdx, xx, dtype):
         s = {k: v.to(dtype).requires_grad_(True) for k, v in sdx.items() if k.startswith(pre)}
-        xx = xx.to(dtype).requires_grad_(True)
+        xx = xx.detach().clone().to(dtype).requires_grad_(True)
         y = O.container(xx, s, 'transformer_layers.', 1, ['time_attn', 'space_attn', 'ffn'], T, H, False)
         (y * w.to(y.dtype)).sum().backward()
         return y.detach(), xx.grad, {k: v.grad for k, v in s.items()}
@@ -111,7 +111,7 @@ def test_layer_backward_at_timesformer_b_shape():
     y64, dx64, g64 = run(sd, x, torch.float64)
     with torch.autocast('cpu', dtype=torch.bfloat16):
         yac, dxac, gac = run(sd, x, torch.float32)
-    xg = x.cuda().requires_grad_(True)
+    xg = x.detach().clone().cuda().requires_grad_(True)
     y = blk(xg)
     (y * w.cuda()).sum().backward()
     e_y, e_dx = rel_err(y.detach().cpu(), y64), rel_err(xg.grad.cpu(), dx64)
