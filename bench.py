@@ -72,8 +72,20 @@ def cpu_step_factory(batch):
     return step
 
 
+def host_threads():
+    """CPU threads this process can really use: min(affinity mask, cgroup v2 cpu.max quota)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    try:
+        quota, period = open('/sys/fs/cgroup/cpu.max').read().split()
+        if quota != 'max':
+            n = max(1, min(n, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return n
+
+
 def run_cpu(steps, warmup, batch=1):
-    cores = os.cpu_count() or 1
+    cores = host_threads()
     torch.set_num_threads(cores)
     step = cpu_step_factory(batch)
     for _ in range(warmup):

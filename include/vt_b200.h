@@ -146,16 +146,22 @@ int vt_gather_cast_bf16(const vt_gather_cast_params* p, void* stream);
  *   qkv bf16 [Bp, N, 3, H, hd] (the layout produced by transformer.py:167's reshape), hd = 64
  *   ctx bf16 [Bp, N, H*hd] = softmax(q k^T * scale) v      (transformer.py:170-174)
  *   lse fp32 [Bp, H, N]   (saved for backward);  probs fp32 [Bp,H,N,N] optional (Attention returns it, :177)
- * vt_attn_fwd/bwd: generic warp-per-query kernels for any N <= 256 (temporal N=8, ViViT N=9, tests).
+ * Three kernels behind one entry point: a tcgen05/TMEM flash kernel for the spatial pass (N = 197: S, dP and the
+ * gradient accumulators in TMEM, K/V resident in shared memory, P/dS re-read transposed through MN-major UMMA
+ * descriptors), a warp-per-problem kernel for the temporal pass (N = 8, 18 816 problems/layer), and a generic
+ * warp-per-query kernel for any other N <= 256 (ViViT N = 9, tests, probs output).
  * ------------------------------------------------------------------------------------------- */
+enum { VT_ATTN_AUTO = 0, VT_ATTN_GENERIC = 1, VT_ATTN_TCGEN05 = 2, VT_ATTN_WARP8 = 3 };
 typedef struct {
   const void* qkv; void* ctx; float* lse; float* probs;
   int32_t Bp, N, H, hd; float scale;
+  int32_t impl;   /* VT_ATTN_AUTO picks: N == 8 -> warp-per-problem kernel; 32 < N <= 256 -> tcgen05 flash kernel; else generic */
 } vt_attn_fwd_params;
 int vt_attn_fwd(const vt_attn_fwd_params* p, void* stream);
 typedef struct {
   const void* qkv; const void* ctx; const void* dctx; const float* lse; void* dqkv;
   int32_t Bp, N, H, hd; float scale;
+  int32_t impl;
 } vt_attn_bwd_params;
 int vt_attn_bwd(const vt_attn_bwd_params* p, void* stream);
 

@@ -137,7 +137,7 @@ class EmuKernels:
             v = v * self._up(row_scale)[:, None]
         return self._h(v)
 
-    def attn_fwd(self, qkv, Bp, N, H, hd, scale, want_probs=False):
+    def attn_fwd(self, qkv, Bp, N, H, hd, scale, want_probs=False, impl=0):
         q = self._up(qkv).reshape(Bp, N, 3, H, hd).permute(2, 0, 3, 1, 4)
         s = (q[0] @ q[1].transpose(-1, -2)) * scale
         lse = torch.logsumexp(s, dim=-1)
@@ -145,7 +145,7 @@ class EmuKernels:
         o = (p @ q[2]).transpose(1, 2).reshape(Bp * N, H * hd)
         return self._h(o), lse.to(self.f), (p.to(self.f) if want_probs else None)
 
-    def attn_bwd(self, qkv, ctx, dctx, lse, Bp, N, H, hd, scale):
+    def attn_bwd(self, qkv, ctx, dctx, lse, Bp, N, H, hd, scale, impl=0):
         q = self._up(qkv).reshape(Bp, N, 3, H, hd).permute(2, 0, 3, 1, 4)
         Q, Kk, V = q[0], q[1], q[2]
         O = self._up(ctx).reshape(Bp, N, H, hd).transpose(1, 2)

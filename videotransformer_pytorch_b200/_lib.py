@@ -64,12 +64,12 @@ class GatherCastParams(C.Structure):
 
 class AttnFwdParams(C.Structure):
     _fields_ = [('qkv', c_vp), ('ctx', c_vp), ('lse', c_vp), ('probs', c_vp),
-                ('Bp', c_i32), ('N', c_i32), ('H', c_i32), ('hd', c_i32), ('scale', c_f32)]
+                ('Bp', c_i32), ('N', c_i32), ('H', c_i32), ('hd', c_i32), ('scale', c_f32), ('impl', c_i32)]
 
 
 class AttnBwdParams(C.Structure):
     _fields_ = [('qkv', c_vp), ('ctx', c_vp), ('dctx', c_vp), ('lse', c_vp), ('dqkv', c_vp),
-                ('Bp', c_i32), ('N', c_i32), ('H', c_i32), ('hd', c_i32), ('scale', c_f32)]
+                ('Bp', c_i32), ('N', c_i32), ('H', c_i32), ('hd', c_i32), ('scale', c_f32), ('impl', c_i32)]
 
 
 class Im2colParams(C.Structure):
@@ -282,7 +282,7 @@ class CudaKernels:
         return out
 
     # -- attention ----------------------------------------------------------------------------
-    def attn_fwd(self, qkv, Bp, N, H, hd, scale, want_probs=False):
+    def attn_fwd(self, qkv, Bp, N, H, hd, scale, want_probs=False, impl=0):
         lib = load_library()
         _req(qkv, torch.bfloat16, 'attn.qkv')
         if not qkv.is_contiguous() or qkv.numel() != Bp * N * 3 * H * hd:
@@ -292,11 +292,11 @@ class CudaKernels:
         probs = torch.empty((Bp, H, N, N), dtype=torch.float32, device=qkv.device) if want_probs else None
         p = AttnFwdParams()
         p.qkv, p.ctx, p.lse, p.probs = qkv.data_ptr(), ctx.data_ptr(), lse.data_ptr(), _ptr(probs)
-        p.Bp, p.N, p.H, p.hd, p.scale = Bp, N, H, hd, scale
+        p.Bp, p.N, p.H, p.hd, p.scale, p.impl = Bp, N, H, hd, scale, impl
         _check(lib.vt_attn_fwd(C.byref(p), _stream()), 'vt_attn_fwd')
         return ctx, lse, probs
 
-    def attn_bwd(self, qkv, ctx, dctx, lse, Bp, N, H, hd, scale):
+    def attn_bwd(self, qkv, ctx, dctx, lse, Bp, N, H, hd, scale, impl=0):
         lib = load_library()
         for t, n in ((qkv, 'qkv'), (ctx, 'ctx'), (dctx, 'dctx')):
             _req(t, torch.bfloat16, 'attn_bwd.' + n)
@@ -305,7 +305,7 @@ class CudaKernels:
         dqkv = torch.empty_like(qkv)
         p = AttnBwdParams()
         p.qkv, p.ctx, p.dctx, p.lse, p.dqkv = qkv.data_ptr(), ctx.data_ptr(), dctx.data_ptr(), lse.data_ptr(), dqkv.data_ptr()
-        p.Bp, p.N, p.H, p.hd, p.scale = Bp, N, H, hd, scale
+        p.Bp, p.N, p.H, p.hd, p.scale, p.impl = Bp, N, H, hd, scale, impl
         _check(lib.vt_attn_bwd(C.byref(p), _stream()), 'vt_attn_bwd')
         return dqkv
 

@@ -220,6 +220,19 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
   }
 }
 
+int attn_tc_fwd_launch(const vt_attn_fwd_params* q, cudaStream_t st);
+int attn_tc_bwd_launch(const vt_attn_bwd_params* q, cudaStream_t st);
+int attn8_fwd_launch(const vt_attn_fwd_params* p, cudaStream_t st);
+int attn8_bwd_launch(const vt_attn_bwd_params* p, cudaStream_t st);
+
+static int pick_impl(int impl, int N, bool probs) {
+  if (impl != VT_ATTN_AUTO) return impl;
+  if (probs) return VT_ATTN_GENERIC;
+  if (N == 8) return VT_ATTN_WARP8;
+  if (N > 32 && N <= 256) return VT_ATTN_TCGEN05;
+  return VT_ATTN_GENERIC;
+}
+
 }  // namespace vt
 
 using namespace vt;
@@ -229,6 +242,15 @@ extern "C" int vt_attn_fwd(const vt_attn_fwd_params* p, void* stream) {
   VT_REQUIRE(p->hd == HD, "vt_attn_fwd: head dim %d unsupported (64 only)", p->hd);
   VT_REQUIRE(p->N >= 1 && p->N <= MAX_N, "vt_attn_fwd: N=%d unsupported (1..%d)", p->N, MAX_N);
   VT_REQUIRE(p->Bp > 0 && p->H > 0, "vt_attn_fwd: bad Bp/H");
+  const int impl = pick_impl(p->impl, p->N, p->probs != nullptr);
+  if (impl == VT_ATTN_TCGEN05) {
+    VT_REQUIRE(p->probs == nullptr && p->N >= 16, "vt_attn_fwd: tcgen05 kernel needs N >= 16 and no probs output");
+    return attn_tc_fwd_launch(p, static_cast<cudaStream_t>(stream));
+  }
+  if (impl == VT_ATTN_WARP8) {
+    VT_REQUIRE(p->probs == nullptr && p->N == 8, "vt_attn_fwd: warp8 kernel needs N == 8 and no probs output");
+    return attn8_fwd_launch(p, static_cast<cudaStream_t>(stream));
+  }
   const int npad = (p->N + 31) & ~31;
   const int smem = (2 * p->N * PITCH + AT_WARPS * npad) * 4;
   static int max_set = 0;
@@ -246,6 +268,15 @@ extern "C" int vt_attn_bwd(const vt_attn_bwd_params* p, void* stream) {
   VT_REQUIRE(p && p->qkv && p->ctx && p->dctx && p->lse && p->dqkv, "vt_attn_bwd: null pointer");
   VT_REQUIRE(p->hd == HD, "vt_attn_bwd: head dim %d unsupported (64 only)", p->hd);
   VT_REQUIRE(p->N >= 1 && p->N <= MAX_N, "vt_attn_bwd: N=%d unsupported (1..%d)", p->N, MAX_N);
+  const int impl = pick_impl(p->impl, p->N, false);
+  if (impl == VT_ATTN_TCGEN05) {
+    VT_REQUIRE(p->N >= 16, "vt_attn_bwd: tcgen05 kernel needs N >= 16");
+    return attn_tc_bwd_launch(p, static_cast<cudaStream_t>(stream));
+  }
+  if (impl == VT_ATTN_WARP8) {
+    VT_REQUIRE(p->N == 8, "vt_attn_bwd: warp8 kernel needs N == 8");
+    return attn8_bwd_launch(p, static_cast<cudaStream_t>(stream));
+  }
   const int npad = (p->N + 31) & ~31;
   const int smem = (4 * p->N * PITCH + 2 * npad + 2 * AT_WARPS * npad) * 4;
   static int max_set = 0;
