@@ -1,0 +1,68 @@
+"""GradientBuckets on CPU with the gloo backend, world_size 2 (host-side logic of the N>1 path)."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket(); s.bind(('127.0.0.1', 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from videotransformer_pytorch_b200.ddp import GradientBuckets
+    torch.manual_seed(rank)          # different init per rank: the constructor must broadcast rank 0's values
+    net = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.GELU(), torch.nn.Linear(32, 8), torch.nn.Linear(8, 4))
+    red = GradientBuckets(net, bucket_bytes=64)          # tiny buckets -> several of them
+    assert len(red.buckets) >= 3
+    w0 = [p.detach().clone() for p in net.parameters()]
+    for step in range(2):
+        red.zero_grad()
+        g = torch.Generator().manual_seed(100 * step + rank)
+        x = torch.randn(5, 16, generator=g)
+        net(x).square().mean().backward()
+        red.finish()
+    grads = [p.grad.detach().clone() for p in net.parameters()]
+    # every p.grad must still be a view of its flat bucket
+    for p in net.parameters():
+        assert any(p.grad.data_ptr() >= b.data_ptr() and p.grad.data_ptr() < b.data_ptr() + b.numel() * 4 for b in red.buckets)
+    q.put((rank, [w.numpy() for w in w0], [g.numpy() for g in grads]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gradient_buckets_average_across_ranks():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, w0, g0), (r1, w1, g1) = res
+    import numpy as np
+    for a, b in zip(w0, w1):
+        assert np.array_equal(a, b)                      # parameters broadcast from rank 0
+    for a, b in zip(g0, g1):
+        assert np.allclose(a, b, atol=1e-7)              # identical averaged gradients on both ranks
+    # reference: same net, mean of the two ranks' local gradients of the last step
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.GELU(), torch.nn.Linear(32, 8), torch.nn.Linear(8, 4))
+    ref = None
+    for rank in range(2):
+        for p in net.parameters():
+            p.grad = None
+        g = torch.Generator().manual_seed(100 * 1 + rank)
+        net(torch.randn(5, 16, generator=g)).square().mean().backward()
+        cur = [p.grad.clone() for p in net.parameters()]
+        ref = cur if ref is None else [a + b for a, b in zip(ref, cur)]
+    for a, r in zip(g0, ref):
+        assert np.allclose(a, (r / 2).numpy(), atol=1e-6)

@@ -1,8 +1,8 @@
 // Persistent warp-specialised bf16 GEMM for sm_100a:
 //   TMA (cp.async.bulk.tensor, 128B swizzle) -> shared-memory ring -> tcgen05.mma (fp32 accum in TMEM,
 //   two accumulator stages) -> tcgen05.ld epilogue fused with bias / GELU / dGELU / residual / row maps.
-// One CTA per SM, 256 threads: warp0 = TMA producer, warp1 = MMA issuer, warp2 = TMEM allocator,
-// warps4-7 = epilogue (warp w drains TMEM lanes 32*(w%4)..+31).
+// One CTA per SM, 384 threads: warp0 = TMA producer, warp1 = MMA issuer, warp2 = TMEM allocator,
+// warps4-11 = epilogue (warp w drains TMEM lanes 32*(w%4)..+31; the two warpgroups interleave column chunks).
 // Tile: 128 x BN x 64, BN in {128, 256}.  Both operands may be K-major or MN-major (UMMA descriptors),
 // so forward (X W^T), dgrad (dY W) and wgrad (dY^T X) all run without transposed copies.
 #include "vt_common.cuh"
@@ -12,8 +12,10 @@ namespace vt {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 384;        // 4 control warps + 8 epilogue warps
 constexpr int CHUNK_BYTES = 64 * BK * 2;  // one 64-wide MN chunk of an MN-major tile (8 KiB)
+constexpr int EPI_PITCH = 33;             // words per staged row (32 + 1 pad: conflict-free row writes and column-group reads)
+constexpr int EPI_WARPS = 8;
 
 template <int BN>
 struct GemmCfg {
@@ -22,7 +24,7 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : 6;
   static constexpr int TMEM_COLS = 2 * BN;  // 512 or 256: two accumulator stages
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_WARPS * 32 * EPI_PITCH * 4 /*epilogue staging*/;
 };
 
 struct GemmDev {
@@ -39,71 +41,6 @@ struct GemmDev {
   const float* row_scale;
   long long split_stride;  // elements between split partials (EPI_F32 only)
 };
-
-template <int BN>
-__device__ __forceinline__ void epilogue_chunk(const GemmDev& p, int row, int n0, int split, const uint32_t (&r)[32]) {
-  // row < M guaranteed by caller; columns n0..n0+31 clipped to N in groups of 8.
-  const float s = p.row_scale ? p.row_scale[row] : 1.0f;
-  const int orow = p.out_row ? p.out_row[row] : row;
-  if (orow < 0) return;
-#pragma unroll
-  for (int j = 0; j < 32; j += 8) {
-    const int n = n0 + j;
-    if (n >= p.N) break;
-    float v[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[j + i]);
-    if (p.bias) {
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
-      v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-      v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-    }
-    if (p.epi == VT_EPI_BF16) {
-      uint4 o;
-      o.x = pack_bf16x2(s * v[0], s * v[1]);
-      o.y = pack_bf16x2(s * v[2], s * v[3]);
-      o.z = pack_bf16x2(s * v[4], s * v[5]);
-      o.w = pack_bf16x2(s * v[6], s * v[7]);
-      *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + (long long)orow * p.ldo + n) = o;
-    } else if (p.epi == VT_EPI_F32) {
-      float4 o0 = make_float4(s * v[0], s * v[1], s * v[2], s * v[3]);
-      float4 o1 = make_float4(s * v[4], s * v[5], s * v[6], s * v[7]);
-      if (p.aux) {
-        const int arow = p.aux_row ? p.aux_row[row] : row;
-        if (arow >= 0) {  // negative => no addend for this row
-          const float* ap = static_cast<const float*>(p.aux) + (long long)arow * p.ldaux + n;
-          const float4 a0 = *reinterpret_cast<const float4*>(ap);
-          const float4 a1 = *reinterpret_cast<const float4*>(ap + 4);
-          o0.x += a0.x; o0.y += a0.y; o0.z += a0.z; o0.w += a0.w;
-          o1.x += a1.x; o1.y += a1.y; o1.z += a1.z; o1.w += a1.w;
-        }
-      }
-      float* op = static_cast<float*>(p.out) + (long long)split * p.split_stride + (long long)orow * p.ldo + n;
-      *reinterpret_cast<float4*>(op) = o0;
-      *reinterpret_cast<float4*>(op + 4) = o1;
-    } else if (p.epi == VT_EPI_GELU) {
-      uint4 z, h;
-      z.x = pack_bf16x2(v[0], v[1]); z.y = pack_bf16x2(v[2], v[3]);
-      z.z = pack_bf16x2(v[4], v[5]); z.w = pack_bf16x2(v[6], v[7]);
-      h.x = pack_bf16x2(gelu_erf(v[0]), gelu_erf(v[1])); h.y = pack_bf16x2(gelu_erf(v[2]), gelu_erf(v[3]));
-      h.z = pack_bf16x2(gelu_erf(v[4]), gelu_erf(v[5])); h.w = pack_bf16x2(gelu_erf(v[6]), gelu_erf(v[7]));
-      *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + (long long)orow * p.ldo + n) = z;
-      *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out2) + (long long)orow * p.ldo2 + n) = h;
-    } else {  // VT_EPI_DGELU
-      const uint4 zz =
-          *reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.aux) + (long long)row * p.ldaux + n);
-      const float2 z0 = unpack_bf16x2(zz.x), z1 = unpack_bf16x2(zz.y), z2 = unpack_bf16x2(zz.z),
-                   z3 = unpack_bf16x2(zz.w);
-      uint4 o;
-      o.x = pack_bf16x2(v[0] * dgelu_erf(z0.x), v[1] * dgelu_erf(z0.y));
-      o.y = pack_bf16x2(v[2] * dgelu_erf(z1.x), v[3] * dgelu_erf(z1.y));
-      o.z = pack_bf16x2(v[4] * dgelu_erf(z2.x), v[5] * dgelu_erf(z2.y));
-      o.w = pack_bf16x2(v[6] * dgelu_erf(z3.x), v[7] * dgelu_erf(z3.y));
-      *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + (long long)orow * p.ldo + n) = o;
-    }
-  }
-}
 
 template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -132,7 +69,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[i], EPI_WARPS);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -205,22 +142,105 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else if (warp >= 4) {
-    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    // Epilogue: 8 warps = two warpgroups; warpgroup `half` drains the 32-column chunks c = half, half+2, ...
+    // tcgen05.ld hands each thread one accumulator ROW (32 columns); written straight to global memory that is
+    // 32 different rows per store instruction.  Instead every 32x32 fp32 block takes a trip through a per-warp
+    // shared-memory tile (pitch 33 words, conflict-free both ways) and comes back transposed: 8 lanes x 4 columns
+    // cover 128 contiguous bytes of ONE row, 4 rows per instruction, so residual / z loads and all stores are
+    // whole sectors of contiguous rows.  Loads of the epilogue operand (residual or z) are issued one chunk
+    // ahead so their latency hides behind the TMEM drain + transpose of the current chunk.
+    const int q = warp & 3;             // TMEM lane quadrant this warp may access
+    const int half = (warp - 4) >> 2;   // which warpgroup
+    float* stg = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256) + (warp - 4) * (32 * EPI_PITCH);
+    const int rsub = lane >> 3, cg = lane & 7;
+    const bool f32_aux = p.epi == VT_EPI_F32 && p.aux != nullptr;
+    const bool z_aux = p.epi == VT_EPI_DGELU;
     int acc = 0, acc_phase = 0;
     for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
       const int tile = unit / p.splits, split = unit - tile * p.splits;
       const int m_blk = tile % p.num_m, n_blk = tile / p.num_m;
+      // per-row metadata of the 8 rows this lane serves in the transposed phase
+      float rs[8];
+      int orow[8], arow[8];
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int row = m_blk * BM + q * 32 + it * 4 + rsub;
+        const bool ok = row < p.M;
+        rs[it] = (ok && p.row_scale) ? p.row_scale[row] : 1.0f;
+        orow[it] = ok ? (p.out_row ? p.out_row[row] : row) : -1;
+        arow[it] = !ok ? -1 : (f32_aux ? (p.aux_row ? p.aux_row[row] : row) : (z_aux ? row : -1));
+      }
+      uint4 pre[8];
+#pragma unroll
+      for (int it = 0; it < 8; ++it) pre[it] = make_uint4(0u, 0u, 0u, 0u);   // no epilogue operand => adds 0
+      auto prefetch = [&](int c) {
+        const int n = n_blk * BN + c * 32 + cg * 4;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          pre[it] = make_uint4(0u, 0u, 0u, 0u);
+          if (arow[it] >= 0 && orow[it] >= 0 && n < p.N) {
+            if (f32_aux) {
+              pre[it] = *reinterpret_cast<const uint4*>(static_cast<const float*>(p.aux) + (long long)arow[it] * p.ldaux + n);
+            } else if (z_aux) {
+              const uint2 z = *reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(p.aux) + (long long)arow[it] * p.ldaux + n);
+              pre[it].x = z.x; pre[it].y = z.y;
+            }
+          }
+        }
+      };
+      if (f32_aux || z_aux) prefetch(half);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const int row = m_blk * BM + q * 32 + lane;
       const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = half; c < BN / 32; c += 2) {
         uint32_t r[32];
         tmem_ld32(t_base + c * 32, r);
         tmem_ld_wait();
-        const int n0 = n_blk * BN + c * 32;
-        if (row < p.M && n0 < p.N) epilogue_chunk<BN>(p, row, n0, split, r);
+        const int n = n_blk * BN + c * 32 + cg * 4;
+        if (n_blk * BN + c * 32 >= p.N) break;   // warp-uniform
+#pragma unroll
+        for (int j = 0; j < 32; ++j) stg[lane * EPI_PITCH + j] = __uint_as_float(r[j]);
+        uint4 cur[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) cur[it] = pre[it];
+        if ((f32_aux || z_aux) && c + 2 < BN / 32) prefetch(c + 2);
+        __syncwarp();
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias && n < p.N) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const float* sp = stg + (it * 4 + rsub) * EPI_PITCH + cg * 4;
+          float4 v = make_float4(sp[0], sp[1], sp[2], sp[3]);
+          if (orow[it] < 0 || n >= p.N) continue;
+          v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
+          const long long o = (long long)orow[it];
+          if (p.epi == VT_EPI_BF16) {
+            const float s = rs[it];
+            uint2 w;
+            w.x = pack_bf16x2(s * v.x, s * v.y);
+            w.y = pack_bf16x2(s * v.z, s * v.w);
+            *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.out) + o * p.ldo + n) = w;
+          } else if (p.epi == VT_EPI_F32) {
+            const float s = rs[it];
+            v.x = fmaf(s, v.x, __uint_as_float(cur[it].x)); v.y = fmaf(s, v.y, __uint_as_float(cur[it].y));
+            v.z = fmaf(s, v.z, __uint_as_float(cur[it].z)); v.w = fmaf(s, v.w, __uint_as_float(cur[it].w));
+            *reinterpret_cast<float4*>(static_cast<float*>(p.out) + (long long)split * p.split_stride + o * p.ldo + n) = v;
+          } else if (p.epi == VT_EPI_GELU) {
+            uint2 z, h;
+            z.x = pack_bf16x2(v.x, v.y); z.y = pack_bf16x2(v.z, v.w);
+            h.x = pack_bf16x2(gelu_fast(v.x), gelu_fast(v.y)); h.y = pack_bf16x2(gelu_fast(v.z), gelu_fast(v.w));
+            *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.out) + o * p.ldo + n) = z;
+            *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.out2) + o * p.ldo2 + n) = h;
+          } else {  // VT_EPI_DGELU: cur = z (bf16 x4)
+            const float2 z0 = unpack_bf16x2(cur[it].x), z1 = unpack_bf16x2(cur[it].y);
+            uint2 w;
+            w.x = pack_bf16x2(v.x * dgelu_fast(z0.x), v.y * dgelu_fast(z0.y));
+            w.y = pack_bf16x2(v.z * dgelu_fast(z1.x), v.w * dgelu_fast(z1.y));
+            *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.out) + o * p.ldo + n) = w;
+          }
+        }
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
@@ -292,10 +312,42 @@ __global__ void reduce_rows_kernel(const float* __restrict__ in, float* __restri
   }
 }
 
+// Tall reductions (many partial rows, few columns — LayerNorm dgamma/dbeta partials): 16 column quads x 16 row
+// lanes per CTA, rows strided over the row lanes, then a shared-memory tree.  Deterministic.
+__global__ void __launch_bounds__(256)
+reduce_rows_tall_kernel(const float* __restrict__ in, float* __restrict__ out, long long stride, int S, long long n4,
+                        int accumulate, float scale) {
+  const int cq = threadIdx.x & 15, rl = threadIdx.x >> 4;
+  const long long i = blockIdx.x * 16LL + cq;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i < n4) {
+    for (int s = rl; s < S; s += 16) {
+      const float4 v = *reinterpret_cast<const float4*>(in + (long long)s * stride + i * 4);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
+  __shared__ float4 sh[16][16];
+  sh[rl][cq] = acc;
+  __syncthreads();
+  if (rl == 0 && i < n4) {
+    float4 a = sh[0][cq];
+#pragma unroll
+    for (int r = 1; r < 16; ++r) { a.x += sh[r][cq].x; a.y += sh[r][cq].y; a.z += sh[r][cq].z; a.w += sh[r][cq].w; }
+    a.x *= scale; a.y *= scale; a.z *= scale; a.w *= scale;
+    float4* o = reinterpret_cast<float4*>(out + i * 4);
+    if (accumulate) { const float4 p = *o; a.x += p.x; a.y += p.y; a.z += p.z; a.w += p.w; }
+    *o = a;
+  }
+}
+
 int launch_reduce_rows(const float* in, float* out, long long stride, int S, long long n, int accumulate, float scale,
                        cudaStream_t st) {
   VT_REQUIRE(n % 4 == 0 && stride % 4 == 0, "vt_reduce_rows: n and stride must be multiples of 4");
   const long long n4 = n / 4;
+  if (S >= 32 && n4 <= 16 * 4096) {
+    reduce_rows_tall_kernel<<<(int)((n4 + 15) / 16), 256, 0, st>>>(in, out, stride, S, n4, accumulate, scale);
+    return check_launch("reduce_rows_tall_kernel");
+  }
   int blocks = (int)((n4 + 255) / 256);
   const int cap = sm_count() * 8;
   if (blocks > cap) blocks = cap;

@@ -79,6 +79,11 @@ class GradientBuckets:
             b.zero_()
         self._pending = [len(ps) for ps in self._bucket_params]
 
+    def reset_counters(self):
+        """CUDA-graph replays run no Python hooks: the captured graph already contains the zeroing and the
+        all-reduces in the right order; only the host-side bookkeeping is reset."""
+        self._pending = [0 for _ in self._bucket_params]
+
     def _hook(self, p):
         bi = self._owner[p]
         self._pending[bi] -= 1

@@ -31,6 +31,15 @@ def K():
     return _lib.K
 
 
+_MASK_ARENA = None
+
+
+def set_mask_arena(arena):
+    """Installed by graph.GraphedTrainStep while a step is being captured."""
+    global _MASK_ARENA
+    _MASK_ARENA = arena
+
+
 # --------------------------------------------------------------------------------------------------
 # index maps (int32, cached per geometry/device)
 # --------------------------------------------------------------------------------------------------
@@ -84,6 +93,11 @@ def drop_path_scale(p: float, training: bool, n0: int, repeat: int, device):
     if p == 0.0 or not training:
         return None
     keep = 1.0 - p
+    if _MASK_ARENA is not None and _MASK_ARENA.recording:
+        # CUDA-graph capture (graph.py): the factors live in a static arena refilled before every replay;
+        # only the expansion to per-row granularity is part of the graph.
+        r = _MASK_ARENA.register(n0, keep)
+        return r.repeat_interleave(repeat).contiguous() if repeat > 1 else r.contiguous()
     r = (keep + torch.rand((n0, 1, 1))).floor_().reshape(n0) / keep
     r = r.to(device=device, dtype=torch.float32, non_blocking=True)
     return r.repeat_interleave(repeat).contiguous() if repeat > 1 else r.contiguous()
@@ -361,7 +375,7 @@ class PatchTokensFn(torch.autograd.Function):
         if mode == 'timesformer':
             dtab = dout[:, 1:].sum(dim=0).view(P, Tp, D)
             dpos = torch.cat((dcls[None], dtab.sum(dim=1)), dim=0).view(pshape)
-            dtime = dtab.sum(dim=0).view(tshape)
+            dtime = dtab.sum(dim=0).reshape(tshape).clone()
         else:
             dpos = torch.cat((dcls[None], dout[:, 1:].sum(dim=0)), dim=0).view(pshape)
             dtime = None
@@ -369,7 +383,8 @@ class PatchTokensFn(torch.autograd.Function):
         if need_dx:
             dcols = _dgrad(g, wh.reshape(D, Kc), M, Kc, D, epi='f32')
             dx = k.col2im(dcols, xshape, tube, wshape[-2], wshape[-1])
-        return dx, dw, db, dcls.view(cshape), dpos, dtime, None, None, None
+        # small grads are returned as fresh contiguous tensors (not views) so autograd can adopt them in place
+        return dx, dw.contiguous(), db, dcls.reshape(cshape).clone(), dpos.contiguous(), dtime, None, None, None
 
 
 # --------------------------------------------------------------------------------------------------

@@ -39,12 +39,15 @@ class ShadowWeights:
     def get(self, name: str, param: torch.Tensor) -> torch.Tensor:
         key = (param._version, param.data_ptr(), param.device)
         hit = self._cache.get(name)
-        if hit is not None and hit[0] == key:
+        capturing = param.is_cuda and torch.cuda.is_current_stream_capturing()
+        if hit is not None and hit[0] == key and not capturing:
             return hit[1]
         with torch.no_grad():
             w = param.detach()
             if w.dtype != torch.float32:
                 w = w.float()
+            # while a CUDA graph is being captured the cast is always issued, so every replay re-derives the
+            # shadow from the current fp32 values (the optimizer runs between replays)
             sh = _lib.K.cast_bf16(w.reshape(w.shape[0], -1).contiguous())
         self._cache[name] = (key, sh)
         return sh
