@@ -248,6 +248,7 @@ def main_gpu(args):
         return float(ms.item())
 
     eager_step = step
+    graphed = None
     if not args.no_graph:
         # whole step (fwd + bwd [+ bucket all-reduces]) captured once, replayed with one launch per step
         from videotransformer_pytorch_b200.graph import GraphedTrainStep
@@ -335,7 +336,13 @@ def main_gpu(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
-        dist.destroy_process_group()
+        # captured graphs hold NCCL kernels: release them before the communicator goes away
+        step = eager_step = graphed = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 def main():

@@ -141,6 +141,14 @@ int vt_cast_f32_bf16(const vt_cast_params* p, void* stream);
 typedef struct { const float* src; int64_t lds; const int32_t* in_row; const float* row_scale; void* dst; int32_t rows, D; } vt_gather_cast_params;
 int vt_gather_cast_bf16(const vt_gather_cast_params* p, void* stream);
 
+/* Exact-erf GELU on bf16 (nn.GELU default, transformer.py:483 / :502) as stand-alone bandwidth kernels:
+ *   vt_gelu_fwd_bf16: out = gelu(z)            vt_gelu_bwd_bf16: out = dh * gelu'(z)
+ * The FFN uses them instead of the fused GEMM epilogues when the epilogue's erf math would out-cost the tile's
+ * MMAs (4 erf per 4 columns in 8 epilogue warps); both forms are kept and tested. n = element count (n % 8 == 0). */
+typedef struct { const void* z; const void* dh; void* out; int64_t n; } vt_gelu_params;
+int vt_gelu_fwd_bf16(const vt_gelu_params* p, void* stream);
+int vt_gelu_bwd_bf16(const vt_gelu_params* p, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Multi-head softmax attention core on a packed qkv tensor (no projection):
  *   qkv bf16 [Bp, N, 3, H, hd] (the layout produced by transformer.py:167's reshape), hd = 64

@@ -137,6 +137,16 @@ class EmuKernels:
             v = v * self._up(row_scale)[:, None]
         return self._h(v)
 
+    def gelu(self, z):
+        zz = self._up(z)
+        return self._h(0.5 * zz * (1 + torch.erf(zz / math.sqrt(2.0))))
+
+    def dgelu(self, dh, z):
+        zz = self._up(z)
+        cdf = 0.5 * (1 + torch.erf(zz / math.sqrt(2.0)))
+        pdf = torch.exp(-0.5 * zz * zz) / math.sqrt(2 * math.pi)
+        return self._h(self._up(dh) * (cdf + zz * pdf))
+
     def attn_fwd(self, qkv, Bp, N, H, hd, scale, want_probs=False, impl=0):
         q = self._up(qkv).reshape(Bp, N, 3, H, hd).permute(2, 0, 3, 1, 4)
         s = (q[0] @ q[1].transpose(-1, -2)) * scale

@@ -44,7 +44,7 @@ def test_gemm_plain_f32(M, N, Kd, a_mn, b_mn):
     assert rel(out, r) < 1e-5, rel(out, r)
 
 
-@pytest.mark.parametrize('bn', [128, 256])
+@pytest.mark.parametrize('bn', [128, 192, 256])
 def test_gemm_bf16_bias_rowscale(bn):
     M, N, Kd = 640, 512, 256
     a, b = mk((M, Kd), 3).bfloat16(), mk((N, Kd), 4).bfloat16()
@@ -116,3 +116,24 @@ def test_gemm_rejects_bad_args():
         K().gemm(a.float(), b, 64, 64, 64)
     with pytest.raises(RuntimeError):
         K().gemm(a, b, 64, 60, 64)        # N not a multiple of 8 / shape mismatch
+
+
+@pytest.mark.parametrize('M,N,Kd', [(12552, 768, 3072), (12608, 2304, 768), (1000, 576, 192)])
+def test_gemm_bn192_and_auto_config(M, N, Kd):
+    a, b = mk((M, Kd), 21, 0.2).bfloat16(), mk((N, Kd), 22, 0.2).bfloat16()
+    r = ref_mm(a, b, False, False)
+    for bn in (0, 192):
+        out = K().gemm(a, b, M, N, Kd, epi='f32', force_bn=bn)
+        assert rel(out, r) < 1e-5, bn
+
+
+def test_gelu_kernels():
+    torch.manual_seed(3)
+    z = (torch.randn(1000, 3072) * 1.5).cuda().bfloat16()
+    h = K().gelu(z)
+    zf = z.float().requires_grad_(True)
+    ref = torch.nn.functional.gelu(zf)
+    assert rel(h, ref) < 3e-3
+    dh = torch.randn(1000, 3072).cuda().bfloat16()
+    ref.backward(dh.float())
+    assert rel(K().dgelu(dh, z), zf.grad) < 3e-3

@@ -31,7 +31,7 @@ def test_graphed_step_matches_eager_and_tracks_weight_updates():
     for trial in range(2):
         x2 = torch.randn(2, 4, 3, 48, 48).cuda()
         torch.manual_seed(123 + trial)
-        loss_g = float(step(x2, y))
+        loss_g = float(step(x2, y).detach())
         gg = {n: p.grad.clone() for n, p in net.named_parameters()}
         for p in net.parameters():
             p.grad = None
@@ -39,8 +39,8 @@ def test_graphed_step_matches_eager_and_tracks_weight_updates():
         loss_e = net(x2, y)
         loss_e.backward()
         assert abs(loss_g - float(loss_e)) < 1e-5, (loss_g, float(loss_e))
-        for n, p in net.named_parameters():
-            assert torch.allclose(gg[n], p.grad, rtol=1e-4, atol=1e-6), n
+        bad = [n for n, p in net.named_parameters() if not torch.allclose(gg[n], p.grad, rtol=1e-4, atol=1e-6)]
+        assert not bad, (len(bad), bad[:10])
         # emulate an optimizer step: the next replay must see the new weights (shadows re-cast in-graph)
         with torch.no_grad():
             for p in net.parameters():

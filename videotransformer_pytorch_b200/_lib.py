@@ -62,6 +62,10 @@ class GatherCastParams(C.Structure):
                 ('rows', c_i32), ('D', c_i32)]
 
 
+class GeluParams(C.Structure):
+    _fields_ = [('z', c_vp), ('dh', c_vp), ('out', c_vp), ('n', c_i64)]
+
+
 class AttnFwdParams(C.Structure):
     _fields_ = [('qkv', c_vp), ('ctx', c_vp), ('lse', c_vp), ('probs', c_vp),
                 ('Bp', c_i32), ('N', c_i32), ('H', c_i32), ('hd', c_i32), ('scale', c_f32), ('impl', c_i32)]
@@ -84,7 +88,7 @@ class HogParams(C.Structure):
 
 EXPORTS = ['vt_version', 'vt_last_error', 'vt_sm_count', 'vt_launch_count', 'vt_gemm', 'vt_layernorm_fwd', 'vt_ln_bwd_blocks',
            'vt_layernorm_bwd', 'vt_reduce_rows', 'vt_colsum_chunks', 'vt_colsum_bf16', 'vt_cast_f32_bf16',
-           'vt_gather_cast_bf16', 'vt_attn_fwd', 'vt_attn_bwd', 'vt_im2col_bf16', 'vt_col2im_f32', 'vt_hog']
+           'vt_gather_cast_bf16', 'vt_gelu_fwd_bf16', 'vt_gelu_bwd_bf16', 'vt_attn_fwd', 'vt_attn_bwd', 'vt_im2col_bf16', 'vt_col2im_f32', 'vt_hog']
 
 _dll = None
 
@@ -279,6 +283,29 @@ class CudaKernels:
         p.in_row, p.row_scale = _ptr(in_row), _ptr(row_scale)
         p.dst, p.rows, p.D = out.data_ptr(), rows, D
         _check(lib.vt_gather_cast_bf16(C.byref(p), _stream()), 'vt_gather_cast_bf16')
+        return out
+
+    def gelu(self, z):
+        lib = load_library()
+        z = _req(z, torch.bfloat16, 'gelu.z')
+        if not z.is_contiguous():
+            raise RuntimeError('gelu: z must be contiguous')
+        out = torch.empty_like(z)
+        p = GeluParams()
+        p.z, p.dh, p.out, p.n = z.data_ptr(), None, out.data_ptr(), z.numel()
+        _check(lib.vt_gelu_fwd_bf16(C.byref(p), _stream()), 'vt_gelu_fwd_bf16')
+        return out
+
+    def dgelu(self, dh, z):
+        lib = load_library()
+        for t, n in ((dh, 'dh'), (z, 'z')):
+            _req(t, torch.bfloat16, 'dgelu.' + n)
+            if not t.is_contiguous():
+                raise RuntimeError(f'dgelu: {n} must be contiguous')
+        out = torch.empty_like(z)
+        p = GeluParams()
+        p.z, p.dh, p.out, p.n = z.data_ptr(), dh.data_ptr(), out.data_ptr(), z.numel()
+        _check(lib.vt_gelu_bwd_bf16(C.byref(p), _stream()), 'vt_gelu_bwd_bf16')
         return out
 
     # -- attention ----------------------------------------------------------------------------

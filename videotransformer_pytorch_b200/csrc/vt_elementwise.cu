@@ -322,6 +322,36 @@ __global__ void col2im_kernel(const float* __restrict__ cols, float* __restrict_
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// exact-erf GELU on bf16 rows, forward (h = gelu(z)) and backward (dz = dh * gelu'(z)); 8 elements per thread
+// ------------------------------------------------------------------------------------------------
+__global__ void gelu_fwd_kernel(const uint4* __restrict__ z, uint4* __restrict__ h, long long n8) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 v = z[i];
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = unpack_bf16x2(w[k]);
+      o[k] = pack_bf16x2(gelu_fast(f.x), gelu_fast(f.y));
+    }
+    h[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+__global__ void gelu_bwd_kernel(const uint4* __restrict__ dh, const uint4* __restrict__ z, uint4* __restrict__ dz, long long n8) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 g = dh[i], v = z[i];
+    const uint32_t gw[4] = {g.x, g.y, g.z, g.w}, zw[4] = {v.x, v.y, v.z, v.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 a = unpack_bf16x2(gw[k]), f = unpack_bf16x2(zw[k]);
+      o[k] = pack_bf16x2(a.x * dgelu_fast(f.x), a.y * dgelu_fast(f.y));
+    }
+    dz[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 static int grid_for(long long work, int threads) {
   long long b = (work + threads - 1) / threads;
   const long long cap = (long long)sm_count() * 16;
@@ -444,4 +474,20 @@ extern "C" int vt_col2im_f32(const vt_col2im_params* p, void* stream) {
   col2im_kernel<<<grid_for(total4, 256), 256, 0, st>>>(p->cols, p->dx, p->B, p->T, p->C, p->H, p->W, p->tube, p->ph, p->pw,
                                                        total4);
   return check_launch("col2im_kernel");
+}
+
+extern "C" int vt_gelu_fwd_bf16(const vt_gelu_params* p, void* stream) {
+  VT_REQUIRE(p && p->z && p->out && p->n > 0 && p->n % 8 == 0, "vt_gelu_fwd_bf16: bad params (n %% 8 == 0 required)");
+  const long long n8 = p->n / 8;
+  gelu_fwd_kernel<<<grid_for(n8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint4*>(p->z),
+                                                                                   static_cast<uint4*>(p->out), n8);
+  return check_launch("gelu_fwd_kernel");
+}
+
+extern "C" int vt_gelu_bwd_bf16(const vt_gelu_params* p, void* stream) {
+  VT_REQUIRE(p && p->z && p->dh && p->out && p->n > 0 && p->n % 8 == 0, "vt_gelu_bwd_bf16: bad params");
+  const long long n8 = p->n / 8;
+  gelu_bwd_kernel<<<grid_for(n8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(p->dh), static_cast<const uint4*>(p->z), static_cast<uint4*>(p->out), n8);
+  return check_launch("gelu_bwd_kernel");
 }

@@ -22,8 +22,8 @@ struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
-  static constexpr int TMEM_COLS = 2 * BN;  // 512 or 256: two accumulator stages
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 192 ? 4 : 6);
+  static constexpr int TMEM_COLS = (BN == 128) ? 256 : 512;  // two accumulator stages, power of two
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_WARPS * 32 * EPI_PITCH * 4 /*epilogue staging*/;
 };
 
@@ -385,10 +385,7 @@ static int launch_gemm(const vt_gemm_params* q, GemmDev& d, cudaStream_t st) {
   const long long tile_out = (long long)q->M * q->N;
   if (q->epilogue == VT_EPI_F32 && q->workspace && !q->out_row && !q->aux && !q->row_scale && !q->bias) {
     if (q->force_splits > 0) splits = q->force_splits;
-    else if (tiles * 2 <= sms && d.kblocks >= 16) {
-      splits = (2 * sms) / tiles;                 // about two waves of work units
-      if (splits > d.kblocks / 4) splits = d.kblocks / 4;
-    }
+    else splits = d.splits > 0 ? d.splits : 1;    // chosen together with BN by choose_config()
     const long long max_by_ws = q->workspace_bytes / (tile_out * 4);
     if (splits > max_by_ws) splits = (int)max_by_ws;
     if (splits > d.kblocks) splits = d.kblocks;
@@ -449,9 +446,38 @@ extern "C" int vt_gemm(const vt_gemm_params* q, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 
   int bn = q->force_bn;
-  if (bn == 0) bn = (q->N % 256 == 0 || q->N > 512) ? 256 : 128;
-  VT_REQUIRE(bn == 128 || bn == 256, "vt_gemm: force_bn must be 128 or 256");
+  d.splits = 0;
+  {
+    // Wave-quantisation aware configuration: cost ~ rounds over the SMs x per-unit time, where a unit (tile x
+    // K-split) costs (its k-blocks + a fixed prologue/epilogue overhead) x BN, with a small penalty for narrower
+    // tiles (they re-read A more often and leave less slack on the smem port).  Splitting K is only possible for
+    // plain fp32 outputs with a workspace (weight gradients).
+    const int sms = sm_count();
+    const int num_m = (q->M + BM - 1) / BM;
+    const int kblocks = (q->K + BK - 1) / BK;
+    const bool can_split = q->epilogue == VT_EPI_F32 && q->workspace && !q->out_row && !q->aux && !q->row_scale && !q->bias;
+    const int cand[3] = {256, 192, 128};
+    const double penalty[3] = {1.0, 1.04, 1.10};
+    double best = 1e30;
+    int best_bn = 256, best_s = 1;
+    for (int i = 0; i < 3; ++i) {
+      if (q->force_bn && cand[i] != q->force_bn) continue;
+      const int tiles = num_m * ((q->N + cand[i] - 1) / cand[i]);
+      const int smax = can_split ? 16 : 1;
+      for (int sp = 1; sp <= smax; ++sp) {
+        if (sp > 1 && (kblocks / sp < 4 || (long long)sp * q->M * q->N * 4 > q->workspace_bytes)) break;
+        const long long units = (long long)tiles * sp;
+        const long long rounds = (units + sms - 1) / sms;
+        const double cost = (double)rounds * ((double)kblocks / sp + 8.0) * cand[i] * penalty[i];
+        if (cost < best - 1e-9) { best = cost; best_bn = cand[i]; best_s = sp; }
+      }
+    }
+    if (bn == 0) bn = best_bn;
+    d.splits = best_s;
+  }
+  VT_REQUIRE(bn == 128 || bn == 192 || bn == 256, "vt_gemm: force_bn must be 128, 192 or 256");
   if (bn == 256) return launch_gemm<256>(q, d, st);
+  if (bn == 192) return launch_gemm<192>(q, d, st);
   return launch_gemm<128>(q, d, st);
 }
 

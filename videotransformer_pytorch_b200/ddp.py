@@ -104,6 +104,16 @@ class GradientBuckets:
             dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
             flat.div_(self.world)
 
+    def reduce_into_buckets(self, params, grads):
+        """Graph-capture path: gradients arrive as a list (torch.autograd.grad); copy them into the flat buckets
+        (p.grad stays the bucket view) and all-reduce bucket by bucket on the communication stream."""
+        by_param = {id(p): g for p, g in zip(params, grads)}
+        for bi, ps in enumerate(self._bucket_params):
+            torch._foreach_copy_([p.grad for p in ps], [by_param[id(p)] for p in ps])
+            self._pending[bi] = 0
+            self._launch(bi)
+        self.finish()
+
     def finish(self):
         """Call after backward(): the compute stream waits for all bucket reductions."""
         missing = [i for i, n in enumerate(self._pending) if n != 0]

@@ -90,18 +90,23 @@ class GraphedTrainStep:
         self.arena.recording = True
         try:
             with torch.cuda.graph(self.graph, stream=side):
-                if reducer is not None:
-                    reducer.zero_grad()
                 self.static_loss = loss_fn(*self.static_inputs)
-                self.static_loss.backward()
+                # torch.autograd.grad instead of .backward(): the gradients come back as plain tensors produced by
+                # captured kernels.  (.backward() would route them through per-parameter AccumulateGrad nodes, which
+                # are bound to the stream they were first created on and may execute outside the capture.)
+                grads = torch.autograd.grad(self.static_loss, self.params)
                 if reducer is not None:
-                    reducer.finish()
+                    reducer.reduce_into_buckets(self.params, grads)     # copy into flat buckets + all-reduce, captured
         finally:
             self.arena.recording = False
             ops.set_mask_arena(None)
         # drop the captured autograd graph (its kernels are recorded; keeping the Python graph alive would pin
         # AccumulateGrad nodes to the capture stream for later eager steps)
         self.static_loss = self.static_loss.detach()
+        if reducer is None:
+            self.static_grads = [g.detach() for g in grads]
+            for p_, g_ in zip(self.params, self.static_grads):
+                p_.grad = g_                                             # rewritten in place by every replay
 
     def _zero(self, set_to_none=True):
         if self.reducer is not None:
@@ -118,4 +123,8 @@ class GraphedTrainStep:
         if self.reducer is not None:
             self.reducer.reset_counters()
         self.graph.replay()
+        if self.reducer is None:
+            for p_, g_ in zip(self.params, self.static_grads):
+                if p_.grad is not g_:
+                    p_.grad = g_
         return self.static_loss

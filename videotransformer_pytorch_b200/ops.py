@@ -33,6 +33,11 @@ def K():
 
 _MASK_ARENA = None
 
+# FFN activation: fused into the FC1 / FC2-dgrad GEMM epilogues (VT_EPI_GELU / VT_EPI_DGELU) or as stand-alone
+# bandwidth kernels after a plain bf16 epilogue.  Measured on B200 (profiles/): the erf math in the 8 epilogue
+# warps costs more than the extra 150 MB of HBM traffic, so the split form is the default.
+FUSED_GELU_EPILOGUE = False
+
 
 def set_mask_arena(arena):
     """Installed by graph.GraphedTrainStep while a step is being captured."""
@@ -283,7 +288,11 @@ class FFNFn(torch.autograd.Function):
         Dh = w1h.shape[0]
         x2 = x.reshape(M, D)
         xn, mean, rstd = k.ln_fwd(x2, ln_w, ln_b, eps)
-        z, h = k.gemm(xn, w1h, M, Dh, D, bias=b1, epi='gelu')
+        if FUSED_GELU_EPILOGUE:
+            z, h = k.gemm(xn, w1h, M, Dh, D, bias=b1, epi='gelu')
+        else:
+            z = k.gemm(xn, w1h, M, Dh, D, bias=b1, epi='bf16')
+            h = k.gelu(z)
         y = torch.empty_like(x)
         k.gemm(h, w2h, M, D, Dh, bias=b2, epi='f32', aux=x2, out=y.view(M, D), row_scale=dp)
         ctx.save_for_backward(x, ln_w, mean, rstd, xn, z, h, w1h, w2h, dp)
@@ -302,7 +311,10 @@ class FFNFn(torch.autograd.Function):
         g = k.gather_cast(dy2, row_scale=dp)
         d_w2 = _wgrad(g, h, D, Dh, M)
         d_b2 = k.colsum(g)
-        dz = _dgrad(g, w2h, M, Dh, D, epi='dgelu', aux=z)
+        if FUSED_GELU_EPILOGUE:
+            dz = _dgrad(g, w2h, M, Dh, D, epi='dgelu', aux=z)
+        else:
+            dz = k.dgelu(_dgrad(g, w2h, M, Dh, D, epi='bf16'), z)
         d_w1 = _wgrad(dz, xn, Dh, D, M)
         d_b1 = k.colsum(dz)
         dxn = _dgrad(dz, w1h, M, D, Dh, epi='bf16')
