@@ -79,7 +79,8 @@ typedef struct {
   void* workspace;         /* fp32 scratch for split-K or NULL */
   int64_t workspace_bytes;
   int32_t force_splits;    /* 0 = heuristic, >0 = exactly this many K splits (tests) */
-  int32_t force_bn;        /* 0 = heuristic, 128 or 256 (tests) */
+  int32_t force_bn;        /* 0 = heuristic, 128 / 192 / 256 (tests) */
+  int32_t force_cluster;   /* 0/1 = single CTAs (default), 2 = clusters of 2 CTAs along M sharing each B tile by TMA multicast */
 } vt_gemm_params;
 
 int vt_gemm(const vt_gemm_params* p, void* stream);

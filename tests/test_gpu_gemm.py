@@ -137,3 +137,18 @@ def test_gelu_kernels():
     dh = torch.randn(1000, 3072).cuda().bfloat16()
     ref.backward(dh.float())
     assert rel(K().dgelu(dh, z), zf.grad) < 3e-3
+
+
+@pytest.mark.parametrize('cluster', [1, 2])
+@pytest.mark.parametrize('M,N,Kd,a_mn,b_mn,bn', [(128, 256, 128, False, False, 256), (100, 128, 64, False, False, 128),
+                                                  (1000, 768, 768, False, False, 0), (12544, 768, 768, False, True, 0),
+                                                  (12552, 3072, 768, False, False, 256), (12608, 768, 768, False, True, 192),
+                                                  (2304, 768, 12544, True, True, 0), (640, 576, 320, True, True, 192),
+                                                  (640, 384, 320, True, False, 128)])
+def test_gemm_cluster_multicast(M, N, Kd, a_mn, b_mn, bn, cluster):
+    a = mk((Kd, M) if a_mn else (M, Kd), 31, 0.3).bfloat16()
+    b = mk((Kd, N) if b_mn else (N, Kd), 32, 0.3).bfloat16()
+    out = K().gemm(a, b, M, N, Kd, a_mn=a_mn, b_mn=b_mn, epi='f32', force_bn=bn, force_cluster=cluster,
+                   split_ok=a_mn and b_mn)
+    torch.cuda.synchronize()
+    assert rel(out, ref_mm(a, b, a_mn, b_mn)) < 1e-5

@@ -25,7 +25,7 @@ def bench(fn, reps=8):
     return ts[len(ts) // 2]
 
 
-def case(name, M, N, Kd, a_mn=False, b_mn=False, epi='bf16', split=False, resid=False, bns=(0,), splits=(0,)):
+def case(name, M, N, Kd, a_mn=False, b_mn=False, epi='bf16', split=False, resid=False, bns=(0,), splits=(0,), clusters=(1, 2)):
     a = torch.randn((Kd, M) if a_mn else (M, Kd), device=dev).bfloat16()
     b = torch.randn((Kd, N) if b_mn else (N, Kd), device=dev).bfloat16()
     bias = torch.randn(N, device=dev) if epi in ('bf16', 'gelu') or resid else None
@@ -46,29 +46,30 @@ def case(name, M, N, Kd, a_mn=False, b_mn=False, epi='bf16', split=False, resid=
     res = []
     for bn in bns:
         for sp in splits:
-            t = bench(lambda: K.gemm(a, b, M, N, Kd, a_mn=a_mn, b_mn=b_mn, epi=epi, bias=bias, out=out, out2=out2,
-                                     split_ok=split, force_bn=bn, force_splits=sp, **kw))
-            res.append(f'bn={bn or "auto"},sp={sp or "auto"}: {t * 1e3:7.1f}us {fl / t / 1e9:6.0f}TF')
+            for cl in clusters:
+                t = bench(lambda: K.gemm(a, b, M, N, Kd, a_mn=a_mn, b_mn=b_mn, epi=epi, bias=bias, out=out, out2=out2,
+                                         split_ok=split, force_bn=bn, force_splits=sp, force_cluster=cl, **kw))
+                res.append(f'bn={bn or "auto"},sp={sp or "auto"},cl={cl}: {t * 1e3:6.1f}us {fl / t / 1e9:5.0f}TF')
     print(f'{name:28s} M={M:6d} N={N:5d} K={Kd:6d} | cuBLAS {t_ref * 1e3:7.1f}us {fl / t_ref / 1e9:6.0f}TF | ' + ' | '.join(res), flush=True)
 
 
 print('== forward')
-case('qkv temporal', 12544, 2304, 768, bns=(256, 128))
-case('proj (bf16,rowscale)', 12544, 768, 768, bns=(256, 128))
-case('temporal_fc (f32 resid map)', 12544, 768, 768, epi='f32', resid=True, bns=(256, 128))
-case('qkv spatial', 12608, 2304, 768, bns=(256, 128))
-case('fc1 gelu', 12552, 3072, 768, epi='gelu', bns=(256, 128))
-case('fc2 (f32 resid)', 12552, 768, 3072, epi='f32', resid=True, bns=(256, 128))
+case('qkv temporal', 12544, 2304, 768, bns=(0,))
+case('proj (bf16,rowscale)', 12544, 768, 768, bns=(0,))
+case('temporal_fc (f32 resid map)', 12544, 768, 768, epi='f32', resid=True, bns=(0,))
+case('qkv spatial', 12608, 2304, 768, bns=(0,))
+case('fc1 gelu', 12552, 3072, 768, epi='gelu', bns=(0,))
+case('fc2 (f32 resid)', 12552, 768, 3072, epi='f32', resid=True, bns=(0,))
 print('== dgrad (B MN-major)')
-case('d proj', 12544, 768, 768, b_mn=True, bns=(256, 128))
-case('d qkv', 12544, 768, 2304, b_mn=True, bns=(256, 128))
-case('d fc2 dgelu', 12552, 3072, 768, b_mn=True, epi='dgelu', bns=(256, 128))
-case('d fc1', 12552, 768, 3072, b_mn=True, bns=(256, 128))
+case('d proj', 12544, 768, 768, b_mn=True, bns=(0,))
+case('d qkv', 12544, 768, 2304, b_mn=True, bns=(0,))
+case('d fc2 dgelu', 12552, 3072, 768, b_mn=True, epi='dgelu', bns=(0,))
+case('d fc1', 12552, 768, 3072, b_mn=True, bns=(0,))
 print('== wgrad (A,B MN-major, split-K)')
-case('w 768x768', 768, 768, 12544, a_mn=True, b_mn=True, epi='f32', split=True, bns=(256, 128), splits=(0, 4, 8, 16))
-case('w qkv 2304x768', 2304, 768, 12544, a_mn=True, b_mn=True, epi='f32', split=True, bns=(256, 128), splits=(0, 1, 3, 5, 8))
-case('w fc1 3072x768', 3072, 768, 12552, a_mn=True, b_mn=True, epi='f32', split=True, bns=(256, 128), splits=(0, 1, 2, 4))
-case('w fc2 768x3072', 768, 3072, 12552, a_mn=True, b_mn=True, epi='f32', split=True, bns=(256, 128), splits=(0, 1, 2, 4))
+case('w 768x768', 768, 768, 12544, a_mn=True, b_mn=True, epi='f32', split=True, bns=(0,), splits=(0,))
+case('w qkv 2304x768', 2304, 768, 12544, a_mn=True, b_mn=True, epi='f32', split=True, bns=(0,), splits=(0,))
+case('w fc1 3072x768', 3072, 768, 12552, a_mn=True, b_mn=True, epi='f32', split=True, bns=(0,), splits=(0,))
+case('w fc2 768x3072', 768, 3072, 12552, a_mn=True, b_mn=True, epi='f32', split=True, bns=(0,), splits=(0,))
 print('== K sweep at M=12544 N=768 (epilogue share)')
-for kd in (256, 768, 1536, 3072, 6144):
+for kd in (768, 3072):
     case(f'K={kd}', 12544, 768, kd, bns=(256,))

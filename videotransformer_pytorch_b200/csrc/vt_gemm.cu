@@ -30,6 +30,7 @@ struct GemmCfg {
 struct GemmDev {
   int M, N, K;
   int num_m, num_n, splits, kblocks;
+  int num_mp;   // macro row-tiles: ceil(num_m / cluster size)
   int a_mn, b_mn, epi;
   const float* bias;
   void* out;
@@ -57,6 +58,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // Optional cluster of 2 CTAs along M: both work on the same (n, k) sequence, so each loads only half of
+  // every B tile and multicasts it into both CTAs' shared memory (L2 -> SM traffic per CTA drops from
+  // A + B to A + B/2); a stage is released by a multicast tcgen05.commit from both MMA issuers.
+  const uint32_t csize = cluster_nctarank();
+  const uint32_t crank = cluster_ctarank();
+  const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -65,7 +72,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < Cfg::STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], csize);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
@@ -76,17 +83,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
+  if (csize > 1) cluster_sync_all();   // peer barriers are initialised before any multicast can target them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int total_units = p.num_m * p.num_n * p.splits;
+  const int total_units = p.num_mp * p.num_n * p.splits;
+  const int unit0 = blockIdx.x / csize, unit_step = gridDim.x / csize;
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0, phase = 0;
-      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+      for (int unit = unit0; unit < total_units; unit += unit_step) {
         const int tile = unit / p.splits, split = unit - tile * p.splits;
-        const int m_blk = tile % p.num_m, n_blk = tile / p.num_m;
+        const int m_blk = (tile % p.num_mp) * (int)csize + (int)crank, n_blk = tile / p.num_mp;
         const int kb0 = (int)(((long long)p.kblocks * split) / p.splits);
         const int kb1 = (int)(((long long)p.kblocks * (split + 1)) / p.splits);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -101,12 +110,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int c = 0; c < BM / 64; ++c)
               tma_load_2d(sA + c * CHUNK_BYTES, &tmA, &full_bar[stage], m_blk * BM + c * 64, kb * BK);
           }
-          if (!p.b_mn) {
-            tma_load_2d(sB, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
-          } else {
+          if (csize == 1) {
+            if (!p.b_mn) {
+              tma_load_2d(sB, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
+            } else {
 #pragma unroll
-            for (int c = 0; c < BN / 64; ++c)
-              tma_load_2d(sB + c * CHUNK_BYTES, &tmB, &full_bar[stage], n_blk * BN + c * 64, kb * BK);
+              for (int c = 0; c < BN / 64; ++c)
+                tma_load_2d(sB + c * CHUNK_BYTES, &tmB, &full_bar[stage], n_blk * BN + c * 64, kb * BK);
+            }
+          } else {
+            // my half of the B tile, delivered to both CTAs (the peer sends the other half)
+            if (!p.b_mn) {
+              const int r0 = (int)crank * (BN / 2);
+              tma_load_2d_mc(sB + r0 * 128, &tmB, &full_bar[stage], kb * BK, n_blk * BN + r0, cmask);
+            } else {
+              constexpr int NCH = BN / 64;
+              const int c0 = crank == 0 ? 0 : (NCH + 1) / 2, c1 = crank == 0 ? (NCH + 1) / 2 : NCH;
+              for (int c = c0; c < c1; ++c)
+                tma_load_2d_mc(sB + c * CHUNK_BYTES, &tmB, &full_bar[stage], n_blk * BN + c * 64, kb * BK, cmask);
+            }
           }
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -116,7 +138,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(BM, BN, (uint32_t)p.a_mn, (uint32_t)p.b_mn);
       int stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+      for (int unit = unit0; unit < total_units; unit += unit_step) {
         const int tile = unit / p.splits, split = unit - tile * p.splits;
         const int kb0 = (int)(((long long)p.kblocks * split) / p.splits);
         const int kb1 = (int)(((long long)p.kblocks * (split + 1)) / p.splits);
@@ -134,7 +156,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const uint64_t bdesc = p.b_mn ? sdesc_mnmajor(b_addr + k * 2048, CHUNK_BYTES) : sdesc_kmajor(b_addr + k * 32);
             umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          // frees the smem slot (in both CTAs of a cluster: the peer multicasts into it) when these MMAs retire
+          if (csize == 1) umma_commit(&empty_bar[stage]);
+          else umma_commit_mc(&empty_bar[stage], cmask);
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
@@ -156,9 +180,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const bool f32_aux = p.epi == VT_EPI_F32 && p.aux != nullptr;
     const bool z_aux = p.epi == VT_EPI_DGELU;
     int acc = 0, acc_phase = 0;
-    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+    for (int unit = unit0; unit < total_units; unit += unit_step) {
       const int tile = unit / p.splits, split = unit - tile * p.splits;
-      const int m_blk = tile % p.num_m, n_blk = tile / p.num_m;
+      const int m_blk = (tile % p.num_mp) * (int)csize + (int)crank, n_blk = tile / p.num_mp;
       // per-row metadata of the 8 rows this lane serves in the transposed phase
       float rs[8];
       int orow[8], arow[8];
@@ -251,6 +275,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
+  if (csize > 1) cluster_sync_all();   // no CTA leaves while its peer may still multicast into it
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
@@ -371,14 +396,19 @@ static int launch_gemm(const vt_gemm_params* q, GemmDev& d, cudaStream_t st) {
   if (!q->a_mn_major) rc = make_tmap_bf16_2d(&tmA, q->a, q->M, q->K, q->lda, BM);
   else rc = make_tmap_bf16_2d(&tmA, q->a, q->K, q->M, q->lda, BK);
   if (rc) return rc;
-  if (!q->b_mn_major) rc = make_tmap_bf16_2d(&tmB, q->b, q->N, q->K, q->ldb, BN);
+  d.num_m = (q->M + BM - 1) / BM;
+  // clusters of 2 along M whenever there are at least two row tiles (force_cluster: 1 = never, 2 = always)
+  // Measured on B200 (profiles/): sharing B by multicast does not speed this kernel up — its mainloop is limited by
+  // shared-memory capacity (bytes in flight per SM), not by L2->SM bandwidth — so clusters are opt-in.
+  const int csize = q->force_cluster == 2 ? 2 : 1;
+  if (!q->b_mn_major) rc = make_tmap_bf16_2d(&tmB, q->b, q->N, q->K, q->ldb, BN / csize);
   else rc = make_tmap_bf16_2d(&tmB, q->b, q->K, q->N, q->ldb, BK);
   if (rc) return rc;
+  d.num_mp = (d.num_m + csize - 1) / csize;
 
-  d.num_m = (q->M + BM - 1) / BM;
   d.num_n = (q->N + BN - 1) / BN;
   d.kblocks = (q->K + BK - 1) / BK;
-  const int tiles = d.num_m * d.num_n;
+  const int tiles = d.num_mp * d.num_n;     // macro tiles (one per cluster)
   const int sms = sm_count();
 
   int splits = 1;
@@ -401,8 +431,25 @@ static int launch_gemm(const vt_gemm_params* q, GemmDev& d, cudaStream_t st) {
     d.split_stride = 0;
   }
   const int units = tiles * splits;
-  const int grid = units < sms ? units : sms;
-  gemm_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, d);
+  const int max_clusters = sms / csize;
+  const int grid = (units < max_clusters ? units : max_clusters) * csize;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)csize;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN>, tmA, tmB, d);
+  if (le != cudaSuccess) {
+    set_error("gemm_tcgen05_kernel: cudaLaunchKernelEx failed: %s", cudaGetErrorString(le));
+    return 2;
+  }
   rc = check_launch("gemm_tcgen05_kernel");
   if (rc) return rc;
   if (splits > 1) {
@@ -462,12 +509,14 @@ extern "C" int vt_gemm(const vt_gemm_params* q, void* stream) {
     int best_bn = 256, best_s = 1;
     for (int i = 0; i < 3; ++i) {
       if (q->force_bn && cand[i] != q->force_bn) continue;
-      const int tiles = num_m * ((q->N + cand[i] - 1) / cand[i]);
+      const int cs = q->force_cluster == 2 ? 2 : 1;
+      const int tiles = ((num_m + cs - 1) / cs) * ((q->N + cand[i] - 1) / cand[i]);   // macro tiles, one per cluster
+      const int slots = sms / cs;
       const int smax = can_split ? 16 : 1;
       for (int sp = 1; sp <= smax; ++sp) {
         if (sp > 1 && (kblocks / sp < 4 || (long long)sp * q->M * q->N * 4 > q->workspace_bytes)) break;
         const long long units = (long long)tiles * sp;
-        const long long rounds = (units + sms - 1) / sms;
+        const long long rounds = (units + slots - 1) / slots;
         const double cost = (double)rounds * ((double)kblocks / sp + 8.0) * cand[i] * penalty[i];
         if (cost < best - 1e-9) { best = cost; best_bn = cand[i]; best_s = sp; }
       }
