@@ -80,7 +80,9 @@ typedef struct {
   int64_t workspace_bytes;
   int32_t force_splits;    /* 0 = heuristic, >0 = exactly this many K splits (tests) */
   int32_t force_bn;        /* 0 = heuristic, 128 / 192 / 256 (tests) */
-  int32_t force_cluster;   /* 0/1 = single CTAs (default), 2 = clusters of 2 CTAs along M sharing each B tile by TMA multicast */
+  int32_t force_cluster;   /* 0/1 = single CTAs, 2 = clusters of 2 CTAs along M sharing each B tile by TMA multicast,
+                              3 = CTA pairs issuing tcgen05.mma.cta_group::2 (256 x BN tiles, half of B per SM) */
+  void* debug;             /* diagnostics only: int64 [grid][16] clock64 stamps of the kernel's phases, or NULL */
 } vt_gemm_params;
 
 int vt_gemm(const vt_gemm_params* p, void* stream);

@@ -37,7 +37,7 @@ class EmuKernels:
 
     def gemm(self, a, b, M, N, Kdim, *, a_mn=False, b_mn=False, epi='bf16', bias=None, out=None, out2=None,
              aux=None, out_row=None, aux_row=None, row_scale=None, out_rows=None, split_ok=False,
-             force_splits=0, force_bn=0, force_cluster=0):
+             force_splits=0, force_bn=0, force_cluster=0, debug=None):
         self.calls.append(('gemm', M, N, Kdim, a_mn, b_mn, epi))
         A = self._up(a).t() if a_mn else self._up(a)
         Bm = self._up(b) if b_mn else self._up(b).t()

@@ -139,16 +139,46 @@ def test_gelu_kernels():
     assert rel(K().dgelu(dh, z), zf.grad) < 3e-3
 
 
-@pytest.mark.parametrize('cluster', [1, 2])
+@pytest.mark.parametrize('cluster', [1, 2, 3])
 @pytest.mark.parametrize('M,N,Kd,a_mn,b_mn,bn', [(128, 256, 128, False, False, 256), (100, 128, 64, False, False, 128),
                                                   (1000, 768, 768, False, False, 0), (12544, 768, 768, False, True, 0),
                                                   (12552, 3072, 768, False, False, 256), (12608, 768, 768, False, True, 192),
                                                   (2304, 768, 12544, True, True, 0), (640, 576, 320, True, True, 192),
                                                   (640, 384, 320, True, False, 128)])
 def test_gemm_cluster_multicast(M, N, Kd, a_mn, b_mn, bn, cluster):
+    if cluster == 3 and bn == 192:
+        bn = 256          # the CTA-pair kernel has BN 128 / 256
     a = mk((Kd, M) if a_mn else (M, Kd), 31, 0.3).bfloat16()
     b = mk((Kd, N) if b_mn else (N, Kd), 32, 0.3).bfloat16()
     out = K().gemm(a, b, M, N, Kd, a_mn=a_mn, b_mn=b_mn, epi='f32', force_bn=bn, force_cluster=cluster,
                    split_ok=a_mn and b_mn)
     torch.cuda.synchronize()
     assert rel(out, ref_mm(a, b, a_mn, b_mn)) < 1e-5
+
+
+@pytest.mark.parametrize('epi', ['bf16', 'f32res', 'gelu', 'dgelu'])
+def test_gemm_pair_kernel_epilogues(epi):
+    M, N, Kd = 1000, 512, 256
+    a, b = mk((M, Kd), 41, 0.3).bfloat16(), mk((N, Kd), 42, 0.3).bfloat16()
+    bias = mk((N,), 43)
+    r = ref_mm(a, b, False, False)
+    if epi == 'bf16':
+        out = K().gemm(a, b, M, N, Kd, epi='bf16', bias=bias, force_cluster=3)
+        assert rel(out, r + bias) < 4e-3
+    elif epi == 'f32res':
+        aux = mk((M, N), 44)
+        perm = torch.randperm(M).to(torch.int32).cuda()
+        out = torch.zeros(M, N, device='cuda')
+        K().gemm(a, b, M, N, Kd, epi='f32', bias=bias, aux=aux, aux_row=perm, out_row=perm, out=out, force_cluster=3)
+        exp = torch.zeros(M, N, device='cuda')
+        exp[perm.long()] = r + bias + aux[perm.long()]
+        assert rel(out, exp) < 1e-5
+    elif epi == 'gelu':
+        z, h = K().gemm(a, b, M, N, Kd, epi='gelu', bias=bias, force_cluster=3)
+        assert rel(z, r + bias) < 4e-3 and rel(h, torch.nn.functional.gelu(r + bias)) < 4e-3
+    else:
+        z = mk((M, N), 45).bfloat16()
+        out = K().gemm(a, b, M, N, Kd, epi='dgelu', aux=z, force_cluster=3)
+        zz = z.float().requires_grad_(True)
+        torch.nn.functional.gelu(zz).sum().backward()
+        assert rel(out, r * zz.grad) < 4e-3

@@ -25,7 +25,7 @@ def bench(fn, reps=8):
     return ts[len(ts) // 2]
 
 
-def case(name, M, N, Kd, a_mn=False, b_mn=False, epi='bf16', split=False, resid=False, bns=(0,), splits=(0,), clusters=(1, 2)):
+def case(name, M, N, Kd, a_mn=False, b_mn=False, epi='bf16', split=False, resid=False, bns=(0,), splits=(0,), clusters=(1, 3)):
     a = torch.randn((Kd, M) if a_mn else (M, Kd), device=dev).bfloat16()
     b = torch.randn((Kd, N) if b_mn else (N, Kd), device=dev).bfloat16()
     bias = torch.randn(N, device=dev) if epi in ('bf16', 'gelu') or resid else None

@@ -28,7 +28,7 @@ class GemmParams(C.Structure):
                 ('ldo', c_i64), ('ldo2', c_i64), ('ldaux', c_i64),
                 ('out_row', c_vp), ('aux_row', c_vp), ('row_scale', c_vp),
                 ('workspace', c_vp), ('workspace_bytes', c_i64),
-                ('force_splits', c_i32), ('force_bn', c_i32), ('force_cluster', c_i32)]
+                ('force_splits', c_i32), ('force_bn', c_i32), ('force_cluster', c_i32), ('debug', c_vp)]
 
 
 class LnFwdParams(C.Structure):
@@ -159,7 +159,7 @@ class CudaKernels:
     # -- GEMM ---------------------------------------------------------------------------------
     def gemm(self, a, b, M, N, Kdim, *, a_mn=False, b_mn=False, epi='bf16', bias=None, out=None, out2=None,
              aux=None, out_row=None, aux_row=None, row_scale=None, out_rows=None, split_ok=False,
-             force_splits=0, force_bn=0, force_cluster=0):
+             force_splits=0, force_bn=0, force_cluster=0, debug=None):
         lib = load_library()
         _rows2d(_req(a, torch.bfloat16, 'gemm.a'), 'gemm.a')
         _rows2d(_req(b, torch.bfloat16, 'gemm.b'), 'gemm.b')
@@ -202,6 +202,7 @@ class CudaKernels:
             ws = self.workspace(a.device, 16 * M * N * 4)
             p.workspace, p.workspace_bytes = ws.data_ptr(), ws.numel() * 4
         p.force_splits, p.force_bn, p.force_cluster = force_splits, force_bn, force_cluster
+        p.debug = _ptr(debug)
         _check(lib.vt_gemm(C.byref(p), _stream()), 'vt_gemm')
         return (out, out2) if epi == 'gelu' else out
 

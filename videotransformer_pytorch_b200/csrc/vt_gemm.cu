@@ -5,17 +5,12 @@
 // warps4-11 = epilogue (warp w drains TMEM lanes 32*(w%4)..+31; the two warpgroups interleave column chunks).
 // Tile: 128 x BN x 64, BN in {128, 256}.  Both operands may be K-major or MN-major (UMMA descriptors),
 // so forward (X W^T), dgrad (dY W) and wgrad (dY^T X) all run without transposed copies.
-#include "vt_common.cuh"
-#include "vt_umma.cuh"
+#include <stdlib.h>
+#include <string.h>
+
+#include "vt_gemm_common.cuh"
 
 namespace vt {
-
-constexpr int BM = 128;
-constexpr int BK = 64;
-constexpr int GEMM_THREADS = 384;        // 4 control warps + 8 epilogue warps
-constexpr int CHUNK_BYTES = 64 * BK * 2;  // one 64-wide MN chunk of an MN-major tile (8 KiB)
-constexpr int EPI_PITCH = 33;             // words per staged row (32 + 1 pad: conflict-free row writes and column-group reads)
-constexpr int EPI_WARPS = 8;
 
 template <int BN>
 struct GemmCfg {
@@ -27,30 +22,15 @@ struct GemmCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_WARPS * 32 * EPI_PITCH * 4 /*epilogue staging*/;
 };
 
-struct GemmDev {
-  int M, N, K;
-  int num_m, num_n, splits, kblocks;
-  int num_mp;   // macro row-tiles: ceil(num_m / cluster size)
-  int a_mn, b_mn, epi;
-  const float* bias;
-  void* out;
-  void* out2;
-  const void* aux;
-  long long ldo, ldo2, ldaux;
-  const int* out_row;
-  const int* aux_row;
-  const float* row_scale;
-  long long split_stride;  // elements between split partials (EPI_F32 only)
-};
-
 template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const GemmDev p) {
+                    const __grid_constant__ CUtensorMap tmC, const GemmDev p) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint8_t* staging = smem + Cfg::STAGES * Cfg::STAGE_BYTES;                       // 1024-aligned epilogue staging
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + EPI_WARPS * 32 * EPI_PITCH * 4);
   uint64_t* empty_bar = full_bar + Cfg::STAGES;
   uint64_t* tfull_bar = empty_bar + Cfg::STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -58,6 +38,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  long long* dbg = p.dbg ? p.dbg + (long long)blockIdx.x * 16 : nullptr;
+  if (dbg && threadIdx.x == 0) dbg[0] = clock64();
   // Optional cluster of 2 CTAs along M: both work on the same (n, k) sequence, so each loads only half of
   // every B tile and multicasts it into both CTAs' shared memory (L2 -> SM traffic per CTA drops from
   // A + B to A + B/2); a stage is released by a multicast tcgen05.commit from both MMA issuers.
@@ -68,6 +50,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.tma_store) tma_prefetch_desc(&tmC);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < Cfg::STAGES; ++i) {
@@ -86,6 +69,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (csize > 1) cluster_sync_all();   // peer barriers are initialised before any multicast can target them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (dbg && threadIdx.x == 0) dbg[1] = clock64();   // setup done
 
   const int total_units = p.num_mp * p.num_n * p.splits;
   const int unit0 = blockIdx.x / csize, unit_step = gridDim.x / csize;
@@ -148,6 +132,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          if (dbg && unit == unit0 && kb == kb0) dbg[2] = clock64();   // first operands landed
           const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint32_t b_addr = a_addr + Cfg::A_BYTES;
 #pragma unroll
@@ -162,6 +147,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        if (dbg) { if (unit == unit0) dbg[3] = clock64(); dbg[4] = clock64(); }   // MMAs of first / last tile issued
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -175,97 +161,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ahead so their latency hides behind the TMEM drain + transpose of the current chunk.
     const int q = warp & 3;             // TMEM lane quadrant this warp may access
     const int half = (warp - 4) >> 2;   // which warpgroup
-    float* stg = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256) + (warp - 4) * (32 * EPI_PITCH);
-    const int rsub = lane >> 3, cg = lane & 7;
-    const bool f32_aux = p.epi == VT_EPI_F32 && p.aux != nullptr;
-    const bool z_aux = p.epi == VT_EPI_DGELU;
+    float* stg = reinterpret_cast<float*>(staging) + (warp - 4) * (32 * EPI_PITCH);
+    uint8_t* slot = staging + (warp - 4) * 4096;
     int acc = 0, acc_phase = 0;
     for (int unit = unit0; unit < total_units; unit += unit_step) {
       const int tile = unit / p.splits, split = unit - tile * p.splits;
       const int m_blk = (tile % p.num_mp) * (int)csize + (int)crank, n_blk = tile / p.num_mp;
-      // per-row metadata of the 8 rows this lane serves in the transposed phase
-      float rs[8];
-      int orow[8], arow[8];
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int row = m_blk * BM + q * 32 + it * 4 + rsub;
-        const bool ok = row < p.M;
-        rs[it] = (ok && p.row_scale) ? p.row_scale[row] : 1.0f;
-        orow[it] = ok ? (p.out_row ? p.out_row[row] : row) : -1;
-        arow[it] = !ok ? -1 : (f32_aux ? (p.aux_row ? p.aux_row[row] : row) : (z_aux ? row : -1));
-      }
-      uint4 pre[8];
-#pragma unroll
-      for (int it = 0; it < 8; ++it) pre[it] = make_uint4(0u, 0u, 0u, 0u);   // no epilogue operand => adds 0
-      auto prefetch = [&](int c) {
-        const int n = n_blk * BN + c * 32 + cg * 4;
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          pre[it] = make_uint4(0u, 0u, 0u, 0u);
-          if (arow[it] >= 0 && orow[it] >= 0 && n < p.N) {
-            if (f32_aux) {
-              pre[it] = *reinterpret_cast<const uint4*>(static_cast<const float*>(p.aux) + (long long)arow[it] * p.ldaux + n);
-            } else if (z_aux) {
-              const uint2 z = *reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(p.aux) + (long long)arow[it] * p.ldaux + n);
-              pre[it].x = z.x; pre[it].y = z.y;
-            }
-          }
-        }
-      };
-      if (f32_aux || z_aux) prefetch(half);
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
       const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-#pragma unroll 1
-      for (int c = half; c < BN / 32; c += 2) {
-        uint32_t r[32];
-        tmem_ld32(t_base + c * 32, r);
-        tmem_ld_wait();
-        const int n = n_blk * BN + c * 32 + cg * 4;
-        if (n_blk * BN + c * 32 >= p.N) break;   // warp-uniform
-#pragma unroll
-        for (int j = 0; j < 32; ++j) stg[lane * EPI_PITCH + j] = __uint_as_float(r[j]);
-        uint4 cur[8];
-#pragma unroll
-        for (int it = 0; it < 8; ++it) cur[it] = pre[it];
-        if ((f32_aux || z_aux) && c + 2 < BN / 32) prefetch(c + 2);
-        __syncwarp();
-        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.bias && n < p.N) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const float* sp = stg + (it * 4 + rsub) * EPI_PITCH + cg * 4;
-          float4 v = make_float4(sp[0], sp[1], sp[2], sp[3]);
-          if (orow[it] < 0 || n >= p.N) continue;
-          v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
-          const long long o = (long long)orow[it];
-          if (p.epi == VT_EPI_BF16) {
-            const float s = rs[it];
-            uint2 w;
-            w.x = pack_bf16x2(s * v.x, s * v.y);
-            w.y = pack_bf16x2(s * v.z, s * v.w);
-            *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.out) + o * p.ldo + n) = w;
-          } else if (p.epi == VT_EPI_F32) {
-            const float s = rs[it];
-            v.x = fmaf(s, v.x, __uint_as_float(cur[it].x)); v.y = fmaf(s, v.y, __uint_as_float(cur[it].y));
-            v.z = fmaf(s, v.z, __uint_as_float(cur[it].z)); v.w = fmaf(s, v.w, __uint_as_float(cur[it].w));
-            *reinterpret_cast<float4*>(static_cast<float*>(p.out) + (long long)split * p.split_stride + o * p.ldo + n) = v;
-          } else if (p.epi == VT_EPI_GELU) {
-            uint2 z, h;
-            z.x = pack_bf16x2(v.x, v.y); z.y = pack_bf16x2(v.z, v.w);
-            h.x = pack_bf16x2(gelu_fast(v.x), gelu_fast(v.y)); h.y = pack_bf16x2(gelu_fast(v.z), gelu_fast(v.w));
-            *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.out) + o * p.ldo + n) = z;
-            *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.out2) + o * p.ldo2 + n) = h;
-          } else {  // VT_EPI_DGELU: cur = z (bf16 x4)
-            const float2 z0 = unpack_bf16x2(cur[it].x), z1 = unpack_bf16x2(cur[it].y);
-            uint2 w;
-            w.x = pack_bf16x2(v.x * dgelu_fast(z0.x), v.y * dgelu_fast(z0.y));
-            w.y = pack_bf16x2(v.z * dgelu_fast(z1.x), v.w * dgelu_fast(z1.y));
-            *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.out) + o * p.ldo + n) = w;
-          }
-        }
-        __syncwarp();
-      }
+      if (p.tma_store) epilogue_tile_tma<BN>(p, &tmC, slot, t_base, m_blk, n_blk, split, q, half, lane, &tfull_bar[acc], (uint32_t)acc_phase);
+      else epilogue_tile<BN>(p, stg, t_base, m_blk, n_blk, split, q, half, lane, &tfull_bar[acc], (uint32_t)acc_phase);
+      if (dbg && warp == 4 && lane == 0) { if (unit == unit0) dbg[5] = clock64(); dbg[6] = clock64(); }   // first / last tile drained
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -276,6 +181,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tc_fence_before();
   __syncthreads();
   if (csize > 1) cluster_sync_all();   // no CTA leaves while its peer may still multicast into it
+  if (dbg && threadIdx.x == 0) dbg[7] = clock64();
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
@@ -316,6 +222,36 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* base, long long rows, long l
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   VT_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld box_rows=%d", (int)r,
              rows, cols, ld, box_rows);
+  return 0;
+}
+
+// Output map for the TMA-store epilogue: [splits][M][N] (bf16 or fp32), box {32 cols, 32 rows, 1}, swizzle = row bytes.
+int make_tmap_out_3d(CUtensorMap* map, const void* base, int fp32, long long M, long long N, long long ld, long long splits,
+                     long long split_stride) {
+  EncodeTiledFn fn = get_encode_fn();
+  VT_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
+  const int esz = fp32 ? 4 : 2;
+  cuuint64_t gdim[3] = {(cuuint64_t)N, (cuuint64_t)M, (cuuint64_t)splits};
+  cuuint64_t gstr[2] = {(cuuint64_t)(ld * esz), (cuuint64_t)((splits > 1 ? split_stride : M * ld) * esz)};
+  cuuint32_t box[3] = {32u, 32u, 1u};
+  cuuint32_t estr[3] = {1u, 1u, 1u};
+  CUresult r = fn(map, fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim,
+                  gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, fp32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  VT_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(out) failed (%d) M=%lld N=%lld ld=%lld", (int)r, M, N, ld);
+  return 0;
+}
+
+// Decide whether the plain TMA-store epilogue applies and build its map (called after the split decision).
+int setup_out_map(const vt_gemm_params* q, GemmDev& d, CUtensorMap* tmC) {
+  d.tma_store = 0;
+  memset(tmC, 0, sizeof(*tmC));
+  const bool plain = (q->epilogue == VT_EPI_BF16 || q->epilogue == VT_EPI_F32) && !q->out_row && !q->aux && q->force_cluster != 9;
+  if (!plain || getenv("VT_NO_TMA_STORE")) return 0;
+  const int fp32 = q->epilogue == VT_EPI_F32;
+  int rc = make_tmap_out_3d(tmC, d.out, fp32, q->M, q->N, d.ldo, d.splits, d.split_stride);
+  if (rc) return rc;
+  d.tma_store = 1;
   return 0;
 }
 
@@ -430,6 +366,9 @@ static int launch_gemm(const vt_gemm_params* q, GemmDev& d, cudaStream_t st) {
   } else {
     d.split_stride = 0;
   }
+  CUtensorMap tmC;
+  rc = setup_out_map(q, d, &tmC);
+  if (rc) return rc;
   const int units = tiles * splits;
   const int max_clusters = sms / csize;
   const int grid = (units < max_clusters ? units : max_clusters) * csize;
@@ -445,7 +384,7 @@ static int launch_gemm(const vt_gemm_params* q, GemmDev& d, cudaStream_t st) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN>, tmA, tmB, d);
+  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN>, tmA, tmB, tmC, d);
   if (le != cudaSuccess) {
     set_error("gemm_tcgen05_kernel: cudaLaunchKernelEx failed: %s", cudaGetErrorString(le));
     return 2;
@@ -463,6 +402,8 @@ static int launch_gemm(const vt_gemm_params* q, GemmDev& d, cudaStream_t st) {
   }
   return 0;
 }
+
+int launch_gemm2(const vt_gemm_params* q, GemmDev& d, int bn, cudaStream_t st);
 
 }  // namespace vt
 
@@ -490,6 +431,7 @@ extern "C" int vt_gemm(const vt_gemm_params* q, void* stream) {
   d.out = q->out; d.out2 = q->out2; d.aux = q->aux;
   d.ldo = q->ldo; d.ldo2 = q->ldo2; d.ldaux = q->ldaux;
   d.out_row = q->out_row; d.aux_row = q->aux_row; d.row_scale = q->row_scale;
+  d.dbg = static_cast<long long*>(q->debug);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 
   int bn = q->force_bn;
@@ -503,26 +445,39 @@ extern "C" int vt_gemm(const vt_gemm_params* q, void* stream) {
     const int num_m = (q->M + BM - 1) / BM;
     const int kblocks = (q->K + BK - 1) / BK;
     const bool can_split = q->epilogue == VT_EPI_F32 && q->workspace && !q->out_row && !q->aux && !q->row_scale && !q->bias;
+    // kernel variants: 0 = one CTA per 128 x BN tile (optionally clusters with multicast B), 1 = CTA pairs with
+    // tcgen05.mma.cta_group::2 (256 x BN macro tiles, half of B per SM, 6-8 stages).  The pair kernel's unit time is
+    // ~8% shorter (measured, profiles/) but its macro tiles quantise worse and it has no BN = 192; it is skipped
+    // for small MN-major weight-gradient shapes, where it measured slower.
+    const bool pair_forced = q->force_cluster == 3;
+    const bool pair_ok = pair_forced || (q->force_cluster == 0 && num_m >= 2 &&
+                                         (!q->a_mn_major || (long long)q->M * q->N >= 2000000LL));
     const int cand[3] = {256, 192, 128};
     const double penalty[3] = {1.0, 1.04, 1.10};
     double best = 1e30;
-    int best_bn = 256, best_s = 1;
-    for (int i = 0; i < 3; ++i) {
-      if (q->force_bn && cand[i] != q->force_bn) continue;
-      const int cs = q->force_cluster == 2 ? 2 : 1;
-      const int tiles = ((num_m + cs - 1) / cs) * ((q->N + cand[i] - 1) / cand[i]);   // macro tiles, one per cluster
-      const int slots = sms / cs;
-      const int smax = can_split ? 16 : 1;
-      for (int sp = 1; sp <= smax; ++sp) {
-        if (sp > 1 && (kblocks / sp < 4 || (long long)sp * q->M * q->N * 4 > q->workspace_bytes)) break;
-        const long long units = (long long)tiles * sp;
-        const long long rounds = (units + slots - 1) / slots;
-        const double cost = (double)rounds * ((double)kblocks / sp + 8.0) * cand[i] * penalty[i];
-        if (cost < best - 1e-9) { best = cost; best_bn = cand[i]; best_s = sp; }
+    int best_bn = 256, best_s = 1, best_pair = 0;
+    for (int variant = 0; variant < 2; ++variant) {
+      if (variant == 1 && !pair_ok) continue;
+      if (variant == 0 && pair_forced) continue;
+      for (int i = 0; i < 3; ++i) {
+        if (q->force_bn && cand[i] != q->force_bn) continue;
+        if (variant == 1 && cand[i] == 192) continue;
+        const int cs = (q->force_cluster == 2 || variant == 1) ? 2 : 1;
+        const int tiles = ((num_m + cs - 1) / cs) * ((q->N + cand[i] - 1) / cand[i]);   // (macro) tiles, one per cluster
+        const int slots = sms / cs;
+        const int smax = can_split ? 16 : 1;
+        for (int sp = 1; sp <= smax; ++sp) {
+          if (sp > 1 && (kblocks / sp < 4 || (long long)sp * q->M * q->N * 4 > q->workspace_bytes)) break;
+          const long long units = (long long)tiles * sp;
+          const long long rounds = (units + slots - 1) / slots;
+          const double cost = (double)rounds * ((double)kblocks / sp + 8.0) * cand[i] * penalty[i] * (variant == 1 ? 0.92 : 1.0);
+          if (cost < best - 1e-9) { best = cost; best_bn = cand[i]; best_s = sp; best_pair = variant; }
+        }
       }
     }
-    if (bn == 0) bn = best_bn;
+    if (bn == 0 || best_pair) bn = best_bn;
     d.splits = best_s;
+    if (best_pair) return launch_gemm2(q, d, bn, st);
   }
   VT_REQUIRE(bn == 128 || bn == 192 || bn == 256, "vt_gemm: force_bn must be 128, 192 or 256");
   if (bn == 256) return launch_gemm<256>(q, d, st);
