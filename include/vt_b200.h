@@ -132,8 +132,10 @@ typedef struct { const float* in; float* out; int64_t stride; int32_t S; int64_t
 int vt_reduce_rows(const vt_reduce_params* p, void* stream);
 
 /* Column sums of a bf16 [M,N] matrix (bias gradients): out_f32[n] = sum_m in[m,n].
- * workspace: fp32 [vt_colsum_chunks(M), N]. */
-typedef struct { const void* in; int64_t ld; int32_t M, N; float* out; float* workspace; } vt_colsum_params;
+ * workspace: fp32 [vt_colsum_chunks(M), N].  Deterministic (fixed summation order) in both forms. */
+typedef struct { const void* in; int64_t ld; int32_t M, N; float* out; float* workspace;
+                 int32_t* counters; /* optional: >= ceil(N/64) zeroed ints -> single-launch form (the last CTA sums the partials and
+                                       re-zeroes its counter); NULL -> partials are reduced by a second launch */ } vt_colsum_params;
 int vt_colsum_chunks(int32_t M);
 int vt_colsum_bf16(const vt_colsum_params* p, void* stream);
 
@@ -175,6 +177,8 @@ typedef struct {
   int32_t impl;
 } vt_attn_bwd_params;
 int vt_attn_bwd(const vt_attn_bwd_params* p, void* stream);
+/* diagnostics only: int64 [grid][32] clock64 phase stamps of the tcgen05 attention kernels (NULL disables) */
+int vt_debug_buffer(void* device_ptr);
 
 /* ---------------------------------------------------------------------------------------------
  * Patch / tubelet embedding operand: non-overlapping Conv2d k16 s16 (transformer.py:116-120,:145-147)

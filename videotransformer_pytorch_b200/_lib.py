@@ -50,7 +50,7 @@ class ReduceParams(C.Structure):
 
 
 class ColsumParams(C.Structure):
-    _fields_ = [('inp', c_vp), ('ld', c_i64), ('M', c_i32), ('N', c_i32), ('out', c_vp), ('workspace', c_vp)]
+    _fields_ = [('inp', c_vp), ('ld', c_i64), ('M', c_i32), ('N', c_i32), ('out', c_vp), ('workspace', c_vp), ('counters', c_vp)]
 
 
 class CastParams(C.Structure):
@@ -88,7 +88,7 @@ class HogParams(C.Structure):
 
 EXPORTS = ['vt_version', 'vt_last_error', 'vt_sm_count', 'vt_launch_count', 'vt_gemm', 'vt_layernorm_fwd', 'vt_ln_bwd_blocks',
            'vt_layernorm_bwd', 'vt_reduce_rows', 'vt_colsum_chunks', 'vt_colsum_bf16', 'vt_cast_f32_bf16',
-           'vt_gather_cast_bf16', 'vt_gelu_fwd_bf16', 'vt_gelu_bwd_bf16', 'vt_attn_fwd', 'vt_attn_bwd', 'vt_im2col_bf16', 'vt_col2im_f32', 'vt_hog']
+           'vt_gather_cast_bf16', 'vt_gelu_fwd_bf16', 'vt_gelu_bwd_bf16', 'vt_attn_fwd', 'vt_attn_bwd', 'vt_debug_buffer', 'vt_im2col_bf16', 'vt_col2im_f32', 'vt_hog']
 
 _dll = None
 
@@ -146,6 +146,7 @@ class CudaKernels:
 
     def __init__(self):
         self._ws = {}
+        self._counters = {}
 
     # -- scratch ------------------------------------------------------------------------------
     def workspace(self, device, nbytes: int) -> torch.Tensor:
@@ -259,8 +260,13 @@ class CudaKernels:
         M, N = x.shape
         out = torch.empty(N, dtype=torch.float32, device=x.device)
         ws = torch.empty((lib.vt_colsum_chunks(M), N), dtype=torch.float32, device=x.device)
+        key = (x.device.index, torch.cuda.current_stream(x.device).cuda_stream)
+        cnt = self._counters.get(key)
+        if cnt is None:
+            cnt = self._counters[key] = torch.zeros(1024, dtype=torch.int32, device=x.device)
         p = ColsumParams()
         p.inp, p.ld, p.M, p.N, p.out, p.workspace = x.data_ptr(), x.stride(0), M, N, out.data_ptr(), ws.data_ptr()
+        p.counters = cnt.data_ptr() if N <= 64 * 1024 else None
         _check(lib.vt_colsum_bf16(C.byref(p), _stream()), 'vt_colsum_bf16')
         return out
 

@@ -25,6 +25,26 @@ __device__ __forceinline__ void stage_rows8(uint32_t* dst, const __nv_bfloat16* 
   }
 }
 
+// software pipelining: the next problem's rows are fetched into registers while the current one is computed
+struct Rows8 { uint4 v[2]; };
+__device__ __forceinline__ Rows8 fetch_rows8(const __nv_bfloat16* base, long long row_stride, int lane) {
+  Rows8 r;
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int row = (lane >> 3) + 4 * it, c = lane & 7;
+    r.v[it] = *reinterpret_cast<const uint4*>(base + (long long)row * row_stride + c * 8);
+  }
+  return r;
+}
+__device__ __forceinline__ void put_rows8(uint32_t* dst, const Rows8& r, int lane) {
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int row = (lane >> 3) + 4 * it, c = lane & 7;
+    uint32_t* d = dst + row * SM_PITCH + c * 4;
+    d[0] = r.v[it].x; d[1] = r.v[it].y; d[2] = r.v[it].z; d[3] = r.v[it].w;
+  }
+}
+
 __global__ void __launch_bounds__(SM_WARPS * 32)
 attn8_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ ctx, float* __restrict__ lse,
                  int nprob, int H, float scale) {
@@ -37,13 +57,22 @@ attn8_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
   float* Ps = shp[warp];
   const long long rs = 3LL * H * SM_HD, cs = (long long)H * SM_HD;
   const int i = lane >> 2, g = lane & 3;
-  for (int prob = blockIdx.x * SM_WARPS + warp; prob < nprob; prob += gridDim.x * SM_WARPS) {
+  const int pstep = gridDim.x * SM_WARPS;
+  int prob = blockIdx.x * SM_WARPS + warp;
+  Rows8 rq, rk, rv;
+  if (prob < nprob) {
+    const __nv_bfloat16* b0 = qkv + (long long)(prob / H) * SM_N * rs + (prob % H) * SM_HD;
+    rq = fetch_rows8(b0, rs, lane); rk = fetch_rows8(b0 + cs, rs, lane); rv = fetch_rows8(b0 + 2 * cs, rs, lane);
+  }
+  for (; prob < nprob; prob += pstep) {
     const int bp = prob / H, h = prob - bp * H;
-    const __nv_bfloat16* base = qkv + (long long)bp * SM_N * rs + h * SM_HD;
-    stage_rows8(Qs, base, rs, lane);
-    stage_rows8(Ks, base + cs, rs, lane);
-    stage_rows8(Vs, base + 2 * cs, rs, lane);
+    put_rows8(Qs, rq, lane); put_rows8(Ks, rk, lane); put_rows8(Vs, rv, lane);
     __syncwarp();
+    if (prob + pstep < nprob) {
+      const int np = prob + pstep;
+      const __nv_bfloat16* b1 = qkv + (long long)(np / H) * SM_N * rs + (np % H) * SM_HD;
+      rq = fetch_rows8(b1, rs, lane); rk = fetch_rows8(b1 + cs, rs, lane); rv = fetch_rows8(b1 + 2 * cs, rs, lane);
+    }
     float s0 = 0.f, s1 = 0.f;
 #pragma unroll 8
     for (int w = 0; w < 32; ++w) {
@@ -106,15 +135,24 @@ attn8_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __r
   float* Ds = shp[warp][1];     // dS
   const long long rs = 3LL * H * SM_HD, cs = (long long)H * SM_HD;
   const int i = lane >> 2, g = lane & 3;
-  for (int prob = blockIdx.x * SM_WARPS + warp; prob < nprob; prob += gridDim.x * SM_WARPS) {
+  const int pstep = gridDim.x * SM_WARPS;
+  int prob = blockIdx.x * SM_WARPS + warp;
+  Rows8 rq, rk, rv, rg;
+  if (prob < nprob) {
+    const __nv_bfloat16* b0 = qkv + (long long)(prob / H) * SM_N * rs + (prob % H) * SM_HD;
+    rq = fetch_rows8(b0, rs, lane); rk = fetch_rows8(b0 + cs, rs, lane); rv = fetch_rows8(b0 + 2 * cs, rs, lane);
+    rg = fetch_rows8(dctx + (long long)(prob / H) * SM_N * cs + (prob % H) * SM_HD, cs, lane);
+  }
+  for (; prob < nprob; prob += pstep) {
     const int bp = prob / H, h = prob - bp * H;
-    const __nv_bfloat16* base = qkv + (long long)bp * SM_N * rs + h * SM_HD;
-    const __nv_bfloat16* gbase = dctx + (long long)bp * SM_N * cs + h * SM_HD;
-    stage_rows8(Qs, base, rs, lane);
-    stage_rows8(Ks, base + cs, rs, lane);
-    stage_rows8(Vs, base + 2 * cs, rs, lane);
-    stage_rows8(Gs, gbase, cs, lane);
+    put_rows8(Qs, rq, lane); put_rows8(Ks, rk, lane); put_rows8(Vs, rv, lane); put_rows8(Gs, rg, lane);
     __syncwarp();
+    if (prob + pstep < nprob) {
+      const int np = prob + pstep;
+      const __nv_bfloat16* b1 = qkv + (long long)(np / H) * SM_N * rs + (np % H) * SM_HD;
+      rq = fetch_rows8(b1, rs, lane); rk = fetch_rows8(b1 + cs, rs, lane); rv = fetch_rows8(b1 + 2 * cs, rs, lane);
+      rg = fetch_rows8(dctx + (long long)(np / H) * SM_N * cs + (np % H) * SM_HD, cs, lane);
+    }
     // delta_i = dO_i . O_i  (each lane: its 16 features, then reduce over the 4 lanes of the row)
     float del = 0.f;
     {
@@ -190,22 +228,24 @@ attn8_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __r
   }
 }
 
-static int small_grid(int nprob) {
+// persistent grid = resident CTAs (register-limited: 3/SM forward, 2/SM backward) so that every warp walks several
+// problems and the register prefetch of the next problem overlaps the current one
+static int small_grid(int nprob, int ctas_per_sm) {
   int blocks = (nprob + SM_WARPS - 1) / SM_WARPS;
-  const int cap = sm_count() * 8;
+  const int cap = sm_count() * ctas_per_sm;
   return blocks < cap ? blocks : cap;
 }
 
 int attn8_fwd_launch(const vt_attn_fwd_params* p, cudaStream_t st) {
   const int nprob = p->Bp * p->H;
-  attn8_fwd_kernel<<<small_grid(nprob), SM_WARPS * 32, 0, st>>>(static_cast<const __nv_bfloat16*>(p->qkv),
+  attn8_fwd_kernel<<<small_grid(nprob, 3), SM_WARPS * 32, 0, st>>>(static_cast<const __nv_bfloat16*>(p->qkv),
                                                                 static_cast<__nv_bfloat16*>(p->ctx), p->lse, nprob, p->H, p->scale);
   return check_launch("attn8_fwd_kernel");
 }
 
 int attn8_bwd_launch(const vt_attn_bwd_params* p, cudaStream_t st) {
   const int nprob = p->Bp * p->H;
-  attn8_bwd_kernel<<<small_grid(nprob), SM_WARPS * 32, 0, st>>>(
+  attn8_bwd_kernel<<<small_grid(nprob, 2), SM_WARPS * 32, 0, st>>>(
       static_cast<const __nv_bfloat16*>(p->qkv), static_cast<const __nv_bfloat16*>(p->ctx),
       static_cast<const __nv_bfloat16*>(p->dctx), p->lse, static_cast<__nv_bfloat16*>(p->dqkv), nprob, p->H, p->scale);
   return check_launch("attn8_bwd_kernel");

@@ -17,6 +17,10 @@ namespace vt {
 
 int make_tmap_bf16_2d(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows);
 
+// diagnostics: per-CTA clock64 stamps [cta][32], set through vt_debug_buffer(); NULL in production
+__device__ long long* g_attn_dbg = nullptr;
+#define VT_STAMP(i) do { if (dbg) dbg[(i)] = clock64(); } while (0)
+
 constexpr int TC_HD = 64;
 constexpr int TILE_BYTES = 128 * 128;  // 128 rows x 64 bf16 (one swizzled K-major block) = 16 KiB
 constexpr float LOG2E = 1.4426950408889634f;
@@ -59,6 +63,8 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bh = blockIdx.x, bp = bh / p.H, h = bh - bp * p.H;
   const int row0 = bp * p.N;
+  long long* dbg = (g_attn_dbg && (lane == 0) && (warp == 8 || warp == 0)) ? g_attn_dbg + (long long)blockIdx.x * 32 + (warp == 8 ? 0 : 16) : nullptr;
+  VT_STAMP(0);
 
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -82,9 +88,11 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_arrive_expect_tx(bar_v, p.NK * 128);
       tma_load_2d(sV, &tmKV, bar_v, (2 * p.H + h) * TC_HD, row0);
 
+      VT_STAMP(1);
       mbar_wait(bar_q, 0);
       mbar_wait(bar_k, 0);
       tc_fence_after();
+      VT_STAMP(2);
       const uint32_t idesc_s = make_idesc_bf16(128, (uint32_t)p.NK, 0, 0);
       for (int t = 0; t < p.tiles; ++t) {
         const uint32_t qa = smem_u32(sQ + t * TILE_BYTES), ka = smem_u32(sK);
@@ -94,11 +102,13 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         umma_commit(&bar_s[t]);
       }
       mbar_wait(bar_v, 0);
+      VT_STAMP(3);
       const uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);
       const int ksteps = p.NK / 16;
       for (int t = 0; t < p.tiles; ++t) {
         mbar_wait(&bar_p[t], 0);
         tc_fence_after();
+        VT_STAMP(4 + t);
         const uint32_t pa = smem_u32(sP + t * 4 * TILE_BYTES), va = smem_u32(sV);
         for (int s = 0; s < ksteps; ++s)
           umma_bf16_ss(tmem_base + t * 256, sdesc_kmajor(pa + (s >> 2) * TILE_BYTES + (s & 3) * 32),
@@ -115,15 +125,22 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const int nchunks = (p.NK + 31) / 32;
       mbar_wait(&bar_s[t], 0);
       tc_fence_after();
+      VT_STAMP(1);
       float mx = -INFINITY;
       for (int c = 0; c < nchunks; ++c) {
         uint32_t v[32];
         tmem_ld32(taddr + c * 32, v);
         tmem_ld_wait();
+        if (c * 32 + 32 <= p.N) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (c * 32 + j < p.N) mx = fmaxf(mx, __uint_as_float(v[j]));
+          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (c * 32 + j < p.N) mx = fmaxf(mx, __uint_as_float(v[j]));
+        }
       }
+      VT_STAMP(2);
       const float mb = mx * sl2;
       float l = 0.f;
       uint8_t* Pt = sP + t * 4 * TILE_BYTES;
@@ -132,10 +149,18 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tmem_ld32(taddr + c * 32, v);
         tmem_ld_wait();
         float e[32];
+        if (c * 32 + 32 <= p.N) {      // full chunk: no key masking
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          e[j] = (c * 32 + j < p.N) ? exp2f(fmaf(__uint_as_float(v[j]), sl2, -mb)) : 0.f;
-          l += e[j];
+          for (int j = 0; j < 32; ++j) {
+            e[j] = fast_exp2(fmaf(__uint_as_float(v[j]), sl2, -mb));
+            l += e[j];
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            e[j] = (c * 32 + j < p.N) ? fast_exp2(fmaf(__uint_as_float(v[j]), sl2, -mb)) : 0.f;
+            l += e[j];
+          }
         }
         uint8_t* blk = Pt + (c >> 1) * TILE_BYTES;
 #pragma unroll
@@ -151,8 +176,10 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tc_fence_before();
       fence_proxy_async();
       mbar_arrive(&bar_p[t]);
+      VT_STAMP(3);
       mbar_wait(&bar_o[t], 0);
       tc_fence_after();
+      VT_STAMP(4);
       const int q = t * 128 + r;
       const float inv = 1.0f / l;
       uint32_t o0[32], o1[32];
@@ -181,10 +208,12 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
         p.lse[(long long)bh * p.N + q] = mx * p.scale + __logf(l);
       }
+      VT_STAMP(5);
     }
   }
   tc_fence_before();
   __syncthreads();
+  VT_STAMP(15);
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
@@ -251,18 +280,21 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   uint64_t* bar_dkv_full = bars + 3;
   uint64_t* bar_dkv_free = bars + 4;  // 256 arrivals
   uint64_t* bar_dq = bars + 5;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  uint64_t* bar_load2 = bars + 6;     // second query tile / second key tile
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bh = blockIdx.x, bp = bh / p.H, h = bh - bp * p.H;
   const int row0 = bp * p.N;
   const int n_it = p.nq * p.nk;
+  long long* dbg = (g_attn_dbg && (lane == 0) && (warp == 8 || warp == 0)) ? g_attn_dbg + (long long)blockIdx.x * 32 + (warp == 8 ? 0 : 16) : nullptr;
+  VT_STAMP(0);
 
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmQKV);
     tma_prefetch_desc(&tmDO);
     mbar_init(bar_load, 1); mbar_init(bar_sdp, 1); mbar_init(bar_pds, 256);
-    mbar_init(bar_dkv_full, 1); mbar_init(bar_dkv_free, 256); mbar_init(bar_dq, 1);
+    mbar_init(bar_dkv_full, 1); mbar_init(bar_dkv_free, 256); mbar_init(bar_dq, 1); mbar_init(bar_load2, 1);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc<512>(tmem_slot);
@@ -273,23 +305,30 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
 
   if (warp == 8) {
     if (lane == 0) {
-      mbar_arrive_expect_tx(bar_load, (2 * p.nq + 2 * p.nk) * TILE_BYTES);
-      for (int t = 0; t < p.nq; ++t) {
-        tma_load_2d(sQ + t * TILE_BYTES, &tmQKV, bar_load, h * TC_HD, row0 + t * 128);
-        tma_load_2d(sDO + t * TILE_BYTES, &tmDO, bar_load, h * TC_HD, row0 + t * 128);
+      // first (query, key) tile pair on its own barrier so iteration 0 starts while the rest is in flight
+      mbar_arrive_expect_tx(bar_load, 4 * TILE_BYTES);
+      tma_load_2d(sQ, &tmQKV, bar_load, h * TC_HD, row0);
+      tma_load_2d(sK, &tmQKV, bar_load, (p.H + h) * TC_HD, row0);
+      tma_load_2d(sDO, &tmDO, bar_load, h * TC_HD, row0);
+      tma_load_2d(sV, &tmQKV, bar_load, (2 * p.H + h) * TC_HD, row0);
+      if (p.nq > 1) {
+        mbar_arrive_expect_tx(bar_load2, 4 * TILE_BYTES);
+        tma_load_2d(sQ + TILE_BYTES, &tmQKV, bar_load2, h * TC_HD, row0 + 128);
+        tma_load_2d(sDO + TILE_BYTES, &tmDO, bar_load2, h * TC_HD, row0 + 128);
+        tma_load_2d(sK + TILE_BYTES, &tmQKV, bar_load2, (p.H + h) * TC_HD, row0 + 128);
+        tma_load_2d(sV + TILE_BYTES, &tmQKV, bar_load2, (2 * p.H + h) * TC_HD, row0 + 128);
       }
-      for (int t = 0; t < p.nk; ++t) {
-        tma_load_2d(sK + t * TILE_BYTES, &tmQKV, bar_load, (p.H + h) * TC_HD, row0 + t * 128);
-        tma_load_2d(sV + t * TILE_BYTES, &tmQKV, bar_load, (2 * p.H + h) * TC_HD, row0 + t * 128);
-      }
+      VT_STAMP(1);
       mbar_wait(bar_load, 0);
       tc_fence_after();
+      VT_STAMP(2);
       const uint32_t idesc_t = make_idesc_bf16(128, 64, 1, 1);   // dK, dV: A, B MN-major
       const uint32_t idesc_q = make_idesc_bf16(128, 64, 0, 1);   // dQ: A K-major, B MN-major
       const uint32_t pa = smem_u32(sP), dsa = smem_u32(sDS);
       for (int it = 0; it < n_it; ++it) {
         const int kt = it / p.nq, qt = it - kt * p.nq;
         const int NKt = kt == 0 ? p.NK0 : p.NK1;
+        if (it == 1) { mbar_wait(bar_load2, 0); tc_fence_after(); }
         const uint32_t idesc_s = make_idesc_bf16(128, (uint32_t)NKt, 0, 0);
         const uint32_t qa = smem_u32(sQ + qt * TILE_BYTES), doa = smem_u32(sDO + qt * TILE_BYTES);
         const uint32_t ka = smem_u32(sK + kt * TILE_BYTES), va = smem_u32(sV + kt * TILE_BYTES);
@@ -300,8 +339,10 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         for (int k = 0; k < 4; ++k)
           umma_bf16_ss(tmem_base + COL_DP, sdesc_kmajor(doa + k * 32), sdesc_kmajor(va + k * 32), idesc_s, k > 0);
         umma_commit(bar_sdp);
+        VT_STAMP(3 + 2 * it);
         mbar_wait(bar_pds, it & 1);
         tc_fence_after();
+        VT_STAMP(4 + 2 * it);
         if (qt == 0 && kt > 0) {
           mbar_wait(bar_dkv_free, (kt - 1) & 1);
           tc_fence_after();
@@ -322,6 +363,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         if (qt == p.nq - 1) umma_commit(bar_dkv_full);
       }
       umma_commit(bar_dq);
+      VT_STAMP(11);
     }
   } else {
     const int quad = warp & 3, half = warp >> 2;
@@ -346,12 +388,14 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       lse_s[q] = ls * LOG2E;
     }
     named_bar_sync(1, 256);
+    VT_STAMP(1);
     const float sl2 = p.scale * LOG2E;
     for (int it = 0; it < n_it; ++it) {
       const int kt = it / p.nq, qt = it - kt * p.nq;
       const int NKt = kt == 0 ? p.NK0 : p.NK1;
       mbar_wait(bar_sdp, it & 1);
       tc_fence_after();
+      VT_STAMP(2 + 2 * it);
       const int q = qt * 128 + r;
       const float lq = lse_s[q], dq = del_s[q];
       const bool qok = q < p.N;
@@ -367,7 +411,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const bool ok = qok && (kt * 128 + c0 + j < p.N);
-          const float pj = ok ? exp2f(fmaf(__uint_as_float(sv[j]), sl2, -lq)) : 0.f;
+          const float pj = ok ? fast_exp2(fmaf(__uint_as_float(sv[j]), sl2, -lq)) : 0.f;
           pv[j] = pj;
           ds[j] = pj * (__uint_as_float(dv[j]) - dq) * p.scale;
         }
@@ -387,6 +431,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       tc_fence_before();
       fence_proxy_async();
       mbar_arrive(bar_pds);
+      VT_STAMP(3 + 2 * it);
       if (qt == p.nq - 1) {
         mbar_wait(bar_dkv_full, kt & 1);
         tc_fence_after();
@@ -404,6 +449,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
     }
     mbar_wait(bar_dq, 0);
     tc_fence_after();
+    VT_STAMP(12);
     if (half < p.nq) {
       uint32_t a[32], b[32];
       tmem_ld32(tlane + COL_DQ + half * 64, a);
@@ -412,9 +458,11 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       const int q = half * 128 + r;
       if (q < p.N) store_row64_bf16(p.dqkv + ((long long)(row0 + q) * 3) * p.H * TC_HD + h * TC_HD, a, b);
     }
+    VT_STAMP(13);
   }
   tc_fence_before();
   __syncthreads();
+  VT_STAMP(15);
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
@@ -469,7 +517,7 @@ int attn_tc_bwd_launch(const vt_attn_bwd_params* q, cudaStream_t st) {
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tmDO, q->dctx, rows, (long long)H * TC_HD, (long long)H * TC_HD, 128);
   if (rc) return rc;
-  const int smem = 12 * TILE_BYTES + 2 * 256 * 4 + 256 + 1024;
+  const int smem = 12 * TILE_BYTES + 2 * 256 * 4 + 256 + 1024;   // 6 operand/P/dS tile pairs + lse/delta + barriers
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(attn_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
@@ -481,3 +529,10 @@ int attn_tc_bwd_launch(const vt_attn_bwd_params* q, cudaStream_t st) {
 }
 
 }  // namespace vt
+
+extern "C" int vt_debug_buffer(void* ptr) {
+  long long* p = static_cast<long long*>(ptr);
+  cudaError_t e = cudaMemcpyToSymbol(vt::g_attn_dbg, &p, sizeof(p));
+  if (e != cudaSuccess) { vt::set_error("vt_debug_buffer: %s", cudaGetErrorString(e)); return 1; }
+  return 0;
+}

@@ -44,6 +44,13 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   return __bfloat1622float2(t);
 }
 
+// 2^x on the SFU (ex2.approx: 2 ulp; inputs here are <= 0 after max subtraction)
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // exact-erf GELU (nn.GELU default) and its derivative
 __device__ __forceinline__ float gelu_erf(float z) { return 0.5f * z * (1.0f + erff(z * 0.70710678118654752f)); }
 __device__ __forceinline__ float dgelu_erf(float z) {

@@ -248,7 +248,8 @@ __global__ void gather_cast_kernel(const float* __restrict__ src, long long lds,
 constexpr int COLSUM_ROWS = 512;  // rows per chunk
 
 __global__ void __launch_bounds__(256)
-colsum_kernel(const __nv_bfloat16* __restrict__ in, long long ld, int M, int N, float* __restrict__ ws) {
+colsum_kernel(const __nv_bfloat16* __restrict__ in, long long ld, int M, int N, float* __restrict__ ws, float* __restrict__ out,
+              int* __restrict__ counters) {
   const int cp = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int col = blockIdx.x * 64 + cp * 2;
   const int r0 = blockIdx.y * COLSUM_ROWS;
@@ -269,6 +270,27 @@ colsum_kernel(const __nv_bfloat16* __restrict__ in, long long ld, int M, int N, 
     float2 s = sh[0][cp];
     for (int w = 1; w < 8; ++w) { s.x += sh[w][cp].x; s.y += sh[w][cp].y; }
     *reinterpret_cast<float2*>(ws + (long long)blockIdx.y * N + col) = s;
+  }
+  if (counters == nullptr) return;   // two-launch form: the caller reduces the partials
+  // single-launch form: the last row-chunk CTA of this column block sums the partials (fixed order => deterministic)
+  __shared__ int is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int done = atomicAdd(&counters[blockIdx.x], 1);
+    is_last = (done == (int)gridDim.y - 1);
+    if (is_last) counters[blockIdx.x] = 0;   // self-cleaning for the next call
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  if (rl == 0 && col < N) {
+    float2 t = make_float2(0.f, 0.f);
+    for (int c = 0; c < (int)gridDim.y; ++c) {
+      const float2 v = __ldcg(reinterpret_cast<const float2*>(ws + (long long)c * N + col));
+      t.x += v.x; t.y += v.y;
+    }
+    *reinterpret_cast<float2*>(out + col) = t;
   }
 }
 
@@ -449,9 +471,10 @@ extern "C" int vt_colsum_bf16(const vt_colsum_params* p, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int chunks = vt_colsum_chunks(p->M);
   dim3 grid((p->N + 63) / 64, chunks);
-  colsum_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(p->in), p->ld, p->M, p->N, p->workspace);
+  colsum_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(p->in), p->ld, p->M, p->N, p->workspace, p->out,
+                                      p->counters);
   int rc = check_launch("colsum_kernel");
-  if (rc) return rc;
+  if (rc || p->counters) return rc;
   return launch_reduce_rows(p->workspace, p->out, p->N, chunks, p->N, 0, 1.0f, st);
 }
 

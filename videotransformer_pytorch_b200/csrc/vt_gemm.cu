@@ -79,7 +79,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int stage = 0, phase = 0;
       for (int unit = unit0; unit < total_units; unit += unit_step) {
         const int tile = unit / p.splits, split = unit - tile * p.splits;
-        const int m_blk = (tile % p.num_mp) * (int)csize + (int)crank, n_blk = tile / p.num_mp;
+        const int m_blk = (tile / p.num_n) * (int)csize + (int)crank, n_blk = tile % p.num_n;   // n fastest: the A row-block stays hot in L2
         const int kb0 = (int)(((long long)p.kblocks * split) / p.splits);
         const int kb1 = (int)(((long long)p.kblocks * (split + 1)) / p.splits);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -166,7 +166,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int acc = 0, acc_phase = 0;
     for (int unit = unit0; unit < total_units; unit += unit_step) {
       const int tile = unit / p.splits, split = unit - tile * p.splits;
-      const int m_blk = (tile % p.num_mp) * (int)csize + (int)crank, n_blk = tile / p.num_mp;
+      const int m_blk = (tile / p.num_n) * (int)csize + (int)crank, n_blk = tile % p.num_n;   // n fastest: the A row-block stays hot in L2
       const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
       if (p.tma_store) epilogue_tile_tma<BN>(p, &tmC, slot, t_base, m_blk, n_blk, split, q, half, lane, &tfull_bar[acc], (uint32_t)acc_phase);
       else epilogue_tile<BN>(p, stg, t_base, m_blk, n_blk, split, q, half, lane, &tfull_bar[acc], (uint32_t)acc_phase);

@@ -104,6 +104,16 @@ class GradientBuckets:
             dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
             flat.div_(self.world)
 
+    def grad_ready(self, p, grad):
+        """Tensor-hook entry (graph capture with torch.autograd.grad): copy one finished gradient into its bucket
+        view and, when the bucket is complete, start its all-reduce on the communication stream — so the
+        exchange overlaps the rest of the backward pass inside the captured graph."""
+        p.grad.copy_(grad)
+        bi = self._owner[p]
+        self._pending[bi] -= 1
+        if self._pending[bi] == 0:
+            self._launch(bi)
+
     def reduce_into_buckets(self, params, grads):
         """Graph-capture path: gradients arrive as a list (torch.autograd.grad); copy them into the flat buckets
         (p.grad stays the bucket view) and all-reduce bucket by bucket on the communication stream."""

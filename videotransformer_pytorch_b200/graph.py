@@ -84,7 +84,9 @@ class GraphedTrainStep:
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
 
+        from . import _lib
         self.graph = torch.cuda.CUDAGraph()
+        launches_before = _lib.launch_count()
         self._zero(set_to_none=True)
         ops.set_mask_arena(self.arena)
         self.arena.recording = True
@@ -94,15 +96,27 @@ class GraphedTrainStep:
                 # torch.autograd.grad instead of .backward(): the gradients come back as plain tensors produced by
                 # captured kernels.  (.backward() would route them through per-parameter AccumulateGrad nodes, which
                 # are bound to the stream they were first created on and may execute outside the capture.)
-                grads = torch.autograd.grad(self.static_loss, self.params)
-                if reducer is not None:
-                    reducer.reduce_into_buckets(self.params, grads)     # copy into flat buckets + all-reduce, captured
+                if reducer is None:
+                    grads = torch.autograd.grad(self.static_loss, self.params)
+                else:
+                    # per-parameter tensor hooks fire as soon as a gradient is final: it is copied into its flat
+                    # bucket and completed buckets are all-reduced on the side stream while backward continues
+                    reducer._pending = [len(ps) for ps in reducer._bucket_params]
+                    handles = [p_.register_hook(lambda g_, p_=p_: reducer.grad_ready(p_, g_)) for p_ in self.params]
+                    try:
+                        grads = torch.autograd.grad(self.static_loss, self.params)
+                    finally:
+                        for h_ in handles:
+                            h_.remove()
+                    reducer.finish()
         finally:
             self.arena.recording = False
             ops.set_mask_arena(None)
         # drop the captured autograd graph (its kernels are recorded; keeping the Python graph alive would pin
         # AccumulateGrad nodes to the capture stream for later eager steps)
         self.static_loss = self.static_loss.detach()
+        # libvt_b200 kernels recorded in the graph == launched by every replay
+        self.kernels_per_replay = _lib.launch_count() - launches_before
         if reducer is None:
             self.static_grads = [g.detach() for g in grads]
             for p_, g_ in zip(self.params, self.static_grads):
