@@ -208,6 +208,8 @@ def main_gpu(args):
     torch.manual_seed(0)
     net = Trainee().to(dev).train()
     reducer = GradientBuckets(net) if world > 1 else None
+    if world > 1 and args.reserve_sms:
+        _lib.set_reserved_sms(args.reserve_sms)      # room for the overlapped NCCL all-reduce kernels
     g = torch.Generator().manual_seed(100 + rank)
     x_host = torch.randn(B, T, 3, IMG, IMG, generator=g).pin_memory()
     y_host = torch.randint(0, NUM_CLASSES, (B,), generator=g).pin_memory()
@@ -301,22 +303,46 @@ def main_gpu(args):
         pk = peaks()
         rec = []
         orig = _lib.K.gemm
+        ext = {'external': True}
 
         def timed_gemm(a, b, M, N, Kd, **kw):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0, e1 = torch.cuda.Event(enable_timing=True, **ext), torch.cuda.Event(enable_timing=True, **ext)
             e0.record()
             out = orig(a, b, M, N, Kd, **kw)
             e1.record()
             rec.append((e0, e1, 2.0 * M * N * Kd))
             return out
         _lib.K.gemm = timed_gemm
+        reps = 2
+        timing = None
         try:
-            for _ in range(2):
-                # eager issue of the same step with every GEMM bracketed by CUDA events; a spin kernel keeps the
-                # GPU busy while the host queues the step, so the events see back-to-back execution, not launch gaps
-                torch.cuda._sleep(120_000_000)
-                eager_step(x_dev, y_dev)
-            torch.cuda.synchronize()
+            probe = None
+            if not args.no_graph:
+                try:
+                    # Preferred: the SAME step captured once more with an external CUDA-event record node before and
+                    # after every GEMM launch on the capture stream; a replay yields the in-situ duration of each launch.
+                    from videotransformer_pytorch_b200.graph import GraphedTrainStep
+                    rec.clear()
+                    probe = GraphedTrainStep(net, (x_dev, y_dev), reducer=reducer, warmup=0)
+                except Exception as exc:          # e.g. external events unsupported by this torch build
+                    sys.stderr.write(f'roofline: graph-event probe unavailable ({exc}); falling back to eager events\n')
+                    probe = None
+            if probe is not None:
+                for _ in range(2):
+                    probe(x_dev, y_dev)
+                torch.cuda.synchronize()
+                reps = 1
+                timing = 'external CUDA-event nodes around every GEMM launch inside the replayed step graph'
+            else:
+                ext.clear()
+                rec.clear()
+                for _ in range(2):
+                    # eager issue of the same step with every GEMM bracketed by CUDA events; a spin kernel keeps the
+                    # GPU busy while the host queues the step
+                    torch.cuda._sleep(120_000_000)
+                    eager_step(x_dev, y_dev)
+                torch.cuda.synchronize()
+                timing = 'CUDA events around every GEMM of an eagerly issued step'
         finally:
             _lib.K.gemm = orig
         t_ms = sum(a.elapsed_time(b) for a, b, _ in rec)
@@ -330,7 +356,7 @@ def main_gpu(args):
             pass
         roof = {'kernel': 'gemm_tcgen05_kernel', 'bound': 'tensor', 'achieved': ach, 'peak': pk['tflops'],
                 'unit': 'TFLOP/s', 'frac': ach / pk['tflops'], 'traffic': traffic,
-                'launches_timed': len(rec), 'gemm_ms_per_step': t_ms / 2, 'gemm_flop_per_step': fl / 2,
+                'launches_timed': len(rec), 'gemm_ms_per_step': t_ms / reps, 'gemm_flop_per_step': fl / reps, 'timing': timing,
                 'peak_source': pk['source'],
                 'whole_step_frac_of_tensor_roofline': (FLOP_PER_CLIP * B / (ms_dev / args.steps * 1e-3) / 1e12) / pk['tflops']}
 
@@ -349,7 +375,7 @@ def main_gpu(args):
             'config': {'workload': 'TimeSformer-B divided_space_time 8x224x224 fwd+bwd (+cls head, CE), train mode, '
                                    'DropPath 0..0.1', 'batch_per_gpu': B, 'global_batch': B * world,
                        'parallelism': f'dp{world}', 'residual_stream': 'fp32', 'gemm_operands': 'bf16/fp32-accum',
-                       'optimizer': 'excluded (metric is fwd+bwd)', 'launch': 'eager' if args.no_graph else 'cuda-graph replay (fwd+bwd captured once)', 'grad_allreduce': 'fp32 buckets, NCCL AVG' if world > 1 else 'n/a',
+                       'optimizer': 'excluded (metric is fwd+bwd)', 'launch': 'eager' if args.no_graph else 'cuda-graph replay (fwd+bwd captured once)', 'grad_allreduce': f'fp32 buckets, NCCL AVG, overlapped with backward inside the graph, {args.reserve_sms} SMs reserved' if world > 1 else 'n/a',
                        'l2': 'per-step working set ~5 GB >> 126 MB L2 (no flush needed)'},
             'e2e': {'value': e2e, 'unit': UNIT, 'ms_per_step': ms_e2e / args.steps,
                     'h2d_bytes_per_step': x_host.numel() * 4 + y_host.numel() * 8, 'd2h_bytes_per_step': 4},
@@ -375,6 +401,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--batch', type=int, default=8, help='clips per GPU (BASELINE config 2: 8)')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--reserve-sms', type=int, default=0, help='SMs kept free of persistent GEMM CTAs when N > 1 (NCCL overlap)')
     ap.add_argument('--no-graph', action='store_true', help='issue the step kernel by kernel instead of replaying a CUDA graph')
     args = ap.parse_args()
     if args.impl == 'reference':

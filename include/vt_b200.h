@@ -32,6 +32,9 @@ int vt_version(void);
 int vt_last_error(char* buf, size_t buf_bytes);
 /* number of SMs of the current device (grid sizing is done inside the library) */
 int vt_sm_count(void);
+/* leave n SMs free of the persistent GEMM CTAs (each pins an SM's whole shared memory) so that NCCL's all-reduce
+ * kernels, issued on a side stream while backward is still running, can be scheduled; 0 restores the default */
+int vt_set_reserved_sms(int n);
 /* number of kernels this library has launched in this process (mod 2^31); bench.py's gpu_launches */
 int vt_launch_count(void);
 

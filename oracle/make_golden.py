@@ -188,6 +188,48 @@ def vivit_case(vt, name, cfg, B, seed):
     np.savez_compressed(os.path.join(GOLD, name + '.npz'), **save)
 
 
+def space_only_case(vt, name, cfg, B, seed):
+    from oracle import vt_oracle as O
+    torch.manual_seed(seed)
+    m = vt.TimeSformer(num_frames=cfg['num_frames'], img_size=cfg['img_size'], patch_size=cfg['patch_size'],
+                       embed_dims=cfg['embed_dims'], num_heads=cfg['num_heads'],
+                       num_transformer_layers=cfg['num_transformer_layers'], attention_type='space_only')
+    randomize(m, seed + 1)
+    m = m.double()
+    sd = {k: v.detach().clone().float().double() for k, v in m.state_dict().items()}
+    m.load_state_dict(sd)
+    x = torch.randn(B, cfg['num_frames'], 3, cfg['img_size'], cfg['img_size'], dtype=torch.float64).float().double()
+    m.eval()
+    with torch.no_grad():
+        y_eval = m(x)
+        assert rel(O.timesformer_space_only_forward(sd, x, cfg), y_eval) < 1e-12
+    m.train()
+    torch.manual_seed(3000 + seed)
+    y_tr = m(x)
+    w = torch.linspace(-1, 1, y_tr.numel(), dtype=torch.float64).reshape(y_tr.shape)
+    (y_tr * w).sum().backward()
+    grads = {n: p.grad.detach().clone() for n, p in m.named_parameters()}
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    torch.manual_seed(3000 + seed)
+    yo = O.timesformer_space_only_forward(sdg, x, cfg, training=True)
+    (yo * w).sum().backward()
+    assert rel(yo.detach(), y_tr.detach()) < 1e-12
+    for n, g in grads.items():
+        assert rel(sdg[n].grad, g) < 1e-9, n
+    print(f'[{name}] oracle == reference (eval, train fwd, all {len(grads)} grads)')
+    save = {'x': x.float().numpy(), 'train_seed': np.int64(3000 + seed), 'B': np.int64(B)}
+    for k, v in cfg.items():
+        if isinstance(v, int):
+            save['cfg_' + k] = np.int64(v)
+    for k, v in sd.items():
+        save['sd::' + k] = v.float().numpy()
+    save['out::y_eval'] = y_eval.numpy()
+    save['out::y_train'] = y_tr.detach().numpy()
+    save['out::loss_w'] = w.numpy()
+    pack_grads(save, grads)
+    np.savez_compressed(os.path.join(GOLD, name + '.npz'), **save)
+
+
 def mask_cases(mg):
     from oracle.mask_oracle import CubeMaskOracle
     rows = {}
@@ -231,6 +273,7 @@ def main():
               num_transformer_layers=2)
     vivit_case(vt, 'vivit_tiny_b1', vv, B=1, seed=2)
     vivit_case(vt, 'vivit_tiny_b3', vv, B=3, seed=3)
+    space_only_case(vt, 'timesformer_space_only_tiny', tiny, B=2, seed=5)
     mask_cases(mg)
 
 

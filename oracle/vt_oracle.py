@@ -206,6 +206,20 @@ def timesformer_forward(sd, x, cfg, training=False, return_tokens=False):
     return tok[:, 0]                                                      # :254
 
 
+def timesformer_space_only_forward(sd, x, cfg, training=False):
+    """TimeSformer.forward with attention_type='space_only' (video_transformer.py:193-212, :242-256): per-frame
+    tokens (no time embedding), joint attention per frame, mean over frames, final norm, cls."""
+    B, T = x.shape[0], x.shape[1]
+    tok = patch_embed(x, sd['patch_embed.projection.weight'], sd['patch_embed.projection.bias'])
+    BT, P, D = tok.shape
+    tok = torch.cat((sd['cls_token'].expand(BT, 1, D), tok), dim=1) + sd['pos_embed']          # :207-209
+    tok = container(tok, sd, 'transformer_layers.', cfg['num_transformer_layers'], ['self_attn', 'ffn'],
+                    cfg['num_frames'], cfg['num_heads'], training)
+    tok = tok.reshape(B, T, P + 1, D).mean(dim=1)                                               # :248-249
+    tok = layer_norm(tok, sd['norm.weight'], sd['norm.bias'], 1e-6)
+    return tok[:, 0]
+
+
 def timesformer_last_selfattention(sd, x, cfg):
     """TimeSformer.get_last_selfattention, video_transformer.py:258-261."""
     tok = timesformer_tokens(sd, x, cfg)

@@ -163,3 +163,19 @@ def test_no_silent_fallback_on_cpu_tensor():
     f = FFNWithPreNorm(embed_dims=128, hidden_channels=512)
     with pytest.raises(RuntimeError):
         f(torch.randn(2, 4, 128))
+
+
+def test_space_only_small_vs_oracle():
+    from oracle import vt_oracle as O
+    from videotransformer_pytorch_b200 import TimeSformer
+    torch.manual_seed(6)
+    cfg = dict(num_frames=4, img_size=48, patch_size=16, embed_dims=128, num_heads=2, num_transformer_layers=2)
+    m = TimeSformer(attention_type='space_only', **cfg)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    x = torch.randn(2, 4, 3, 48, 48)
+    with torch.no_grad():
+        ref = O.timesformer_space_only_forward({k: v.double() for k, v in sd.items()}, x.double(), cfg)
+        got = m.cuda().eval()(x.cuda())
+    e = rel_err(got.cpu(), ref)
+    print(f'space_only small eval: {e:.2e}')
+    assert e < 1.5e-2

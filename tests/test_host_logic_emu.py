@@ -97,3 +97,30 @@ def test_standalone_modules_shapes(emu):
     ref = torch.nn.functional.conv2d(x.reshape(6, 3, 32, 32), pe.projection.weight, pe.projection.bias, stride=16)
     ref = ref.flatten(2).transpose(1, 2)
     assert rel_err(y, ref) < 1e-5
+
+
+def test_timesformer_space_only(golden, emu):
+    from videotransformer_pytorch_b200 import TimeSformer
+    g = golden('timesformer_space_only_tiny')
+    c = g.cfg
+    m = TimeSformer(num_frames=c['num_frames'], img_size=c['img_size'], patch_size=c['patch_size'],
+                    embed_dims=c['embed_dims'], num_heads=c['num_heads'],
+                    num_transformer_layers=c['num_transformer_layers'], attention_type='space_only')
+    assert list(m.state_dict().keys()) == list(g.sd.keys())          # no time_embed in space_only
+    m.load_state_dict(g.sd, strict=True)
+    m.eval()
+    with torch.no_grad():
+        assert rel_err(m(g.x), g.out['y_eval']) < 2e-5
+    m.train()
+    torch.manual_seed(g.train_seed)
+    y = m(g.x)
+    assert rel_err(y, g.out['y_train']) < 2e-5
+    (y.double() * g.out['loss_w']).sum().backward()
+    check_grads({n: p.grad for n, p in m.named_parameters()}, g, 2e-4)
+
+
+def test_joint_space_time_is_refused_not_faked():
+    from videotransformer_pytorch_b200 import TimeSformer
+    with pytest.raises(NotImplementedError):
+        TimeSformer(num_frames=4, img_size=32, embed_dims=64, num_heads=1, num_transformer_layers=1,
+                    attention_type='joint_space_time')

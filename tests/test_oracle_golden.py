@@ -114,3 +114,18 @@ def test_hog_oracle_properties():
     # the product's LUT is the same table
     from videotransformer_pytorch_b200.hog import _bin_lut_host
     assert np.array_equal(_bin_lut_host(), lut)
+
+
+def test_space_only_oracle_vs_golden(golden):
+    from oracle import vt_oracle as O
+    g = golden('timesformer_space_only_tiny')
+    sd = {k: v.double() for k, v in g.sd.items()}
+    x = g.x.double()
+    with torch.no_grad():
+        assert rel_err(O.timesformer_space_only_forward(sd, x, g.cfg), g.out['y_eval']) < 1e-12
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    torch.manual_seed(g.train_seed)
+    y = O.timesformer_space_only_forward(sdg, x, g.cfg, training=True)
+    assert rel_err(y, g.out['y_train']) < 1e-12
+    (y * g.out['loss_w']).sum().backward()
+    check_grads({k: v.grad for k, v in sdg.items()}, g, 1e-6)

@@ -86,7 +86,7 @@ class HogParams(C.Structure):
                 ('F', c_i32), ('H', c_i32), ('W', c_i32)]
 
 
-EXPORTS = ['vt_version', 'vt_last_error', 'vt_sm_count', 'vt_launch_count', 'vt_gemm', 'vt_layernorm_fwd', 'vt_ln_bwd_blocks',
+EXPORTS = ['vt_version', 'vt_last_error', 'vt_sm_count', 'vt_set_reserved_sms', 'vt_launch_count', 'vt_gemm', 'vt_layernorm_fwd', 'vt_ln_bwd_blocks',
            'vt_layernorm_bwd', 'vt_reduce_rows', 'vt_colsum_chunks', 'vt_colsum_bf16', 'vt_cast_f32_bf16',
            'vt_gather_cast_bf16', 'vt_gelu_fwd_bf16', 'vt_gelu_bwd_bf16', 'vt_attn_fwd', 'vt_attn_bwd', 'vt_debug_buffer', 'vt_im2col_bf16', 'vt_col2im_f32', 'vt_hog']
 
@@ -381,6 +381,11 @@ class CudaKernels:
         p.F, p.H, p.W = F, H, W
         _check(lib.vt_hog(C.byref(p), _stream()), 'vt_hog')
         return feat, bins
+
+
+def set_reserved_sms(n: int) -> None:
+    """Keep n SMs free of persistent GEMM CTAs (for overlapped NCCL kernels); see vt_set_reserved_sms."""
+    _check(load_library().vt_set_reserved_sms(int(n)), 'vt_set_reserved_sms')
 
 
 def launch_count() -> int:

@@ -22,6 +22,7 @@ int check_launch(const char* what);   // cudaGetLastError -> error code
   } while (0)
 
 int sm_count();
+int persistent_sm_count();   // sm_count() minus the SMs reserved for concurrent communication kernels
 
 // ---- device helpers ---------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {

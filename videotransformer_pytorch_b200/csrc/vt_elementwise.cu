@@ -32,6 +32,15 @@ int check_launch(const char* what) {
   return 0;
 }
 
+// SMs left free by the persistent kernels (GEMMs) so that concurrently running communication kernels (NCCL
+// all-reduce of the gradient buckets, overlapped with backward) find an SM to run on.  0 by default.
+static int g_reserved_sms = 0;
+
+int persistent_sm_count() {
+  const int n = sm_count() - g_reserved_sms;
+  return n < 2 ? 2 : n;
+}
+
 int sm_count() {
   static int cached[64] = {0};
   int dev = 0;
@@ -399,6 +408,12 @@ extern "C" int vt_last_error(char* buf, size_t n) {
 }
 
 extern "C" int vt_sm_count(void) { return sm_count(); }
+
+extern "C" int vt_set_reserved_sms(int n) {
+  if (n < 0 || n > 64) { set_error("vt_set_reserved_sms: %d out of range [0, 64]", n); return 1; }
+  g_reserved_sms = n;
+  return 0;
+}
 
 extern "C" int vt_launch_count(void) { return (int)(__atomic_load_n(&g_launches, __ATOMIC_RELAXED) & 0x7fffffffull); }
 

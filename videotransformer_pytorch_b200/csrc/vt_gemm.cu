@@ -345,7 +345,7 @@ static int launch_gemm(const vt_gemm_params* q, GemmDev& d, cudaStream_t st) {
   d.num_n = (q->N + BN - 1) / BN;
   d.kblocks = (q->K + BK - 1) / BK;
   const int tiles = d.num_mp * d.num_n;     // macro tiles (one per cluster)
-  const int sms = sm_count();
+  const int sms = persistent_sm_count();
 
   int splits = 1;
   const long long tile_out = (long long)q->M * q->N;
@@ -441,7 +441,7 @@ extern "C" int vt_gemm(const vt_gemm_params* q, void* stream) {
     // K-split) costs (its k-blocks + a fixed prologue/epilogue overhead) x BN, with a small penalty for narrower
     // tiles (they re-read A more often and leave less slack on the smem port).  Splitting K is only possible for
     // plain fp32 outputs with a workspace (weight gradients).
-    const int sms = sm_count();
+    const int sms = persistent_sm_count();
     const int num_m = (q->M + BM - 1) / BM;
     const int kblocks = (q->K + BK - 1) / BK;
     const bool can_split = q->epilogue == VT_EPI_F32 && q->workspace && !q->out_row && !q->aux && !q->row_scale && !q->bias;

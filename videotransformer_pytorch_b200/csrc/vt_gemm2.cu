@@ -234,7 +234,7 @@ static int launch_gemm2_t(const vt_gemm_params* q, GemmDev& d, cudaStream_t st) 
   d.num_n = (q->N + BN - 1) / BN;
   d.kblocks = (q->K + BK - 1) / BK;
   const int tiles = d.num_mp * d.num_n;
-  const int pairs = sm_count() / 2;
+  const int pairs = persistent_sm_count() / 2;
   const long long tile_out = (long long)q->M * q->N;
   int splits = 1;
   if (q->epilogue == VT_EPI_F32 && q->workspace && !q->out_row && !q->aux && !q->row_scale && !q->bias) {

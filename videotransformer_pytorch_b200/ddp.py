@@ -68,6 +68,7 @@ class GradientBuckets:
                 p.register_post_accumulate_grad_hook(self._hook)
             self.buckets.append(flat)
         self._pending = [len(ps) for ps in self._bucket_params]
+        self._arrived = [[] for _ in self._bucket_params]
         self._works = []
         self.comm_stream = torch.cuda.Stream(device=self.device) if self.cuda else None
         self.bytes_per_step = sum(b.numel() * 4 for b in self.buckets)
@@ -108,10 +109,17 @@ class GradientBuckets:
         """Tensor-hook entry (graph capture with torch.autograd.grad): copy one finished gradient into its bucket
         view and, when the bucket is complete, start its all-reduce on the communication stream — so the
         exchange overlaps the rest of the backward pass inside the captured graph."""
-        p.grad.copy_(grad)
         bi = self._owner[p]
+        self._arrived[bi].append((p, grad))
         self._pending[bi] -= 1
         if self._pending[bi] == 0:
+            # one multi-tensor copy per bucket (not one tiny kernel per parameter), then the bucket's all-reduce
+            ps = [q for q, g in self._arrived[bi] if g.data_ptr() != q.grad.data_ptr()]
+            gs = [g for q, g in self._arrived[bi] if g.data_ptr() != q.grad.data_ptr()]
+            if ps:
+                with torch.no_grad():
+                    torch._foreach_copy_([q.grad for q in ps], gs)
+            self._arrived[bi] = []
             self._launch(bi)
 
     def reduce_into_buckets(self, params, grads):

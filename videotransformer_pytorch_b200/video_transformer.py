@@ -34,8 +34,9 @@ class TimeSformer(nn.Module):
                  use_learnable_pos_emb=True, return_cls_token=True, **kwargs):
         super().__init__()
         assert attention_type in self.supported_attention_types, f'Unsupported Attention Type {attention_type}!'
-        if attention_type != 'divided_space_time':
-            raise NotImplementedError(f'{attention_type}: only divided_space_time is on the B200 hot path (SURVEY §8f)')
+        if attention_type == 'joint_space_time':
+            raise NotImplementedError('joint_space_time (one 1569-token attention per clip) is not on the B200 hot path yet '
+                                      '(SURVEY §8f rank 4); divided_space_time and space_only are')
         if dropout_p:
             raise NotImplementedError('dropout_p > 0 is not on the reference hot path (always 0.)')
         self.num_frames = num_frames
@@ -52,7 +53,7 @@ class TimeSformer(nn.Module):
         self.patch_embed = PatchEmbed(img_size=img_size, patch_size=patch_size, in_channels=in_channels,
                                       embed_dims=embed_dims, conv_type=conv_type)
         num_patches = self.patch_embed.num_patches
-        operator_order = ['time_attn', 'space_attn', 'ffn']
+        operator_order = ['time_attn', 'space_attn', 'ffn'] if attention_type == 'divided_space_time' else ['self_attn', 'ffn']
         self.transformer_layers = TransformerContainer(
             num_transformer_layers=num_transformer_layers, embed_dims=embed_dims, num_heads=num_heads,
             num_frames=num_frames, norm_layer=norm_layer, hidden_channels=embed_dims * 4,
@@ -64,18 +65,22 @@ class TimeSformer(nn.Module):
         num_patches = num_patches + 1
         if use_learnable_pos_emb:
             self.pos_embed = nn.Parameter(torch.zeros(1, num_patches, embed_dims))
-            self.time_embed = nn.Parameter(torch.zeros(1, num_frames, embed_dims))
         else:
             self.pos_embed = get_sine_cosine_pos_emb(num_patches, embed_dims)
-            self.time_embed = get_sine_cosine_pos_emb(num_frames, embed_dims)
         self.drop_after_pos = nn.Dropout(p=dropout_p)
-        self.drop_after_time = nn.Dropout(p=dropout_p)
+        if attention_type != 'space_only':          # space_only has no temporal embedding (reference :137-142)
+            if use_learnable_pos_emb:
+                self.time_embed = nn.Parameter(torch.zeros(1, num_frames, embed_dims))
+            else:
+                self.time_embed = get_sine_cosine_pos_emb(num_frames, embed_dims)
+            self.drop_after_time = nn.Dropout(p=dropout_p)
         self.init_weights()
 
     def init_weights(self):
         if self.use_learnable_pos_emb:
             nn.init.trunc_normal_(self.pos_embed, std=.02)
-            nn.init.trunc_normal_(self.time_embed, std=.02)
+            if self.attention_type != 'space_only':
+                nn.init.trunc_normal_(self.time_embed, std=.02)
         trunc_normal_(self.cls_token, std=.02)
         _no_pretrain(self.pretrain_pth)
 
@@ -91,9 +96,11 @@ class TimeSformer(nn.Module):
         raise NotImplementedError('bicubic pos-embed interpolation (img_size != training size) is outside the hot path')
 
     def _embeds(self, x):
-        pos, tim = self.pos_embed, self.time_embed
+        pos = self.pos_embed
+        tim = self.time_embed if self.attention_type != 'space_only' else None
         if not self.use_learnable_pos_emb:
-            pos, tim = pos.to(x.device).detach(), tim.to(x.device).detach()
+            pos = pos.to(x.device).detach()
+            tim = None if tim is None else tim.to(x.device).detach()
         return pos, tim
 
     def prepare_tokens(self, x):
@@ -103,15 +110,21 @@ class TimeSformer(nn.Module):
             raise NotImplementedError('input size must match img_size (no pos-embed interpolation on the hot path)')
         pos, tim = self._embeds(x)
         pe = self.patch_embed
+        mode = 'timesformer' if self.attention_type == 'divided_space_time' else 'frames'   # space_only: per-frame tokens
         tok = ops.PatchTokensFn.apply(x, _f32(pe.projection.weight), _f32(pe.projection.bias), self.cls_token, pos, tim,
-                                      pe.shadow(), 'timesformer', 1)
+                                      pe.shadow(), mode, 1)
         return tok, b
 
     def forward(self, x):
         x, b = self.prepare_tokens(x)
         x = self.transformer_layers(x)
+        if self.attention_type == 'space_only':      # '(b t) p d -> b p d' mean over frames (reference :247-249)
+            x = x.view(b, x.shape[0] // b, x.shape[1], x.shape[2]).mean(dim=1)
         S = x.shape[1]
         if self.return_cls_token:
+            if self.attention_type == 'space_only':
+                rows = (torch.arange(b, device=x.device, dtype=torch.int32) * S).contiguous()
+                return ops.RowsNormFn.apply(x, _f32(self.norm.weight), _f32(self.norm.bias), self.norm.eps, rows)
             rows = ops.token_maps(b, self.num_frames, (S - 1) // self.num_frames, str(x.device))['cls_rows']
             return ops.RowsNormFn.apply(x, _f32(self.norm.weight), _f32(self.norm.bias), self.norm.eps, rows)
         y = ops.RowsNormFn.apply(x, _f32(self.norm.weight), _f32(self.norm.bias), self.norm.eps, None)
