@@ -14,17 +14,6 @@ constexpr int SM_HD = 64;
 constexpr int SM_PITCH = 33;
 constexpr int SM_WARPS = 8;
 
-__device__ __forceinline__ void stage_rows8(uint32_t* dst, const __nv_bfloat16* base, long long row_stride, int lane) {
-  // 8 rows x 128 B -> dst[8][33]; two 16-byte loads per lane
-#pragma unroll
-  for (int it = 0; it < 2; ++it) {
-    const int row = (lane >> 3) + 4 * it, c = lane & 7;
-    const uint4 v = *reinterpret_cast<const uint4*>(base + (long long)row * row_stride + c * 8);
-    uint32_t* d = dst + row * SM_PITCH + c * 4;
-    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
-  }
-}
-
 // software pipelining: the next problem's rows are fetched into registers while the current one is computed
 struct Rows8 { uint4 v[2]; };
 __device__ __forceinline__ Rows8 fetch_rows8(const __nv_bfloat16* base, long long row_stride, int lane) {

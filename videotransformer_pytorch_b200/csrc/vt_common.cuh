@@ -52,15 +52,7 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
-// exact-erf GELU (nn.GELU default) and its derivative
-__device__ __forceinline__ float gelu_erf(float z) { return 0.5f * z * (1.0f + erff(z * 0.70710678118654752f)); }
-__device__ __forceinline__ float dgelu_erf(float z) {
-  const float cdf = 0.5f * (1.0f + erff(z * 0.70710678118654752f));
-  const float pdf = 0.39894228040143268f * __expf(-0.5f * z * z);
-  return cdf + z * pdf;
-}
-
-// Fast erf (Abramowitz-Stegun 7.1.26, |abs err| < 1.5e-7 — far below bf16 resolution of the stored results):
+// exact-erf GELU (nn.GELU default) and its derivative, via a fast erf (Abramowitz-Stegun 7.1.26, |abs err| < 1.5e-7 — far below bf16 resolution of the stored results):
 // one exp + one reciprocal + 5 FMA instead of erff's ~40 instructions; used by the GEMM epilogues where four
 // erf per thread per 4 columns would otherwise out-cost the tile's MMAs.
 __device__ __forceinline__ float erf_fast_pos(float x, float e /* = exp(-x*x) */) {

@@ -246,7 +246,7 @@ int make_tmap_out_3d(CUtensorMap* map, const void* base, int fp32, long long M, 
 int setup_out_map(const vt_gemm_params* q, GemmDev& d, CUtensorMap* tmC) {
   d.tma_store = 0;
   memset(tmC, 0, sizeof(*tmC));
-  const bool plain = (q->epilogue == VT_EPI_BF16 || q->epilogue == VT_EPI_F32) && !q->out_row && !q->aux && q->force_cluster != 9;
+  const bool plain = (q->epilogue == VT_EPI_BF16 || q->epilogue == VT_EPI_F32) && !q->out_row && !q->aux;
   if (!plain || getenv("VT_NO_TMA_STORE")) return 0;
   const int fp32 = q->epilogue == VT_EPI_F32;
   int rc = make_tmap_out_3d(tmC, d.out, fp32, q->M, q->N, d.ldo, d.splits, d.split_stride);
