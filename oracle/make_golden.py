@@ -37,11 +37,9 @@ def import_reference():
     stub('matplotlib'); stub('matplotlib.pyplot')
     stub('pytorch_lightning'); stub('pytorch_lightning.utilities')
     stub('pytorch_lightning.utilities.distributed', rank_zero_only=lambda f: f)
-    stub('pytorchvideo')
-    stub('pytorchvideo.layers', MultiScaleBlock=None, SpatioTemporalClsPositionalEncoding=None)
-    stub('pytorchvideo.layers.utils', round_width=None, set_attributes=None)
-    stub('pytorchvideo.models')
-    stub('pytorchvideo.models.vision_transformers', MultiscaleVisionTransformers=None)
+    # pytorchvideo is absent: bind its five names to the restatement so the real MaskFeat can be built
+    from oracle.pytorchvideo_restated import install_stub_modules
+    install_stub_modules()
     sys.path.insert(0, REF)
     import transformer, video_transformer, mask_generator  # noqa
     return transformer, video_transformer, mask_generator
@@ -260,6 +258,68 @@ def mask_cases(mg):
     print('[cube_mask] oracle == reference for seeds 0..7 x 3 calls; Appendix-D hashes ok')
 
 
+def maskfeat_case(vt, name, kwargs, B, seed, with_grads=True):
+    """Real ``MaskFeat`` (video_transformer.py:803-922; blocks = restated pytorchvideo) vs oracle/mvit_oracle.py."""
+    from oracle import mvit_oracle as mo
+    cfg = mo.maskfeat_config(**kwargs)
+    ref_kwargs = dict(kwargs)
+    for k in ('pool_q_stride_size', 'embed_dim_mul', 'atten_head_mul'):
+        if k in ref_kwargs:
+            ref_kwargs[k] = [list(r) for r in ref_kwargs[k]]
+    torch.manual_seed(seed)
+    model = vt.MaskFeat(**ref_kwargs).double()
+    # block configuration derived by the reference factory (:707-761) == oracle's maskfeat_config
+    for blk, mine in zip(model.mvit.blocks, cfg['blocks']):
+        assert blk.blk == mine, (blk.blk, mine)
+    assert model.embed_dims == cfg['embed_dims'] and model.downsample_rate == cfg['downsample_rate']
+    sd = mo.random_maskfeat_state(cfg, seed=seed, dtype=torch.float64)
+    model.load_state_dict(sd, strict=True)            # key names and shapes agree with the reference module tree
+    model.train()
+    g = torch.Generator().manual_seed(seed + 100)
+    T, S = cfg['num_frames'], cfg['img_size']
+    t, h, w = cfg['thw'][0], cfg['thw'][1] // cfg['downsample_rate'], cfg['thw'][2] // cfg['downsample_rate']
+    x = torch.randn(B, T, 3, S, S, generator=g, dtype=torch.float64).float().double()   # stored as fp32
+    mask = (torch.rand(B, t, h, w, generator=g) < 0.4).to(torch.float64)
+    cube_marker = [[[0, 2], [t - 1, 1]] if i % 2 == 0 else [[1, t - 1]] for i in range(B)]
+    target = torch.randn(B, T, h, w, cfg['feature_dim'] // cfg['stride'][0], generator=g, dtype=torch.float64).float().double()
+
+    feats_ref = model.forward_features(x, mask)
+    feats_nomask_ref = model.forward_features(x)
+    pred_ref, loss_ref = model(x, target, mask.clone(), cube_marker)
+    params = dict(model.named_parameters())
+    grads_ref = torch.autograd.grad(loss_ref, list(params.values()), allow_unused=True)
+
+    sdo = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    feats = mo.maskfeat_forward_features(sdo, x, mask, cfg)
+    feats_nomask = mo.maskfeat_forward_features(sdo, x, None, cfg)
+    pred, loss = mo.maskfeat_forward(sdo, x, target, mask, cube_marker, cfg)
+    grads = torch.autograd.grad(loss, [sdo[k] for k in params], allow_unused=True)
+    assert rel(feats, feats_ref) < 1e-12 and rel(feats_nomask, feats_nomask_ref) < 1e-12
+    assert rel(pred, pred_ref) < 1e-12 and abs(loss.item() - loss_ref.item()) < 1e-12 * max(1, abs(loss_ref.item()))
+    worst = 0.0
+    for k, a, b in zip(params, grads, grads_ref):
+        assert (a is None) == (b is None), k
+        if a is not None:
+            r = float((a - b).norm() / (b.norm() + 1e-6 * b.numel() ** 0.5))   # norm_k.bias grads are exactly 0 in theory
+            if r > 1e-10:
+                print('   grad mismatch', k, r, float(a.norm()), float(b.norm()))
+            worst = max(worst, r)
+    assert worst < 1e-10, worst
+    save = dict(seed=np.int64(seed), B=np.int64(B), x=x.numpy().astype(np.float32), mask=mask.numpy().astype(np.float32),
+                target=target.numpy().astype(np.float32),
+                cube_marker=np.array([str(cube_marker)]),
+                feats=feats_ref.detach().numpy(), feats_nomask_cls=feats_nomask_ref[:, 0].detach().numpy(),
+                pred=pred_ref.detach().numpy(), loss=np.float64(loss_ref.item()),
+                cfg_kwargs=np.array([repr(kwargs)]))
+    if with_grads:
+        # norm_k.bias shifts every score of a query equally => its gradient is 0 up to rounding noise: not stored
+        pack_grads(save, {k: gr for k, gr in zip(params, grads_ref)
+                          if gr is not None and not k.endswith('attn.norm_k.bias')})
+    np.savez_compressed(os.path.join(GOLD, name + '.npz'), **save)
+    print(f'[{name}] oracle == reference MaskFeat: feats/pred/loss < 1e-12, worst grad rel {worst:.2e}; '
+          f'loss {loss_ref.item():.6f}')
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     tr, vt, mg = import_reference()
@@ -275,6 +335,13 @@ def main():
     vivit_case(vt, 'vivit_tiny_b3', vv, B=3, seed=3)
     space_only_case(vt, 'timesformer_space_only_tiny', tiny, B=2, seed=5)
     mask_cases(mg)
+    two_stage = dict(pool_q_stride_size=((1, 1, 2, 2), (3, 1, 2, 2)), feature_dim=216)     # model_trainer.py:54
+    maskfeat_case(vt, 'maskfeat_s32', dict(img_size=32, num_frames=8, **two_stage), B=2, seed=7)
+    maskfeat_case(vt, 'maskfeat_s64', dict(img_size=64, num_frames=4, **two_stage), B=1, seed=8)
+    # MaskFeat.__init__ defaults (three Q-pool stages, video_transformer.py:821): configuration logic only
+    maskfeat_case(vt, 'maskfeat_s64_3stage',
+                  dict(img_size=64, num_frames=4, feature_dim=2 * 108,
+                       pool_q_stride_size=((1, 1, 2, 2), (3, 1, 2, 2), (14, 1, 2, 2))), B=1, seed=9, with_grads=False)
 
 
 if __name__ == '__main__':

@@ -40,6 +40,44 @@ class Golden:
         self.B = int(z['B'])
 
 
+class MaskFeatGolden:
+    """MaskFeat fixture: inputs + reference outputs; the (large) state is regenerated from its seed with
+    ``oracle.mvit_oracle.random_maskfeat_state`` exactly as oracle/make_golden.py did."""
+
+    def __init__(self, name):
+        import ast
+        from oracle import mvit_oracle as mo
+        z = np.load(os.path.join(GOLD, name + '.npz'))
+        self.kwargs = ast.literal_eval(str(z['cfg_kwargs'][0]))
+        self.cfg = mo.maskfeat_config(**self.kwargs)
+        self.seed, self.B = int(z['seed']), int(z['B'])
+        self.x = torch.from_numpy(z['x'])
+        self.mask = torch.from_numpy(z['mask'])
+        self.target = torch.from_numpy(z['target'])
+        self.cube_marker = ast.literal_eval(str(z['cube_marker'][0]))
+        self.feats = torch.from_numpy(z['feats'])
+        self.feats_nomask_cls = torch.from_numpy(z['feats_nomask_cls'])
+        self.pred = torch.from_numpy(z['pred'])
+        self.loss = float(z['loss'])
+        self.grad = {k[6:]: torch.from_numpy(z[k]) for k in z.files if k.startswith('grad::')}
+        self.gradsum = {k[9:]: z[k] for k in z.files if k.startswith('gradsum::')}
+
+    def state(self, dtype=torch.float64):
+        from oracle import mvit_oracle as mo
+        return mo.random_maskfeat_state(self.cfg, seed=self.seed, dtype=dtype)
+
+
+@pytest.fixture(scope='session')
+def maskfeat_golden():
+    cache = {}
+
+    def get(name):
+        if name not in cache:
+            cache[name] = MaskFeatGolden(name)
+        return cache[name]
+    return get
+
+
 @pytest.fixture(scope='session')
 def golden():
     cache = {}
