@@ -203,6 +203,118 @@ int vt_col2im_f32(const vt_col2im_params* p, void* stream);
 typedef struct { const uint8_t* frames; const uint8_t* lut; float* feat; uint8_t* bins; int32_t F, H, W; } vt_hog_params;
 int vt_hog(const vt_hog_params* p, void* stream);
 
+/* =============================================================================================
+ * MaskFeat / MViT path.  Block arithmetic = pytorchvideo MultiScaleBlock as configured at
+ * video_transformer.py:764-785 (restated in oracle/mvit_oracle.py); head dim is 96 in every block.
+ * vt_layernorm_fwd/bwd additionally accept D = 32..256 in steps of 32 (block widths 96 and 192) without row maps.
+ * ============================================================================================= */
+
+/* Depthwise Conv3d pooling of one of q/k/v + LayerNorm(hd)  (pytorchvideo _attention_pool, pool_mode="conv"):
+ *   element (b, n, h, c) of the input lives at in[b*in_bs + n*in_rs + h*hd + c] (bf16; n = 0 is the cls row, rows
+ *   1.. are the (T,Hin,Win) tokens, t-major) — i.e. a q/k/v slice of the fused projection output is read in place.
+ *   pooled fp32 [B,H,1+Lo,hd] = cls row copied, other rows conv3d(kernel 3x3x3, stride (st,sh,sw), padding 1, groups=hd)
+ *   out    bf16 [B,H,1+Lo,hd] = LayerNorm(pooled; gamma, beta, eps) over hd;  mean/rstd [B*H*(1+Lo)] saved.
+ * Lo = To*Ho*Wo with To = (T + 2 - 3)/st + 1 etc.   w: fp32 [hd, 27] (nn.Conv3d weight [hd,1,3,3,3]). */
+typedef struct {
+  const void* in; int64_t in_bs, in_rs;
+  const float* w; const float* gamma; const float* beta;
+  float* pooled; void* out; float* mean; float* rstd;
+  int32_t B, H, hd, T, Hin, Win, st, sh, sw, To, Ho, Wo;
+  float eps;
+} vt_pool_fwd_params;
+int vt_pool_fwd(const vt_pool_fwd_params* p, void* stream);
+
+/* Backward of vt_pool_fwd.  dout: gradient of `out` (bf16, or fp32 if dout_fp32).  Produces
+ *   din (bf16, addressed like `in` with din_bs/din_rs: every (b,n,h,:) is written), dw [hd,27], dgamma, dbeta [hd].
+ * scratch: fp32, at least vt_pool_bwd_scratch(rows_out, hd) floats (dpooled + per-CTA partial sums). */
+typedef struct {
+  const void* dout; int32_t dout_fp32;
+  const float* pooled; const float* mean; const float* rstd; const float* gamma;
+  const void* in; int64_t in_bs, in_rs; const float* w;
+  void* din; int64_t din_bs, din_rs;
+  float* dw; float* dgamma; float* dbeta;
+  float* scratch; int64_t scratch_floats;
+  int32_t B, H, hd, T, Hin, Win, st, sh, sw, To, Ho, Wo;
+} vt_pool_bwd_params;
+int vt_pool_bwd_scratch(int32_t rows_out, int32_t hd);   /* floats */
+int vt_pool_bwd(const vt_pool_bwd_params* p, void* stream);
+
+/* Softmax attention with separate, strided Q / K / V and Nq != Nk (pooling attention):
+ *   element (b, h, n, c) of q at q[b*q_bs + h*q_hs + n*q_rs + c] (bf16), same for k, v, o (and dout, dq).
+ *   o = softmax(scale * q k^T) v ;  lse fp32 [B,H,Nq] = log sum exp(scale * q k^T).
+ * CUDA-core kernels (two threads per query row, K/V tiles staged in shared memory): the head dim of 96 does not fit the
+ * 128-byte swizzle atoms the tcgen05 kernels of vt_attn_* are built around; see DESIGN.md §4. */
+typedef struct {
+  const void* q; const void* k; const void* v; void* o; float* lse;
+  int64_t q_bs, q_hs, q_rs, k_bs, k_hs, k_rs, v_bs, v_hs, v_rs, o_bs, o_hs, o_rs;
+  int32_t B, H, Nq, Nk, hd; float scale;
+} vt_xattn_fwd_params;
+int vt_xattn_fwd(const vt_xattn_fwd_params* p, void* stream);
+/* dq: bf16 with its own strides.  dk, dv: fp32 [B,H,Nk,hd] contiguous (zeroed by the call, accumulated with atomics).
+ * delta: fp32 scratch [B,H,Nq]. */
+typedef struct {
+  const void* q; const void* k; const void* v; const void* o; const void* dout; const float* lse;
+  float* delta; void* dq; float* dk; float* dv;
+  int64_t q_bs, q_hs, q_rs, k_bs, k_hs, k_rs, v_bs, v_hs, v_rs, o_bs, o_hs, o_rs, dq_bs, dq_hs, dq_rs;
+  int32_t B, H, Nq, Nk, hd; float scale;
+} vt_xattn_bwd_params;
+int vt_xattn_bwd(const vt_xattn_bwd_params* p, void* stream);
+
+/* Skip-path MaxPool3d on the fp32 token stream (pytorchvideo MultiScaleBlock.pool_skip: kernel s+1, stride s, padding
+ * k//2 per axis; cls row copied).  x [B,1+T*H*W,D] -> y [B,1+To*Ho*Wo,D]; idx u8 same shape as y = winning tap
+ * ((dt*kh+dh)*kw+dw, first maximum in scan order like torch).  Backward routes dy to the winners. */
+typedef struct {
+  const float* x; float* y; uint8_t* idx;
+  int32_t B, D, T, H, W, kt, kh, kw, st, sh, sw, To, Ho, Wo;
+} vt_maxpool_fwd_params;
+int vt_maxpool_fwd(const vt_maxpool_fwd_params* p, void* stream);
+typedef struct {
+  const float* dy; const uint8_t* idx; float* dx;
+  int32_t B, D, T, H, W, kt, kh, kw, st, sh, sw, To, Ho, Wo;
+} vt_maxpool_bwd_params;
+int vt_maxpool_bwd(const vt_maxpool_bwd_params* p, void* stream);
+
+/* Overlapping Conv3d patch embedding operand (create_conv_patch_embed, video_transformer.py:585-618: kernel (3,7,7),
+ * stride (2,4,4), padding (1,3,3)):  x fp32 [B,T,C,H,W] (the clip as the reference receives it, before its
+ * transpose(1,2) at :912) -> cols bf16 [B*To*Ho*Wo, Kpad], column ((c*kt+dt)*kh+dh)*kw+dw, zero padded to Kpad. */
+typedef struct {
+  const float* x; void* cols;
+  int32_t B, T, C, H, W, kt, kh, kw, st, sh, sw, pt, ph, pw, To, Ho, Wo, Kpad;
+} vt_im2col3d_params;
+int vt_im2col3d_bf16(const vt_im2col3d_params* p, void* stream);
+
+/* Token preparation (MaskFeat.forward_features :915-919 + SpatioTemporalClsPositionalEncoding):
+ *   x[b,0,:]   = cls_token + pos_cls
+ *   x[b,1+l,:] = t[b,l,:]*(1-w[b,l]) + mask_token*w[b,l] + pos_s[l % HW,:] + pos_t[l / HW,:]      (w NULL => 0)
+ * t fp32 [B*L, C] (conv output incl. bias), x fp32 [B,1+L,C], L = T*HW.
+ * Backward: dt bf16 [B*L, C] = dx[b,1+l,:]*(1-w[b,l]) (parameter-table gradients are plain reductions of dx). */
+typedef struct {
+  const float* t; const float* wmask; const float* mask_token; const float* cls_token;
+  const float* pos_s; const float* pos_t; const float* pos_cls; float* x;
+  int32_t B, T, HW, C;
+} vt_mvit_tokens_fwd_params;
+int vt_mvit_tokens_fwd(const vt_mvit_tokens_fwd_params* p, void* stream);
+typedef struct { const float* dx; const float* wmask; void* dt; int32_t B, T, HW, C; } vt_mvit_tokens_bwd_params;
+int vt_mvit_tokens_bwd(const vt_mvit_tokens_bwd_params* p, void* stream);
+
+/* Masked MSE of MaskFeat.forward (video_transformer.py:882-901):
+ *   pred fp32 [B, 1+t*h*w, dt*dc] (decoder output incl. the cls row), target fp32 [B, t*dt, h, w, dc],
+ *   mask fp32 [B, t*dt, h, w] (already restricted to the cube centre frames, :889-896)
+ *   num[0] = sum_{cells} mask * mean_dc (pred - target)^2        (the caller divides by mask.sum() + 1e-5)
+ * Backward: dpred bf16 [B*(1+t*h*w), dt*dc] = coef[0] * mask * (pred - target), cls rows zero; coef is a device
+ * scalar (2 * dloss / (dc * (mask.sum() + 1e-5))).  partials: fp32 scratch [vt_mse_blocks(cells) * 4]. */
+typedef struct {
+  const float* pred; const float* target; const float* mask; float* num; float* partials;
+  int32_t B, t, dt, h, w, dc;
+} vt_mse_fwd_params;
+int vt_mse_blocks(int32_t cells);
+int vt_mse_fwd(const vt_mse_fwd_params* p, void* stream);
+typedef struct {
+  const float* pred; const float* target; const float* mask; const float* coef; void* dpred;
+  int32_t B, t, dt, h, w, dc;
+} vt_mse_bwd_params;
+int vt_mse_bwd(const vt_mse_bwd_params* p, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -40,3 +40,44 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(_lib, 'LIB_PATH', '/nonexistent/libvt_b200.so')
     with pytest.raises(RuntimeError, match='no CPU / library fallback'):
         _lib.load_library()
+
+
+def test_ctypes_structs_match_the_header(tmp_path):
+    """Every ctypes Structure in _lib.py has the size and field offsets of its C twin in include/vt_b200.h."""
+    import shutil
+    import subprocess
+    from videotransformer_pytorch_b200 import _lib
+    if not shutil.which('gcc'):
+        return
+    pairs = {'vt_gemm_params': _lib.GemmParams, 'vt_ln_fwd_params': _lib.LnFwdParams, 'vt_ln_bwd_params': _lib.LnBwdParams,
+             'vt_reduce_params': _lib.ReduceParams, 'vt_colsum_params': _lib.ColsumParams, 'vt_cast_params': _lib.CastParams,
+             'vt_gather_cast_params': _lib.GatherCastParams, 'vt_gelu_params': _lib.GeluParams,
+             'vt_attn_fwd_params': _lib.AttnFwdParams, 'vt_attn_bwd_params': _lib.AttnBwdParams,
+             'vt_im2col_params': _lib.Im2colParams, 'vt_hog_params': _lib.HogParams,
+             'vt_pool_fwd_params': _lib.PoolFwdParams, 'vt_pool_bwd_params': _lib.PoolBwdParams,
+             'vt_xattn_fwd_params': _lib.XattnFwdParams, 'vt_xattn_bwd_params': _lib.XattnBwdParams,
+             'vt_maxpool_fwd_params': _lib.MaxpoolFwdParams, 'vt_maxpool_bwd_params': _lib.MaxpoolBwdParams,
+             'vt_im2col3d_params': _lib.Im2col3dParams, 'vt_mvit_tokens_fwd_params': _lib.MvitTokensFwdParams,
+             'vt_mvit_tokens_bwd_params': _lib.MvitTokensBwdParams, 'vt_mse_fwd_params': _lib.MseFwdParams,
+             'vt_mse_bwd_params': _lib.MseBwdParams}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "vt_b200.h")}"',
+             'int main(void) {']
+    for cname, cls in pairs.items():
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            cf = 'in' if fname == 'inp' else fname
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {cf}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / 'layout.c'
+    src.write_text('\n'.join(lines))
+    exe = tmp_path / 'layout'
+    subprocess.check_call(['gcc', str(src), '-o', str(exe)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout
+    got = {}
+    for ln in out.splitlines():
+        c, f, v = ln.split()
+        got[(c, f)] = int(v)
+    for cname, cls in pairs.items():
+        assert got[(cname, 'size')] == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert got[(cname, fname)] == getattr(cls, fname).offset, (cname, fname)

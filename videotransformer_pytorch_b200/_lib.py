@@ -86,9 +86,79 @@ class HogParams(C.Structure):
                 ('F', c_i32), ('H', c_i32), ('W', c_i32)]
 
 
+class PoolFwdParams(C.Structure):
+    _fields_ = [('inp', c_vp), ('in_bs', c_i64), ('in_rs', c_i64), ('w', c_vp), ('gamma', c_vp), ('beta', c_vp),
+                ('pooled', c_vp), ('out', c_vp), ('mean', c_vp), ('rstd', c_vp),
+                ('B', c_i32), ('H', c_i32), ('hd', c_i32), ('T', c_i32), ('Hin', c_i32), ('Win', c_i32),
+                ('st', c_i32), ('sh', c_i32), ('sw', c_i32), ('To', c_i32), ('Ho', c_i32), ('Wo', c_i32), ('eps', c_f32)]
+
+
+class PoolBwdParams(C.Structure):
+    _fields_ = [('dout', c_vp), ('dout_fp32', c_i32), ('pooled', c_vp), ('mean', c_vp), ('rstd', c_vp), ('gamma', c_vp),
+                ('inp', c_vp), ('in_bs', c_i64), ('in_rs', c_i64), ('w', c_vp),
+                ('din', c_vp), ('din_bs', c_i64), ('din_rs', c_i64),
+                ('dw', c_vp), ('dgamma', c_vp), ('dbeta', c_vp), ('scratch', c_vp), ('scratch_floats', c_i64),
+                ('B', c_i32), ('H', c_i32), ('hd', c_i32), ('T', c_i32), ('Hin', c_i32), ('Win', c_i32),
+                ('st', c_i32), ('sh', c_i32), ('sw', c_i32), ('To', c_i32), ('Ho', c_i32), ('Wo', c_i32)]
+
+
+_XA_STRIDES = [(t + s, c_i64) for t in ('q', 'k', 'v', 'o') for s in ('_bs', '_hs', '_rs')]
+
+
+class XattnFwdParams(C.Structure):
+    _fields_ = [('q', c_vp), ('k', c_vp), ('v', c_vp), ('o', c_vp), ('lse', c_vp)] + _XA_STRIDES + \
+               [('B', c_i32), ('H', c_i32), ('Nq', c_i32), ('Nk', c_i32), ('hd', c_i32), ('scale', c_f32)]
+
+
+class XattnBwdParams(C.Structure):
+    _fields_ = [('q', c_vp), ('k', c_vp), ('v', c_vp), ('o', c_vp), ('dout', c_vp), ('lse', c_vp),
+                ('delta', c_vp), ('dq', c_vp), ('dk', c_vp), ('dv', c_vp)] + _XA_STRIDES + \
+               [('dq_bs', c_i64), ('dq_hs', c_i64), ('dq_rs', c_i64),
+                ('B', c_i32), ('H', c_i32), ('Nq', c_i32), ('Nk', c_i32), ('hd', c_i32), ('scale', c_f32)]
+
+
+_MP_DIMS = [(n, c_i32) for n in ('B', 'D', 'T', 'H', 'W', 'kt', 'kh', 'kw', 'st', 'sh', 'sw', 'To', 'Ho', 'Wo')]
+
+
+class MaxpoolFwdParams(C.Structure):
+    _fields_ = [('x', c_vp), ('y', c_vp), ('idx', c_vp)] + _MP_DIMS
+
+
+class MaxpoolBwdParams(C.Structure):
+    _fields_ = [('dy', c_vp), ('idx', c_vp), ('dx', c_vp)] + _MP_DIMS
+
+
+class Im2col3dParams(C.Structure):
+    _fields_ = [('x', c_vp), ('cols', c_vp)] + [(n, c_i32) for n in (
+        'B', 'T', 'C', 'H', 'W', 'kt', 'kh', 'kw', 'st', 'sh', 'sw', 'pt', 'ph', 'pw', 'To', 'Ho', 'Wo', 'Kpad')]
+
+
+class MvitTokensFwdParams(C.Structure):
+    _fields_ = [('t', c_vp), ('wmask', c_vp), ('mask_token', c_vp), ('cls_token', c_vp), ('pos_s', c_vp),
+                ('pos_t', c_vp), ('pos_cls', c_vp), ('x', c_vp), ('B', c_i32), ('T', c_i32), ('HW', c_i32), ('C', c_i32)]
+
+
+class MvitTokensBwdParams(C.Structure):
+    _fields_ = [('dx', c_vp), ('wmask', c_vp), ('dt', c_vp), ('B', c_i32), ('T', c_i32), ('HW', c_i32), ('C', c_i32)]
+
+
+_MSE_DIMS = [(n, c_i32) for n in ('B', 't', 'dt', 'h', 'w', 'dc')]
+
+
+class MseFwdParams(C.Structure):
+    _fields_ = [('pred', c_vp), ('target', c_vp), ('mask', c_vp), ('num', c_vp), ('partials', c_vp)] + _MSE_DIMS
+
+
+class MseBwdParams(C.Structure):
+    _fields_ = [('pred', c_vp), ('target', c_vp), ('mask', c_vp), ('coef', c_vp), ('dpred', c_vp)] + _MSE_DIMS
+
+
 EXPORTS = ['vt_version', 'vt_last_error', 'vt_sm_count', 'vt_set_reserved_sms', 'vt_launch_count', 'vt_gemm', 'vt_layernorm_fwd', 'vt_ln_bwd_blocks',
            'vt_layernorm_bwd', 'vt_reduce_rows', 'vt_colsum_chunks', 'vt_colsum_bf16', 'vt_cast_f32_bf16',
-           'vt_gather_cast_bf16', 'vt_gelu_fwd_bf16', 'vt_gelu_bwd_bf16', 'vt_attn_fwd', 'vt_attn_bwd', 'vt_debug_buffer', 'vt_im2col_bf16', 'vt_col2im_f32', 'vt_hog']
+           'vt_gather_cast_bf16', 'vt_gelu_fwd_bf16', 'vt_gelu_bwd_bf16', 'vt_attn_fwd', 'vt_attn_bwd', 'vt_debug_buffer', 'vt_im2col_bf16', 'vt_col2im_f32', 'vt_hog',
+           'vt_pool_fwd', 'vt_pool_bwd_scratch', 'vt_pool_bwd', 'vt_xattn_fwd', 'vt_xattn_bwd', 'vt_maxpool_fwd',
+           'vt_maxpool_bwd', 'vt_im2col3d_bf16', 'vt_mvit_tokens_fwd', 'vt_mvit_tokens_bwd', 'vt_mse_blocks',
+           'vt_mse_fwd', 'vt_mse_bwd']
 
 _dll = None
 
@@ -381,6 +451,246 @@ class CudaKernels:
         p.F, p.H, p.W = F, H, W
         _check(lib.vt_hog(C.byref(p), _stream()), 'vt_hog')
         return feat, bins
+
+
+    # -- MViT / MaskFeat (include/vt_b200.h, second half) -----------------------------------------
+    @staticmethod
+    def pool_out_thw(thw, stride):
+        return tuple((n + 2 - 3) // s + 1 for n, s in zip(thw, stride))
+
+    @staticmethod
+    def _tok_view(t, name, B, H, hd):
+        """[B, N, H*hd] bf16 view with unit last stride (a q/k/v slice of the fused projection output)."""
+        _req(t, torch.bfloat16, name)
+        if t.dim() != 3 or t.shape[0] != B or t.shape[2] != H * hd or t.stride(2) != 1:
+            raise RuntimeError(f'{name}: expected a [B, N, H*hd] view with unit last stride, got {tuple(t.shape)} {t.stride()}')
+        return t
+
+    def pool_fwd(self, src, H, hd, thw, stride, w, gamma, beta, eps):
+        """src: [B, 1+T*Hin*Win, H*hd] bf16 view -> (out bf16 [B,H,1+Lo,hd], pooled fp32, mean, rstd, out_thw)"""
+        lib = load_library()
+        B = src.shape[0]
+        self._tok_view(src, 'pool_fwd.src', B, H, hd)
+        T, Hin, Win = thw
+        if src.shape[1] != 1 + T * Hin * Win:
+            raise RuntimeError('pool_fwd: token count does not match thw')
+        To, Ho, Wo = self.pool_out_thw(thw, stride)
+        Lo1 = 1 + To * Ho * Wo
+        dev = src.device
+        pooled = torch.empty((B, H, Lo1, hd), dtype=torch.float32, device=dev)
+        out = torch.empty((B, H, Lo1, hd), dtype=torch.bfloat16, device=dev)
+        mean = torch.empty(B * H * Lo1, dtype=torch.float32, device=dev)
+        rstd = torch.empty_like(mean)
+        p = PoolFwdParams()
+        p.inp, p.in_bs, p.in_rs = src.data_ptr(), src.stride(0), src.stride(1)
+        p.w = _req(w, torch.float32, 'pool_fwd.w').contiguous().data_ptr()
+        p.gamma, p.beta = _req(gamma, torch.float32, 'gamma').data_ptr(), _req(beta, torch.float32, 'beta').data_ptr()
+        p.pooled, p.out, p.mean, p.rstd = pooled.data_ptr(), out.data_ptr(), mean.data_ptr(), rstd.data_ptr()
+        p.B, p.H, p.hd, p.T, p.Hin, p.Win = B, H, hd, T, Hin, Win
+        p.st, p.sh, p.sw = stride
+        p.To, p.Ho, p.Wo, p.eps = To, Ho, Wo, eps
+        _check(lib.vt_pool_fwd(C.byref(p), _stream()), 'vt_pool_fwd')
+        return out, pooled, mean, rstd, (To, Ho, Wo)
+
+    def pool_bwd(self, dout, pooled, mean, rstd, gamma, src, w, din, H, hd, thw, stride):
+        """Writes din (a [B, N, H*hd] bf16 view like src) in place -> (dw [hd,27], dgamma, dbeta)"""
+        lib = load_library()
+        B = src.shape[0]
+        self._tok_view(src, 'pool_bwd.src', B, H, hd)
+        self._tok_view(din, 'pool_bwd.din', B, H, hd)
+        if dout.dtype not in (torch.float32, torch.bfloat16) or not dout.is_contiguous() or dout.shape != pooled.shape:
+            raise RuntimeError('pool_bwd: dout must be contiguous [B,H,1+Lo,hd] in fp32 or bf16')
+        T, Hin, Win = thw
+        To, Ho, Wo = self.pool_out_thw(thw, stride)
+        rows_out = B * H * (1 + To * Ho * Wo)
+        dev = src.device
+        need = lib.vt_pool_bwd_scratch(rows_out, hd)
+        if need <= 0:
+            raise RuntimeError('pool_bwd: problem too large')
+        scratch = torch.empty(need, dtype=torch.float32, device=dev)
+        dw = torch.empty((hd, 27), dtype=torch.float32, device=dev)
+        dgamma = torch.empty(hd, dtype=torch.float32, device=dev)
+        dbeta = torch.empty(hd, dtype=torch.float32, device=dev)
+        p = PoolBwdParams()
+        p.dout, p.dout_fp32 = dout.data_ptr(), int(dout.dtype == torch.float32)
+        p.pooled, p.mean, p.rstd, p.gamma = pooled.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr()
+        p.inp, p.in_bs, p.in_rs = src.data_ptr(), src.stride(0), src.stride(1)
+        p.w = _req(w, torch.float32, 'pool_bwd.w').contiguous().data_ptr()
+        p.din, p.din_bs, p.din_rs = din.data_ptr(), din.stride(0), din.stride(1)
+        p.dw, p.dgamma, p.dbeta = dw.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr()
+        p.scratch, p.scratch_floats = scratch.data_ptr(), need
+        p.B, p.H, p.hd, p.T, p.Hin, p.Win = B, H, hd, T, Hin, Win
+        p.st, p.sh, p.sw = stride
+        p.To, p.Ho, p.Wo = To, Ho, Wo
+        _check(lib.vt_pool_bwd(C.byref(p), _stream()), 'vt_pool_bwd')
+        return dw, dgamma, dbeta
+
+    @staticmethod
+    def _bhnd(t, name):
+        """[B, H, N, hd] bf16 view, unit last stride -> (ptr, bs, hs, rs)"""
+        _req(t, torch.bfloat16, name)
+        if t.dim() != 4 or t.stride(3) != 1:
+            raise RuntimeError(f'{name}: expected a [B,H,N,hd] view with unit last stride')
+        return t.data_ptr(), t.stride(0), t.stride(1), t.stride(2)
+
+    def xattn_fwd(self, q, k, v, scale):
+        """q [B,H,Nq,hd], k/v [B,H,Nk,hd] bf16 views -> (o bf16 [B, Nq, H*hd], lse fp32 [B,H,Nq])"""
+        lib = load_library()
+        B, H, Nq, hd = q.shape
+        Nk = k.shape[2]
+        o = torch.empty((B, Nq, H * hd), dtype=torch.bfloat16, device=q.device)
+        lse = torch.empty((B, H, Nq), dtype=torch.float32, device=q.device)
+        p = XattnFwdParams()
+        p.q, p.q_bs, p.q_hs, p.q_rs = self._bhnd(q, 'xattn.q')
+        p.k, p.k_bs, p.k_hs, p.k_rs = self._bhnd(k, 'xattn.k')
+        p.v, p.v_bs, p.v_hs, p.v_rs = self._bhnd(v, 'xattn.v')
+        p.o, p.o_bs, p.o_hs, p.o_rs = o.data_ptr(), Nq * H * hd, hd, H * hd
+        p.lse = lse.data_ptr()
+        p.B, p.H, p.Nq, p.Nk, p.hd, p.scale = B, H, Nq, Nk, hd, scale
+        _check(lib.vt_xattn_fwd(C.byref(p), _stream()), 'vt_xattn_fwd')
+        return o, lse
+
+    def xattn_bwd(self, q, k, v, o, dout, lse, scale, dq):
+        """o, dout: bf16 [B, Nq, H*hd] contiguous; dq: bf16 [B,H,Nq,hd] view written in place -> (dk, dv) fp32 [B,H,Nk,hd]"""
+        lib = load_library()
+        B, H, Nq, hd = q.shape
+        Nk = k.shape[2]
+        for t, n in ((o, 'o'), (dout, 'dout')):
+            _req(t, torch.bfloat16, 'xattn_bwd.' + n)
+            if not t.is_contiguous() or t.numel() != B * Nq * H * hd:
+                raise RuntimeError(f'xattn_bwd: {n} must be contiguous [B, Nq, H*hd]')
+        dev = q.device
+        delta = torch.empty((B, H, Nq), dtype=torch.float32, device=dev)
+        dk = torch.empty((B, H, Nk, hd), dtype=torch.float32, device=dev)
+        dv = torch.empty_like(dk)
+        p = XattnBwdParams()
+        p.q, p.q_bs, p.q_hs, p.q_rs = self._bhnd(q, 'xattn.q')
+        p.k, p.k_bs, p.k_hs, p.k_rs = self._bhnd(k, 'xattn.k')
+        p.v, p.v_bs, p.v_hs, p.v_rs = self._bhnd(v, 'xattn.v')
+        p.dq, p.dq_bs, p.dq_hs, p.dq_rs = self._bhnd(dq, 'xattn.dq')
+        p.o, p.dout = o.data_ptr(), dout.data_ptr()
+        p.o_bs, p.o_hs, p.o_rs = Nq * H * hd, hd, H * hd
+        p.lse, p.delta, p.dk, p.dv = lse.data_ptr(), delta.data_ptr(), dk.data_ptr(), dv.data_ptr()
+        p.B, p.H, p.Nq, p.Nk, p.hd, p.scale = B, H, Nq, Nk, hd, scale
+        _check(lib.vt_xattn_bwd(C.byref(p), _stream()), 'vt_xattn_bwd')
+        return dk, dv
+
+    @staticmethod
+    def maxpool_out_thw(thw, kernel, stride):
+        return tuple((n + 2 * (k // 2) - k) // s + 1 for n, k, s in zip(thw, kernel, stride))
+
+    def _mp_dims(self, p, B, D, thw, kernel, stride):
+        p.B, p.D = B, D
+        p.T, p.H, p.W = thw
+        p.kt, p.kh, p.kw = kernel
+        p.st, p.sh, p.sw = stride
+        p.To, p.Ho, p.Wo = self.maxpool_out_thw(thw, kernel, stride)
+
+    def maxpool_fwd(self, x, thw, kernel, stride):
+        """x fp32 [B, 1+T*H*W, D] -> (y fp32 [B, 1+Lo, D], idx u8, out_thw)"""
+        lib = load_library()
+        x = _req(x, torch.float32, 'maxpool.x')
+        if not x.is_contiguous() or x.shape[1] != 1 + thw[0] * thw[1] * thw[2]:
+            raise RuntimeError('maxpool_fwd: x must be contiguous [B, 1+T*H*W, D]')
+        B, _, D = x.shape
+        out_thw = self.maxpool_out_thw(thw, kernel, stride)
+        Lo1 = 1 + out_thw[0] * out_thw[1] * out_thw[2]
+        y = torch.empty((B, Lo1, D), dtype=torch.float32, device=x.device)
+        idx = torch.empty((B, Lo1, D), dtype=torch.uint8, device=x.device)
+        p = MaxpoolFwdParams()
+        p.x, p.y, p.idx = x.data_ptr(), y.data_ptr(), idx.data_ptr()
+        self._mp_dims(p, B, D, thw, kernel, stride)
+        _check(lib.vt_maxpool_fwd(C.byref(p), _stream()), 'vt_maxpool_fwd')
+        return y, idx, out_thw
+
+    def maxpool_bwd(self, dy, idx, thw, kernel, stride):
+        lib = load_library()
+        dy = _req(dy, torch.float32, 'maxpool_bwd.dy')
+        if not dy.is_contiguous() or dy.shape != idx.shape:
+            raise RuntimeError('maxpool_bwd: dy must be contiguous and match idx')
+        B, _, D = dy.shape
+        dx = torch.empty((B, 1 + thw[0] * thw[1] * thw[2], D), dtype=torch.float32, device=dy.device)
+        p = MaxpoolBwdParams()
+        p.dy, p.idx, p.dx = dy.data_ptr(), idx.data_ptr(), dx.data_ptr()
+        self._mp_dims(p, B, D, thw, kernel, stride)
+        _check(lib.vt_maxpool_bwd(C.byref(p), _stream()), 'vt_maxpool_bwd')
+        return dx
+
+    def im2col3d(self, x, kernel, stride, padding, kpad):
+        """x fp32 [B,T,C,H,W] -> (cols bf16 [B*To*Ho*Wo, kpad], (To,Ho,Wo))"""
+        lib = load_library()
+        x = _req(x, torch.float32, 'im2col3d.x').contiguous()
+        B, T, Cc, H, W = x.shape
+        out = tuple((n + 2 * pd - k) // s + 1 for n, pd, k, s in zip((T, H, W), padding, kernel, stride))
+        cols = torch.empty((B * out[0] * out[1] * out[2], kpad), dtype=torch.bfloat16, device=x.device)
+        p = Im2col3dParams()
+        p.x, p.cols = x.data_ptr(), cols.data_ptr()
+        p.B, p.T, p.C, p.H, p.W = B, T, Cc, H, W
+        p.kt, p.kh, p.kw = kernel
+        p.st, p.sh, p.sw = stride
+        p.pt, p.ph, p.pw = padding
+        p.To, p.Ho, p.Wo = out
+        p.Kpad = kpad
+        _check(lib.vt_im2col3d_bf16(C.byref(p), _stream()), 'vt_im2col3d_bf16')
+        return cols, out
+
+    def mvit_tokens_fwd(self, t, wmask, mask_token, cls_token, pos_s, pos_t, pos_cls, B, T, HW):
+        lib = load_library()
+        t = _req(t, torch.float32, 'tokens.t')
+        Cc = t.shape[1]
+        if not t.is_contiguous() or t.shape[0] != B * T * HW:
+            raise RuntimeError('mvit_tokens_fwd: t must be contiguous [B*T*HW, C]')
+        x = torch.empty((B, 1 + T * HW, Cc), dtype=torch.float32, device=t.device)
+        p = MvitTokensFwdParams()
+        p.t, p.wmask = t.data_ptr(), _ptr(None if wmask is None else _req(wmask, torch.float32, 'tokens.wmask').contiguous())
+        for n, v in (('mask_token', mask_token), ('cls_token', cls_token), ('pos_s', pos_s), ('pos_t', pos_t), ('pos_cls', pos_cls)):
+            setattr(p, n, _req(v, torch.float32, 'tokens.' + n).contiguous().data_ptr())
+        p.x, p.B, p.T, p.HW, p.C = x.data_ptr(), B, T, HW, Cc
+        _check(lib.vt_mvit_tokens_fwd(C.byref(p), _stream()), 'vt_mvit_tokens_fwd')
+        return x
+
+    def mvit_tokens_bwd(self, dx, wmask, B, T, HW):
+        lib = load_library()
+        dx = _req(dx, torch.float32, 'tokens_bwd.dx')
+        if not dx.is_contiguous():
+            raise RuntimeError('mvit_tokens_bwd: dx must be contiguous')
+        Cc = dx.shape[-1]
+        dt = torch.empty((B * T * HW, Cc), dtype=torch.bfloat16, device=dx.device)
+        p = MvitTokensBwdParams()
+        p.dx, p.wmask, p.dt = dx.data_ptr(), _ptr(wmask), dt.data_ptr()
+        p.B, p.T, p.HW, p.C = B, T, HW, Cc
+        _check(lib.vt_mvit_tokens_bwd(C.byref(p), _stream()), 'vt_mvit_tokens_bwd')
+        return dt
+
+    def mse_fwd(self, pred, target, mask, dims):
+        """dims = (B, t, dt, h, w, dc) -> fp32 [4]; element 0 = sum_cells mask * mean_dc (pred-target)^2"""
+        lib = load_library()
+        for tns, n in ((pred, 'pred'), (target, 'target'), (mask, 'mask')):
+            _req(tns, torch.float32, 'mse.' + n)
+            if not tns.is_contiguous():
+                raise RuntimeError(f'mse_fwd: {n} must be contiguous')
+        B, t, dt, h, w, dc = dims
+        cells = B * t * dt * h * w
+        if pred.numel() != B * (1 + t * h * w) * dt * dc or target.numel() != cells * dc or mask.numel() != cells:
+            raise RuntimeError('mse_fwd: shape mismatch')
+        num = torch.empty(4, dtype=torch.float32, device=pred.device)
+        partials = torch.empty(lib.vt_mse_blocks(cells) * 4, dtype=torch.float32, device=pred.device)
+        p = MseFwdParams()
+        p.pred, p.target, p.mask, p.num, p.partials = pred.data_ptr(), target.data_ptr(), mask.data_ptr(), num.data_ptr(), partials.data_ptr()
+        p.B, p.t, p.dt, p.h, p.w, p.dc = dims
+        _check(lib.vt_mse_fwd(C.byref(p), _stream()), 'vt_mse_fwd')
+        return num
+
+    def mse_bwd(self, pred, target, mask, coef, dims):
+        lib = load_library()
+        B, t, dt, h, w, dc = dims
+        dpred = torch.empty((B * (1 + t * h * w), dt * dc), dtype=torch.bfloat16, device=pred.device)
+        p = MseBwdParams()
+        p.pred, p.target, p.mask = pred.data_ptr(), target.data_ptr(), mask.data_ptr()
+        p.coef, p.dpred = _req(coef, torch.float32, 'mse.coef').data_ptr(), dpred.data_ptr()
+        p.B, p.t, p.dt, p.h, p.w, p.dc = dims
+        _check(lib.vt_mse_bwd(C.byref(p), _stream()), 'vt_mse_bwd')
+        return dpred
 
 
 def set_reserved_sms(n: int) -> None:

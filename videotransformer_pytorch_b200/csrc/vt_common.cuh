@@ -22,6 +22,9 @@ int check_launch(const char* what);   // cudaGetLastError -> error code
   } while (0)
 
 int sm_count();
+// narrow-row LayerNorm (D = 32..256 step 32, vt_mvit.cu); vt_layernorm_fwd/bwd dispatch here when D % 128 != 0
+int layernorm_fwd_small(const vt_ln_fwd_params* p, void* stream);
+int layernorm_bwd_small(const vt_ln_bwd_params* p, void* stream);
 int persistent_sm_count();   // sm_count() minus the SMs reserved for concurrent communication kernels
 
 // ---- device helpers ---------------------------------------------------------------------------

@@ -420,6 +420,7 @@ extern "C" int vt_launch_count(void) { return (int)(__atomic_load_n(&g_launches,
 extern "C" int vt_layernorm_fwd(const vt_ln_fwd_params* p, void* stream) {
   VT_REQUIRE(p && p->x && p->gamma && p->beta && p->y && p->mean && p->rstd, "vt_layernorm_fwd: null pointer");
   VT_REQUIRE(p->rows > 0, "vt_layernorm_fwd: rows=%d", p->rows);
+  if (p->D % 128 != 0) return layernorm_fwd_small(p, stream);
   VT_REQUIRE(p->D % 128 == 0 && p->D >= 128 && p->D <= 1024, "vt_layernorm_fwd: D=%d unsupported (multiple of 128, <=1024)", p->D);
   VT_REQUIRE(p->ldx % 4 == 0, "vt_layernorm_fwd: ldx must be a multiple of 4");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -440,8 +441,9 @@ extern "C" int vt_ln_bwd_blocks(int32_t rows) { return ln_blocks(rows); }
 
 extern "C" int vt_layernorm_bwd(const vt_ln_bwd_params* p, void* stream) {
   VT_REQUIRE(p && p->dy && p->x && p->mean && p->rstd && p->gamma && p->dx && p->partials, "vt_layernorm_bwd: null pointer");
-  VT_REQUIRE(p->D % 128 == 0 && p->D >= 128 && p->D <= 1024, "vt_layernorm_bwd: D=%d unsupported", p->D);
   VT_REQUIRE(p->rows > 0, "vt_layernorm_bwd: rows=%d", p->rows);
+  if (p->D % 128 != 0) return layernorm_bwd_small(p, stream);
+  VT_REQUIRE(p->D % 128 == 0 && p->D >= 128 && p->D <= 1024, "vt_layernorm_bwd: D=%d unsupported", p->D);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int blocks = ln_blocks(p->rows);
 #define VT_LN_BWD(V)                                                                                                    \

@@ -1,0 +1,1098 @@
+// MaskFeat / MViT kernels: depthwise-conv pooling + LayerNorm of q/k/v, strided pooling attention
+// (head dim 96), skip-path max pooling, overlapping Conv3d im2col, token preparation and the masked-MSE loss.
+// Block arithmetic follows pytorchvideo's MultiScaleBlock as configured by video_transformer.py:764-785; the CPU
+// restatement is oracle/mvit_oracle.py.
+#include <math.h>
+#include <string.h>
+
+#include "vt_common.cuh"
+
+namespace vt {
+
+constexpr int ROW_WARPS = 8;   // warp-per-row kernels: 8 rows per CTA step
+
+static int row_blocks(long long rows, int per_sm) {
+  long long blocks = (rows + ROW_WARPS - 1) / ROW_WARPS;
+  const long long cap = (long long)sm_count() * per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+static int flat_blocks(long long n, int threads) {
+  long long blocks = (n + threads - 1) / threads;
+  const long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+__device__ __forceinline__ float bf2f(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+// ================================================================================================
+// LayerNorm for narrow rows: D = 32*E, one warp per row, lane owns columns lane + 32*i (coalesced 128-B segments).
+// Same contract as ln_fwd_kernel / ln_bwd_kernel of vt_elementwise.cu without row maps.
+// ================================================================================================
+template <int E>
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+ln_small_fwd_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, void* __restrict__ y, float* __restrict__ mean,
+                    float* __restrict__ rstd, int rows, float eps, int y_fp32) {
+  constexpr int D = 32 * E;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float g[E], b[E];
+#pragma unroll
+  for (int i = 0; i < E; ++i) {
+    g[i] = __ldg(gamma + lane + 32 * i);
+    b[i] = __ldg(beta + lane + 32 * i);
+  }
+  for (int m = blockIdx.x * ROW_WARPS + warp; m < rows; m += gridDim.x * ROW_WARPS) {
+    const float* xr = x + (long long)m * ldx;
+    float v[E];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+      v[i] = xr[lane + 32 * i];
+      s += v[i];
+    }
+    const float mu = warp_sum(s) * (1.0f / D);
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+      const float d = v[i] - mu;
+      ss += d * d;
+    }
+    const float rs = rsqrtf(warp_sum(ss) * (1.0f / D) + eps);
+    if (lane == 0) {
+      mean[m] = mu;
+      rstd[m] = rs;
+    }
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+      const float o = (v[i] - mu) * rs * g[i] + b[i];
+      if (y_fp32) static_cast<float*>(y)[(long long)m * D + lane + 32 * i] = o;
+      else static_cast<__nv_bfloat16*>(y)[(long long)m * D + lane + 32 * i] = __float2bfloat16_rn(o);
+    }
+  }
+}
+
+// partials: [gridDim.x][2][D] (dgamma row, dbeta row) like ln_bwd_kernel
+template <int E>
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+ln_small_bwd_kernel(const void* __restrict__ dy, int dy_fp32, const float* __restrict__ x, long long ldx,
+                    const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+                    const float* __restrict__ dres, float* __restrict__ dx, long long lddx,
+                    float* __restrict__ partials, int rows) {
+  constexpr int D = 32 * E;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float g[E], dg[E], db[E];
+#pragma unroll
+  for (int i = 0; i < E; ++i) {
+    g[i] = __ldg(gamma + lane + 32 * i);
+    dg[i] = 0.f;
+    db[i] = 0.f;
+  }
+  for (int m = blockIdx.x * ROW_WARPS + warp; m < rows; m += gridDim.x * ROW_WARPS) {
+    const float* xr = x + (long long)m * ldx;
+    const float mu = mean[m], rs = rstd[m];
+    float xh[E], gy[E];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+      const long long at = (long long)m * D + lane + 32 * i;
+      const float d = dy_fp32 ? static_cast<const float*>(dy)[at] : __bfloat162float(static_cast<const __nv_bfloat16*>(dy)[at]);
+      xh[i] = (xr[lane + 32 * i] - mu) * rs;
+      dg[i] += d * xh[i];
+      db[i] += d;
+      gy[i] = d * g[i];
+      s1 += gy[i];
+      s2 += gy[i] * xh[i];
+    }
+    const float m1 = warp_sum(s1) * (1.0f / D);
+    const float m2 = warp_sum(s2) * (1.0f / D);
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+      float o = rs * (gy[i] - m1 - xh[i] * m2);
+      if (dres) o += dres[(long long)m * lddx + lane + 32 * i];
+      dx[(long long)m * lddx + lane + 32 * i] = o;
+    }
+  }
+  __shared__ float sh[ROW_WARPS][32];
+  float* pg = partials + (long long)blockIdx.x * 2 * D;
+#pragma unroll
+  for (int i = 0; i < E; ++i) {
+    for (int pass = 0; pass < 2; ++pass) {
+      __syncthreads();
+      sh[warp][lane] = pass == 0 ? dg[i] : db[i];
+      __syncthreads();
+      if (warp == 0) {
+        float a = sh[0][lane];
+        for (int w = 1; w < ROW_WARPS; ++w) a += sh[w][lane];
+        pg[pass * D + lane + 32 * i] = a;
+      }
+    }
+  }
+}
+
+// ================================================================================================
+// q/k/v pooling: depthwise 3x3x3 Conv3d (padding 1) over the (T,H,W) token grid + LayerNorm(hd), one warp per output
+// row (b, h, l).  Filter taps sit in shared memory as [tap][hd] so a lane reads its own channels conflict-free.
+// ================================================================================================
+struct PoolDims {
+  int B, H, T, Hin, Win, st, sh, sw, To, Ho, Wo;
+};
+
+template <int E>
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+pool_ln_fwd_kernel(const __nv_bfloat16* __restrict__ in, long long in_bs, long long in_rs,
+                   const float* __restrict__ w, const float* __restrict__ gamma, const float* __restrict__ beta,
+                   float* __restrict__ pooled, __nv_bfloat16* __restrict__ out, float* __restrict__ mean,
+                   float* __restrict__ rstd, PoolDims d, float eps) {
+  constexpr int HD = 32 * E;
+  __shared__ float sw[27 * HD];
+  for (int i = threadIdx.x; i < 27 * HD; i += blockDim.x) {
+    const int tap = i / HD, c = i % HD;
+    sw[i] = w[c * 27 + tap];
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float g[E], bt[E];
+#pragma unroll
+  for (int i = 0; i < E; ++i) {
+    g[i] = __ldg(gamma + lane + 32 * i);
+    bt[i] = __ldg(beta + lane + 32 * i);
+  }
+  const int Lo1 = 1 + d.To * d.Ho * d.Wo;
+  const long long rows = (long long)d.B * d.H * Lo1;
+  for (long long r = (long long)blockIdx.x * ROW_WARPS + warp; r < rows; r += (long long)gridDim.x * ROW_WARPS) {
+    const int l = (int)(r % Lo1);
+    const int bh = (int)(r / Lo1);
+    const int h = bh % d.H, b = bh / d.H;
+    const __nv_bfloat16* base = in + (long long)b * in_bs + (long long)h * HD;
+    float acc[E];
+#pragma unroll
+    for (int i = 0; i < E; ++i) acc[i] = 0.f;
+    if (l == 0) {
+#pragma unroll
+      for (int i = 0; i < E; ++i) acc[i] = bf2f(base + lane + 32 * i);
+    } else {
+      const int o = l - 1;
+      const int ow = o % d.Wo, oh = (o / d.Wo) % d.Ho, ot = o / (d.Wo * d.Ho);
+      for (int dt = 0; dt < 3; ++dt) {
+        const int ti = ot * d.st - 1 + dt;
+        if (ti < 0 || ti >= d.T) continue;
+        for (int dh = 0; dh < 3; ++dh) {
+          const int hi = oh * d.sh - 1 + dh;
+          if (hi < 0 || hi >= d.Hin) continue;
+          for (int dw = 0; dw < 3; ++dw) {
+            const int wi = ow * d.sw - 1 + dw;
+            if (wi < 0 || wi >= d.Win) continue;
+            const long long n = 1 + ((long long)ti * d.Hin + hi) * d.Win + wi;
+            const __nv_bfloat16* src = base + n * in_rs;
+            const float* f = sw + ((dt * 3 + dh) * 3 + dw) * HD;
+#pragma unroll
+            for (int i = 0; i < E; ++i) acc[i] = fmaf(bf2f(src + lane + 32 * i), f[lane + 32 * i], acc[i]);
+          }
+        }
+      }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < E; ++i) s += acc[i];
+    const float mu = warp_sum(s) * (1.0f / HD);
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+      const float c = acc[i] - mu;
+      ss += c * c;
+    }
+    const float rs = rsqrtf(warp_sum(ss) * (1.0f / HD) + eps);
+    if (lane == 0) {
+      mean[r] = mu;
+      rstd[r] = rs;
+    }
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+      pooled[r * HD + lane + 32 * i] = acc[i];
+      out[r * HD + lane + 32 * i] = __float2bfloat16_rn((acc[i] - mu) * rs * g[i] + bt[i]);
+    }
+  }
+}
+
+// gradient w.r.t. the pooling input: one warp per input row (b, n, h); gathers the outputs whose window covers it.
+template <int E>
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+pool_din_kernel(const float* __restrict__ dpooled, const float* __restrict__ w, __nv_bfloat16* __restrict__ din,
+                long long din_bs, long long din_rs, PoolDims d) {
+  constexpr int HD = 32 * E;
+  __shared__ float sw[27 * HD];
+  for (int i = threadIdx.x; i < 27 * HD; i += blockDim.x) {
+    const int tap = i / HD, c = i % HD;
+    sw[i] = w[c * 27 + tap];
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int L1 = 1 + d.T * d.Hin * d.Win;
+  const int Lo1 = 1 + d.To * d.Ho * d.Wo;
+  const long long rows = (long long)d.B * L1 * d.H;
+  for (long long r = (long long)blockIdx.x * ROW_WARPS + warp; r < rows; r += (long long)gridDim.x * ROW_WARPS) {
+    const int h = (int)(r % d.H);
+    const int n = (int)((r / d.H) % L1);
+    const int b = (int)(r / ((long long)d.H * L1));
+    const float* dp = dpooled + ((long long)b * d.H + h) * Lo1 * HD;
+    float acc[E];
+#pragma unroll
+    for (int i = 0; i < E; ++i) acc[i] = 0.f;
+    if (n == 0) {
+#pragma unroll
+      for (int i = 0; i < E; ++i) acc[i] = dp[lane + 32 * i];
+    } else {
+      const int idx = n - 1;
+      const int wi = idx % d.Win, hi = (idx / d.Win) % d.Hin, ti = idx / (d.Win * d.Hin);
+      for (int dt = 0; dt < 3; ++dt) {
+        const int nt = ti + 1 - dt;
+        if (nt < 0 || nt % d.st != 0) continue;
+        const int ot = nt / d.st;
+        if (ot >= d.To) continue;
+        for (int dh = 0; dh < 3; ++dh) {
+          const int nh = hi + 1 - dh;
+          if (nh < 0 || nh % d.sh != 0) continue;
+          const int oh = nh / d.sh;
+          if (oh >= d.Ho) continue;
+          for (int dw = 0; dw < 3; ++dw) {
+            const int nw = wi + 1 - dw;
+            if (nw < 0 || nw % d.sw != 0) continue;
+            const int ow = nw / d.sw;
+            if (ow >= d.Wo) continue;
+            const float* src = dp + (1 + ((long long)ot * d.Ho + oh) * d.Wo + ow) * HD;
+            const float* f = sw + ((dt * 3 + dh) * 3 + dw) * HD;
+#pragma unroll
+            for (int i = 0; i < E; ++i) acc[i] = fmaf(src[lane + 32 * i], f[lane + 32 * i], acc[i]);
+          }
+        }
+      }
+    }
+    __nv_bfloat16* dst = din + (long long)b * din_bs + (long long)n * din_rs + (long long)h * HD;
+#pragma unroll
+    for (int i = 0; i < E; ++i) dst[lane + 32 * i] = __float2bfloat16_rn(acc[i]);
+  }
+}
+
+// filter gradient: dw[c][tap] = sum over output rows of dpooled[row][c] * in[window tap][c].
+// Each warp keeps 27 x E partial sums in registers; per-CTA partial rows [hd*27] are summed by reduce_rows.
+template <int E>
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+pool_dw_kernel(const float* __restrict__ dpooled, const __nv_bfloat16* __restrict__ in, long long in_bs, long long in_rs,
+               float* __restrict__ partials, PoolDims d) {
+  constexpr int HD = 32 * E;
+  __shared__ float red[27 * HD];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float acc[27][E];
+#pragma unroll
+  for (int t = 0; t < 27; ++t)
+#pragma unroll
+    for (int i = 0; i < E; ++i) acc[t][i] = 0.f;
+  const int Lo = d.To * d.Ho * d.Wo;
+  const long long rows = (long long)d.B * d.H * Lo;
+  for (long long r = (long long)blockIdx.x * ROW_WARPS + warp; r < rows; r += (long long)gridDim.x * ROW_WARPS) {
+    const int o = (int)(r % Lo);
+    const int bh = (int)(r / Lo);
+    const int h = bh % d.H, b = bh / d.H;
+    const int ow = o % d.Wo, oh = (o / d.Wo) % d.Ho, ot = o / (d.Wo * d.Ho);
+    const float* dp = dpooled + (((long long)b * d.H + h) * (Lo + 1) + 1 + o) * HD;
+    float g[E];
+#pragma unroll
+    for (int i = 0; i < E; ++i) g[i] = dp[lane + 32 * i];
+    const __nv_bfloat16* base = in + (long long)b * in_bs + (long long)h * HD;
+#pragma unroll
+    for (int dt = 0; dt < 3; ++dt) {
+      const int ti = ot * d.st - 1 + dt;
+#pragma unroll
+      for (int dh = 0; dh < 3; ++dh) {
+        const int hi = oh * d.sh - 1 + dh;
+#pragma unroll
+        for (int dw = 0; dw < 3; ++dw) {
+          const int wi = ow * d.sw - 1 + dw;
+          if (ti >= 0 && ti < d.T && hi >= 0 && hi < d.Hin && wi >= 0 && wi < d.Win) {
+            const __nv_bfloat16* src = base + (1 + ((long long)ti * d.Hin + hi) * d.Win + wi) * in_rs;
+#pragma unroll
+            for (int i = 0; i < E; ++i) acc[(dt * 3 + dh) * 3 + dw][i] = fmaf(g[i], bf2f(src + lane + 32 * i), acc[(dt * 3 + dh) * 3 + dw][i]);
+          }
+        }
+      }
+    }
+  }
+  for (int i = threadIdx.x; i < 27 * HD; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  for (int wv = 0; wv < ROW_WARPS; ++wv) {
+    if (warp == wv) {
+#pragma unroll
+      for (int t = 0; t < 27; ++t)
+#pragma unroll
+        for (int i = 0; i < E; ++i) red[(lane + 32 * i) * 27 + t] += acc[t][i];
+    }
+    __syncthreads();
+  }
+  float* pg = partials + (long long)blockIdx.x * 27 * HD;
+  for (int i = threadIdx.x; i < 27 * HD; i += blockDim.x) pg[i] = red[i];
+}
+
+// ================================================================================================
+// Pooling attention, head dim HD (96): CUDA-core flash kernels.
+//   forward / dQ: two threads per query row (each owns HD/2 dims), 64 queries per CTA, K/V tiles of 16 keys in smem
+//   dK/dV: four threads per key row (each owns HD/4 dims), 32 keys per CTA, Q/dO tiles of 16 queries in smem,
+//          query range split over blockIdx.y, fp32 atomics into dk/dv.
+// Scores are kept in the log2 domain (q pre-multiplied by scale*log2(e)) so softmax uses ex2.approx.
+// ================================================================================================
+constexpr int XA_KT = 16;        // keys per shared-memory tile (fwd / dQ)
+constexpr int XA_QPB = 64;       // queries per CTA (fwd / dQ)
+constexpr int XA_QT = 16;        // queries per shared-memory tile (dK/dV)
+constexpr int XA_KPB = 32;       // keys per CTA (dK/dV)
+constexpr int XA_QCHUNK = 512;   // queries per CTA along blockIdx.y (dK/dV)
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+
+struct XaStrides {
+  long long q_bs, q_hs, q_rs, k_bs, k_hs, k_rs, v_bs, v_hs, v_rs, o_bs, o_hs, o_rs, dq_bs, dq_hs, dq_rs;
+};
+
+// stage `rows` rows of HD bf16 (row r at src + (r0 + r) * rs) as fp32 into dst[r][HD]; rows past `limit` are zero
+template <int HD, int ROWS, int THREADS>
+__device__ __forceinline__ void stage_rows(float* __restrict__ dst, const __nv_bfloat16* __restrict__ src, long long rs,
+                                           int r0, int limit) {
+  constexpr int PAIRS = ROWS * HD / 2;
+  for (int i = threadIdx.x; i < PAIRS; i += THREADS) {
+    const int r = i / (HD / 2), c2 = i % (HD / 2);
+    float2 v = make_float2(0.f, 0.f);
+    if (r0 + r < limit) {
+      const uint32_t u = *reinterpret_cast<const uint32_t*>(src + (long long)(r0 + r) * rs + 2 * c2);
+      v = unpack_bf16x2(u);
+    }
+    dst[r * HD + 2 * c2] = v.x;
+    dst[r * HD + 2 * c2 + 1] = v.y;
+  }
+}
+
+template <int HD>
+__global__ void __launch_bounds__(2 * XA_QPB)
+xattn_fwd_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
+                 const __nv_bfloat16* __restrict__ v, __nv_bfloat16* __restrict__ o, float* __restrict__ lse,
+                 XaStrides s, int H, int Nq, int Nk, float scale) {
+  constexpr int HALF = HD / 2;
+  __shared__ __align__(16) float Ks[XA_KT * HD];
+  __shared__ __align__(16) float Vs[XA_KT * HD];
+  const int bh = blockIdx.y, b = bh / H, h = bh % H;
+  const int pair = threadIdx.x >> 1, half = threadIdx.x & 1;
+  const int qi = blockIdx.x * XA_QPB + pair;
+  const bool valid = qi < Nq;
+  const __nv_bfloat16* kb = k + (long long)b * s.k_bs + (long long)h * s.k_hs;
+  const __nv_bfloat16* vb = v + (long long)b * s.v_bs + (long long)h * s.v_hs;
+  float qr[HALF], acc[HALF];
+  {
+    const __nv_bfloat16* qp = q + (long long)b * s.q_bs + (long long)h * s.q_hs + (long long)(valid ? qi : 0) * s.q_rs + half * HALF;
+    const float c = scale * LOG2E;
+#pragma unroll
+    for (int d2 = 0; d2 < HALF / 2; ++d2) {
+      const float2 t = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(qp + 2 * d2));
+      qr[2 * d2] = t.x * c;
+      qr[2 * d2 + 1] = t.y * c;
+    }
+#pragma unroll
+    for (int d = 0; d < HALF; ++d) acc[d] = 0.f;
+  }
+  float m = -INFINITY, l = 0.f;
+  for (int k0 = 0; k0 < Nk; k0 += XA_KT) {
+    __syncthreads();
+    stage_rows<HD, XA_KT, 2 * XA_QPB>(Ks, kb, s.k_rs, k0, Nk);
+    stage_rows<HD, XA_KT, 2 * XA_QPB>(Vs, vb, s.v_rs, k0, Nk);
+    __syncthreads();
+    const int nk = min(XA_KT, Nk - k0);
+    float sc[XA_KT];
+    float mt = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < XA_KT; ++j) {
+      const float4* kr = reinterpret_cast<const float4*>(Ks + j * HD + half * HALF);
+      float p = 0.f;
+#pragma unroll
+      for (int d4 = 0; d4 < HALF / 4; ++d4) {
+        const float4 kv = kr[d4];
+        p = fmaf(qr[4 * d4], kv.x, p);
+        p = fmaf(qr[4 * d4 + 1], kv.y, p);
+        p = fmaf(qr[4 * d4 + 2], kv.z, p);
+        p = fmaf(qr[4 * d4 + 3], kv.w, p);
+      }
+      p += __shfl_xor_sync(0xffffffffu, p, 1);
+      sc[j] = j < nk ? p : -INFINITY;
+      mt = fmaxf(mt, sc[j]);
+    }
+    const float mn = fmaxf(m, mt);            // finite: every tile holds at least one key
+    const float corr = fast_exp2(m - mn);     // m = -inf on the first tile -> 0
+    l *= corr;
+#pragma unroll
+    for (int d = 0; d < HALF; ++d) acc[d] *= corr;
+#pragma unroll
+    for (int j = 0; j < XA_KT; ++j) {
+      const float pj = fast_exp2(sc[j] - mn);
+      l += pj;
+      const float4* vr = reinterpret_cast<const float4*>(Vs + j * HD + half * HALF);
+#pragma unroll
+      for (int d4 = 0; d4 < HALF / 4; ++d4) {
+        const float4 vv = vr[d4];
+        acc[4 * d4] = fmaf(pj, vv.x, acc[4 * d4]);
+        acc[4 * d4 + 1] = fmaf(pj, vv.y, acc[4 * d4 + 1]);
+        acc[4 * d4 + 2] = fmaf(pj, vv.z, acc[4 * d4 + 2]);
+        acc[4 * d4 + 3] = fmaf(pj, vv.w, acc[4 * d4 + 3]);
+      }
+    }
+    m = mn;
+  }
+  if (valid) {
+    const float inv = 1.0f / l;
+    __nv_bfloat16* op = o + (long long)b * s.o_bs + (long long)h * s.o_hs + (long long)qi * s.o_rs + half * HALF;
+#pragma unroll
+    for (int d2 = 0; d2 < HALF / 2; ++d2)
+      *reinterpret_cast<uint32_t*>(op + 2 * d2) = pack_bf16x2(acc[2 * d2] * inv, acc[2 * d2 + 1] * inv);
+    if (half == 0) lse[(long long)bh * Nq + qi] = (m + log2f(l)) * LN2;
+  }
+}
+
+template <int HD>
+__global__ void __launch_bounds__(2 * XA_QPB)
+xattn_dq_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
+                const __nv_bfloat16* __restrict__ v, const __nv_bfloat16* __restrict__ o,
+                const __nv_bfloat16* __restrict__ dout, const float* __restrict__ lse, float* __restrict__ delta,
+                __nv_bfloat16* __restrict__ dq, XaStrides s, int H, int Nq, int Nk, float scale) {
+  constexpr int HALF = HD / 2;
+  __shared__ __align__(16) float Ks[XA_KT * HD];
+  __shared__ __align__(16) float Vs[XA_KT * HD];
+  const int bh = blockIdx.y, b = bh / H, h = bh % H;
+  const int pair = threadIdx.x >> 1, half = threadIdx.x & 1;
+  const int qi = blockIdx.x * XA_QPB + pair;
+  const bool valid = qi < Nq;
+  const int qrow = valid ? qi : 0;
+  const __nv_bfloat16* kb = k + (long long)b * s.k_bs + (long long)h * s.k_hs;
+  const __nv_bfloat16* vb = v + (long long)b * s.v_bs + (long long)h * s.v_hs;
+  float qr[HALF], dor[HALF], dqr[HALF];
+  float dl = 0.f;
+  {
+    const __nv_bfloat16* qp = q + (long long)b * s.q_bs + (long long)h * s.q_hs + (long long)qrow * s.q_rs + half * HALF;
+    const __nv_bfloat16* op = o + (long long)b * s.o_bs + (long long)h * s.o_hs + (long long)qrow * s.o_rs + half * HALF;
+    const __nv_bfloat16* dp = dout + (long long)b * s.o_bs + (long long)h * s.o_hs + (long long)qrow * s.o_rs + half * HALF;
+    const float c = scale * LOG2E;
+#pragma unroll
+    for (int d2 = 0; d2 < HALF / 2; ++d2) {
+      const float2 tq = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(qp + 2 * d2));
+      const float2 to = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(op + 2 * d2));
+      const float2 td = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dp + 2 * d2));
+      qr[2 * d2] = tq.x * c;
+      qr[2 * d2 + 1] = tq.y * c;
+      dor[2 * d2] = td.x;
+      dor[2 * d2 + 1] = td.y;
+      dl = fmaf(td.x, to.x, dl);
+      dl = fmaf(td.y, to.y, dl);
+      dqr[2 * d2] = 0.f;
+      dqr[2 * d2 + 1] = 0.f;
+    }
+  }
+  dl += __shfl_xor_sync(0xffffffffu, dl, 1);
+  const float lse2 = valid ? lse[(long long)bh * Nq + qi] * LOG2E : INFINITY;   // invalid rows: p = 0
+  for (int k0 = 0; k0 < Nk; k0 += XA_KT) {
+    __syncthreads();
+    stage_rows<HD, XA_KT, 2 * XA_QPB>(Ks, kb, s.k_rs, k0, Nk);
+    stage_rows<HD, XA_KT, 2 * XA_QPB>(Vs, vb, s.v_rs, k0, Nk);
+    __syncthreads();
+    const int nk = min(XA_KT, Nk - k0);
+#pragma unroll 4
+    for (int j = 0; j < XA_KT; ++j) {
+      const float4* kr = reinterpret_cast<const float4*>(Ks + j * HD + half * HALF);
+      const float4* vr = reinterpret_cast<const float4*>(Vs + j * HD + half * HALF);
+      float p1 = 0.f, p2 = 0.f;
+#pragma unroll
+      for (int d4 = 0; d4 < HALF / 4; ++d4) {
+        const float4 kv = kr[d4], vv = vr[d4];
+        p1 = fmaf(qr[4 * d4], kv.x, p1);
+        p1 = fmaf(qr[4 * d4 + 1], kv.y, p1);
+        p1 = fmaf(qr[4 * d4 + 2], kv.z, p1);
+        p1 = fmaf(qr[4 * d4 + 3], kv.w, p1);
+        p2 = fmaf(dor[4 * d4], vv.x, p2);
+        p2 = fmaf(dor[4 * d4 + 1], vv.y, p2);
+        p2 = fmaf(dor[4 * d4 + 2], vv.z, p2);
+        p2 = fmaf(dor[4 * d4 + 3], vv.w, p2);
+      }
+      p1 += __shfl_xor_sync(0xffffffffu, p1, 1);
+      p2 += __shfl_xor_sync(0xffffffffu, p2, 1);
+      const float pj = j < nk ? fast_exp2(p1 - lse2) : 0.f;
+      const float ds = pj * (p2 - dl);
+#pragma unroll
+      for (int d4 = 0; d4 < HALF / 4; ++d4) {
+        const float4 kv = kr[d4];
+        dqr[4 * d4] = fmaf(ds, kv.x, dqr[4 * d4]);
+        dqr[4 * d4 + 1] = fmaf(ds, kv.y, dqr[4 * d4 + 1]);
+        dqr[4 * d4 + 2] = fmaf(ds, kv.z, dqr[4 * d4 + 2]);
+        dqr[4 * d4 + 3] = fmaf(ds, kv.w, dqr[4 * d4 + 3]);
+      }
+    }
+  }
+  if (valid) {
+    __nv_bfloat16* dst = dq + (long long)b * s.dq_bs + (long long)h * s.dq_hs + (long long)qi * s.dq_rs + half * HALF;
+#pragma unroll
+    for (int d2 = 0; d2 < HALF / 2; ++d2)
+      *reinterpret_cast<uint32_t*>(dst + 2 * d2) = pack_bf16x2(dqr[2 * d2] * scale, dqr[2 * d2 + 1] * scale);
+    if (half == 0) delta[(long long)bh * Nq + qi] = dl;
+  }
+}
+
+template <int HD>
+__global__ void __launch_bounds__(4 * XA_KPB)
+xattn_dkv_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
+                 const __nv_bfloat16* __restrict__ v, const __nv_bfloat16* __restrict__ dout,
+                 const float* __restrict__ lse, const float* __restrict__ delta, float* __restrict__ dk,
+                 float* __restrict__ dv, XaStrides s, int H, int Nq, int Nk, float scale) {
+  constexpr int QUART = HD / 4;
+  __shared__ __align__(16) float Qs[XA_QT * HD];
+  __shared__ __align__(16) float Ds[XA_QT * HD];
+  __shared__ float Ls[XA_QT], Dl[XA_QT];
+  const int bh = blockIdx.z, b = bh / H, h = bh % H;
+  const int kl = threadIdx.x >> 2, quart = threadIdx.x & 3;
+  const int kj = blockIdx.x * XA_KPB + kl;
+  const bool valid = kj < Nk;
+  const __nv_bfloat16* qb = q + (long long)b * s.q_bs + (long long)h * s.q_hs;
+  const __nv_bfloat16* db = dout + (long long)b * s.o_bs + (long long)h * s.o_hs;
+  float kr[QUART], vr[QUART], dkr[QUART], dvr[QUART];
+  {
+    const __nv_bfloat16* kp = k + (long long)b * s.k_bs + (long long)h * s.k_hs + (long long)(valid ? kj : 0) * s.k_rs + quart * QUART;
+    const __nv_bfloat16* vp = v + (long long)b * s.v_bs + (long long)h * s.v_hs + (long long)(valid ? kj : 0) * s.v_rs + quart * QUART;
+    const float c = scale * LOG2E;
+#pragma unroll
+    for (int d2 = 0; d2 < QUART / 2; ++d2) {
+      const float2 tk = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(kp + 2 * d2));
+      const float2 tv = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(vp + 2 * d2));
+      kr[2 * d2] = valid ? tk.x * c : 0.f;
+      kr[2 * d2 + 1] = valid ? tk.y * c : 0.f;
+      vr[2 * d2] = valid ? tv.x : 0.f;
+      vr[2 * d2 + 1] = valid ? tv.y : 0.f;
+      dkr[2 * d2] = dkr[2 * d2 + 1] = 0.f;
+      dvr[2 * d2] = dvr[2 * d2 + 1] = 0.f;
+    }
+  }
+  const int q_begin = blockIdx.y * XA_QCHUNK;
+  const int q_end = min(Nq, q_begin + XA_QCHUNK);
+  for (int q0 = q_begin; q0 < q_end; q0 += XA_QT) {
+    __syncthreads();
+    stage_rows<HD, XA_QT, 4 * XA_KPB>(Qs, qb, s.q_rs, q0, q_end);
+    stage_rows<HD, XA_QT, 4 * XA_KPB>(Ds, db, s.o_rs, q0, q_end);
+    if (threadIdx.x < XA_QT) {
+      const int qi = q0 + threadIdx.x;
+      Ls[threadIdx.x] = qi < q_end ? lse[(long long)bh * Nq + qi] * LOG2E : INFINITY;   // past the end: p = 0
+      Dl[threadIdx.x] = qi < q_end ? delta[(long long)bh * Nq + qi] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int i = 0; i < XA_QT; ++i) {
+      const float4* qv = reinterpret_cast<const float4*>(Qs + i * HD + quart * QUART);
+      const float4* dv4 = reinterpret_cast<const float4*>(Ds + i * HD + quart * QUART);
+      float p1 = 0.f, p2 = 0.f;
+#pragma unroll
+      for (int d4 = 0; d4 < QUART / 4; ++d4) {
+        const float4 a = qv[d4], g = dv4[d4];
+        p1 = fmaf(kr[4 * d4], a.x, p1);
+        p1 = fmaf(kr[4 * d4 + 1], a.y, p1);
+        p1 = fmaf(kr[4 * d4 + 2], a.z, p1);
+        p1 = fmaf(kr[4 * d4 + 3], a.w, p1);
+        p2 = fmaf(vr[4 * d4], g.x, p2);
+        p2 = fmaf(vr[4 * d4 + 1], g.y, p2);
+        p2 = fmaf(vr[4 * d4 + 2], g.z, p2);
+        p2 = fmaf(vr[4 * d4 + 3], g.w, p2);
+      }
+      p1 += __shfl_xor_sync(0xffffffffu, p1, 1);
+      p1 += __shfl_xor_sync(0xffffffffu, p1, 2);
+      p2 += __shfl_xor_sync(0xffffffffu, p2, 1);
+      p2 += __shfl_xor_sync(0xffffffffu, p2, 2);
+      const float pj = fast_exp2(p1 - Ls[i]);
+      const float ds = pj * (p2 - Dl[i]);
+#pragma unroll
+      for (int d4 = 0; d4 < QUART / 4; ++d4) {
+        const float4 a = qv[d4], g = dv4[d4];
+        dvr[4 * d4] = fmaf(pj, g.x, dvr[4 * d4]);
+        dvr[4 * d4 + 1] = fmaf(pj, g.y, dvr[4 * d4 + 1]);
+        dvr[4 * d4 + 2] = fmaf(pj, g.z, dvr[4 * d4 + 2]);
+        dvr[4 * d4 + 3] = fmaf(pj, g.w, dvr[4 * d4 + 3]);
+        dkr[4 * d4] = fmaf(ds, a.x, dkr[4 * d4]);
+        dkr[4 * d4 + 1] = fmaf(ds, a.y, dkr[4 * d4 + 1]);
+        dkr[4 * d4 + 2] = fmaf(ds, a.z, dkr[4 * d4 + 2]);
+        dkr[4 * d4 + 3] = fmaf(ds, a.w, dkr[4 * d4 + 3]);
+      }
+    }
+  }
+  if (valid) {
+    float* dkp = dk + ((long long)bh * Nk + kj) * HD + quart * QUART;
+    float* dvp = dv + ((long long)bh * Nk + kj) * HD + quart * QUART;
+#pragma unroll
+    for (int d = 0; d < QUART; ++d) {
+      atomicAdd(dkp + d, dkr[d] * scale);
+      atomicAdd(dvp + d, dvr[d]);
+    }
+  }
+}
+
+// ================================================================================================
+// skip-path max pooling on the fp32 stream (cls row copied)
+// ================================================================================================
+struct MpDims {
+  int B, D, T, H, W, kt, kh, kw, st, sh, sw, To, Ho, Wo;
+};
+
+__global__ void maxpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, uint8_t* __restrict__ idx, MpDims d) {
+  const int Lo1 = 1 + d.To * d.Ho * d.Wo, L1 = 1 + d.T * d.H * d.W;
+  const long long n = (long long)d.B * Lo1 * d.D;
+  const int pt = d.kt / 2, ph = d.kh / 2, pw = d.kw / 2;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(e % d.D);
+    const int l = (int)((e / d.D) % Lo1);
+    const int b = (int)(e / ((long long)d.D * Lo1));
+    const float* xb = x + (long long)b * L1 * d.D + c;
+    if (l == 0) {
+      y[e] = xb[0];
+      idx[e] = 0;
+      continue;
+    }
+    const int o = l - 1;
+    const int ow = o % d.Wo, oh = (o / d.Wo) % d.Ho, ot = o / (d.Wo * d.Ho);
+    float best = -INFINITY;
+    int arg = 255;
+    for (int dt = 0; dt < d.kt; ++dt) {
+      const int ti = ot * d.st - pt + dt;
+      if (ti < 0 || ti >= d.T) continue;
+      for (int dh = 0; dh < d.kh; ++dh) {
+        const int hi = oh * d.sh - ph + dh;
+        if (hi < 0 || hi >= d.H) continue;
+        for (int dw = 0; dw < d.kw; ++dw) {
+          const int wi = ow * d.sw - pw + dw;
+          if (wi < 0 || wi >= d.W) continue;
+          const float val = xb[(1 + ((long long)ti * d.H + hi) * d.W + wi) * d.D];
+          if (val > best || arg == 255) {     // first maximum in scan order
+            best = val;
+            arg = (dt * d.kh + dh) * d.kw + dw;
+          }
+        }
+      }
+    }
+    y[e] = best;
+    idx[e] = (uint8_t)arg;
+  }
+}
+
+__global__ void maxpool_bwd_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ idx, float* __restrict__ dx, MpDims d) {
+  const int Lo1 = 1 + d.To * d.Ho * d.Wo, L1 = 1 + d.T * d.H * d.W;
+  const long long n = (long long)d.B * L1 * d.D;
+  const int pt = d.kt / 2, ph = d.kh / 2, pw = d.kw / 2;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(e % d.D);
+    const int l = (int)((e / d.D) % L1);
+    const int b = (int)(e / ((long long)d.D * L1));
+    const float* gb = dy + (long long)b * Lo1 * d.D + c;
+    const uint8_t* ib = idx + (long long)b * Lo1 * d.D + c;
+    if (l == 0) {
+      dx[e] = gb[0];
+      continue;
+    }
+    const int i = l - 1;
+    const int wi = i % d.W, hi = (i / d.W) % d.H, ti = i / (d.W * d.H);
+    float acc = 0.f;
+    for (int dt = 0; dt < d.kt; ++dt) {
+      const int nt = ti + pt - dt;
+      if (nt < 0 || nt % d.st != 0) continue;
+      const int ot = nt / d.st;
+      if (ot >= d.To) continue;
+      for (int dh = 0; dh < d.kh; ++dh) {
+        const int nh = hi + ph - dh;
+        if (nh < 0 || nh % d.sh != 0) continue;
+        const int oh = nh / d.sh;
+        if (oh >= d.Ho) continue;
+        for (int dw = 0; dw < d.kw; ++dw) {
+          const int nw = wi + pw - dw;
+          if (nw < 0 || nw % d.sw != 0) continue;
+          const int ow = nw / d.sw;
+          if (ow >= d.Wo) continue;
+          const long long at = (1 + ((long long)ot * d.Ho + oh) * d.Wo + ow) * d.D;
+          if (ib[at] == (dt * d.kh + dh) * d.kw + dw) acc += gb[at];
+        }
+      }
+    }
+    dx[e] = acc;
+  }
+}
+
+// ================================================================================================
+// overlapping Conv3d im2col
+// ================================================================================================
+struct I3Dims {
+  int B, T, C, H, W, kt, kh, kw, st, sh, sw, pt, ph, pw, To, Ho, Wo, Kpad;
+};
+
+__global__ void im2col3d_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ cols, I3Dims d) {
+  const long long rows = (long long)d.B * d.To * d.Ho * d.Wo;
+  const long long n = rows * d.Kpad;
+  const int Kreal = d.C * d.kt * d.kh * d.kw;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const int col = (int)(e % d.Kpad);
+    const long long row = e / d.Kpad;
+    float val = 0.f;
+    if (col < Kreal) {
+      const int dw = col % d.kw, dh = (col / d.kw) % d.kh, dt = (col / (d.kw * d.kh)) % d.kt, c = col / (d.kw * d.kh * d.kt);
+      const int ow = (int)(row % d.Wo), oh = (int)((row / d.Wo) % d.Ho), ot = (int)((row / ((long long)d.Wo * d.Ho)) % d.To);
+      const int b = (int)(row / ((long long)d.Wo * d.Ho * d.To));
+      const int ti = ot * d.st - d.pt + dt, hi = oh * d.sh - d.ph + dh, wi = ow * d.sw - d.pw + dw;
+      if (ti >= 0 && ti < d.T && hi >= 0 && hi < d.H && wi >= 0 && wi < d.W)
+        val = x[((((long long)b * d.T + ti) * d.C + c) * d.H + hi) * d.W + wi];
+    }
+    cols[e] = __float2bfloat16_rn(val);
+  }
+}
+
+// ================================================================================================
+// token preparation
+// ================================================================================================
+__global__ void mvit_tokens_fwd_kernel(const float* __restrict__ t, const float* __restrict__ wmask,
+                                       const float* __restrict__ mask_token, const float* __restrict__ cls_token,
+                                       const float* __restrict__ pos_s, const float* __restrict__ pos_t,
+                                       const float* __restrict__ pos_cls, float* __restrict__ x, int B, int T, int HW, int C) {
+  const int L = T * HW;
+  const long long n = (long long)B * (L + 1) * C;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(e % C);
+    const int l1 = (int)((e / C) % (L + 1));
+    const int b = (int)(e / ((long long)C * (L + 1)));
+    float val;
+    if (l1 == 0) {
+      val = cls_token[c] + pos_cls[c];
+    } else {
+      const int l = l1 - 1;
+      const float w = wmask ? wmask[(long long)b * L + l] : 0.f;
+      val = t[((long long)b * L + l) * C + c] * (1.0f - w) + mask_token[c] * w + pos_s[(long long)(l % HW) * C + c] +
+            pos_t[(long long)(l / HW) * C + c];
+    }
+    x[e] = val;
+  }
+}
+
+__global__ void mvit_tokens_bwd_kernel(const float* __restrict__ dx, const float* __restrict__ wmask,
+                                       __nv_bfloat16* __restrict__ dt, int B, int L, int C) {
+  const long long n = (long long)B * L * C;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(e % C);
+    const long long bl = e / C;
+    const int l = (int)(bl % L);
+    const int b = (int)(bl / L);
+    const float w = wmask ? wmask[bl] : 0.f;
+    dt[e] = __float2bfloat16_rn(dx[((long long)b * (L + 1) + 1 + l) * C + c] * (1.0f - w));
+  }
+}
+
+// ================================================================================================
+// masked MSE (one warp per (b, frame, h, w) cell)
+// ================================================================================================
+struct MseDims {
+  int B, t, dt, h, w, dc;
+};
+
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+mse_fwd_kernel(const float* __restrict__ pred, const float* __restrict__ target, const float* __restrict__ mask,
+               float* __restrict__ partials, MseDims d) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int F = d.t * d.dt, hw = d.h * d.w;
+  const long long cells = (long long)d.B * F * hw;
+  const int L1 = 1 + d.t * hw, PD = d.dt * d.dc;
+  float acc = 0.f;
+  for (long long cell = (long long)blockIdx.x * ROW_WARPS + warp; cell < cells; cell += (long long)gridDim.x * ROW_WARPS) {
+    const float m = mask[cell];
+    if (m == 0.f) continue;
+    const int p = (int)(cell % hw);
+    const int f = (int)((cell / hw) % F);
+    const int b = (int)(cell / ((long long)hw * F));
+    const float* pr = pred + ((long long)b * L1 + 1 + (long long)(f / d.dt) * hw + p) * PD + (f % d.dt) * d.dc;
+    const float* tg = target + cell * d.dc;
+    float s = 0.f;
+    for (int c = lane; c < d.dc; c += 32) {
+      const float e = pr[c] - tg[c];
+      s = fmaf(e, e, s);
+    }
+    acc += m * s / (float)d.dc;
+  }
+  acc = warp_sum(acc);
+  __shared__ float sh[ROW_WARPS];
+  if (lane == 0) sh[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f;
+    for (int i = 0; i < ROW_WARPS; ++i) a += sh[i];
+    float4* o = reinterpret_cast<float4*>(partials) + blockIdx.x;
+    *o = make_float4(a, 0.f, 0.f, 0.f);
+  }
+}
+
+__global__ void mse_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ target,
+                               const float* __restrict__ mask, const float* __restrict__ coef,
+                               __nv_bfloat16* __restrict__ dpred, MseDims d) {
+  const int hw = d.h * d.w, F = d.t * d.dt;
+  const int L1 = 1 + d.t * hw, PD = d.dt * d.dc;
+  const long long n = (long long)d.B * L1 * PD;
+  const float cf = coef[0];
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(e % PD);
+    const int l1 = (int)((e / PD) % L1);
+    const int b = (int)(e / ((long long)PD * L1));
+    float g = 0.f;
+    if (l1 > 0) {
+      const int l = l1 - 1;
+      const int tt = l / hw, p = l % hw;
+      const int f = tt * d.dt + j / d.dc, c = j % d.dc;
+      const long long cell = ((long long)b * F + f) * hw + p;
+      const float m = mask[cell];
+      if (m != 0.f) g = cf * m * (pred[e] - target[cell * d.dc + c]);
+    }
+    dpred[e] = __float2bfloat16_rn(g);
+  }
+}
+
+}  // namespace vt
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+using namespace vt;
+
+int vt::layernorm_fwd_small(const vt_ln_fwd_params* p, void* stream) {
+  VT_REQUIRE(p->D % 32 == 0 && p->D >= 32 && p->D <= 256, "vt_layernorm_fwd: D=%d unsupported", p->D);
+  VT_REQUIRE(p->in_row == nullptr, "vt_layernorm_fwd: row maps need D %% 128 == 0 (D=%d)", p->D);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int blocks = row_blocks(p->rows, 4);
+#define VT_CASE(E)                                                                                                    \
+  case E:                                                                                                             \
+    ln_small_fwd_kernel<E><<<blocks, ROW_WARPS * 32, 0, st>>>(p->x, p->ldx, p->gamma, p->beta, p->y, p->mean, p->rstd, \
+                                                              p->rows, p->eps, p->y_fp32);                            \
+    break;
+  switch (p->D / 32) { VT_CASE(1) VT_CASE(2) VT_CASE(3) VT_CASE(4) VT_CASE(5) VT_CASE(6) VT_CASE(7) VT_CASE(8) }
+#undef VT_CASE
+  return check_launch("ln_small_fwd_kernel");
+}
+
+int vt::layernorm_bwd_small(const vt_ln_bwd_params* p, void* stream) {
+  VT_REQUIRE(p->D % 32 == 0 && p->D >= 32 && p->D <= 256, "vt_layernorm_bwd: D=%d unsupported", p->D);
+  VT_REQUIRE(p->in_row == nullptr && p->out_row == nullptr && p->dx_aux == nullptr,
+             "vt_layernorm_bwd: row maps need D %% 128 == 0 (D=%d)", p->D);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int blocks = vt_ln_bwd_blocks(p->rows);   // the caller sized `partials` with this
+#define VT_CASE(E)                                                                                                     \
+  case E:                                                                                                              \
+    ln_small_bwd_kernel<E><<<blocks, ROW_WARPS * 32, 0, st>>>(p->dy, p->dy_fp32, p->x, p->ldx, p->mean, p->rstd,       \
+                                                              p->gamma, p->dres, p->dx, p->lddx, p->partials, p->rows); \
+    break;
+  switch (p->D / 32) { VT_CASE(1) VT_CASE(2) VT_CASE(3) VT_CASE(4) VT_CASE(5) VT_CASE(6) VT_CASE(7) VT_CASE(8) }
+#undef VT_CASE
+  return check_launch("ln_small_bwd_kernel");
+}
+
+static int pool_dims_ok(int T, int Hin, int Win, int st, int sh, int sw, int To, int Ho, int Wo) {
+  return st >= 1 && sh >= 1 && sw >= 1 && To == (T + 2 - 3) / st + 1 && Ho == (Hin + 2 - 3) / sh + 1 && Wo == (Win + 2 - 3) / sw + 1;
+}
+
+extern "C" int vt_pool_fwd(const vt_pool_fwd_params* p, void* stream) {
+  VT_REQUIRE(p && p->in && p->w && p->gamma && p->beta && p->pooled && p->out && p->mean && p->rstd, "vt_pool_fwd: null pointer");
+  VT_REQUIRE(p->hd == 96, "vt_pool_fwd: head dim %d unsupported (96 only)", p->hd);
+  VT_REQUIRE(p->B > 0 && p->H > 0 && p->T > 0 && p->Hin > 0 && p->Win > 0, "vt_pool_fwd: bad dims");
+  VT_REQUIRE(pool_dims_ok(p->T, p->Hin, p->Win, p->st, p->sh, p->sw, p->To, p->Ho, p->Wo), "vt_pool_fwd: output dims inconsistent");
+  const PoolDims d{p->B, p->H, p->T, p->Hin, p->Win, p->st, p->sh, p->sw, p->To, p->Ho, p->Wo};
+  const long long rows = (long long)p->B * p->H * (1 + (long long)p->To * p->Ho * p->Wo);
+  pool_ln_fwd_kernel<3><<<row_blocks(rows, 8), ROW_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(p->in), p->in_bs, p->in_rs, p->w, p->gamma, p->beta, p->pooled,
+      static_cast<__nv_bfloat16*>(p->out), p->mean, p->rstd, d, p->eps);
+  return check_launch("pool_ln_fwd_kernel");
+}
+
+static int pool_dw_blocks(long long rows) { return row_blocks(rows, 2); }
+
+extern "C" int vt_pool_bwd_scratch(int32_t rows_out, int32_t hd) {
+  // dpooled [rows_out, hd] + LN partials [blocks, 2, hd] + filter partials [blocks, 27*hd]
+  const long long f = (long long)rows_out * hd + (long long)vt_ln_bwd_blocks(rows_out) * 2 * hd +
+                      (long long)pool_dw_blocks(rows_out) * 27 * hd;
+  return f > 0x7fffffffll ? -1 : (int)f;
+}
+
+extern "C" int vt_pool_bwd(const vt_pool_bwd_params* p, void* stream) {
+  VT_REQUIRE(p && p->dout && p->pooled && p->mean && p->rstd && p->gamma && p->in && p->w && p->din && p->dw && p->dgamma &&
+                 p->dbeta && p->scratch, "vt_pool_bwd: null pointer");
+  VT_REQUIRE(p->hd == 96, "vt_pool_bwd: head dim %d unsupported (96 only)", p->hd);
+  VT_REQUIRE(pool_dims_ok(p->T, p->Hin, p->Win, p->st, p->sh, p->sw, p->To, p->Ho, p->Wo), "vt_pool_bwd: output dims inconsistent");
+  const long long Lo = (long long)p->To * p->Ho * p->Wo;
+  const long long rows_out = (long long)p->B * p->H * (1 + Lo);
+  VT_REQUIRE(rows_out < 0x7fffffffll, "vt_pool_bwd: too many rows");
+  const int need = vt_pool_bwd_scratch((int)rows_out, p->hd);
+  VT_REQUIRE(need > 0 && p->scratch_floats >= need, "vt_pool_bwd: scratch too small (%lld < %d floats)", (long long)p->scratch_floats, need);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int hd = p->hd;
+  float* dpooled = p->scratch;
+  float* ln_part = dpooled + rows_out * hd;
+  const int ln_blocks_n = vt_ln_bwd_blocks((int)rows_out);
+  float* dw_part = ln_part + (long long)ln_blocks_n * 2 * hd;
+  const PoolDims d{p->B, p->H, p->T, p->Hin, p->Win, p->st, p->sh, p->sw, p->To, p->Ho, p->Wo};
+  // 1. LayerNorm backward over every pooled row (cls included) -> dpooled, dgamma/dbeta partials
+  ln_small_bwd_kernel<3><<<ln_blocks_n, ROW_WARPS * 32, 0, st>>>(p->dout, p->dout_fp32, p->pooled, hd, p->mean, p->rstd, p->gamma,
+                                                                 nullptr, dpooled, hd, ln_part, (int)rows_out);
+  int rc = check_launch("ln_small_bwd_kernel(pool)");
+  if (rc) return rc;
+  {
+    // dgamma and dbeta live in two separate buffers: reduce each half of the [blocks, 2, hd] partials
+    vt_reduce_params r{ln_part, p->dgamma, 2ll * hd, ln_blocks_n, hd, 0, 1.0f};
+    rc = vt_reduce_rows(&r, stream);
+    if (rc) return rc;
+    vt_reduce_params r2{ln_part + hd, p->dbeta, 2ll * hd, ln_blocks_n, hd, 0, 1.0f};
+    rc = vt_reduce_rows(&r2, stream);
+    if (rc) return rc;
+  }
+  // 2. gradient w.r.t. the input tokens
+  const long long rows_in = (long long)p->B * p->H * (1 + (long long)p->T * p->Hin * p->Win);
+  pool_din_kernel<3><<<row_blocks(rows_in, 8), ROW_WARPS * 32, 0, st>>>(dpooled, p->w, static_cast<__nv_bfloat16*>(p->din),
+                                                                        p->din_bs, p->din_rs, d);
+  rc = check_launch("pool_din_kernel");
+  if (rc) return rc;
+  // 3. filter gradient
+  const int dwb = pool_dw_blocks(rows_out);
+  pool_dw_kernel<3><<<dwb, ROW_WARPS * 32, 0, st>>>(dpooled, static_cast<const __nv_bfloat16*>(p->in), p->in_bs, p->in_rs, dw_part, d);
+  rc = check_launch("pool_dw_kernel");
+  if (rc) return rc;
+  vt_reduce_params r3{dw_part, p->dw, 27ll * hd, dwb, 27ll * hd, 0, 1.0f};
+  return vt_reduce_rows(&r3, stream);
+}
+
+static int xa_strides_ok(const long long* s, int n) {
+  for (int i = 0; i < n; ++i)
+    if (s[i] % 2 != 0) return 0;
+  return 1;
+}
+
+extern "C" int vt_xattn_fwd(const vt_xattn_fwd_params* p, void* stream) {
+  VT_REQUIRE(p && p->q && p->k && p->v && p->o && p->lse, "vt_xattn_fwd: null pointer");
+  VT_REQUIRE(p->hd == 96, "vt_xattn_fwd: head dim %d unsupported (96 only)", p->hd);
+  VT_REQUIRE(p->B > 0 && p->H > 0 && p->Nq > 0 && p->Nk > 0 && (long long)p->B * p->H <= 65535, "vt_xattn_fwd: bad dims");
+  const long long ss[12] = {p->q_bs, p->q_hs, p->q_rs, p->k_bs, p->k_hs, p->k_rs, p->v_bs, p->v_hs, p->v_rs, p->o_bs, p->o_hs, p->o_rs};
+  VT_REQUIRE(xa_strides_ok(ss, 12), "vt_xattn_fwd: strides must be even (4-byte aligned bf16 pairs)");
+  VT_REQUIRE(((uintptr_t)p->q | (uintptr_t)p->k | (uintptr_t)p->v | (uintptr_t)p->o) % 4 == 0, "vt_xattn_fwd: pointers must be 4-byte aligned");
+  const XaStrides s{p->q_bs, p->q_hs, p->q_rs, p->k_bs, p->k_hs, p->k_rs, p->v_bs, p->v_hs, p->v_rs, p->o_bs, p->o_hs, p->o_rs, 0, 0, 0};
+  dim3 grid((p->Nq + XA_QPB - 1) / XA_QPB, p->B * p->H);
+  xattn_fwd_kernel<96><<<grid, 2 * XA_QPB, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(p->q), static_cast<const __nv_bfloat16*>(p->k), static_cast<const __nv_bfloat16*>(p->v),
+      static_cast<__nv_bfloat16*>(p->o), p->lse, s, p->H, p->Nq, p->Nk, p->scale);
+  return check_launch("xattn_fwd_kernel");
+}
+
+extern "C" int vt_xattn_bwd(const vt_xattn_bwd_params* p, void* stream) {
+  VT_REQUIRE(p && p->q && p->k && p->v && p->o && p->dout && p->lse && p->delta && p->dq && p->dk && p->dv, "vt_xattn_bwd: null pointer");
+  VT_REQUIRE(p->hd == 96, "vt_xattn_bwd: head dim %d unsupported (96 only)", p->hd);
+  VT_REQUIRE(p->B > 0 && p->H > 0 && p->Nq > 0 && p->Nk > 0 && (long long)p->B * p->H <= 65535, "vt_xattn_bwd: bad dims");
+  const long long ss[15] = {p->q_bs, p->q_hs, p->q_rs, p->k_bs, p->k_hs, p->k_rs, p->v_bs, p->v_hs, p->v_rs, p->o_bs, p->o_hs, p->o_rs,
+                            p->dq_bs, p->dq_hs, p->dq_rs};
+  VT_REQUIRE(xa_strides_ok(ss, 15), "vt_xattn_bwd: strides must be even");
+  VT_REQUIRE(((uintptr_t)p->q | (uintptr_t)p->k | (uintptr_t)p->v | (uintptr_t)p->o | (uintptr_t)p->dout | (uintptr_t)p->dq) % 4 == 0,
+             "vt_xattn_bwd: pointers must be 4-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const XaStrides s{p->q_bs, p->q_hs, p->q_rs, p->k_bs, p->k_hs, p->k_rs, p->v_bs, p->v_hs, p->v_rs, p->o_bs, p->o_hs, p->o_rs,
+                    p->dq_bs, p->dq_hs, p->dq_rs};
+  const size_t kv_bytes = (size_t)p->B * p->H * p->Nk * p->hd * sizeof(float);
+  cudaError_t e = cudaMemsetAsync(p->dk, 0, kv_bytes, st);
+  VT_REQUIRE(e == cudaSuccess, "vt_xattn_bwd: memset dk: %s", cudaGetErrorString(e));
+  e = cudaMemsetAsync(p->dv, 0, kv_bytes, st);
+  VT_REQUIRE(e == cudaSuccess, "vt_xattn_bwd: memset dv: %s", cudaGetErrorString(e));
+  dim3 gq((p->Nq + XA_QPB - 1) / XA_QPB, p->B * p->H);
+  xattn_dq_kernel<96><<<gq, 2 * XA_QPB, 0, st>>>(
+      static_cast<const __nv_bfloat16*>(p->q), static_cast<const __nv_bfloat16*>(p->k), static_cast<const __nv_bfloat16*>(p->v),
+      static_cast<const __nv_bfloat16*>(p->o), static_cast<const __nv_bfloat16*>(p->dout), p->lse, p->delta,
+      static_cast<__nv_bfloat16*>(p->dq), s, p->H, p->Nq, p->Nk, p->scale);
+  int rc = check_launch("xattn_dq_kernel");
+  if (rc) return rc;
+  const int qchunks = (p->Nq + XA_QCHUNK - 1) / XA_QCHUNK;
+  VT_REQUIRE(qchunks <= 65535, "vt_xattn_bwd: Nq too large");
+  dim3 gk((p->Nk + XA_KPB - 1) / XA_KPB, qchunks, p->B * p->H);
+  xattn_dkv_kernel<96><<<gk, 4 * XA_KPB, 0, st>>>(
+      static_cast<const __nv_bfloat16*>(p->q), static_cast<const __nv_bfloat16*>(p->k), static_cast<const __nv_bfloat16*>(p->v),
+      static_cast<const __nv_bfloat16*>(p->dout), p->lse, p->delta, p->dk, p->dv, s, p->H, p->Nq, p->Nk, p->scale);
+  return check_launch("xattn_dkv_kernel");
+}
+
+static int mp_dims_ok(const MpDims& d) {
+  return d.kt >= 1 && d.kh >= 1 && d.kw >= 1 && d.kt * d.kh * d.kw < 255 && d.st >= 1 && d.sh >= 1 && d.sw >= 1 &&
+         d.To == (d.T + 2 * (d.kt / 2) - d.kt) / d.st + 1 && d.Ho == (d.H + 2 * (d.kh / 2) - d.kh) / d.sh + 1 &&
+         d.Wo == (d.W + 2 * (d.kw / 2) - d.kw) / d.sw + 1;
+}
+
+extern "C" int vt_maxpool_fwd(const vt_maxpool_fwd_params* p, void* stream) {
+  VT_REQUIRE(p && p->x && p->y && p->idx && p->B > 0 && p->D > 0, "vt_maxpool_fwd: bad params");
+  const MpDims d{p->B, p->D, p->T, p->H, p->W, p->kt, p->kh, p->kw, p->st, p->sh, p->sw, p->To, p->Ho, p->Wo};
+  VT_REQUIRE(mp_dims_ok(d), "vt_maxpool_fwd: inconsistent geometry");
+  const long long n = (long long)p->B * (1 + (long long)p->To * p->Ho * p->Wo) * p->D;
+  maxpool_fwd_kernel<<<flat_blocks(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p->x, p->y, p->idx, d);
+  return check_launch("maxpool_fwd_kernel");
+}
+
+extern "C" int vt_maxpool_bwd(const vt_maxpool_bwd_params* p, void* stream) {
+  VT_REQUIRE(p && p->dy && p->idx && p->dx && p->B > 0 && p->D > 0, "vt_maxpool_bwd: bad params");
+  const MpDims d{p->B, p->D, p->T, p->H, p->W, p->kt, p->kh, p->kw, p->st, p->sh, p->sw, p->To, p->Ho, p->Wo};
+  VT_REQUIRE(mp_dims_ok(d), "vt_maxpool_bwd: inconsistent geometry");
+  const long long n = (long long)p->B * (1 + (long long)p->T * p->H * p->W) * p->D;
+  maxpool_bwd_kernel<<<flat_blocks(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p->dy, p->idx, p->dx, d);
+  return check_launch("maxpool_bwd_kernel");
+}
+
+extern "C" int vt_im2col3d_bf16(const vt_im2col3d_params* p, void* stream) {
+  VT_REQUIRE(p && p->x && p->cols, "vt_im2col3d_bf16: null pointer");
+  VT_REQUIRE(p->To == (p->T + 2 * p->pt - p->kt) / p->st + 1 && p->Ho == (p->H + 2 * p->ph - p->kh) / p->sh + 1 &&
+                 p->Wo == (p->W + 2 * p->pw - p->kw) / p->sw + 1, "vt_im2col3d_bf16: output dims inconsistent");
+  VT_REQUIRE(p->Kpad >= p->C * p->kt * p->kh * p->kw && p->Kpad % 8 == 0, "vt_im2col3d_bf16: Kpad must cover C*kt*kh*kw and be a multiple of 8");
+  const I3Dims d{p->B, p->T, p->C, p->H, p->W, p->kt, p->kh, p->kw, p->st, p->sh, p->sw, p->pt, p->ph, p->pw, p->To, p->Ho, p->Wo, p->Kpad};
+  const long long n = (long long)p->B * p->To * p->Ho * p->Wo * p->Kpad;
+  im2col3d_kernel<<<flat_blocks(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p->x, static_cast<__nv_bfloat16*>(p->cols), d);
+  return check_launch("im2col3d_kernel");
+}
+
+extern "C" int vt_mvit_tokens_fwd(const vt_mvit_tokens_fwd_params* p, void* stream) {
+  VT_REQUIRE(p && p->t && p->mask_token && p->cls_token && p->pos_s && p->pos_t && p->pos_cls && p->x, "vt_mvit_tokens_fwd: null pointer");
+  VT_REQUIRE(p->B > 0 && p->T > 0 && p->HW > 0 && p->C > 0, "vt_mvit_tokens_fwd: bad dims");
+  const long long n = (long long)p->B * (1 + (long long)p->T * p->HW) * p->C;
+  mvit_tokens_fwd_kernel<<<flat_blocks(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      p->t, p->wmask, p->mask_token, p->cls_token, p->pos_s, p->pos_t, p->pos_cls, p->x, p->B, p->T, p->HW, p->C);
+  return check_launch("mvit_tokens_fwd_kernel");
+}
+
+extern "C" int vt_mvit_tokens_bwd(const vt_mvit_tokens_bwd_params* p, void* stream) {
+  VT_REQUIRE(p && p->dx && p->dt && p->B > 0 && p->T > 0 && p->HW > 0 && p->C > 0, "vt_mvit_tokens_bwd: bad params");
+  const long long n = (long long)p->B * p->T * p->HW * p->C;
+  mvit_tokens_bwd_kernel<<<flat_blocks(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      p->dx, p->wmask, static_cast<__nv_bfloat16*>(p->dt), p->B, p->T * p->HW, p->C);
+  return check_launch("mvit_tokens_bwd_kernel");
+}
+
+extern "C" int vt_mse_blocks(int32_t cells) { return row_blocks(cells, 2); }
+
+extern "C" int vt_mse_fwd(const vt_mse_fwd_params* p, void* stream) {
+  VT_REQUIRE(p && p->pred && p->target && p->mask && p->num && p->partials, "vt_mse_fwd: null pointer");
+  VT_REQUIRE(p->B > 0 && p->t > 0 && p->dt > 0 && p->h > 0 && p->w > 0 && p->dc > 0, "vt_mse_fwd: bad dims");
+  VT_REQUIRE(((uintptr_t)p->partials & 15) == 0 && ((uintptr_t)p->num & 15) == 0, "vt_mse_fwd: partials/num must be 16-byte aligned");
+  const MseDims d{p->B, p->t, p->dt, p->h, p->w, p->dc};
+  const long long cells = (long long)p->B * p->t * p->dt * p->h * p->w;
+  VT_REQUIRE(cells < 0x7fffffffll, "vt_mse_fwd: too many cells");
+  const int blocks = vt_mse_blocks((int)cells);
+  mse_fwd_kernel<<<blocks, ROW_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(p->pred, p->target, p->mask, p->partials, d);
+  int rc = check_launch("mse_fwd_kernel");
+  if (rc) return rc;
+  vt_reduce_params r{p->partials, p->num, 4, blocks, 4, 0, 1.0f};    // num[0] = sum, num[1..3] = 0
+  return vt_reduce_rows(&r, stream);
+}
+
+extern "C" int vt_mse_bwd(const vt_mse_bwd_params* p, void* stream) {
+  VT_REQUIRE(p && p->pred && p->target && p->mask && p->coef && p->dpred, "vt_mse_bwd: null pointer");
+  VT_REQUIRE(p->B > 0 && p->t > 0 && p->dt > 0 && p->h > 0 && p->w > 0 && p->dc > 0, "vt_mse_bwd: bad dims");
+  const MseDims d{p->B, p->t, p->dt, p->h, p->w, p->dc};
+  const long long n = (long long)p->B * (1 + (long long)p->t * p->h * p->w) * p->dt * p->dc;
+  mse_bwd_kernel<<<flat_blocks(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p->pred, p->target, p->mask, p->coef,
+                                                                                     static_cast<__nv_bfloat16*>(p->dpred), d);
+  return check_launch("mse_bwd_kernel");
+}
