@@ -182,3 +182,143 @@ class EmuKernels:
         Tp, Hp, Wp = T // tube, H // ph, W // pw
         xx = self._up(cols).reshape(B, Tp, Hp, Wp, C, tube, ph, pw).permute(0, 1, 5, 4, 2, 6, 3, 7)
         return xx.reshape(shape).to(self.f)
+
+    # ------------------------------------------------------------------------------------------
+    # MViT / MaskFeat kernels (include/vt_b200.h, second half)
+    # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def pool_out_thw(thw, stride):
+        return tuple((n + 2 - 3) // s + 1 for n, s in zip(thw, stride))
+
+    @staticmethod
+    def maxpool_out_thw(thw, kernel, stride):
+        return tuple((n + 2 * (k // 2) - k) // s + 1 for n, k, s in zip(thw, kernel, stride))
+
+    def _pool_core(self, x, H, hd, thw, stride, w, gamma, beta, eps):
+        """x: [B, N, H*hd] (float) -> (normalised [B,H,1+Lo,hd], pooled, mean, rstd)"""
+        import torch.nn.functional as F
+        B, N1, _ = x.shape
+        T, Hin, Win = thw
+        t = x.reshape(B, N1, H, hd).permute(0, 2, 1, 3)
+        cls, body = t[:, :, :1], t[:, :, 1:]
+        vol = body.reshape(B * H, T, Hin, Win, hd).permute(0, 4, 1, 2, 3)
+        pv = F.conv3d(vol, w.reshape(hd, 1, 3, 3, 3), None, stride=tuple(stride), padding=1, groups=hd)
+        pooled = torch.cat([cls, pv.reshape(B, H, hd, -1).transpose(2, 3)], dim=2)
+        mu = pooled.mean(-1, keepdim=True)
+        var = ((pooled - mu) ** 2).mean(-1, keepdim=True)
+        rstd = torch.rsqrt(var + eps)
+        out = (pooled - mu) * rstd * gamma + beta
+        return out, pooled, mu, rstd
+
+    def pool_fwd(self, src, H, hd, thw, stride, w, gamma, beta, eps):
+        out, pooled, mu, rstd = self._pool_core(self._up(src), H, hd, thw, stride, self._up(w), self._up(gamma),
+                                                self._up(beta), eps)
+        return self._h(out), pooled.to(self.f), mu.reshape(-1).to(self.f), rstd.reshape(-1).to(self.f), \
+            self.pool_out_thw(thw, stride)
+
+    def pool_bwd(self, dout, pooled, mean, rstd, gamma, src, w, din, H, hd, thw, stride):
+        shp = pooled.shape[:-1] + (1,)
+        xh = (self._up(pooled) - self._up(mean).reshape(shp)) * self._up(rstd).reshape(shp)
+        d = self._up(dout)
+        g = d * self._up(gamma)
+        m1 = g.mean(-1, keepdim=True)
+        m2 = (g * xh).mean(-1, keepdim=True)
+        dpooled = self._up(rstd).reshape(shp) * (g - m1 - xh * m2)            # LayerNorm backward, closed form
+        with torch.enable_grad():                                              # conv adjoint by autograd
+            xs = self._up(src).detach().clone().requires_grad_(True)
+            ws = self._up(w).detach().clone().requires_grad_(True)
+            one, zero = torch.ones(hd, dtype=self.f), torch.zeros(hd, dtype=self.f)
+            pooled_r = self._pool_core(xs, H, hd, thw, stride, ws, one, zero, 0.0)[1]
+            gx, gw = torch.autograd.grad(pooled_r, (xs, ws), dpooled)
+        din.copy_(self._h(gx).to(din.dtype))
+        return gw.reshape(hd, 27).to(self.f), (d * xh).sum((0, 1, 2)).to(self.f), d.sum((0, 1, 2)).to(self.f)
+
+    def xattn_fwd(self, q, k, v, scale):
+        Q, Kk, V = self._up(q), self._up(k), self._up(v)
+        B, H, Nq, hd = Q.shape
+        s = (Q @ Kk.transpose(-1, -2)) * scale
+        lse = torch.logsumexp(s, dim=-1)
+        p = torch.exp(s - lse[..., None])
+        o = (p @ V).transpose(1, 2).reshape(B, Nq, H * hd)
+        return self._h(o), lse.to(self.f)
+
+    def xattn_bwd(self, q, k, v, o, dout, lse, scale, dq):
+        Q, Kk, V = self._up(q), self._up(k), self._up(v)
+        B, H, Nq, hd = Q.shape
+        O = self._up(o).reshape(B, Nq, H, hd).transpose(1, 2)
+        dO = self._up(dout).reshape(B, Nq, H, hd).transpose(1, 2)
+        s = (Q @ Kk.transpose(-1, -2)) * scale
+        p = torch.exp(s - self._up(lse)[..., None])
+        dV = p.transpose(-1, -2) @ dO
+        dP = dO @ V.transpose(-1, -2)
+        delta = (dO * O).sum(-1, keepdim=True)
+        dS = p * (dP - delta) * scale
+        dq.copy_(self._h(dS @ Kk).to(dq.dtype))
+        return (dS.transpose(-1, -2) @ Q).to(self.f), dV.to(self.f)
+
+    def maxpool_fwd(self, x, thw, kernel, stride):
+        import torch.nn.functional as F
+        B, L1, D = x.shape
+        T, H, W = thw
+        xx = self._up(x)
+        vol = xx[:, 1:].reshape(B, T, H, W, D).permute(0, 4, 1, 2, 3)
+        y, idx = F.max_pool3d(vol, tuple(kernel), tuple(stride), tuple(k // 2 for k in kernel), return_indices=True)
+        out_thw = tuple(y.shape[2:])
+        yy = torch.cat([xx[:, :1], y.reshape(B, D, -1).transpose(1, 2)], dim=1)
+        return yy.to(self.f), idx.reshape(B, D, -1), out_thw        # idx is opaque to the host logic
+
+    def maxpool_bwd(self, dy, idx, thw, kernel, stride):
+        B, Lo1, D = dy.shape
+        T, H, W = thw
+        d = self._up(dy)
+        vol = torch.zeros((B, D, T * H * W), dtype=d.dtype)
+        vol.scatter_add_(2, idx, d[:, 1:].transpose(1, 2))
+        return torch.cat([d[:, :1], vol.transpose(1, 2)], dim=1).to(self.f)
+
+    def im2col3d(self, x, kernel, stride, padding, kpad):
+        import torch.nn.functional as F
+        B, T, C, H, W = x.shape
+        xp = F.pad(self._up(x).permute(0, 2, 1, 3, 4), (padding[2], padding[2], padding[1], padding[1], padding[0], padding[0]))
+        u = xp.unfold(2, kernel[0], stride[0]).unfold(3, kernel[1], stride[1]).unfold(4, kernel[2], stride[2])
+        To, Ho, Wo = u.shape[2:5]
+        cols = u.permute(0, 2, 3, 4, 1, 5, 6, 7).reshape(B * To * Ho * Wo, -1)
+        cols = F.pad(cols, (0, kpad - cols.shape[1]))
+        return self._h(cols), (To, Ho, Wo)
+
+    def mvit_tokens_fwd(self, t, wmask, mask_token, cls_token, pos_s, pos_t, pos_cls, B, T, HW):
+        C = t.shape[1]
+        tt = self._up(t).reshape(B, T * HW, C)
+        if wmask is not None:
+            w = self._up(wmask).reshape(B, T * HW, 1)
+            tt = tt * (1 - w) + self._up(mask_token).reshape(1, 1, C) * w
+        pos = self._up(pos_s).reshape(1, HW, C).repeat(1, T, 1) + \
+            torch.repeat_interleave(self._up(pos_t).reshape(1, T, C), HW, dim=1)
+        cls = (self._up(cls_token).reshape(1, 1, C) + self._up(pos_cls).reshape(1, 1, C)).expand(B, 1, C)
+        return torch.cat([cls, tt + pos], dim=1).to(self.f)
+
+    def mvit_tokens_bwd(self, dx, wmask, B, T, HW):
+        d = self._up(dx)[:, 1:]
+        if wmask is not None:
+            d = d * (1 - self._up(wmask).reshape(B, T * HW, 1))
+        return self._h(d.reshape(B * T * HW, -1))
+
+    def _mse_pred(self, pred, dims):
+        B, t, dt, h, w, dc = dims
+        p = self._up(pred).reshape(B, 1 + t * h * w, dt * dc)[:, 1:]
+        return p.reshape(B, t, h, w, dt, dc).permute(0, 1, 4, 2, 3, 5).reshape(B, t * dt, h, w, dc)
+
+    def mse_fwd(self, pred, target, mask, dims):
+        B, t, dt, h, w, dc = dims
+        p = self._mse_pred(pred, dims)
+        e = ((p - self._up(target).reshape(p.shape)) ** 2).mean(-1) * self._up(mask).reshape(B, t * dt, h, w)
+        num = torch.zeros(4, dtype=self.f)
+        num[0] = e.sum()
+        return num
+
+    def mse_bwd(self, pred, target, mask, coef, dims):
+        B, t, dt, h, w, dc = dims
+        p = self._mse_pred(pred, dims)
+        g = self._up(coef)[0] * self._up(mask).reshape(B, t * dt, h, w, 1) * (p - self._up(target).reshape(p.shape))
+        g = g.reshape(B, t, dt, h, w, dc).permute(0, 1, 3, 4, 2, 5).reshape(B, t * h * w, dt * dc)
+        g = torch.cat([torch.zeros((B, 1, dt * dc), dtype=g.dtype), g], dim=1)
+        return self._h(g.reshape(B * (1 + t * h * w), dt * dc))

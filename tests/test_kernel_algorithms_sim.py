@@ -1,0 +1,413 @@
+"""CPU walk-through of the index arithmetic and tiling of the MViT CUDA kernels (csrc/vt_mvit.cu).
+
+There is no GPU in the build container, so the kernels' *algorithms* — row decoding, gather conditions of the adjoint
+kernels, tile masking, log2-domain softmax bookkeeping — are transcribed loop-for-loop into numpy here and compared
+with the contract emulation (tests/emu_kernels.py, itself checked against the reference goldens).  This does not
+execute device code; the -m gpu tests do.  It exists to catch index/formula mistakes before spending GPU time.
+"""
+import numpy as np
+import pytest
+import torch
+
+from tests.emu_kernels import EmuKernels
+
+HD = 96
+LOG2E = 1.4426950408889634
+LN2 = 0.6931471805599453
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30))
+
+
+def out_dims(thw, stride):
+    return tuple((n + 2 - 3) // s + 1 for n, s in zip(thw, stride))
+
+
+# ---- pool_ln_fwd_kernel / pool_din_kernel / pool_dw_kernel ------------------------------------------
+def sim_pool_fwd(inp, in_bs, in_rs, w, B, H, thw, stride):
+    T, Hin, Win = thw
+    st, sh, sw = stride
+    To, Ho, Wo = out_dims(thw, stride)
+    Lo1 = 1 + To * Ho * Wo
+    pooled = np.zeros((B * H * Lo1, HD))
+    for r in range(B * H * Lo1):
+        l = r % Lo1
+        bh = r // Lo1
+        h, b = bh % H, bh // H
+        base = b * in_bs + h * HD
+        if l == 0:
+            pooled[r] = inp[base:base + HD]
+            continue
+        o = l - 1
+        ow, oh, ot = o % Wo, (o // Wo) % Ho, o // (Wo * Ho)
+        acc = np.zeros(HD)
+        for dt in range(3):
+            ti = ot * st - 1 + dt
+            if ti < 0 or ti >= T:
+                continue
+            for dh in range(3):
+                hi = oh * sh - 1 + dh
+                if hi < 0 or hi >= Hin:
+                    continue
+                for dw in range(3):
+                    wi = ow * sw - 1 + dw
+                    if wi < 0 or wi >= Win:
+                        continue
+                    n = 1 + (ti * Hin + hi) * Win + wi
+                    acc += inp[base + n * in_rs: base + n * in_rs + HD] * w[:, (dt * 3 + dh) * 3 + dw]
+        pooled[r] = acc
+    return pooled.reshape(B, H, Lo1, HD)
+
+
+def sim_pool_din(dpooled, w, B, H, thw, stride):
+    T, Hin, Win = thw
+    st, sh, sw = stride
+    To, Ho, Wo = out_dims(thw, stride)
+    L1, Lo1 = 1 + T * Hin * Win, 1 + To * Ho * Wo
+    din = np.zeros((B, L1, H, HD))
+    dp = dpooled.reshape(B * H, Lo1, HD)
+    for r in range(B * L1 * H):
+        h = r % H
+        n = (r // H) % L1
+        b = r // (H * L1)
+        g = dp[b * H + h]
+        if n == 0:
+            din[b, n, h] = g[0]
+            continue
+        idx = n - 1
+        wi, hi, ti = idx % Win, (idx // Win) % Hin, idx // (Win * Hin)
+        acc = np.zeros(HD)
+        for dt in range(3):
+            nt = ti + 1 - dt
+            if nt < 0 or nt % st != 0:
+                continue
+            ot = nt // st
+            if ot >= To:
+                continue
+            for dh in range(3):
+                nh = hi + 1 - dh
+                if nh < 0 or nh % sh != 0:
+                    continue
+                oh = nh // sh
+                if oh >= Ho:
+                    continue
+                for dw in range(3):
+                    nw = wi + 1 - dw
+                    if nw < 0 or nw % sw != 0:
+                        continue
+                    ow = nw // sw
+                    if ow >= Wo:
+                        continue
+                    acc += g[1 + (ot * Ho + oh) * Wo + ow] * w[:, (dt * 3 + dh) * 3 + dw]
+        din[b, n, h] = acc
+    return din.reshape(B, L1, H * HD)
+
+
+def sim_pool_dw(dpooled, inp, in_bs, in_rs, B, H, thw, stride):
+    T, Hin, Win = thw
+    st, sh, sw = stride
+    To, Ho, Wo = out_dims(thw, stride)
+    Lo = To * Ho * Wo
+    acc = np.zeros((27, HD))
+    dp = dpooled.reshape(B * H, Lo + 1, HD)
+    for r in range(B * H * Lo):
+        o = r % Lo
+        bh = r // Lo
+        h, b = bh % H, bh // H
+        ow, oh, ot = o % Wo, (o // Wo) % Ho, o // (Wo * Ho)
+        g = dp[b * H + h, 1 + o]
+        base = b * in_bs + h * HD
+        for dt in range(3):
+            ti = ot * st - 1 + dt
+            for dh in range(3):
+                hi = oh * sh - 1 + dh
+                for dw in range(3):
+                    wi = ow * sw - 1 + dw
+                    if 0 <= ti < T and 0 <= hi < Hin and 0 <= wi < Win:
+                        off = base + (1 + (ti * Hin + hi) * Win + wi) * in_rs
+                        acc[(dt * 3 + dh) * 3 + dw] += g * inp[off:off + HD]
+    # red[(c)*27 + t] layout -> [hd, 27]
+    return acc.T.copy()
+
+
+@pytest.mark.parametrize('thw,stride,H', [((2, 4, 4), (1, 2, 2), 2), ((3, 5, 6), (1, 4, 4), 1), ((2, 3, 3), (1, 1, 1), 2),
+                                          ((2, 8, 8), (1, 8, 8), 1)])
+def test_pool_kernels_index_math(thw, stride, H):
+    g = torch.Generator().manual_seed(0)
+    B = 2
+    N1 = 1 + thw[0] * thw[1] * thw[2]
+    d = H * HD
+    emu = EmuKernels(exact=True, dtype=torch.float64)
+    qkv = torch.randn(B * N1, 3 * d, generator=g, dtype=torch.float64)
+    src = qkv.view(B, N1, 3 * d)[:, :, d:2 * d]                   # the k slot
+    w = torch.randn(HD, 27, generator=g, dtype=torch.float64)
+    gamma, beta = torch.randn(HD, generator=g, dtype=torch.float64), torch.randn(HD, generator=g, dtype=torch.float64)
+    out, pooled, mean, rstd, othw = emu.pool_fwd(src, H, HD, thw, stride, w, gamma, beta, 1e-5)
+    assert tuple(othw) == out_dims(thw, stride)
+    flat = qkv.numpy().reshape(-1)
+    off = d                                                      # pointer offset of the slot inside the fused buffer
+    sim = sim_pool_fwd(flat[off:], N1 * 3 * d, 3 * d, w.numpy(), B, H, thw, stride)
+    assert rel(sim, pooled.numpy()) < 1e-12
+    dout = torch.randn(pooled.shape, generator=g, dtype=torch.float64)
+    dqkv = torch.zeros_like(qkv)
+    din = dqkv.view(B, N1, 3 * d)[:, :, d:2 * d]
+    dw, dgamma, dbeta = emu.pool_bwd(dout, pooled, mean, rstd, gamma, src, w, din, H, HD, thw, stride)
+    # LayerNorm backward in closed form (what ln_small_bwd_kernel computes) feeding the two adjoint kernels
+    shp = pooled.shape[:-1] + (1,)
+    xh = (pooled - mean.reshape(shp)) * rstd.reshape(shp)
+    gy = dout * gamma
+    dpooled = rstd.reshape(shp) * (gy - gy.mean(-1, keepdim=True) - xh * (gy * xh).mean(-1, keepdim=True))
+    sim_din = sim_pool_din(dpooled.numpy(), w.numpy(), B, H, thw, stride)
+    assert rel(sim_din, din.numpy()) < 1e-12
+    sim_dw = sim_pool_dw(dpooled.numpy(), flat[off:], N1 * 3 * d, 3 * d, B, H, thw, stride)
+    assert rel(sim_dw, dw.numpy()) < 1e-12
+
+
+# ---- maxpool_fwd_kernel / maxpool_bwd_kernel ---------------------------------------------------------
+def sim_maxpool(x, B, D, thw, kernel, stride):
+    T, H, W = thw
+    kt, kh, kw = kernel
+    st, sh, sw = stride
+    pt, ph, pw = kt // 2, kh // 2, kw // 2
+    To, Ho, Wo = [(n + 2 * (k // 2) - k) // s + 1 for n, k, s in zip(thw, kernel, stride)]
+    Lo1, L1 = 1 + To * Ho * Wo, 1 + T * H * W
+    y = np.zeros((B, Lo1, D))
+    idx = np.zeros((B, Lo1, D), dtype=np.int64)
+    for b in range(B):
+        for l in range(Lo1):
+            if l == 0:
+                y[b, 0] = x[b, 0]
+                continue
+            o = l - 1
+            ow, oh, ot = o % Wo, (o // Wo) % Ho, o // (Wo * Ho)
+            best = np.full(D, -np.inf)
+            arg = np.full(D, 255)
+            for dt in range(kt):
+                ti = ot * st - pt + dt
+                if ti < 0 or ti >= T:
+                    continue
+                for dh in range(kh):
+                    hi = oh * sh - ph + dh
+                    if hi < 0 or hi >= H:
+                        continue
+                    for dw in range(kw):
+                        wi = ow * sw - pw + dw
+                        if wi < 0 or wi >= W:
+                            continue
+                        val = x[b, 1 + (ti * H + hi) * W + wi]
+                        take = (val > best) | (arg == 255)
+                        best = np.where(take, val, best)
+                        arg = np.where(take, (dt * kh + dh) * kw + dw, arg)
+            y[b, l], idx[b, l] = best, arg
+    return y, idx, (To, Ho, Wo)
+
+
+def sim_maxpool_bwd(dy, idx, B, D, thw, kernel, stride, othw):
+    T, H, W = thw
+    kt, kh, kw = kernel
+    st, sh, sw = stride
+    pt, ph, pw = kt // 2, kh // 2, kw // 2
+    To, Ho, Wo = othw
+    L1 = 1 + T * H * W
+    dx = np.zeros((B, L1, D))
+    for b in range(B):
+        for l in range(L1):
+            if l == 0:
+                dx[b, 0] = dy[b, 0]
+                continue
+            i = l - 1
+            wi, hi, ti = i % W, (i // W) % H, i // (W * H)
+            acc = np.zeros(D)
+            for dt in range(kt):
+                nt = ti + pt - dt
+                if nt < 0 or nt % st != 0:
+                    continue
+                ot = nt // st
+                if ot >= To:
+                    continue
+                for dh in range(kh):
+                    nh = hi + ph - dh
+                    if nh < 0 or nh % sh != 0:
+                        continue
+                    oh = nh // sh
+                    if oh >= Ho:
+                        continue
+                    for dw in range(kw):
+                        nw = wi + pw - dw
+                        if nw < 0 or nw % sw != 0:
+                            continue
+                        ow = nw // sw
+                        if ow >= Wo:
+                            continue
+                        at = 1 + (ot * Ho + oh) * Wo + ow
+                        acc += np.where(idx[b, at] == (dt * kh + dh) * kw + dw, dy[b, at], 0.0)
+            dx[b, l] = acc
+    return dx
+
+
+@pytest.mark.parametrize('thw,stride', [((2, 4, 4), (1, 2, 2)), ((3, 5, 7), (1, 2, 2)), ((4, 6, 6), (2, 2, 2))])
+def test_maxpool_kernels_index_math(thw, stride):
+    g = torch.Generator().manual_seed(1)
+    B, D = 2, 5
+    kernel = tuple(s + 1 if s > 1 else s for s in stride)
+    x = torch.randn(B, 1 + thw[0] * thw[1] * thw[2], D, generator=g, dtype=torch.float64)
+    emu = EmuKernels(exact=True, dtype=torch.float64)
+    y, idx_emu, othw = emu.maxpool_fwd(x, thw, kernel, stride)
+    ys, idx, othw_s = sim_maxpool(x.numpy(), B, D, thw, kernel, stride)
+    assert tuple(othw) == tuple(othw_s)
+    assert rel(ys, y.numpy()) == 0.0
+    dy = torch.randn(y.shape, generator=g, dtype=torch.float64)
+    dx = emu.maxpool_bwd(dy, idx_emu, thw, kernel, stride)
+    dxs = sim_maxpool_bwd(dy.numpy(), idx, B, D, thw, kernel, stride, othw_s)
+    assert rel(dxs, dx.numpy()) < 1e-14
+
+
+# ---- im2col3d_kernel -----------------------------------------------------------------------------------
+def test_im2col3d_index_math():
+    g = torch.Generator().manual_seed(2)
+    B, T, C, H, W = 2, 4, 3, 12, 12
+    kernel, stride, padding, kpad = (3, 7, 7), (2, 4, 4), (1, 3, 3), 448
+    x = torch.randn(B, T, C, H, W, generator=g, dtype=torch.float64)
+    emu = EmuKernels(exact=True, dtype=torch.float64)
+    cols, (To, Ho, Wo) = emu.im2col3d(x, kernel, stride, padding, kpad)
+    kt, kh, kw = kernel
+    xs = x.numpy().reshape(-1)
+    sim = np.zeros((B * To * Ho * Wo, kpad))
+    kreal = C * kt * kh * kw
+    for row in range(sim.shape[0]):
+        ow, oh, ot = row % Wo, (row // Wo) % Ho, (row // (Wo * Ho)) % To
+        b = row // (Wo * Ho * To)
+        for col in range(kreal):
+            dw, dh, dt, c = col % kw, (col // kw) % kh, (col // (kw * kh)) % kt, col // (kw * kh * kt)
+            ti, hi, wi = ot * stride[0] - padding[0] + dt, oh * stride[1] - padding[1] + dh, ow * stride[2] - padding[2] + dw
+            if 0 <= ti < T and 0 <= hi < H and 0 <= wi < W:
+                sim[row, col] = xs[(((b * T + ti) * C + c) * H + hi) * W + wi]
+    assert rel(sim, cols.numpy()) == 0.0
+    # and the GEMM against the flattened filter reproduces conv3d on the reference's transposed input
+    w = torch.randn(8, C, kt, kh, kw, generator=g, dtype=torch.float64)
+    ref = torch.nn.functional.conv3d(x.transpose(1, 2), w, None, stride=stride, padding=padding).flatten(2).transpose(1, 2)
+    mine = (cols[:, :kreal] @ w.reshape(8, -1).t()).reshape(B, To * Ho * Wo, 8)
+    assert rel(mine.numpy(), ref.numpy()) < 1e-13
+
+
+# ---- mse kernels ---------------------------------------------------------------------------------------
+def test_mse_index_math():
+    g = torch.Generator().manual_seed(3)
+    dims = (B, t, dt, h, w, dc) = (2, 3, 2, 2, 3, 5)
+    hw, F, L1, PD = h * w, t * dt, 1 + t * h * w, dt * dc
+    pred = torch.randn(B * L1, PD, generator=g, dtype=torch.float64)
+    target = torch.randn(B, F, h, w, dc, generator=g, dtype=torch.float64)
+    mask = (torch.rand(B, F, h, w, generator=g) < 0.5).double()
+    emu = EmuKernels(exact=True, dtype=torch.float64)
+    num = emu.mse_fwd(pred, target, mask, dims)[0].item()
+    p, tg, m = pred.numpy().reshape(-1), target.numpy().reshape(-1), mask.numpy().reshape(-1)
+    acc = 0.0
+    for cell in range(B * F * hw):
+        if m[cell] == 0:
+            continue
+        pp, f, b = cell % hw, (cell // hw) % F, cell // (hw * F)
+        pr = ((b * L1 + 1 + (f // dt) * hw + pp) * PD) + (f % dt) * dc
+        e = p[pr:pr + dc] - tg[cell * dc:(cell + 1) * dc]
+        acc += m[cell] * float((e * e).sum()) / dc
+    assert abs(acc - num) < 1e-12 * max(1.0, abs(num))
+    coef = torch.tensor([0.37], dtype=torch.float64)
+    dp = emu.mse_bwd(pred, target, mask, coef, dims).numpy().reshape(-1)
+    sim = np.zeros(B * L1 * PD)
+    for e in range(sim.size):
+        j, l1, b = e % PD, (e // PD) % L1, e // (PD * L1)
+        if l1 == 0:
+            continue
+        l = l1 - 1
+        tt, pp = l // hw, l % hw
+        f, c = tt * dt + j // dc, j % dc
+        cell = (b * F + f) * hw + pp
+        if m[cell] != 0:
+            sim[e] = 0.37 * m[cell] * (p[e] - tg[cell * dc + c])
+    assert rel(sim, dp) < 1e-14
+
+
+# ---- xattn kernels: tile loop, log2-domain online softmax, masking, scale bookkeeping -------------------
+def sim_xattn_fwd(q, k, v, scale, KT=16):
+    Nq, Nk = q.shape[0], k.shape[0]
+    qr = q * (scale * LOG2E)
+    m = np.full(Nq, -np.inf)
+    l = np.zeros(Nq)
+    acc = np.zeros_like(q)
+    for k0 in range(0, Nk, KT):
+        nk = min(KT, Nk - k0)
+        Ks = np.zeros((KT, HD)); Vs = np.zeros((KT, HD))
+        Ks[:nk], Vs[:nk] = k[k0:k0 + nk], v[k0:k0 + nk]
+        sc = qr @ Ks.T
+        sc[:, nk:] = -np.inf
+        mn = np.maximum(m, sc.max(1))
+        corr = np.exp2(m - mn)
+        l *= corr
+        acc *= corr[:, None]
+        p = np.exp2(sc - mn[:, None])
+        l += p.sum(1)
+        acc += p @ Vs
+        m = mn
+    return acc / l[:, None], (m + np.log2(l)) * LN2
+
+
+def sim_xattn_bwd(q, k, v, o, do, lse, scale, KT=16, QT=16, QCHUNK=32):
+    Nq, Nk = q.shape[0], k.shape[0]
+    # dQ kernel
+    qr = q * (scale * LOG2E)
+    dl = (do * o).sum(1)
+    lse2 = lse * LOG2E
+    dq = np.zeros_like(q)
+    for k0 in range(0, Nk, KT):
+        nk = min(KT, Nk - k0)
+        Ks = np.zeros((KT, HD)); Vs = np.zeros((KT, HD))
+        Ks[:nk], Vs[:nk] = k[k0:k0 + nk], v[k0:k0 + nk]
+        p1, p2 = qr @ Ks.T, do @ Vs.T
+        pj = np.exp2(p1 - lse2[:, None])
+        pj[:, nk:] = 0.0
+        ds = pj * (p2 - dl[:, None])
+        dq += ds @ Ks
+    dq *= scale
+    # dK/dV kernel (query range split in chunks, tiles of QT, atomics across chunks)
+    kr = k * (scale * LOG2E)
+    dk, dv = np.zeros_like(k), np.zeros_like(v)
+    for q_begin in range(0, Nq, QCHUNK):
+        q_end = min(Nq, q_begin + QCHUNK)
+        dkr, dvr = np.zeros_like(k), np.zeros_like(v)
+        for q0 in range(q_begin, q_end, QT):
+            n = max(0, min(QT, q_end - q0))
+            Qs = np.zeros((QT, HD)); Ds = np.zeros((QT, HD))
+            Qs[:n], Ds[:n] = q[q0:q0 + n], do[q0:q0 + n]
+            Ls = np.full(QT, np.inf); Dl = np.zeros(QT)
+            Ls[:n], Dl[:n] = lse2[q0:q0 + n], dl[q0:q0 + n]
+            p1, p2 = kr @ Qs.T, v @ Ds.T                     # [Nk, QT]
+            pj = np.exp2(p1 - Ls[None, :])
+            ds = pj * (p2 - Dl[None, :])
+            dvr += pj @ Ds
+            dkr += ds @ Qs
+        dk += dkr * scale
+        dv += dvr
+    return dq, dk, dv
+
+
+@pytest.mark.parametrize('Nq,Nk', [(70, 37), (16, 16), (5, 1), (33, 50)])
+def test_xattn_tile_algorithm(Nq, Nk):
+    rng = np.random.default_rng(4)
+    q, k, v = rng.standard_normal((Nq, HD)), rng.standard_normal((Nk, HD)), rng.standard_normal((Nk, HD))
+    scale = HD ** -0.5
+    s = (q @ k.T) * scale
+    mx = s.max(1, keepdims=True)
+    lse = (mx + np.log(np.exp(s - mx).sum(1, keepdims=True)))[:, 0]
+    p = np.exp(s - lse[:, None])
+    o = p @ v
+    so, slse = sim_xattn_fwd(q, k, v, scale)
+    assert rel(so, o) < 1e-13 and rel(slse, lse) < 1e-13
+    do = rng.standard_normal((Nq, HD))
+    dv = p.T @ do
+    dp = do @ v.T
+    ds = p * (dp - (do * o).sum(1, keepdims=True)) * scale
+    dq, dk = ds @ k, ds.T @ q
+    sdq, sdk, sdv = sim_xattn_bwd(q, k, v, o, do, lse, scale)
+    for mine, ref in ((sdq, dq), (sdk, dk), (sdv, dv)):      # one key => dq, dk are exactly 0: compare absolutely
+        assert np.abs(mine - ref).max() < 1e-12 * max(1.0, np.abs(ref).max())

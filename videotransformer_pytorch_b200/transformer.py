@@ -53,6 +53,35 @@ class ShadowWeights:
         return sh
 
 
+    def get_cat(self, name: str, params) -> torch.Tensor:
+        """bf16 shadow of several [n_i, k] weights stacked along dim 0 (fused q/k/v projection)."""
+        key = tuple((p._version, p.data_ptr(), p.device) for p in params)
+        hit = self._cache.get(name)
+        capturing = params[0].is_cuda and torch.cuda.is_current_stream_capturing()
+        if hit is not None and hit[0] == key and not capturing:
+            return hit[1]
+        with torch.no_grad():
+            w = torch.cat([_f32(p.detach()).reshape(p.shape[0], -1) for p in params], dim=0)
+            sh = _lib.K.cast_bf16(w.contiguous())
+        self._cache[name] = (key, sh)
+        return sh
+
+    def get_padded(self, name: str, param: torch.Tensor, kpad: int) -> torch.Tensor:
+        """bf16 shadow of a [n, ...] weight flattened to [n, k] and zero-padded to kpad columns (TMA needs 16-byte
+        row pitches; the 3x7x7x3 patch-embed filter has k = 441)."""
+        key = (param._version, param.data_ptr(), param.device, kpad)
+        hit = self._cache.get(name)
+        capturing = param.is_cuda and torch.cuda.is_current_stream_capturing()
+        if hit is not None and hit[0] == key and not capturing:
+            return hit[1]
+        with torch.no_grad():
+            w = _f32(param.detach()).reshape(param.shape[0], -1)
+            w = torch.nn.functional.pad(w, (0, kpad - w.shape[1]))
+            sh = _lib.K.cast_bf16(w.contiguous())
+        self._cache[name] = (key, sh)
+        return sh
+
+
 def _f32(p):
     return p if p.dtype == torch.float32 else p.float()
 
