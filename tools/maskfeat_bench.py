@@ -1,0 +1,73 @@
+"""MaskFeat (MViT-B, reference 2-stage Q-pool config) 16x224^2 fwd+bwd timing on one B200 (BASELINE config 5 shape):
+full MaskFeat.forward with cube masks from CubeMaskGenerator and HOG targets from the HOG kernel.  Eager launches,
+CUDA-event timing, plus a CUPTI kernel-time breakdown of one step.
+
+    python tools/maskfeat_bench.py [--batch 8] [--steps 5] [--profile]
+"""
+import argparse
+import os
+import random
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from videotransformer_pytorch_b200 import MaskFeat, _lib
+from videotransformer_pytorch_b200.hog import hog_targets
+from videotransformer_pytorch_b200.mask_generator import CubeMaskGenerator
+
+ap = argparse.ArgumentParser()
+ap.add_argument('--batch', type=int, default=8)
+ap.add_argument('--steps', type=int, default=5)
+ap.add_argument('--warmup', type=int, default=2)
+ap.add_argument('--profile', action='store_true')
+a = ap.parse_args()
+dev = torch.device('cuda')
+torch.manual_seed(0)
+random.seed(0)
+B = a.batch
+model = MaskFeat(pool_q_stride_size=[[1, 1, 2, 2], [3, 1, 2, 2]], feature_dim=2 * 2 * 2 * 3 * 9).to(dev).train()
+gen = CubeMaskGenerator((8, 14, 14), min_num_patches=16)
+x = torch.randn(B, 16, 3, 224, 224, device=dev)
+u8 = torch.randint(0, 256, (B, 16, 224, 224, 3), dtype=torch.uint8, device=dev)
+masks, markers = [], []
+for _ in range(B):
+    m, cm = gen()
+    masks.append(torch.as_tensor(m))
+    markers.append(cm)
+mask = torch.stack(masks).to(dev)
+target = torch.stack([hog_targets(u8[i], markers[i]) for i in range(B)])
+
+
+def step():
+    for p in model.parameters():
+        p.grad = None
+    pred, loss = model(x, target, mask, markers)
+    loss.backward()
+    return loss
+
+
+for _ in range(a.warmup):
+    loss = step()
+torch.cuda.synchronize()
+print('loss', float(loss), 'finite grads', all(bool(torch.isfinite(p.grad).all()) for p in model.parameters()))
+n0 = _lib.launch_count()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(a.steps):
+    step()
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / a.steps
+print(f'MaskFeat MViT-B 16x224 batch {B} fwd+bwd (eager): {ms:.2f} ms/step = {B / ms * 1e3:.1f} clips/s; '
+      f'{(_lib.launch_count() - n0) // a.steps} kernel launches/step; peak mem {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB')
+if a.profile:
+    from torch.profiler import ProfilerActivity, profile
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        step()
+        torch.cuda.synchronize()
+    rows = sorted(prof.key_averages(), key=lambda r: -r.device_time_total)[:25]
+    tot = sum(r.device_time_total for r in prof.key_averages())
+    print(f'kernel time total {tot / 1e3:.2f} ms')
+    for r in rows:
+        print(f'{r.device_time_total / 1e3:9.3f} ms  {r.count:5d}x  {r.key[:110]}')
