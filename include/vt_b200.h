@@ -242,12 +242,16 @@ int vt_pool_bwd(const vt_pool_bwd_params* p, void* stream);
 /* Softmax attention with separate, strided Q / K / V and Nq != Nk (pooling attention):
  *   element (b, h, n, c) of q at q[b*q_bs + h*q_hs + n*q_rs + c] (bf16), same for k, v, o (and dout, dq).
  *   o = softmax(scale * q k^T) v ;  lse fp32 [B,H,Nq] = log sum exp(scale * q k^T).
- * CUDA-core kernels (two threads per query row, K/V tiles staged in shared memory): the head dim of 96 does not fit the
- * 128-byte swizzle atoms the tcgen05 kernels of vt_attn_* are built around; see DESIGN.md §4. */
+ * Two implementations: tcgen05 flash kernels (vt_xattention_tc.cu: head dim 96 staged as 128 padded columns = two
+ * 128-byte swizzle atoms, S / dP / accumulators in TMEM, K/V streamed by TMA) and CUDA-core kernels for arbitrary
+ * strides (two threads per query row, K/V tiles staged in shared memory). */
+enum { VT_XATTN_AUTO = 0, VT_XATTN_SIMT = 1, VT_XATTN_TCGEN05 = 2 };
 typedef struct {
   const void* q; const void* k; const void* v; void* o; float* lse;
   int64_t q_bs, q_hs, q_rs, k_bs, k_hs, k_rs, v_bs, v_hs, v_rs, o_bs, o_hs, o_rs;
   int32_t B, H, Nq, Nk, hd; float scale;
+  int32_t impl;   /* VT_XATTN_AUTO: tcgen05 kernels when every operand is token-major ([B,N,H*hd] slices) or head-major
+                     contiguous ([B,H,N,hd]) with 16-byte aligned rows, else the CUDA-core kernels */
 } vt_xattn_fwd_params;
 int vt_xattn_fwd(const vt_xattn_fwd_params* p, void* stream);
 /* dq: bf16 with its own strides.  dk, dv: fp32 [B,H,Nk,hd] contiguous (zeroed by the call, accumulated with atomics).
@@ -257,6 +261,7 @@ typedef struct {
   float* delta; void* dq; float* dk; float* dv;
   int64_t q_bs, q_hs, q_rs, k_bs, k_hs, k_rs, v_bs, v_hs, v_rs, o_bs, o_hs, o_rs, dq_bs, dq_hs, dq_rs;
   int32_t B, H, Nq, Nk, hd; float scale;
+  int32_t impl;
 } vt_xattn_bwd_params;
 int vt_xattn_bwd(const vt_xattn_bwd_params* p, void* stream);
 

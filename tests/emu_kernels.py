@@ -233,7 +233,7 @@ class EmuKernels:
         din.copy_(self._h(gx).to(din.dtype))
         return gw.reshape(hd, 27).to(self.f), (d * xh).sum((0, 1, 2)).to(self.f), d.sum((0, 1, 2)).to(self.f)
 
-    def xattn_fwd(self, q, k, v, scale):
+    def xattn_fwd(self, q, k, v, scale, impl=0):
         Q, Kk, V = self._up(q), self._up(k), self._up(v)
         B, H, Nq, hd = Q.shape
         s = (Q @ Kk.transpose(-1, -2)) * scale
@@ -242,7 +242,7 @@ class EmuKernels:
         o = (p @ V).transpose(1, 2).reshape(B, Nq, H * hd)
         return self._h(o), lse.to(self.f)
 
-    def xattn_bwd(self, q, k, v, o, dout, lse, scale, dq):
+    def xattn_bwd(self, q, k, v, o, dout, lse, scale, dq, impl=0):
         Q, Kk, V = self._up(q), self._up(k), self._up(v)
         B, H, Nq, hd = Q.shape
         O = self._up(o).reshape(B, Nq, H, hd).transpose(1, 2)

@@ -107,14 +107,14 @@ _XA_STRIDES = [(t + s, c_i64) for t in ('q', 'k', 'v', 'o') for s in ('_bs', '_h
 
 class XattnFwdParams(C.Structure):
     _fields_ = [('q', c_vp), ('k', c_vp), ('v', c_vp), ('o', c_vp), ('lse', c_vp)] + _XA_STRIDES + \
-               [('B', c_i32), ('H', c_i32), ('Nq', c_i32), ('Nk', c_i32), ('hd', c_i32), ('scale', c_f32)]
+               [('B', c_i32), ('H', c_i32), ('Nq', c_i32), ('Nk', c_i32), ('hd', c_i32), ('scale', c_f32), ('impl', c_i32)]
 
 
 class XattnBwdParams(C.Structure):
     _fields_ = [('q', c_vp), ('k', c_vp), ('v', c_vp), ('o', c_vp), ('dout', c_vp), ('lse', c_vp),
                 ('delta', c_vp), ('dq', c_vp), ('dk', c_vp), ('dv', c_vp)] + _XA_STRIDES + \
                [('dq_bs', c_i64), ('dq_hs', c_i64), ('dq_rs', c_i64),
-                ('B', c_i32), ('H', c_i32), ('Nq', c_i32), ('Nk', c_i32), ('hd', c_i32), ('scale', c_f32)]
+                ('B', c_i32), ('H', c_i32), ('Nq', c_i32), ('Nk', c_i32), ('hd', c_i32), ('scale', c_f32), ('impl', c_i32)]
 
 
 _MP_DIMS = [(n, c_i32) for n in ('B', 'D', 'T', 'H', 'W', 'kt', 'kh', 'kw', 'st', 'sh', 'sw', 'To', 'Ho', 'Wo')]
@@ -533,7 +533,7 @@ class CudaKernels:
             raise RuntimeError(f'{name}: expected a [B,H,N,hd] view with unit last stride')
         return t.data_ptr(), t.stride(0), t.stride(1), t.stride(2)
 
-    def xattn_fwd(self, q, k, v, scale):
+    def xattn_fwd(self, q, k, v, scale, impl=0):
         """q [B,H,Nq,hd], k/v [B,H,Nk,hd] bf16 views -> (o bf16 [B, Nq, H*hd], lse fp32 [B,H,Nq])"""
         lib = load_library()
         B, H, Nq, hd = q.shape
@@ -546,11 +546,11 @@ class CudaKernels:
         p.v, p.v_bs, p.v_hs, p.v_rs = self._bhnd(v, 'xattn.v')
         p.o, p.o_bs, p.o_hs, p.o_rs = o.data_ptr(), Nq * H * hd, hd, H * hd
         p.lse = lse.data_ptr()
-        p.B, p.H, p.Nq, p.Nk, p.hd, p.scale = B, H, Nq, Nk, hd, scale
+        p.B, p.H, p.Nq, p.Nk, p.hd, p.scale, p.impl = B, H, Nq, Nk, hd, scale, impl
         _check(lib.vt_xattn_fwd(C.byref(p), _stream()), 'vt_xattn_fwd')
         return o, lse
 
-    def xattn_bwd(self, q, k, v, o, dout, lse, scale, dq):
+    def xattn_bwd(self, q, k, v, o, dout, lse, scale, dq, impl=0):
         """o, dout: bf16 [B, Nq, H*hd] contiguous; dq: bf16 [B,H,Nq,hd] view written in place -> (dk, dv) fp32 [B,H,Nk,hd]"""
         lib = load_library()
         B, H, Nq, hd = q.shape
@@ -571,7 +571,7 @@ class CudaKernels:
         p.o, p.dout = o.data_ptr(), dout.data_ptr()
         p.o_bs, p.o_hs, p.o_rs = Nq * H * hd, hd, H * hd
         p.lse, p.delta, p.dk, p.dv = lse.data_ptr(), delta.data_ptr(), dk.data_ptr(), dv.data_ptr()
-        p.B, p.H, p.Nq, p.Nk, p.hd, p.scale = B, H, Nq, Nk, hd, scale
+        p.B, p.H, p.Nq, p.Nk, p.hd, p.scale, p.impl = B, H, Nq, Nk, hd, scale, impl
         _check(lib.vt_xattn_bwd(C.byref(p), _stream()), 'vt_xattn_bwd')
         return dk, dv
 

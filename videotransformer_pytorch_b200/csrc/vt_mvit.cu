@@ -854,6 +854,12 @@ __global__ void mse_bwd_kernel(const float* __restrict__ pred, const float* __re
   }
 }
 
+bool xattn_tc_supported(const void* q, long long q_bs, long long q_hs, long long q_rs, const void* k, long long k_bs,
+                        long long k_hs, long long k_rs, const void* v, long long v_bs, long long v_hs, long long v_rs, int B,
+                        int H, int Nq, int Nk, int hd);
+int xattn_tc_fwd_launch(const vt_xattn_fwd_params* q, cudaStream_t st);
+int xattn_tc_bwd_launch(const vt_xattn_bwd_params* q, cudaStream_t st);
+
 }  // namespace vt
 
 // ================================================================================================
@@ -974,6 +980,12 @@ extern "C" int vt_xattn_fwd(const vt_xattn_fwd_params* p, void* stream) {
   VT_REQUIRE(p && p->q && p->k && p->v && p->o && p->lse, "vt_xattn_fwd: null pointer");
   VT_REQUIRE(p->hd == 96, "vt_xattn_fwd: head dim %d unsupported (96 only)", p->hd);
   VT_REQUIRE(p->B > 0 && p->H > 0 && p->Nq > 0 && p->Nk > 0 && (long long)p->B * p->H <= 65535, "vt_xattn_fwd: bad dims");
+  VT_REQUIRE(p->impl >= VT_XATTN_AUTO && p->impl <= VT_XATTN_TCGEN05, "vt_xattn_fwd: bad impl %d", p->impl);
+  if (p->impl == VT_XATTN_TCGEN05 ||
+      (p->impl == VT_XATTN_AUTO && xattn_tc_supported(p->q, p->q_bs, p->q_hs, p->q_rs, p->k, p->k_bs, p->k_hs, p->k_rs, p->v, p->v_bs,
+                                                      p->v_hs, p->v_rs, p->B, p->H, p->Nq, p->Nk, p->hd) &&
+       (p->o_rs * 2) % 16 == 0 && ((uintptr_t)p->o & 15) == 0))
+    return xattn_tc_fwd_launch(p, static_cast<cudaStream_t>(stream));
   const long long ss[12] = {p->q_bs, p->q_hs, p->q_rs, p->k_bs, p->k_hs, p->k_rs, p->v_bs, p->v_hs, p->v_rs, p->o_bs, p->o_hs, p->o_rs};
   VT_REQUIRE(xa_strides_ok(ss, 12), "vt_xattn_fwd: strides must be even (4-byte aligned bf16 pairs)");
   VT_REQUIRE(((uintptr_t)p->q | (uintptr_t)p->k | (uintptr_t)p->v | (uintptr_t)p->o) % 4 == 0, "vt_xattn_fwd: pointers must be 4-byte aligned");
@@ -989,6 +1001,13 @@ extern "C" int vt_xattn_bwd(const vt_xattn_bwd_params* p, void* stream) {
   VT_REQUIRE(p && p->q && p->k && p->v && p->o && p->dout && p->lse && p->delta && p->dq && p->dk && p->dv, "vt_xattn_bwd: null pointer");
   VT_REQUIRE(p->hd == 96, "vt_xattn_bwd: head dim %d unsupported (96 only)", p->hd);
   VT_REQUIRE(p->B > 0 && p->H > 0 && p->Nq > 0 && p->Nk > 0 && (long long)p->B * p->H <= 65535, "vt_xattn_bwd: bad dims");
+  VT_REQUIRE(p->impl >= VT_XATTN_AUTO && p->impl <= VT_XATTN_TCGEN05, "vt_xattn_bwd: bad impl %d", p->impl);
+  if (p->impl == VT_XATTN_TCGEN05 ||
+      (p->impl == VT_XATTN_AUTO && xattn_tc_supported(p->q, p->q_bs, p->q_hs, p->q_rs, p->k, p->k_bs, p->k_hs, p->k_rs, p->v, p->v_bs,
+                                                      p->v_hs, p->v_rs, p->B, p->H, p->Nq, p->Nk, p->hd) &&
+       (p->o_rs * 2) % 16 == 0 && (p->dq_rs * 2) % 16 == 0 && (p->dq_hs * 2) % 16 == 0 && (p->dq_bs * 2) % 16 == 0 &&
+       (((uintptr_t)p->o | (uintptr_t)p->dout | (uintptr_t)p->dq) & 15) == 0))
+    return xattn_tc_bwd_launch(p, static_cast<cudaStream_t>(stream));
   const long long ss[15] = {p->q_bs, p->q_hs, p->q_rs, p->k_bs, p->k_hs, p->k_rs, p->v_bs, p->v_hs, p->v_rs, p->o_bs, p->o_hs, p->o_rs,
                             p->dq_bs, p->dq_hs, p->dq_rs};
   VT_REQUIRE(xa_strides_ok(ss, 15), "vt_xattn_bwd: strides must be even");
