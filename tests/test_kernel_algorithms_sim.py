@@ -42,21 +42,21 @@ def sim_pool_fwd(inp, in_bs, in_rs, w, B, H, thw, stride):
             continue
         o = l - 1
         ow, oh, ot = o % Wo, (o // Wo) % Ho, o // (Wo * Ho)
+        hrow, wcol, hok, wok = [0] * 3, [0] * 3, [False] * 3, [False] * 3
+        for k in range(3):
+            hi, wi = oh * sh - 1 + k, ow * sw - 1 + k
+            hok[k], wok[k] = 0 <= hi < Hin, 0 <= wi < Win
+            hrow[k], wcol[k] = min(max(hi, 0), Hin - 1), min(max(wi, 0), Win - 1)
         acc = np.zeros(HD)
         for dt in range(3):
             ti = ot * st - 1 + dt
             if ti < 0 or ti >= T:
                 continue
             for dh in range(3):
-                hi = oh * sh - 1 + dh
-                if hi < 0 or hi >= Hin:
-                    continue
                 for dw in range(3):
-                    wi = ow * sw - 1 + dw
-                    if wi < 0 or wi >= Win:
-                        continue
-                    n = 1 + (ti * Hin + hi) * Win + wi
-                    acc += inp[base + n * in_rs: base + n * in_rs + HD] * w[:, (dt * 3 + dh) * 3 + dw]
+                    n = 1 + (ti * Hin + hrow[dh]) * Win + wcol[dw]          # clamped address, masked value
+                    x = inp[base + n * in_rs: base + n * in_rs + HD]
+                    acc += (x if (hok[dh] and wok[dw]) else 0.0) * w[:, (dt * 3 + dh) * 3 + dw]
         pooled[r] = acc
     return pooled.reshape(B, H, Lo1, HD)
 
@@ -78,6 +78,13 @@ def sim_pool_din(dpooled, w, B, H, thw, stride):
             continue
         idx = n - 1
         wi, hi, ti = idx % Win, (idx // Win) % Hin, idx // (Win * Hin)
+        ohs, ows, hok, wok = [0] * 3, [0] * 3, [False] * 3, [False] * 3
+        for k in range(3):
+            nh, nw = hi + 1 - k, wi + 1 - k
+            hok[k] = nh >= 0 and nh % sh == 0 and nh // sh < Ho
+            wok[k] = nw >= 0 and nw % sw == 0 and nw // sw < Wo
+            ohs[k] = nh // sh if hok[k] else 0
+            ows[k] = nw // sw if wok[k] else 0
         acc = np.zeros(HD)
         for dt in range(3):
             nt = ti + 1 - dt
@@ -87,49 +94,59 @@ def sim_pool_din(dpooled, w, B, H, thw, stride):
             if ot >= To:
                 continue
             for dh in range(3):
-                nh = hi + 1 - dh
-                if nh < 0 or nh % sh != 0:
-                    continue
-                oh = nh // sh
-                if oh >= Ho:
-                    continue
                 for dw in range(3):
-                    nw = wi + 1 - dw
-                    if nw < 0 or nw % sw != 0:
-                        continue
-                    ow = nw // sw
-                    if ow >= Wo:
-                        continue
-                    acc += g[1 + (ot * Ho + oh) * Wo + ow] * w[:, (dt * 3 + dh) * 3 + dw]
+                    src = g[1 + (ot * Ho + ohs[dh]) * Wo + ows[dw]]
+                    acc += (src if (hok[dh] and wok[dw]) else 0.0) * w[:, (dt * 3 + dh) * 3 + dw]
         din[b, n, h] = acc
     return din.reshape(B, L1, H * HD)
 
 
-def sim_pool_dw(dpooled, inp, in_bs, in_rs, B, H, thw, stride):
+def sim_pool_dw(dpooled, inp, in_bs, in_rs, B, H, thw, stride, rows_per_cta=5, unroll=4):
+    """tap-per-warp kernel: CTAs own row ranges, rows are walked `unroll` at a time with clamped duplicates masked."""
     T, Hin, Win = thw
     st, sh, sw = stride
     To, Ho, Wo = out_dims(thw, stride)
     Lo = To * Ho * Wo
-    acc = np.zeros((27, HD))
+    rows = B * H * Lo
+    nblocks = (rows + rows_per_cta - 1) // rows_per_cta
+    partials = np.zeros((nblocks, HD * 27))
     dp = dpooled.reshape(B * H, Lo + 1, HD)
-    for r in range(B * H * Lo):
-        o = r % Lo
-        bh = r // Lo
-        h, b = bh % H, bh // H
-        ow, oh, ot = o % Wo, (o // Wo) % Ho, o // (Wo * Ho)
-        g = dp[b * H + h, 1 + o]
-        base = b * in_bs + h * HD
-        for dt in range(3):
-            ti = ot * st - 1 + dt
-            for dh in range(3):
-                hi = oh * sh - 1 + dh
-                for dw in range(3):
-                    wi = ow * sw - 1 + dw
-                    if 0 <= ti < T and 0 <= hi < Hin and 0 <= wi < Win:
-                        off = base + (1 + (ti * Hin + hi) * Win + wi) * in_rs
-                        acc[(dt * 3 + dh) * 3 + dw] += g * inp[off:off + HD]
-    # red[(c)*27 + t] layout -> [hd, 27]
-    return acc.T.copy()
+    for blk in range(nblocks):
+        r0, r1 = blk * rows_per_cta, min(rows, (blk + 1) * rows_per_cta)
+        for tap in range(27):
+            dt, dh, dw = tap // 9, (tap // 3) % 3, tap % 3
+            acc = np.zeros(HD)
+            rs = min(r0, rows - 1)
+            o = rs % Lo
+            bh = rs // Lo
+            h, b = bh % H, bh // H
+            ow, oh, ot = o % Wo, (o // Wo) % Ho, o // (Wo * Ho)
+            for rb in range(r0, r1, unroll):
+                for u in range(unroll):
+                    live = rb + u < r1
+                    ti, hi, wi = ot * st - 1 + dt, oh * sh - 1 + dh, ow * sw - 1 + dw
+                    ok = live and 0 <= ti < T and 0 <= hi < Hin and 0 <= wi < Win
+                    tc, hc, wc = min(max(ti, 0), T - 1), min(max(hi, 0), Hin - 1), min(max(wi, 0), Win - 1)
+                    o = (ot * Ho + oh) * Wo + ow
+                    g = dp[b * H + h, 1 + o]
+                    off = b * in_bs + h * HD + (1 + (tc * Hin + hc) * Win + wc) * in_rs
+                    acc += (g if ok else 0.0) * inp[off:off + HD]
+                    if rb + u + 1 < r1:                      # odometer advance
+                        ow += 1
+                        if ow == Wo:
+                            ow = 0
+                            oh += 1
+                            if oh == Ho:
+                                oh = 0
+                                ot += 1
+                                if ot == To:
+                                    ot = 0
+                                    h += 1
+                                    if h == H:
+                                        h = 0
+                                        b += 1
+            partials[blk, np.arange(HD) * 27 + tap] = acc
+    return partials.sum(0).reshape(HD, 27)
 
 
 @pytest.mark.parametrize('thw,stride,H', [((2, 4, 4), (1, 2, 2), 2), ((3, 5, 6), (1, 4, 4), 1), ((2, 3, 3), (1, 1, 1), 2),
@@ -274,16 +291,25 @@ def test_im2col3d_index_math():
     cols, (To, Ho, Wo) = emu.im2col3d(x, kernel, stride, padding, kpad)
     kt, kh, kw = kernel
     xs = x.numpy().reshape(-1)
-    sim = np.zeros((B * To * Ho * Wo, kpad))
+    sim = np.full((B * To * Ho * Wo, kpad), np.nan)
     kreal = C * kt * kh * kw
+    groups = (kpad + kw - 1) // kw
     for row in range(sim.shape[0]):
         ow, oh, ot = row % Wo, (row // Wo) % Ho, (row // (Wo * Ho)) % To
         b = row // (Wo * Ho * To)
-        for col in range(kreal):
-            dw, dh, dt, c = col % kw, (col // kw) % kh, (col // (kw * kh)) % kt, col // (kw * kh * kt)
-            ti, hi, wi = ot * stride[0] - padding[0] + dt, oh * stride[1] - padding[1] + dh, ow * stride[2] - padding[2] + dw
-            if 0 <= ti < T and 0 <= hi < H and 0 <= wi < W:
-                sim[row, col] = xs[(((b * T + ti) * C + c) * H + hi) * W + wi]
+        for grp in range(groups):
+            col0 = grp * kw
+            ncol = min(kw, kpad - col0)
+            if col0 >= kreal:
+                sim[row, col0:col0 + ncol] = 0.0
+                continue
+            dh, dt, c = grp % kh, (grp // kh) % kt, grp // (kh * kt)
+            ti, hi, w0 = ot * stride[0] - padding[0] + dt, oh * stride[1] - padding[1] + dh, ow * stride[2] - padding[2]
+            line_ok = 0 <= ti < T and 0 <= hi < H
+            base = (((b * T + (ti if line_ok else 0)) * C + c) * H + (hi if line_ok else 0)) * W
+            for j in range(ncol):
+                wi = w0 + j
+                sim[row, col0 + j] = xs[base + wi] if (line_ok and 0 <= wi < W) else 0.0
     assert rel(sim, cols.numpy()) == 0.0
     # and the GEMM against the flattened filter reproduces conv3d on the reference's transposed input
     w = torch.randn(8, C, kt, kh, kw, generator=g, dtype=torch.float64)

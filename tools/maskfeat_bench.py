@@ -21,6 +21,7 @@ ap.add_argument('--batch', type=int, default=8)
 ap.add_argument('--steps', type=int, default=5)
 ap.add_argument('--warmup', type=int, default=2)
 ap.add_argument('--profile', action='store_true')
+ap.add_argument('--graph', action='store_true', help='also time the step replayed as one CUDA graph')
 a = ap.parse_args()
 dev = torch.device('cuda')
 torch.manual_seed(0)
@@ -61,6 +62,35 @@ torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / a.steps
 print(f'MaskFeat MViT-B 16x224 batch {B} fwd+bwd (eager): {ms:.2f} ms/step = {B / ms * 1e3:.1f} clips/s; '
       f'{(_lib.launch_count() - n0) // a.steps} kernel launches/step; peak mem {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB')
+if a.graph:
+    from videotransformer_pytorch_b200.graph import GraphedTrainStep
+
+    class Step(torch.nn.Module):
+        def __init__(self, m):
+            super().__init__()
+            self.m = m
+
+        def forward(self, x, target, mask, cmask):
+            return self.m.forward_with_center_mask(x, target, mask, cmask)[1]
+
+    try:
+        cmask = model.center_frame_mask(mask, markers)
+        gstep = GraphedTrainStep(Step(model), (x, target, mask.float(), cmask))
+        for _ in range(2):
+            gl = gstep(x, target, mask.float(), cmask)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(a.steps * 2):
+            gstep(x, target, mask.float(), cmask)
+        e1.record()
+        torch.cuda.synchronize()
+        gms = e0.elapsed_time(e1) / (a.steps * 2)
+        print(f'MaskFeat MViT-B 16x224 batch {B} fwd+bwd (CUDA graph): {gms:.2f} ms/step = {B / gms * 1e3:.1f} clips/s; '
+              f'loss {float(gl):.5f}; {gstep.kernels_per_replay} kernels per replay')
+    except Exception as ex:       # report and keep the eager numbers
+        import traceback
+        traceback.print_exc()
+        print('graph capture failed:', ex)
 if a.profile:
     from torch.profiler import ProfilerActivity, profile
     with profile(activities=[ProfilerActivity.CUDA]) as prof:

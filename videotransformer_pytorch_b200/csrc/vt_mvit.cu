@@ -177,22 +177,39 @@ pool_ln_fwd_kernel(const __nv_bfloat16* __restrict__ in, long long in_bs, long l
     } else {
       const int o = l - 1;
       const int ow = o % d.Wo, oh = (o / d.Wo) % d.Ho, ot = o / (d.Wo * d.Ho);
+      // the nine (dh, dw) taps of a dt plane are loaded unconditionally from clamped coordinates (out-of-range taps are
+      // zeroed after the load) so that all of them are in flight together; dt planes outside the clip are skipped
+      int hrow[3], wcol[3];
+      bool hok[3], wok[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int hi = oh * d.sh - 1 + k, wi = ow * d.sw - 1 + k;
+        hok[k] = hi >= 0 && hi < d.Hin;
+        wok[k] = wi >= 0 && wi < d.Win;
+        hrow[k] = min(max(hi, 0), d.Hin - 1);
+        wcol[k] = min(max(wi, 0), d.Win - 1);
+      }
       for (int dt = 0; dt < 3; ++dt) {
         const int ti = ot * d.st - 1 + dt;
         if (ti < 0 || ti >= d.T) continue;
-        for (int dh = 0; dh < 3; ++dh) {
-          const int hi = oh * d.sh - 1 + dh;
-          if (hi < 0 || hi >= d.Hin) continue;
-          for (int dw = 0; dw < 3; ++dw) {
-            const int wi = ow * d.sw - 1 + dw;
-            if (wi < 0 || wi >= d.Win) continue;
-            const long long n = 1 + ((long long)ti * d.Hin + hi) * d.Win + wi;
-            const __nv_bfloat16* src = base + n * in_rs;
-            const float* f = sw + ((dt * 3 + dh) * 3 + dw) * HD;
+        float x[9][E];
 #pragma unroll
-            for (int i = 0; i < E; ++i) acc[i] = fmaf(bf2f(src + lane + 32 * i), f[lane + 32 * i], acc[i]);
+        for (int dh = 0; dh < 3; ++dh)
+#pragma unroll
+          for (int dw = 0; dw < 3; ++dw) {
+            const __nv_bfloat16* src = base + (1 + ((long long)ti * d.Hin + hrow[dh]) * d.Win + wcol[dw]) * in_rs;
+#pragma unroll
+            for (int i = 0; i < E; ++i) x[dh * 3 + dw][i] = bf2f(src + lane + 32 * i);
           }
-        }
+#pragma unroll
+        for (int dh = 0; dh < 3; ++dh)
+#pragma unroll
+          for (int dw = 0; dw < 3; ++dw) {
+            const float* f = sw + ((dt * 3 + dh) * 3 + dw) * HD;
+            const bool ok = hok[dh] && wok[dw];
+#pragma unroll
+            for (int i = 0; i < E; ++i) acc[i] = fmaf(ok ? x[dh * 3 + dw][i] : 0.f, f[lane + 32 * i], acc[i]);
+          }
       }
     }
     float s = 0.f;
@@ -248,27 +265,40 @@ pool_din_kernel(const float* __restrict__ dpooled, const float* __restrict__ w, 
     } else {
       const int idx = n - 1;
       const int wi = idx % d.Win, hi = (idx / d.Win) % d.Hin, ti = idx / (d.Win * d.Hin);
+      // output coordinate reached through tap k along each axis (o*s - 1 + k == i), clamped to 0 when there is none
+      int ohs[3], ows[3];
+      bool hok[3], wok[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int nh = hi + 1 - k, nw = wi + 1 - k;
+        hok[k] = nh >= 0 && nh % d.sh == 0 && nh / d.sh < d.Ho;
+        wok[k] = nw >= 0 && nw % d.sw == 0 && nw / d.sw < d.Wo;
+        ohs[k] = hok[k] ? nh / d.sh : 0;
+        ows[k] = wok[k] ? nw / d.sw : 0;
+      }
       for (int dt = 0; dt < 3; ++dt) {
         const int nt = ti + 1 - dt;
         if (nt < 0 || nt % d.st != 0) continue;
         const int ot = nt / d.st;
         if (ot >= d.To) continue;
-        for (int dh = 0; dh < 3; ++dh) {
-          const int nh = hi + 1 - dh;
-          if (nh < 0 || nh % d.sh != 0) continue;
-          const int oh = nh / d.sh;
-          if (oh >= d.Ho) continue;
-          for (int dw = 0; dw < 3; ++dw) {
-            const int nw = wi + 1 - dw;
-            if (nw < 0 || nw % d.sw != 0) continue;
-            const int ow = nw / d.sw;
-            if (ow >= d.Wo) continue;
-            const float* src = dp + (1 + ((long long)ot * d.Ho + oh) * d.Wo + ow) * HD;
-            const float* f = sw + ((dt * 3 + dh) * 3 + dw) * HD;
+        float g[9][E];
 #pragma unroll
-            for (int i = 0; i < E; ++i) acc[i] = fmaf(src[lane + 32 * i], f[lane + 32 * i], acc[i]);
+        for (int dh = 0; dh < 3; ++dh)
+#pragma unroll
+          for (int dw = 0; dw < 3; ++dw) {
+            const float* src = dp + (1 + ((long long)ot * d.Ho + ohs[dh]) * d.Wo + ows[dw]) * HD;
+#pragma unroll
+            for (int i = 0; i < E; ++i) g[dh * 3 + dw][i] = src[lane + 32 * i];
           }
-        }
+#pragma unroll
+        for (int dh = 0; dh < 3; ++dh)
+#pragma unroll
+          for (int dw = 0; dw < 3; ++dw) {
+            const float* f = sw + ((dt * 3 + dh) * 3 + dw) * HD;
+            const bool ok = hok[dh] && wok[dw];
+#pragma unroll
+            for (int i = 0; i < E; ++i) acc[i] = fmaf(ok ? g[dh * 3 + dw][i] : 0.f, f[lane + 32 * i], acc[i]);
+          }
       }
     }
     __nv_bfloat16* dst = din + (long long)b * din_bs + (long long)n * din_rs + (long long)h * HD;
@@ -278,62 +308,78 @@ pool_din_kernel(const float* __restrict__ dpooled, const float* __restrict__ w, 
 }
 
 // filter gradient: dw[c][tap] = sum over output rows of dpooled[row][c] * in[window tap][c].
-// Each warp keeps 27 x E partial sums in registers; per-CTA partial rows [hd*27] are summed by reduce_rows.
+// CTA = 27 warps, warp = filter tap, lane = channels (c = lane + 32 i): every (tap, channel) sum is owned by one thread, so
+// there is no cross-warp reduction; rows are walked four at a time with all loads issued before the FMAs.
+// Per-CTA partial rows [hd*27] are summed by reduce_rows.
+constexpr int DW_ROWS_UNROLL = 4;
+
 template <int E>
-__global__ void __launch_bounds__(ROW_WARPS * 32)
+__global__ void __launch_bounds__(27 * 32)
 pool_dw_kernel(const float* __restrict__ dpooled, const __nv_bfloat16* __restrict__ in, long long in_bs, long long in_rs,
-               float* __restrict__ partials, PoolDims d) {
+               float* __restrict__ partials, PoolDims d, int rows_per_cta) {
   constexpr int HD = 32 * E;
-  __shared__ float red[27 * HD];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float acc[27][E];
-#pragma unroll
-  for (int t = 0; t < 27; ++t)
-#pragma unroll
-    for (int i = 0; i < E; ++i) acc[t][i] = 0.f;
+  const int tap = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int dt = tap / 9, dh = (tap / 3) % 3, dw = tap % 3;
   const int Lo = d.To * d.Ho * d.Wo;
   const long long rows = (long long)d.B * d.H * Lo;
-  for (long long r = (long long)blockIdx.x * ROW_WARPS + warp; r < rows; r += (long long)gridDim.x * ROW_WARPS) {
-    const int o = (int)(r % Lo);
-    const int bh = (int)(r / Lo);
-    const int h = bh % d.H, b = bh / d.H;
-    const int ow = o % d.Wo, oh = (o / d.Wo) % d.Ho, ot = o / (d.Wo * d.Ho);
-    const float* dp = dpooled + (((long long)b * d.H + h) * (Lo + 1) + 1 + o) * HD;
-    float g[E];
+  const long long r0 = (long long)blockIdx.x * rows_per_cta;
+  const long long r1 = min(rows, r0 + rows_per_cta);
+  float acc[E];
 #pragma unroll
-    for (int i = 0; i < E; ++i) g[i] = dp[lane + 32 * i];
-    const __nv_bfloat16* base = in + (long long)b * in_bs + (long long)h * HD;
+  for (int i = 0; i < E; ++i) acc[i] = 0.f;
+  // (b, h, ot, oh, ow) of the current row: decoded once, then advanced like an odometer (rows of a CTA are consecutive)
+  int ow, oh, ot, h, b;
+  {
+    const long long rs = min(r0, rows - 1);
+    const int o = (int)(rs % Lo);
+    const int bh = (int)(rs / Lo);
+    h = bh % d.H;
+    b = bh / d.H;
+    ow = o % d.Wo;
+    oh = (o / d.Wo) % d.Ho;
+    ot = o / (d.Wo * d.Ho);
+  }
+  for (long long rb = r0; rb < r1; rb += DW_ROWS_UNROLL) {
+    float g[DW_ROWS_UNROLL][E], x[DW_ROWS_UNROLL][E];
+    bool ok[DW_ROWS_UNROLL];
 #pragma unroll
-    for (int dt = 0; dt < 3; ++dt) {
-      const int ti = ot * d.st - 1 + dt;
+    for (int u = 0; u < DW_ROWS_UNROLL; ++u) {
+      const bool live = rb + u < r1;                             // past the end: re-read the last row, masked
+      const int ti = ot * d.st - 1 + dt, hi = oh * d.sh - 1 + dh, wi = ow * d.sw - 1 + dw;
+      ok[u] = live && ti >= 0 && ti < d.T && hi >= 0 && hi < d.Hin && wi >= 0 && wi < d.Win;
+      const int tc = min(max(ti, 0), d.T - 1), hc = min(max(hi, 0), d.Hin - 1), wc = min(max(wi, 0), d.Win - 1);
+      const int o = (ot * d.Ho + oh) * d.Wo + ow;
+      const float* dp = dpooled + (((long long)b * d.H + h) * (Lo + 1) + 1 + o) * HD;
+      const __nv_bfloat16* src = in + (long long)b * in_bs + (long long)h * HD + (1 + ((long long)tc * d.Hin + hc) * d.Win + wc) * in_rs;
 #pragma unroll
-      for (int dh = 0; dh < 3; ++dh) {
-        const int hi = oh * d.sh - 1 + dh;
-#pragma unroll
-        for (int dw = 0; dw < 3; ++dw) {
-          const int wi = ow * d.sw - 1 + dw;
-          if (ti >= 0 && ti < d.T && hi >= 0 && hi < d.Hin && wi >= 0 && wi < d.Win) {
-            const __nv_bfloat16* src = base + (1 + ((long long)ti * d.Hin + hi) * d.Win + wi) * in_rs;
-#pragma unroll
-            for (int i = 0; i < E; ++i) acc[(dt * 3 + dh) * 3 + dw][i] = fmaf(g[i], bf2f(src + lane + 32 * i), acc[(dt * 3 + dh) * 3 + dw][i]);
+      for (int i = 0; i < E; ++i) {
+        g[u][i] = dp[lane + 32 * i];
+        x[u][i] = bf2f(src + lane + 32 * i);
+      }
+      if (rb + u + 1 < r1) {
+        if (++ow == d.Wo) {
+          ow = 0;
+          if (++oh == d.Ho) {
+            oh = 0;
+            if (++ot == d.To) {
+              ot = 0;
+              if (++h == d.H) {
+                h = 0;
+                ++b;
+              }
+            }
           }
         }
       }
     }
-  }
-  for (int i = threadIdx.x; i < 27 * HD; i += blockDim.x) red[i] = 0.f;
-  __syncthreads();
-  for (int wv = 0; wv < ROW_WARPS; ++wv) {
-    if (warp == wv) {
 #pragma unroll
-      for (int t = 0; t < 27; ++t)
+    for (int u = 0; u < DW_ROWS_UNROLL; ++u)
 #pragma unroll
-        for (int i = 0; i < E; ++i) red[(lane + 32 * i) * 27 + t] += acc[t][i];
-    }
-    __syncthreads();
+      for (int i = 0; i < E; ++i) acc[i] = fmaf(ok[u] ? g[u][i] : 0.f, x[u][i], acc[i]);
   }
   float* pg = partials + (long long)blockIdx.x * 27 * HD;
-  for (int i = threadIdx.x; i < 27 * HD; i += blockDim.x) pg[i] = red[i];
+#pragma unroll
+  for (int i = 0; i < E; ++i) pg[(lane + 32 * i) * 27 + tap] = acc[i];
 }
 
 // ================================================================================================
@@ -641,24 +687,28 @@ struct MpDims {
   int B, D, T, H, W, kt, kh, kw, st, sh, sw, To, Ho, Wo;
 };
 
+// four channels per thread: the window walk (divisions, bounds) is shared by a float4 of channels
 __global__ void maxpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, uint8_t* __restrict__ idx, MpDims d) {
   const int Lo1 = 1 + d.To * d.Ho * d.Wo, L1 = 1 + d.T * d.H * d.W;
-  const long long n = (long long)d.B * Lo1 * d.D;
+  const int D4 = d.D / 4;
+  const long long n = (long long)d.B * Lo1 * D4;
   const int pt = d.kt / 2, ph = d.kh / 2, pw = d.kw / 2;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(e % d.D);
-    const int l = (int)((e / d.D) % Lo1);
-    const int b = (int)(e / ((long long)d.D * Lo1));
-    const float* xb = x + (long long)b * L1 * d.D + c;
+    const int c4 = (int)(e % D4);
+    const int l = (int)((e / D4) % Lo1);
+    const int b = (int)(e / ((long long)D4 * Lo1));
+    const float4* xb = reinterpret_cast<const float4*>(x + (long long)b * L1 * d.D) + c4;
+    float4* yo = reinterpret_cast<float4*>(y) + e;
+    uchar4* io = reinterpret_cast<uchar4*>(idx) + e;
     if (l == 0) {
-      y[e] = xb[0];
-      idx[e] = 0;
+      *yo = xb[0];
+      *io = make_uchar4(0, 0, 0, 0);
       continue;
     }
     const int o = l - 1;
     const int ow = o % d.Wo, oh = (o / d.Wo) % d.Ho, ot = o / (d.Wo * d.Ho);
-    float best = -INFINITY;
-    int arg = 255;
+    float4 best = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    int ax = 255, ay = 255, az = 255, aw = 255;
     for (int dt = 0; dt < d.kt; ++dt) {
       const int ti = ot * d.st - pt + dt;
       if (ti < 0 || ti >= d.T) continue;
@@ -668,36 +718,39 @@ __global__ void maxpool_fwd_kernel(const float* __restrict__ x, float* __restric
         for (int dw = 0; dw < d.kw; ++dw) {
           const int wi = ow * d.sw - pw + dw;
           if (wi < 0 || wi >= d.W) continue;
-          const float val = xb[(1 + ((long long)ti * d.H + hi) * d.W + wi) * d.D];
-          if (val > best || arg == 255) {     // first maximum in scan order
-            best = val;
-            arg = (dt * d.kh + dh) * d.kw + dw;
-          }
+          const float4 v = xb[(1 + ((long long)ti * d.H + hi) * d.W + wi) * D4];
+          const int tap = (dt * d.kh + dh) * d.kw + dw;
+          if (v.x > best.x || ax == 255) { best.x = v.x; ax = tap; }     // first maximum in scan order
+          if (v.y > best.y || ay == 255) { best.y = v.y; ay = tap; }
+          if (v.z > best.z || az == 255) { best.z = v.z; az = tap; }
+          if (v.w > best.w || aw == 255) { best.w = v.w; aw = tap; }
         }
       }
     }
-    y[e] = best;
-    idx[e] = (uint8_t)arg;
+    *yo = best;
+    *io = make_uchar4((unsigned char)ax, (unsigned char)ay, (unsigned char)az, (unsigned char)aw);
   }
 }
 
 __global__ void maxpool_bwd_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ idx, float* __restrict__ dx, MpDims d) {
   const int Lo1 = 1 + d.To * d.Ho * d.Wo, L1 = 1 + d.T * d.H * d.W;
-  const long long n = (long long)d.B * L1 * d.D;
+  const int D4 = d.D / 4;
+  const long long n = (long long)d.B * L1 * D4;
   const int pt = d.kt / 2, ph = d.kh / 2, pw = d.kw / 2;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(e % d.D);
-    const int l = (int)((e / d.D) % L1);
-    const int b = (int)(e / ((long long)d.D * L1));
-    const float* gb = dy + (long long)b * Lo1 * d.D + c;
-    const uint8_t* ib = idx + (long long)b * Lo1 * d.D + c;
+    const int c4 = (int)(e % D4);
+    const int l = (int)((e / D4) % L1);
+    const int b = (int)(e / ((long long)D4 * L1));
+    const float4* gb = reinterpret_cast<const float4*>(dy + (long long)b * Lo1 * d.D) + c4;
+    const uchar4* ib = reinterpret_cast<const uchar4*>(idx + (long long)b * Lo1 * d.D) + c4;
+    float4* out = reinterpret_cast<float4*>(dx) + e;
     if (l == 0) {
-      dx[e] = gb[0];
+      *out = gb[0];
       continue;
     }
     const int i = l - 1;
     const int wi = i % d.W, hi = (i / d.W) % d.H, ti = i / (d.W * d.H);
-    float acc = 0.f;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int dt = 0; dt < d.kt; ++dt) {
       const int nt = ti + pt - dt;
       if (nt < 0 || nt % d.st != 0) continue;
@@ -713,12 +766,18 @@ __global__ void maxpool_bwd_kernel(const float* __restrict__ dy, const uint8_t* 
           if (nw < 0 || nw % d.sw != 0) continue;
           const int ow = nw / d.sw;
           if (ow >= d.Wo) continue;
-          const long long at = (1 + ((long long)ot * d.Ho + oh) * d.Wo + ow) * d.D;
-          if (ib[at] == (dt * d.kh + dh) * d.kw + dw) acc += gb[at];
+          const long long at = (1 + ((long long)ot * d.Ho + oh) * d.Wo + ow) * D4;
+          const uchar4 w = ib[at];
+          const float4 g = gb[at];
+          const int tap = (dt * d.kh + dh) * d.kw + dw;
+          if (w.x == tap) acc.x += g.x;
+          if (w.y == tap) acc.y += g.y;
+          if (w.z == tap) acc.z += g.z;
+          if (w.w == tap) acc.w += g.w;
         }
       }
     }
-    dx[e] = acc;
+    *out = acc;
   }
 }
 
@@ -729,23 +788,35 @@ struct I3Dims {
   int B, T, C, H, W, kt, kh, kw, st, sh, sw, pt, ph, pw, To, Ho, Wo, Kpad;
 };
 
+// one thread per (output row, kw-wide group of columns): the kw taps of a (c, dt, dh) filter row are contiguous both in
+// the clip and in the column layout, so the coordinate arithmetic is shared by kw elements
 __global__ void im2col3d_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ cols, I3Dims d) {
   const long long rows = (long long)d.B * d.To * d.Ho * d.Wo;
-  const long long n = rows * d.Kpad;
+  const int groups = (d.Kpad + d.kw - 1) / d.kw;
   const int Kreal = d.C * d.kt * d.kh * d.kw;
+  const long long n = rows * groups;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
-    const int col = (int)(e % d.Kpad);
-    const long long row = e / d.Kpad;
-    float val = 0.f;
-    if (col < Kreal) {
-      const int dw = col % d.kw, dh = (col / d.kw) % d.kh, dt = (col / (d.kw * d.kh)) % d.kt, c = col / (d.kw * d.kh * d.kt);
-      const int ow = (int)(row % d.Wo), oh = (int)((row / d.Wo) % d.Ho), ot = (int)((row / ((long long)d.Wo * d.Ho)) % d.To);
-      const int b = (int)(row / ((long long)d.Wo * d.Ho * d.To));
-      const int ti = ot * d.st - d.pt + dt, hi = oh * d.sh - d.ph + dh, wi = ow * d.sw - d.pw + dw;
-      if (ti >= 0 && ti < d.T && hi >= 0 && hi < d.H && wi >= 0 && wi < d.W)
-        val = x[((((long long)b * d.T + ti) * d.C + c) * d.H + hi) * d.W + wi];
+    const int grp = (int)(e % groups);
+    const long long row = e / groups;
+    const int col0 = grp * d.kw;
+    __nv_bfloat16* dst = cols + row * d.Kpad + col0;
+    const int ncol = min(d.kw, d.Kpad - col0);
+    const __nv_bfloat16 zero = __float2bfloat16_rn(0.f);
+    if (col0 >= Kreal) {
+      for (int j = 0; j < ncol; ++j) dst[j] = zero;
+      continue;
     }
-    cols[e] = __float2bfloat16_rn(val);
+    const int dh = grp % d.kh, dt = (grp / d.kh) % d.kt, c = grp / (d.kh * d.kt);
+    const int ow = (int)(row % d.Wo), oh = (int)((row / d.Wo) % d.Ho), ot = (int)((row / ((long long)d.Wo * d.Ho)) % d.To);
+    const int b = (int)(row / ((long long)d.Wo * d.Ho * d.To));
+    const int ti = ot * d.st - d.pt + dt, hi = oh * d.sh - d.ph + dh, w0 = ow * d.sw - d.pw;
+    const bool line_ok = ti >= 0 && ti < d.T && hi >= 0 && hi < d.H;
+    const float* src = x + ((((long long)b * d.T + (line_ok ? ti : 0)) * d.C + c) * d.H + (line_ok ? hi : 0)) * d.W;
+    for (int j = 0; j < ncol; ++j) {
+      const int wi = w0 + j;
+      const float v = (line_ok && wi >= 0 && wi < d.W) ? src[wi] : 0.f;
+      dst[j] = __float2bfloat16_rn(v);
+    }
   }
 }
 
@@ -915,7 +986,14 @@ extern "C" int vt_pool_fwd(const vt_pool_fwd_params* p, void* stream) {
   return check_launch("pool_ln_fwd_kernel");
 }
 
-static int pool_dw_blocks(long long rows) { return row_blocks(rows, 2); }
+constexpr int DW_MIN_ROWS_PER_CTA = 64;
+static int pool_dw_blocks(long long rows) {
+  long long blocks = (rows + DW_MIN_ROWS_PER_CTA - 1) / DW_MIN_ROWS_PER_CTA;
+  const long long cap = (long long)sm_count() * 2;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
 
 extern "C" int vt_pool_bwd_scratch(int32_t rows_out, int32_t hd) {
   // dpooled [rows_out, hd] + LN partials [blocks, 2, hd] + filter partials [blocks, 27*hd]
@@ -962,8 +1040,12 @@ extern "C" int vt_pool_bwd(const vt_pool_bwd_params* p, void* stream) {
   rc = check_launch("pool_din_kernel");
   if (rc) return rc;
   // 3. filter gradient
-  const int dwb = pool_dw_blocks(rows_out);
-  pool_dw_kernel<3><<<dwb, ROW_WARPS * 32, 0, st>>>(dpooled, static_cast<const __nv_bfloat16*>(p->in), p->in_bs, p->in_rs, dw_part, d);
+  const long long rows_conv = (long long)p->B * p->H * Lo;         // pooled rows without the cls rows
+  int dwb = pool_dw_blocks(rows_conv);
+  const int rows_per_cta = (int)((rows_conv + dwb - 1) / dwb);
+  dwb = (int)((rows_conv + rows_per_cta - 1) / rows_per_cta);      // no empty CTAs: every partial row is written
+  pool_dw_kernel<3><<<dwb, 27 * 32, 0, st>>>(dpooled, static_cast<const __nv_bfloat16*>(p->in), p->in_bs, p->in_rs, dw_part, d,
+                                             rows_per_cta);
   rc = check_launch("pool_dw_kernel");
   if (rc) return rc;
   vt_reduce_params r3{dw_part, p->dw, 27ll * hd, dwb, 27ll * hd, 0, 1.0f};
@@ -1044,19 +1126,19 @@ static int mp_dims_ok(const MpDims& d) {
 }
 
 extern "C" int vt_maxpool_fwd(const vt_maxpool_fwd_params* p, void* stream) {
-  VT_REQUIRE(p && p->x && p->y && p->idx && p->B > 0 && p->D > 0, "vt_maxpool_fwd: bad params");
+  VT_REQUIRE(p && p->x && p->y && p->idx && p->B > 0 && p->D > 0 && p->D % 4 == 0, "vt_maxpool_fwd: bad params (D %% 4 == 0 required)");
   const MpDims d{p->B, p->D, p->T, p->H, p->W, p->kt, p->kh, p->kw, p->st, p->sh, p->sw, p->To, p->Ho, p->Wo};
   VT_REQUIRE(mp_dims_ok(d), "vt_maxpool_fwd: inconsistent geometry");
-  const long long n = (long long)p->B * (1 + (long long)p->To * p->Ho * p->Wo) * p->D;
+  const long long n = (long long)p->B * (1 + (long long)p->To * p->Ho * p->Wo) * (p->D / 4);
   maxpool_fwd_kernel<<<flat_blocks(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p->x, p->y, p->idx, d);
   return check_launch("maxpool_fwd_kernel");
 }
 
 extern "C" int vt_maxpool_bwd(const vt_maxpool_bwd_params* p, void* stream) {
-  VT_REQUIRE(p && p->dy && p->idx && p->dx && p->B > 0 && p->D > 0, "vt_maxpool_bwd: bad params");
+  VT_REQUIRE(p && p->dy && p->idx && p->dx && p->B > 0 && p->D > 0 && p->D % 4 == 0, "vt_maxpool_bwd: bad params (D %% 4 == 0 required)");
   const MpDims d{p->B, p->D, p->T, p->H, p->W, p->kt, p->kh, p->kw, p->st, p->sh, p->sw, p->To, p->Ho, p->Wo};
   VT_REQUIRE(mp_dims_ok(d), "vt_maxpool_bwd: inconsistent geometry");
-  const long long n = (long long)p->B * (1 + (long long)p->T * p->H * p->W) * p->D;
+  const long long n = (long long)p->B * (1 + (long long)p->T * p->H * p->W) * (p->D / 4);
   maxpool_bwd_kernel<<<flat_blocks(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p->dy, p->idx, p->dx, d);
   return check_launch("maxpool_bwd_kernel");
 }
@@ -1067,7 +1149,7 @@ extern "C" int vt_im2col3d_bf16(const vt_im2col3d_params* p, void* stream) {
                  p->Wo == (p->W + 2 * p->pw - p->kw) / p->sw + 1, "vt_im2col3d_bf16: output dims inconsistent");
   VT_REQUIRE(p->Kpad >= p->C * p->kt * p->kh * p->kw && p->Kpad % 8 == 0, "vt_im2col3d_bf16: Kpad must cover C*kt*kh*kw and be a multiple of 8");
   const I3Dims d{p->B, p->T, p->C, p->H, p->W, p->kt, p->kh, p->kw, p->st, p->sh, p->sw, p->pt, p->ph, p->pw, p->To, p->Ho, p->Wo, p->Kpad};
-  const long long n = (long long)p->B * p->To * p->Ho * p->Wo * p->Kpad;
+  const long long n = (long long)p->B * p->To * p->Ho * p->Wo * ((p->Kpad + p->kw - 1) / p->kw);
   im2col3d_kernel<<<flat_blocks(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p->x, static_cast<__nv_bfloat16*>(p->cols), d);
   return check_launch("im2col3d_kernel");
 }

@@ -276,6 +276,11 @@ class MaskFeat(nn.Module):
     def forward(self, x, target_x, mask, cube_marker, visualize=False):
         if visualize:
             raise NotImplementedError('visualize=True is a debugging path of the reference ("need to update", :903)')
+        return self.forward_with_center_mask(x, target_x, mask, self.center_frame_mask(mask.to(x.device), cube_marker))
+
+    def forward_with_center_mask(self, x, target_x, mask, center_mask):
+        """forward() after its host-side loop over `cube_marker`: device work only, so a whole training step can be
+        captured in a CUDA graph (graph.GraphedTrainStep).  center_mask = self.center_frame_mask(mask, cube_marker)."""
         feats = self.forward_features(x, mask)
         dt = self.stride[0]
         t = self.num_frames // dt
@@ -284,9 +289,9 @@ class MaskFeat(nn.Module):
         fdim = self.decoder_pred.out_features
         dc = fdim // dt
         B = x.shape[0]
-        m = self.center_frame_mask(mask.to(x.device), cube_marker)
         # the reference's targets are fp64 numpy arrays (dataset.py:190); the kernels compute the loss in fp32
         target = target_x.to(device=x.device, dtype=torch.float32).contiguous()
+        m = center_mask.to(device=x.device, dtype=torch.float32).contiguous()
         pred, loss = mvit_ops.MaskedMSEFn.apply(feats, _f32(self.decoder_pred.weight), _f32(self.decoder_pred.bias),
                                                 self._shadow.get('dec', self.decoder_pred.weight), target, m,
                                                 (B, t, dt, h, w, dc))
