@@ -294,3 +294,34 @@ def test_maskfeat_rejects_cpu_tensors(maskfeat_golden):
     m = build(g)
     with pytest.raises(RuntimeError):
         m.forward_features(g.x)          # CPU clip: no fallback
+
+
+def test_maskfeat_step_is_graph_capturable(maskfeat_golden):
+    """The whole MaskFeat step (forward + loss + backward) replayed as one CUDA graph gives the eager result."""
+    from videotransformer_pytorch_b200.graph import GraphedTrainStep
+    g = maskfeat_golden('maskfeat_s32')
+    m = build(g).train()
+    x, target, mask = g.x.cuda(), g.target.cuda(), g.mask.cuda()
+    cmask = m.center_frame_mask(mask, g.cube_marker)
+
+    class Step(torch.nn.Module):
+        def __init__(self, net):
+            super().__init__()
+            self.net = net
+
+        def forward(self, x, target, mask, cmask):
+            return self.net.forward_with_center_mask(x, target, mask, cmask)[1]
+
+    step = GraphedTrainStep(Step(m), (x, target, mask, cmask))        # before any eager backward (see graph.py)
+    loss_g = float(step(x, target, mask, cmask))
+    grads_g = {n: p.grad.clone() for n, p in m.named_parameters()}
+    assert step.kernels_per_replay > 500
+    for p in m.parameters():
+        p.grad = None
+    _, loss_e = m(x, target, mask, g.cube_marker)
+    loss_e.backward()
+    assert abs(loss_g - float(loss_e)) < 1e-5 * abs(float(loss_e))
+    for n, p in m.named_parameters():
+        if n.endswith('attn.norm_k.bias'):
+            continue
+        assert rel_err(grads_g[n].cpu(), p.grad.cpu()) < 2e-3, n       # fp32 atomics in dK/dV: order-dependent rounding

@@ -33,15 +33,18 @@ def sim_pool_fwd(inp, in_bs, in_rs, w, B, H, thw, stride):
     Lo1 = 1 + To * Ho * Wo
     pooled = np.zeros((B * H * Lo1, HD))
     for r in range(B * H * Lo1):
-        l = r % Lo1
         bh = r // Lo1
-        h, b = bh % H, bh // H
+        l = r - bh * Lo1
+        b = bh // H
+        h = bh - b * H
         base = b * in_bs + h * HD
         if l == 0:
             pooled[r] = inp[base:base + HD]
             continue
         o = l - 1
-        ow, oh, ot = o % Wo, (o // Wo) % Ho, o // (Wo * Ho)
+        o2 = o // Wo
+        ow, ot = o - o2 * Wo, o2 // Ho
+        oh = o2 - ot * Ho
         hrow, wcol, hok, wok = [0] * 3, [0] * 3, [False] * 3, [False] * 3
         for k in range(3):
             hi, wi = oh * sh - 1 + k, ow * sw - 1 + k
@@ -62,42 +65,46 @@ def sim_pool_fwd(inp, in_bs, in_rs, w, B, H, thw, stride):
 
 
 def sim_pool_din(dpooled, w, B, H, thw, stride):
+    """token-per-warp kernel with per-axis (tap, coordinate) -> output-coordinate tables"""
     T, Hin, Win = thw
-    st, sh, sw = stride
     To, Ho, Wo = out_dims(thw, stride)
     L1, Lo1 = 1 + T * Hin * Win, 1 + To * Ho * Wo
-    din = np.zeros((B, L1, H, HD))
-    dp = dpooled.reshape(B * H, Lo1, HD)
-    for r in range(B * L1 * H):
-        h = r % H
-        n = (r // H) % L1
-        b = r // (H * L1)
-        g = dp[b * H + h]
-        if n == 0:
-            din[b, n, h] = g[0]
-            continue
-        idx = n - 1
-        wi, hi, ti = idx % Win, (idx // Win) % Hin, idx // (Win * Hin)
-        ohs, ows, hok, wok = [0] * 3, [0] * 3, [False] * 3, [False] * 3
+    tab = np.full((3, 3, 64), -1, dtype=np.int64)
+    for axis, (n_in, s_, n_out) in enumerate(((T, stride[0], To), (Hin, stride[1], Ho), (Win, stride[2], Wo))):
         for k in range(3):
-            nh, nw = hi + 1 - k, wi + 1 - k
-            hok[k] = nh >= 0 and nh % sh == 0 and nh // sh < Ho
-            wok[k] = nw >= 0 and nw % sw == 0 and nw // sw < Wo
-            ohs[k] = nh // sh if hok[k] else 0
-            ows[k] = nw // sw if wok[k] else 0
-        acc = np.zeros(HD)
-        for dt in range(3):
-            nt = ti + 1 - dt
-            if nt < 0 or nt % st != 0:
+            for c in range(64):
+                if c < n_in:
+                    nn = c + 1 - k
+                    if nn >= 0 and nn % s_ == 0 and nn // s_ < n_out:
+                        tab[axis, k, c] = nn // s_
+    din = np.zeros((B, L1, H, HD))
+    dp_all = dpooled.reshape(B * H, Lo1, HD)
+    for tok in range(B * L1):
+        b = tok // L1
+        n = tok - b * L1
+        if n > 0:
+            idx = n - 1
+            t2 = idx // Win
+            wi, ti = idx - t2 * Win, t2 // Hin
+            hi = t2 - ti * Hin
+            ot3, oh3, ow3 = tab[0, :, ti], tab[1, :, hi], tab[2, :, wi]
+        for h in range(H):
+            dp = dp_all[b * H + h]
+            if n == 0:
+                din[b, n, h] = dp[0]
                 continue
-            ot = nt // st
-            if ot >= To:
-                continue
-            for dh in range(3):
-                for dw in range(3):
-                    src = g[1 + (ot * Ho + ohs[dh]) * Wo + ows[dw]]
-                    acc += (src if (hok[dh] and wok[dw]) else 0.0) * w[:, (dt * 3 + dh) * 3 + dw]
-        din[b, n, h] = acc
+            acc = np.zeros(HD)
+            for dt in range(3):
+                if ot3[dt] < 0:
+                    continue
+                for dh in range(3):
+                    if oh3[dh] < 0:
+                        continue
+                    for dw in range(3):
+                        if ow3[dw] < 0:
+                            continue
+                        acc += dp[1 + (ot3[dt] * Ho + oh3[dh]) * Wo + ow3[dw]] * w[:, (dt * 3 + dh) * 3 + dw]
+            din[b, n, h] = acc
     return din.reshape(B, L1, H * HD)
 
 

@@ -48,20 +48,8 @@ def step():
     return loss
 
 
-for _ in range(a.warmup):
-    loss = step()
-torch.cuda.synchronize()
-print('loss', float(loss), 'finite grads', all(bool(torch.isfinite(p.grad).all()) for p in model.parameters()))
-n0 = _lib.launch_count()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-for _ in range(a.steps):
-    step()
-e1.record()
-torch.cuda.synchronize()
-ms = e0.elapsed_time(e1) / a.steps
-print(f'MaskFeat MViT-B 16x224 batch {B} fwd+bwd (eager): {ms:.2f} ms/step = {B / ms * 1e3:.1f} clips/s; '
-      f'{(_lib.launch_count() - n0) // a.steps} kernel launches/step; peak mem {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB')
+# the captured step goes first: autograd's AccumulateGrad nodes are bound to the stream they are first used on, and an
+# eager step on the default stream would pin them there (graph.py)
 if a.graph:
     from videotransformer_pytorch_b200.graph import GraphedTrainStep
 
@@ -79,6 +67,7 @@ if a.graph:
         for _ in range(2):
             gl = gstep(x, target, mask.float(), cmask)
         torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(a.steps * 2):
             gstep(x, target, mask.float(), cmask)
@@ -91,6 +80,20 @@ if a.graph:
         import traceback
         traceback.print_exc()
         print('graph capture failed:', ex)
+for _ in range(a.warmup):
+    loss = step()
+torch.cuda.synchronize()
+print('loss', float(loss), 'finite grads', all(bool(torch.isfinite(p.grad).all()) for p in model.parameters()))
+n0 = _lib.launch_count()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(a.steps):
+    step()
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / a.steps
+print(f'MaskFeat MViT-B 16x224 batch {B} fwd+bwd (eager): {ms:.2f} ms/step = {B / ms * 1e3:.1f} clips/s; '
+      f'{(_lib.launch_count() - n0) // a.steps} kernel launches/step; peak mem {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB')
 if a.profile:
     from torch.profiler import ProfilerActivity, profile
     with profile(activities=[ProfilerActivity.CUDA]) as prof:

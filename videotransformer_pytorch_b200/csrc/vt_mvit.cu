@@ -162,11 +162,10 @@ pool_ln_fwd_kernel(const __nv_bfloat16* __restrict__ in, long long in_bs, long l
     bt[i] = __ldg(beta + lane + 32 * i);
   }
   const int Lo1 = 1 + d.To * d.Ho * d.Wo;
-  const long long rows = (long long)d.B * d.H * Lo1;
-  for (long long r = (long long)blockIdx.x * ROW_WARPS + warp; r < rows; r += (long long)gridDim.x * ROW_WARPS) {
-    const int l = (int)(r % Lo1);
-    const int bh = (int)(r / Lo1);
-    const int h = bh % d.H, b = bh / d.H;
+  const int rows = d.B * d.H * Lo1;                             // < 2^31, checked by the launcher
+  for (int r = blockIdx.x * ROW_WARPS + warp; r < rows; r += gridDim.x * ROW_WARPS) {
+    const int bh = r / Lo1, l = r - bh * Lo1;
+    const int b = bh / d.H, h = bh - b * d.H;
     const __nv_bfloat16* base = in + (long long)b * in_bs + (long long)h * HD;
     float acc[E];
 #pragma unroll
@@ -176,7 +175,8 @@ pool_ln_fwd_kernel(const __nv_bfloat16* __restrict__ in, long long in_bs, long l
       for (int i = 0; i < E; ++i) acc[i] = bf2f(base + lane + 32 * i);
     } else {
       const int o = l - 1;
-      const int ow = o % d.Wo, oh = (o / d.Wo) % d.Ho, ot = o / (d.Wo * d.Ho);
+      const int o2 = o / d.Wo;
+      const int ow = o - o2 * d.Wo, ot = o2 / d.Ho, oh = o2 - ot * d.Ho;
       // the nine (dh, dw) taps of a dt plane are loaded unconditionally from clamped coordinates (out-of-range taps are
       // zeroed after the load) so that all of them are in flight together; dt planes outside the clip are skipped
       int hrow[3], wcol[3];
@@ -229,81 +229,90 @@ pool_ln_fwd_kernel(const __nv_bfloat16* __restrict__ in, long long in_bs, long l
     }
 #pragma unroll
     for (int i = 0; i < E; ++i) {
-      pooled[r * HD + lane + 32 * i] = acc[i];
-      out[r * HD + lane + 32 * i] = __float2bfloat16_rn((acc[i] - mu) * rs * g[i] + bt[i]);
+      pooled[(long long)r * HD + lane + 32 * i] = acc[i];
+      out[(long long)r * HD + lane + 32 * i] = __float2bfloat16_rn((acc[i] - mu) * rs * g[i] + bt[i]);
     }
   }
 }
 
-// gradient w.r.t. the pooling input: one warp per input row (b, n, h); gathers the outputs whose window covers it.
+// gradient w.r.t. the pooling input: one warp per input token (b, n), looping over the heads; gathers the outputs whose
+// window covers the token.  Which output (if any) is reached through tap k along an axis is a pure function of the
+// coordinate, so it is tabulated once per CTA — the row loop itself is free of div/mod chains (they dominated the
+// first version of this kernel).
+constexpr int POOL_MAX_DIM = 64;
+
 template <int E>
 __global__ void __launch_bounds__(ROW_WARPS * 32)
 pool_din_kernel(const float* __restrict__ dpooled, const float* __restrict__ w, __nv_bfloat16* __restrict__ din,
                 long long din_bs, long long din_rs, PoolDims d) {
   constexpr int HD = 32 * E;
   __shared__ float sw[27 * HD];
+  __shared__ short tab[3][3][POOL_MAX_DIM];     // [axis t/h/w][tap][input coordinate] -> output coordinate, -1 = none
   for (int i = threadIdx.x; i < 27 * HD; i += blockDim.x) {
     const int tap = i / HD, c = i % HD;
     sw[i] = w[c * 27 + tap];
+  }
+  for (int i = threadIdx.x; i < 9 * POOL_MAX_DIM; i += blockDim.x) {
+    const int axis = i / (3 * POOL_MAX_DIM), k = (i / POOL_MAX_DIM) % 3, c = i % POOL_MAX_DIM;
+    const int n_in = axis == 0 ? d.T : axis == 1 ? d.Hin : d.Win;
+    const int s = axis == 0 ? d.st : axis == 1 ? d.sh : d.sw;
+    const int n_out = axis == 0 ? d.To : axis == 1 ? d.Ho : d.Wo;
+    int v = -1;
+    if (c < n_in) {
+      const int nn = c + 1 - k;                   // o * s - 1 + k == c
+      if (nn >= 0 && nn % s == 0 && nn / s < n_out) v = nn / s;
+    }
+    tab[axis][k][c] = (short)v;
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int L1 = 1 + d.T * d.Hin * d.Win;
   const int Lo1 = 1 + d.To * d.Ho * d.Wo;
-  const long long rows = (long long)d.B * L1 * d.H;
-  for (long long r = (long long)blockIdx.x * ROW_WARPS + warp; r < rows; r += (long long)gridDim.x * ROW_WARPS) {
-    const int h = (int)(r % d.H);
-    const int n = (int)((r / d.H) % L1);
-    const int b = (int)(r / ((long long)d.H * L1));
-    const float* dp = dpooled + ((long long)b * d.H + h) * Lo1 * HD;
-    float acc[E];
-#pragma unroll
-    for (int i = 0; i < E; ++i) acc[i] = 0.f;
-    if (n == 0) {
-#pragma unroll
-      for (int i = 0; i < E; ++i) acc[i] = dp[lane + 32 * i];
-    } else {
+  const int tokens = d.B * L1;
+  for (int tok = blockIdx.x * ROW_WARPS + warp; tok < tokens; tok += gridDim.x * ROW_WARPS) {
+    const int b = tok / L1, n = tok - b * L1;
+    __nv_bfloat16* dst = din + (long long)b * din_bs + (long long)n * din_rs;
+    int ot3[3], oh3[3], ow3[3];
+    if (n > 0) {
       const int idx = n - 1;
-      const int wi = idx % d.Win, hi = (idx / d.Win) % d.Hin, ti = idx / (d.Win * d.Hin);
-      // output coordinate reached through tap k along each axis (o*s - 1 + k == i), clamped to 0 when there is none
-      int ohs[3], ows[3];
-      bool hok[3], wok[3];
+      const int t2 = idx / d.Win;
+      const int wi = idx - t2 * d.Win, ti = t2 / d.Hin, hi = t2 - ti * d.Hin;
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        const int nh = hi + 1 - k, nw = wi + 1 - k;
-        hok[k] = nh >= 0 && nh % d.sh == 0 && nh / d.sh < d.Ho;
-        wok[k] = nw >= 0 && nw % d.sw == 0 && nw / d.sw < d.Wo;
-        ohs[k] = hok[k] ? nh / d.sh : 0;
-        ows[k] = wok[k] ? nw / d.sw : 0;
-      }
-      for (int dt = 0; dt < 3; ++dt) {
-        const int nt = ti + 1 - dt;
-        if (nt < 0 || nt % d.st != 0) continue;
-        const int ot = nt / d.st;
-        if (ot >= d.To) continue;
-        float g[9][E];
-#pragma unroll
-        for (int dh = 0; dh < 3; ++dh)
-#pragma unroll
-          for (int dw = 0; dw < 3; ++dw) {
-            const float* src = dp + (1 + ((long long)ot * d.Ho + ohs[dh]) * d.Wo + ows[dw]) * HD;
-#pragma unroll
-            for (int i = 0; i < E; ++i) g[dh * 3 + dw][i] = src[lane + 32 * i];
-          }
-#pragma unroll
-        for (int dh = 0; dh < 3; ++dh)
-#pragma unroll
-          for (int dw = 0; dw < 3; ++dw) {
-            const float* f = sw + ((dt * 3 + dh) * 3 + dw) * HD;
-            const bool ok = hok[dh] && wok[dw];
-#pragma unroll
-            for (int i = 0; i < E; ++i) acc[i] = fmaf(ok ? g[dh * 3 + dw][i] : 0.f, f[lane + 32 * i], acc[i]);
-          }
+        ot3[k] = tab[0][k][ti];
+        oh3[k] = tab[1][k][hi];
+        ow3[k] = tab[2][k][wi];
       }
     }
-    __nv_bfloat16* dst = din + (long long)b * din_bs + (long long)n * din_rs + (long long)h * HD;
+    for (int h = 0; h < d.H; ++h) {
+      const float* dp = dpooled + ((long long)b * d.H + h) * Lo1 * HD;
+      float acc[E];
 #pragma unroll
-    for (int i = 0; i < E; ++i) dst[lane + 32 * i] = __float2bfloat16_rn(acc[i]);
+      for (int i = 0; i < E; ++i) acc[i] = 0.f;
+      if (n == 0) {
+#pragma unroll
+        for (int i = 0; i < E; ++i) acc[i] = dp[lane + 32 * i];
+      } else {
+#pragma unroll
+        for (int dt = 0; dt < 3; ++dt) {
+          if (ot3[dt] < 0) continue;
+#pragma unroll
+          for (int dh = 0; dh < 3; ++dh) {
+            if (oh3[dh] < 0) continue;
+#pragma unroll
+            for (int dw = 0; dw < 3; ++dw) {
+              if (ow3[dw] < 0) continue;
+              const float* src = dp + (1 + (ot3[dt] * d.Ho + oh3[dh]) * d.Wo + ow3[dw]) * HD;
+              const float* f = sw + ((dt * 3 + dh) * 3 + dw) * HD;
+#pragma unroll
+              for (int i = 0; i < E; ++i) acc[i] = fmaf(src[lane + 32 * i], f[lane + 32 * i], acc[i]);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < E; ++i) dst[h * HD + lane + 32 * i] = __float2bfloat16_rn(acc[i]);
+    }
   }
 }
 
@@ -980,6 +989,7 @@ extern "C" int vt_pool_fwd(const vt_pool_fwd_params* p, void* stream) {
   VT_REQUIRE(pool_dims_ok(p->T, p->Hin, p->Win, p->st, p->sh, p->sw, p->To, p->Ho, p->Wo), "vt_pool_fwd: output dims inconsistent");
   const PoolDims d{p->B, p->H, p->T, p->Hin, p->Win, p->st, p->sh, p->sw, p->To, p->Ho, p->Wo};
   const long long rows = (long long)p->B * p->H * (1 + (long long)p->To * p->Ho * p->Wo);
+  VT_REQUIRE(rows < 0x7fffffffll, "vt_pool_fwd: too many rows");
   pool_ln_fwd_kernel<3><<<row_blocks(rows, 8), ROW_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(p->in), p->in_bs, p->in_rs, p->w, p->gamma, p->beta, p->pooled,
       static_cast<__nv_bfloat16*>(p->out), p->mean, p->rstd, d, p->eps);
@@ -1034,8 +1044,11 @@ extern "C" int vt_pool_bwd(const vt_pool_bwd_params* p, void* stream) {
     if (rc) return rc;
   }
   // 2. gradient w.r.t. the input tokens
-  const long long rows_in = (long long)p->B * p->H * (1 + (long long)p->T * p->Hin * p->Win);
-  pool_din_kernel<3><<<row_blocks(rows_in, 8), ROW_WARPS * 32, 0, st>>>(dpooled, p->w, static_cast<__nv_bfloat16*>(p->din),
+  VT_REQUIRE(p->T <= POOL_MAX_DIM && p->Hin <= POOL_MAX_DIM && p->Win <= POOL_MAX_DIM, "vt_pool_bwd: token grid %dx%dx%d exceeds %d per axis",
+             p->T, p->Hin, p->Win, POOL_MAX_DIM);
+  const long long tokens_in = (long long)p->B * (1 + (long long)p->T * p->Hin * p->Win);
+  VT_REQUIRE(tokens_in < 0x7fffffffll, "vt_pool_bwd: too many tokens");
+  pool_din_kernel<3><<<row_blocks(tokens_in, 8), ROW_WARPS * 32, 0, st>>>(dpooled, p->w, static_cast<__nv_bfloat16*>(p->din),
                                                                         p->din_bs, p->din_rs, d);
   rc = check_launch("pool_din_kernel");
   if (rc) return rc;
