@@ -96,11 +96,35 @@ print(f'MaskFeat MViT-B 16x224 batch {B} fwd+bwd (eager): {ms:.2f} ms/step = {B 
       f'{(_lib.launch_count() - n0) // a.steps} kernel launches/step; peak mem {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB')
 if a.profile:
     from torch.profiler import ProfilerActivity, profile
+    shapes = []
+    real_gemm = _lib.K.gemm
+
+    def logged_gemm(a_, b_, M, N, Kd, **kw):
+        shapes.append((M, N, Kd, int(kw.get('a_mn', False)), int(kw.get('b_mn', False)), kw.get('epi', 'bf16'),
+                       'aux' if kw.get('aux') is not None else ''))
+        return real_gemm(a_, b_, M, N, Kd, **kw)
+
+    _lib.K.gemm = logged_gemm
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
         step()
         torch.cuda.synchronize()
+    _lib.K.gemm = real_gemm
     rows = sorted(prof.key_averages(), key=lambda r: -r.device_time_total)[:25]
     tot = sum(r.device_time_total for r in prof.key_averages())
     print(f'kernel time total {tot / 1e3:.2f} ms')
     for r in rows:
         print(f'{r.device_time_total / 1e3:9.3f} ms  {r.count:5d}x  {r.key[:110]}')
+    # per-shape GEMM table: every K.gemm call launches exactly one *gemm*_tcgen05_kernel, in call order
+    evs = sorted((e for e in prof.events() if 'tcgen05_kernel' in e.name and 'gemm' in e.name), key=lambda e: e.time_range.start)
+    if len(evs) == len(shapes):
+        agg = {}
+        for sh, e in zip(shapes, evs):
+            c = agg.setdefault(sh, [0, 0.0])
+            c[0] += 1
+            c[1] += e.device_time_total
+        print('GEMM shapes (M, N, K, a_mn, b_mn, epilogue): count, total us, TFLOP/s')
+        for sh, (cnt, us) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
+            fl = 2.0 * sh[0] * sh[1] * sh[2] * cnt
+            print(f'  {str(sh):62s} {cnt:3d}x {us:9.1f} us  {fl / us / 1e6:7.1f}')
+    else:
+        print(f'gemm table skipped: {len(evs)} kernel events vs {len(shapes)} calls')
