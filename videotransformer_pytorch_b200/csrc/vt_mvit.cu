@@ -189,30 +189,27 @@ pool_ln_fwd_kernel(const __nv_bfloat16* __restrict__ in, long long in_bs, long l
         hrow[k] = min(max(hi, 0), d.Hin - 1);
         wcol[k] = min(max(wi, 0), d.Win - 1);
       }
-      int trow[3];
-      bool tok_[3];
+      for (int dt = 0; dt < 3; ++dt) {
+        const int ti = ot * d.st - 1 + dt;
+        if (ti < 0 || ti >= d.T) continue;
+        float x[9][E];
 #pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const int ti = ot * d.st - 1 + k;
-        tok_[k] = ti >= 0 && ti < d.T;
-        trow[k] = min(max(ti, 0), d.T - 1);
-      }
-      float x[27][E];
+        for (int dh = 0; dh < 3; ++dh)
 #pragma unroll
-      for (int tap = 0; tap < 27; ++tap) {
-        const int dt = tap / 9, dh = (tap / 3) % 3, dw = tap % 3;
-        const __nv_bfloat16* src = base + (1 + ((long long)trow[dt] * d.Hin + hrow[dh]) * d.Win + wcol[dw]) * in_rs;
+          for (int dw = 0; dw < 3; ++dw) {
+            const __nv_bfloat16* src = base + (1 + ((long long)ti * d.Hin + hrow[dh]) * d.Win + wcol[dw]) * in_rs;
 #pragma unroll
-        for (int i = 0; i < E; ++i) x[tap][i] = bf2f(src + lane + 32 * i);
-      }
-      asm volatile("" ::: "memory");         // all loads in flight before the first FMA
+            for (int i = 0; i < E; ++i) x[dh * 3 + dw][i] = bf2f(src + lane + 32 * i);
+          }
 #pragma unroll
-      for (int tap = 0; tap < 27; ++tap) {
-        const int dt = tap / 9, dh = (tap / 3) % 3, dw = tap % 3;
-        const bool ok = tok_[dt] && hok[dh] && wok[dw];
-        const float* f = sw + tap * HD;
+        for (int dh = 0; dh < 3; ++dh)
 #pragma unroll
-        for (int i = 0; i < E; ++i) acc[i] = fmaf(ok ? x[tap][i] : 0.f, f[lane + 32 * i], acc[i]);
+          for (int dw = 0; dw < 3; ++dw) {
+            const float* f = sw + ((dt * 3 + dh) * 3 + dw) * HD;
+            const bool ok = hok[dh] && wok[dw];
+#pragma unroll
+            for (int i = 0; i < E; ++i) acc[i] = fmaf(ok ? x[dh * 3 + dw][i] : 0.f, f[lane + 32 * i], acc[i]);
+          }
       }
     }
     float s = 0.f;
@@ -276,7 +273,6 @@ pool_din_kernel(const float* __restrict__ dpooled, const float* __restrict__ w, 
     const int b = tok / L1, n = tok - b * L1;
     __nv_bfloat16* dst = din + (long long)b * din_bs + (long long)n * din_rs;
     int ot3[3], oh3[3], ow3[3];
-    bool any_t = false, any_h = false, any_w = false;
     if (n > 0) {
       const int idx = n - 1;
       const int t2 = idx / d.Win;
@@ -286,9 +282,6 @@ pool_din_kernel(const float* __restrict__ dpooled, const float* __restrict__ w, 
         ot3[k] = tab[0][k][ti];
         oh3[k] = tab[1][k][hi];
         ow3[k] = tab[2][k][wi];
-        any_t |= ot3[k] >= 0;
-        any_h |= oh3[k] >= 0;
-        any_w |= ow3[k] >= 0;
       }
     }
     for (int h = 0; h < d.H; ++h) {
@@ -300,27 +293,20 @@ pool_din_kernel(const float* __restrict__ dpooled, const float* __restrict__ w, 
 #pragma unroll
         for (int i = 0; i < E; ++i) acc[i] = dp[lane + 32 * i];
       } else {
-        // all 27 taps are loaded before the first FMA (one memory latency per token instead of one per tap); taps without
-        // an output read the cls row (always resident in L1) and are masked.  Tokens no output window touches skip it all.
-        if (any_t && any_h && any_w) {
-          float g[27][E];
 #pragma unroll
-          for (int tap = 0; tap < 27; ++tap) {
-            const int dt = tap / 9, dh = (tap / 3) % 3, dw = tap % 3;
-            const bool ok = ot3[dt] >= 0 && oh3[dh] >= 0 && ow3[dw] >= 0;
-            const int row = ok ? 1 + (ot3[dt] * d.Ho + oh3[dh]) * d.Wo + ow3[dw] : 0;
-            const float* src = dp + (long long)row * HD;
+        for (int dt = 0; dt < 3; ++dt) {
+          if (ot3[dt] < 0) continue;
 #pragma unroll
-            for (int i = 0; i < E; ++i) g[tap][i] = src[lane + 32 * i];
-          }
-          asm volatile("" ::: "memory");     // keep the 81 loads ahead of the FMAs (the scheduler would interleave them)
+          for (int dh = 0; dh < 3; ++dh) {
+            if (oh3[dh] < 0) continue;
 #pragma unroll
-          for (int tap = 0; tap < 27; ++tap) {
-            const int dt = tap / 9, dh = (tap / 3) % 3, dw = tap % 3;
-            const bool ok = ot3[dt] >= 0 && oh3[dh] >= 0 && ow3[dw] >= 0;
-            const float* f = sw + tap * HD;
+            for (int dw = 0; dw < 3; ++dw) {
+              if (ow3[dw] < 0) continue;
+              const float* src = dp + (1 + (ot3[dt] * d.Ho + oh3[dh]) * d.Wo + ow3[dw]) * HD;
+              const float* f = sw + ((dt * 3 + dh) * 3 + dw) * HD;
 #pragma unroll
-            for (int i = 0; i < E; ++i) acc[i] = fmaf(ok ? g[tap][i] : 0.f, f[lane + 32 * i], acc[i]);
+              for (int i = 0; i < E; ++i) acc[i] = fmaf(src[lane + 32 * i], f[lane + 32 * i], acc[i]);
+            }
           }
         }
       }
@@ -334,7 +320,7 @@ pool_din_kernel(const float* __restrict__ dpooled, const float* __restrict__ w, 
 // CTA = 27 warps, warp = filter tap, lane = channels (c = lane + 32 i): every (tap, channel) sum is owned by one thread, so
 // there is no cross-warp reduction; rows are walked four at a time with all loads issued before the FMAs.
 // Per-CTA partial rows [hd*27] are summed by reduce_rows.
-constexpr int DW_ROWS_UNROLL = 8;
+constexpr int DW_ROWS_UNROLL = 4;
 
 template <int E>
 __global__ void __launch_bounds__(27 * 32)
@@ -395,7 +381,6 @@ pool_dw_kernel(const float* __restrict__ dpooled, const __nv_bfloat16* __restric
         }
       }
     }
-    asm volatile("" ::: "memory");           // all loads in flight before the first FMA
 #pragma unroll
     for (int u = 0; u < DW_ROWS_UNROLL; ++u)
 #pragma unroll
