@@ -320,6 +320,30 @@ typedef struct {
 } vt_mse_bwd_params;
 int vt_mse_bwd(const vt_mse_bwd_params* p, void* stream);
 
+/* =============================================================================================
+ * Fused per-parameter gradient clipping + optimizer step (reference model_trainer.py:155-170
+ * clip_gradients + optimizer.py:33-38 SGD(momentum 0.9, nesterov) / AdamW(0.9, 0.999)).
+ * Multi-tensor form: tensor i has parameter pptr[i], gradient gptr[i], state s1ptr[i] (momentum buffer / exp_avg) and
+ * s2ptr[i] (exp_avg_sq), all fp32 device addresses stored as int64 in device arrays; `chunks` is a device table of
+ * {int32 tensor, int32 len, int64 offset} (16 bytes each) covering every tensor; lr / wd are per-tensor fp32 arrays.
+ *   vt_opt_norm2 : norm2[i] = sum(grad_i^2)                          (the trainer's total norm = sqrt(sum_i norm2[i]))
+ *   vt_opt_sgd   : g = grad * min(1, clip / (sqrt(norm2) + 1e-6)) [clip > 0];  d = g + wd*p;  buf = first ? d : mom*buf + d;
+ *                  p -= lr * (nesterov ? d + mom*buf : buf)           (torch.optim.SGD, dampening 0)
+ *   vt_opt_adamw : p *= 1 - lr*wd;  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;
+ *                  p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)         (torch.optim.AdamW; bc_k = 1 - beta_k^step)
+ * Gradients are read, never written back (the reference scales p.grad in place; nothing reads it afterwards).
+ * ============================================================================================= */
+typedef struct {
+  const void* chunks; int32_t n_chunks; int32_t n_tensors;
+  const int64_t* pptr; const int64_t* gptr; const int64_t* s1ptr; const int64_t* s2ptr;
+  float* norm2; const float* lr; const float* wd;
+  float clip, momentum, beta1, beta2, eps, bc1, bc2;
+  int32_t nesterov, first_step;
+} vt_opt_params;
+int vt_opt_norm2(const vt_opt_params* p, void* stream);
+int vt_opt_sgd(const vt_opt_params* p, void* stream);
+int vt_opt_adamw(const vt_opt_params* p, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

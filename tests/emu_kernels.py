@@ -322,3 +322,39 @@ class EmuKernels:
         g = g.reshape(B, t, dt, h, w, dc).permute(0, 1, 3, 4, 2, 5).reshape(B, t * h * w, dt * dc)
         g = torch.cat([torch.zeros((B, 1, dt * dc), dtype=g.dtype), g], dim=1)
         return self._h(g.reshape(B * (1 + t * h * w), dt * dc))
+
+    # ------------------------------------------------------------------------------------------
+    # fused clip + optimizer: the emulation works on the tensor lists of optim.TensorTable
+    # ------------------------------------------------------------------------------------------
+    def _opt_tensors(self, tbl):
+        return tbl['_params'], tbl['_grads'](), tbl['_state']
+
+    def opt_norm2(self, tbl):
+        _, grads, _ = self._opt_tensors(tbl)
+        tbl['norm2'].copy_(torch.stack([(g.double() ** 2).sum() for g in grads]).to(tbl['norm2'].dtype))
+        return tbl['norm2']
+
+    def _coef(self, tbl, clip, i):
+        if not clip:
+            return 1.0
+        c = clip / (float(tbl['norm2'][i]) ** 0.5 + 1e-6)
+        return min(c, 1.0)
+
+    def opt_sgd(self, tbl, clip, momentum, nesterov, first_step):
+        params, grads, state = self._opt_tensors(tbl)
+        for i, (p, g) in enumerate(zip(params, grads)):
+            d = g * self._coef(tbl, clip, i) + float(tbl['wd'][i]) * p
+            buf = state[0][i]
+            buf.copy_(d if first_step else momentum * buf + d)
+            d = d + momentum * buf if nesterov else buf
+            p.add_(d, alpha=-float(tbl['lr'][i]))
+
+    def opt_adamw(self, tbl, clip, beta1, beta2, eps, bc1, bc2):
+        params, grads, state = self._opt_tensors(tbl)
+        for i, (p, g) in enumerate(zip(params, grads)):
+            g = g * self._coef(tbl, clip, i)
+            lr, wd = float(tbl['lr'][i]), float(tbl['wd'][i])
+            p.mul_(1 - lr * wd)
+            state[0][i].mul_(beta1).add_(g, alpha=1 - beta1)
+            state[1][i].mul_(beta2).addcmul_(g, g, value=1 - beta2)
+            p.addcdiv_(state[0][i], state[1][i].sqrt() / bc2 ** 0.5 + eps, value=-lr / bc1)

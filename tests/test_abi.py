@@ -59,7 +59,7 @@ def test_ctypes_structs_match_the_header(tmp_path):
              'vt_maxpool_fwd_params': _lib.MaxpoolFwdParams, 'vt_maxpool_bwd_params': _lib.MaxpoolBwdParams,
              'vt_im2col3d_params': _lib.Im2col3dParams, 'vt_mvit_tokens_fwd_params': _lib.MvitTokensFwdParams,
              'vt_mvit_tokens_bwd_params': _lib.MvitTokensBwdParams, 'vt_mse_fwd_params': _lib.MseFwdParams,
-             'vt_mse_bwd_params': _lib.MseBwdParams}
+             'vt_mse_bwd_params': _lib.MseBwdParams, 'vt_opt_params': _lib.OptParams}
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "vt_b200.h")}"',
              'int main(void) {']
     for cname, cls in pairs.items():

@@ -153,12 +153,20 @@ class MseBwdParams(C.Structure):
     _fields_ = [('pred', c_vp), ('target', c_vp), ('mask', c_vp), ('coef', c_vp), ('dpred', c_vp)] + _MSE_DIMS
 
 
+class OptParams(C.Structure):
+    _fields_ = [('chunks', c_vp), ('n_chunks', c_i32), ('n_tensors', c_i32),
+                ('pptr', c_vp), ('gptr', c_vp), ('s1ptr', c_vp), ('s2ptr', c_vp),
+                ('norm2', c_vp), ('lr', c_vp), ('wd', c_vp),
+                ('clip', c_f32), ('momentum', c_f32), ('beta1', c_f32), ('beta2', c_f32), ('eps', c_f32), ('bc1', c_f32),
+                ('bc2', c_f32), ('nesterov', c_i32), ('first_step', c_i32)]
+
+
 EXPORTS = ['vt_version', 'vt_last_error', 'vt_sm_count', 'vt_set_reserved_sms', 'vt_launch_count', 'vt_gemm', 'vt_layernorm_fwd', 'vt_ln_bwd_blocks',
            'vt_layernorm_bwd', 'vt_reduce_rows', 'vt_colsum_chunks', 'vt_colsum_bf16', 'vt_cast_f32_bf16',
            'vt_gather_cast_bf16', 'vt_gelu_fwd_bf16', 'vt_gelu_bwd_bf16', 'vt_attn_fwd', 'vt_attn_bwd', 'vt_debug_buffer', 'vt_im2col_bf16', 'vt_col2im_f32', 'vt_hog',
            'vt_pool_fwd', 'vt_pool_bwd_scratch', 'vt_pool_bwd', 'vt_xattn_fwd', 'vt_xattn_bwd', 'vt_maxpool_fwd',
            'vt_maxpool_bwd', 'vt_im2col3d_bf16', 'vt_mvit_tokens_fwd', 'vt_mvit_tokens_bwd', 'vt_mse_blocks',
-           'vt_mse_fwd', 'vt_mse_bwd']
+           'vt_mse_fwd', 'vt_mse_bwd', 'vt_opt_norm2', 'vt_opt_sgd', 'vt_opt_adamw']
 
 _dll = None
 
@@ -691,6 +699,32 @@ class CudaKernels:
         p.B, p.t, p.dt, p.h, p.w, p.dc = dims
         _check(lib.vt_mse_bwd(C.byref(p), _stream()), 'vt_mse_bwd')
         return dpred
+
+
+    # -- fused clip + optimizer (multi-tensor) ---------------------------------------------------
+    def _opt_params(self, tbl, clip=0.0, **hp):
+        p = OptParams()
+        p.chunks, p.n_chunks, p.n_tensors = tbl['chunks'].data_ptr(), tbl['n_chunks'], tbl['n_tensors']
+        p.pptr, p.gptr = tbl['pptr'].data_ptr(), tbl['gptr'].data_ptr()
+        p.s1ptr, p.s2ptr = tbl['s1ptr'].data_ptr(), _ptr(tbl.get('s2ptr'))
+        p.norm2, p.lr, p.wd = tbl['norm2'].data_ptr(), tbl['lr'].data_ptr(), tbl['wd'].data_ptr()
+        p.clip = float(clip or 0.0)
+        for k, v in hp.items():
+            setattr(p, k, v)
+        return p
+
+    def opt_norm2(self, tbl):
+        """tbl['norm2'][i] = sum(grad_i ** 2) for every tensor of the table (optim.TensorTable)"""
+        _check(load_library().vt_opt_norm2(C.byref(self._opt_params(tbl)), _stream()), 'vt_opt_norm2')
+        return tbl['norm2']
+
+    def opt_sgd(self, tbl, clip, momentum, nesterov, first_step):
+        p = self._opt_params(tbl, clip, momentum=momentum, nesterov=int(nesterov), first_step=int(first_step))
+        _check(load_library().vt_opt_sgd(C.byref(p), _stream()), 'vt_opt_sgd')
+
+    def opt_adamw(self, tbl, clip, beta1, beta2, eps, bc1, bc2):
+        p = self._opt_params(tbl, clip, beta1=beta1, beta2=beta2, eps=eps, bc1=bc1, bc2=bc2)
+        _check(load_library().vt_opt_adamw(C.byref(p), _stream()), 'vt_opt_adamw')
 
 
 def set_reserved_sms(n: int) -> None:
