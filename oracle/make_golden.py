@@ -186,12 +186,13 @@ def vivit_case(vt, name, cfg, B, seed):
     np.savez_compressed(os.path.join(GOLD, name + '.npz'), **save)
 
 
-def space_only_case(vt, name, cfg, B, seed):
+def space_only_case(vt, name, cfg, B, seed, attention_type='space_only'):
     from oracle import vt_oracle as O
+    oracle_fwd = O.timesformer_space_only_forward if attention_type == 'space_only' else O.timesformer_joint_forward
     torch.manual_seed(seed)
     m = vt.TimeSformer(num_frames=cfg['num_frames'], img_size=cfg['img_size'], patch_size=cfg['patch_size'],
                        embed_dims=cfg['embed_dims'], num_heads=cfg['num_heads'],
-                       num_transformer_layers=cfg['num_transformer_layers'], attention_type='space_only')
+                       num_transformer_layers=cfg['num_transformer_layers'], attention_type=attention_type)
     randomize(m, seed + 1)
     m = m.double()
     sd = {k: v.detach().clone().float().double() for k, v in m.state_dict().items()}
@@ -200,7 +201,7 @@ def space_only_case(vt, name, cfg, B, seed):
     m.eval()
     with torch.no_grad():
         y_eval = m(x)
-        assert rel(O.timesformer_space_only_forward(sd, x, cfg), y_eval) < 1e-12
+        assert rel(oracle_fwd(sd, x, cfg), y_eval) < 1e-12
     m.train()
     torch.manual_seed(3000 + seed)
     y_tr = m(x)
@@ -209,7 +210,7 @@ def space_only_case(vt, name, cfg, B, seed):
     grads = {n: p.grad.detach().clone() for n, p in m.named_parameters()}
     sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
     torch.manual_seed(3000 + seed)
-    yo = O.timesformer_space_only_forward(sdg, x, cfg, training=True)
+    yo = oracle_fwd(sdg, x, cfg, training=True)
     (yo * w).sum().backward()
     assert rel(yo.detach(), y_tr.detach()) < 1e-12
     for n, g in grads.items():
@@ -334,6 +335,10 @@ def main():
     vivit_case(vt, 'vivit_tiny_b1', vv, B=1, seed=2)
     vivit_case(vt, 'vivit_tiny_b3', vv, B=3, seed=3)
     space_only_case(vt, 'timesformer_space_only_tiny', tiny, B=2, seed=5)
+    space_only_case(vt, 'timesformer_joint_tiny', tiny, B=2, seed=6, attention_type='joint_space_time')
+    # 1 + 36*8 = 289 tokens per clip: past the 256-token limit of the single-pass attention kernels (head dim 64)
+    joint289 = dict(num_frames=8, img_size=96, patch_size=16, embed_dims=128, num_heads=2, num_transformer_layers=1)
+    space_only_case(vt, 'timesformer_joint_n289', joint289, B=1, seed=7, attention_type='joint_space_time')
     mask_cases(mg)
     two_stage = dict(pool_q_stride_size=((1, 1, 2, 2), (3, 1, 2, 2)), feature_dim=216)     # model_trainer.py:54
     maskfeat_case(vt, 'maskfeat_s32', dict(img_size=32, num_frames=8, **two_stage), B=2, seed=7)

@@ -220,6 +220,17 @@ def timesformer_space_only_forward(sd, x, cfg, training=False):
     return tok[:, 0]
 
 
+def timesformer_joint_forward(sd, x, cfg, training=False):
+    """TimeSformer.forward with attention_type='joint_space_time' (video_transformer.py:104-116, :193-256): the tokens
+    of the divided variant (spatial + temporal embedding, one cls), then ['self_attn', 'ffn'] layers that attend over
+    all 1 + P*T tokens of a clip at once."""
+    tok = timesformer_tokens(sd, x, cfg)
+    tok = container(tok, sd, 'transformer_layers.', cfg['num_transformer_layers'], ['self_attn', 'ffn'],
+                    cfg['num_frames'], cfg['num_heads'], training)
+    tok = layer_norm(tok, sd['norm.weight'], sd['norm.bias'], 1e-6)
+    return tok[:, 0]
+
+
 def timesformer_last_selfattention(sd, x, cfg):
     """TimeSformer.get_last_selfattention, video_transformer.py:258-261."""
     tok = timesformer_tokens(sd, x, cfg)

@@ -234,6 +234,7 @@ class EmuKernels:
         return gw.reshape(hd, 27).to(self.f), (d * xh).sum((0, 1, 2)).to(self.f), d.sum((0, 1, 2)).to(self.f)
 
     def xattn_fwd(self, q, k, v, scale, impl=0):
+        self.calls.append(('xattn', tuple(q.shape), k.shape[2]))
         Q, Kk, V = self._up(q), self._up(k), self._up(v)
         B, H, Nq, hd = Q.shape
         s = (Q @ Kk.transpose(-1, -2)) * scale

@@ -179,3 +179,33 @@ def test_space_only_small_vs_oracle():
     e = rel_err(got.cpu(), ref)
     print(f'space_only small eval: {e:.2e}')
     assert e < 1.5e-2
+
+
+def test_joint_space_time_vs_golden(golden):
+    """joint_space_time with 289 tokens per clip (past the single-pass kernels): streaming tcgen05 attention, head dim 64."""
+    from videotransformer_pytorch_b200 import TimeSformer
+    g = golden('timesformer_joint_n289')
+    c = g.cfg
+    m = TimeSformer(num_frames=c['num_frames'], img_size=c['img_size'], patch_size=c['patch_size'],
+                    embed_dims=c['embed_dims'], num_heads=c['num_heads'],
+                    num_transformer_layers=c['num_transformer_layers'], attention_type='joint_space_time')
+    m.load_state_dict(g.sd, strict=True)
+    m = m.cuda().eval()
+    with torch.no_grad():
+        e = rel_err(m(g.x.cuda()).cpu(), g.out['y_eval'])
+    print(f'joint_space_time n289 eval: {e:.2e}')
+    assert e < 1.5e-2
+    m.train()
+    torch.manual_seed(g.train_seed)
+    y = m(g.x.cuda())
+    assert rel_err(y.detach().cpu(), g.out['y_train']) < 1.5e-2
+    (y.double() * g.out['loss_w'].cuda()).sum().backward()
+    worst = 0.0
+    for n, p in m.named_parameters():
+        if n in g.grad:
+            worst = max(worst, rel_err(p.grad.cpu(), g.grad[n]))
+        elif n in g.gradsum:
+            ref = g.gradsum[n]
+            worst = max(worst, abs(p.grad.double().norm().item() - ref[1]) / ref[1])
+    print(f'joint_space_time n289 train: worst grad rel err {worst:.2e}')
+    assert worst < 5e-2

@@ -139,6 +139,33 @@ def test_xattn_fwd_bwd(B, H, Nq, Nk, impl):
         assert rel_err(dq2.float().cpu(), dq2_c) < tol_g and rel_err(dk2.cpu(), dk2_r) < tol_g
 
 
+@pytest.mark.parametrize('B,H,N', [(1, 2, 300), (2, 12, 289), (1, 2, 1569), (3, 1, 128)])
+def test_xattn_head_dim_64_self_attention(B, H, N):
+    """The same kernels at head dim 64 with q, k, v all read in place from one packed [B*N, 3*H*64] projection
+    (TimeSformer joint space-time attention)."""
+    hd = 64
+    d = H * hd
+    scale = hd ** -0.5
+    e = emu()
+    qkv = rn((B * N, 3 * d), 80).bfloat16()
+    views = lambda t: tuple(t.view(B, N, 3, H, hd)[:, :, s].permute(0, 2, 1, 3) for s in range(3))
+    qc, kc, vc = views(qkv.float())
+    o_r, lse_r = e.xattn_fwd(qc, kc, vc, scale)
+    qg = qkv.cuda()
+    q4, k4, v4 = views(qg)
+    o, lse = K().xattn_fwd(q4, k4, v4, scale)
+    assert rel_err(o.float().cpu(), o_r) < 1e-2 and rel_err(lse.cpu(), lse_r) < 1e-4
+    dout = rn((B, N, d), 81).bfloat16()
+    dq_c = torch.zeros(B, H, N, hd)
+    dk_r, dv_r = e.xattn_bwd(qc, kc, vc, o.float().cpu(), dout.float(), lse.cpu(), scale, dq_c)
+    dqkv = torch.full((B * N, 3 * d), 3.0, dtype=torch.bfloat16, device='cuda')
+    dq4, _, _ = views(dqkv)
+    dk, dv = K().xattn_bwd(q4, k4, v4, o, dout.cuda(), lse, scale, dq4)
+    assert rel_err(dq4.float().cpu(), dq_c) < 2e-2
+    assert rel_err(dk.cpu(), dk_r) < 2e-2 and rel_err(dv.cpu(), dv_r) < 2e-2
+    assert bool((dqkv.view(B, N, 3, d)[:, :, 1:] == 3.0).all())
+
+
 def test_xattn_auto_picks_tensor_cores_and_rejects_bad_layouts():
     B, H, Nq, Nk = 1, 2, 64, 32
     q = rn((B, H, Nq, HD), 25).bfloat16().cuda()

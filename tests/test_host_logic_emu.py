@@ -119,8 +119,26 @@ def test_timesformer_space_only(golden, emu):
     check_grads({n: p.grad for n, p in m.named_parameters()}, g, 2e-4)
 
 
-def test_joint_space_time_is_refused_not_faked():
+@pytest.mark.parametrize('name', ['timesformer_joint_tiny', 'timesformer_joint_n289'])
+def test_timesformer_joint_space_time(golden, emu, name):
+    """joint_space_time (video_transformer.py:104-116): 17 tokens go through the single-pass attention kernel, 289 tokens
+    through the streaming one (ops.ATTN_SINGLE_PASS_MAX)."""
     from videotransformer_pytorch_b200 import TimeSformer
-    with pytest.raises(NotImplementedError):
-        TimeSformer(num_frames=4, img_size=32, embed_dims=64, num_heads=1, num_transformer_layers=1,
-                    attention_type='joint_space_time')
+    g = golden(name)
+    c = g.cfg
+    m = TimeSformer(num_frames=c['num_frames'], img_size=c['img_size'], patch_size=c['patch_size'],
+                    embed_dims=c['embed_dims'], num_heads=c['num_heads'],
+                    num_transformer_layers=c['num_transformer_layers'], attention_type='joint_space_time')
+    assert list(m.state_dict().keys()) == list(g.sd.keys())
+    m.load_state_dict(g.sd, strict=True)
+    m.eval()
+    with torch.no_grad():
+        assert rel_err(m(g.x), g.out['y_eval']) < 2e-5
+    m.train()
+    torch.manual_seed(g.train_seed)
+    y = m(g.x)
+    assert rel_err(y, g.out['y_train']) < 2e-5
+    (y.double() * g.out['loss_w']).sum().backward()
+    check_grads({n: p.grad for n, p in m.named_parameters()}, g, 2e-4)
+    used = {c_[0] for c_ in emu.calls if isinstance(c_, tuple)}
+    assert ('xattn' in used) == (name == 'timesformer_joint_n289')

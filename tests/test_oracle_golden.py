@@ -129,3 +129,19 @@ def test_space_only_oracle_vs_golden(golden):
     assert rel_err(y, g.out['y_train']) < 1e-12
     (y * g.out['loss_w']).sum().backward()
     check_grads({k: v.grad for k, v in sdg.items()}, g, 1e-6)
+
+
+@pytest.mark.parametrize('name', ['timesformer_joint_tiny', 'timesformer_joint_n289'])
+def test_timesformer_joint_oracle_vs_golden(golden, name):
+    from oracle import vt_oracle as O
+    g = golden(name)
+    sd = {k: v.double() for k, v in g.sd.items()}
+    x = g.x.double()
+    with torch.no_grad():
+        assert rel_err(O.timesformer_joint_forward(sd, x, g.cfg), g.out['y_eval']) < 1e-12
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    torch.manual_seed(g.train_seed)
+    y = O.timesformer_joint_forward(sdg, x, g.cfg, training=True)
+    assert rel_err(y, g.out['y_train']) < 1e-12
+    (y * g.out['loss_w']).sum().backward()
+    check_grads({k: v.grad for k, v in sdg.items()}, g, 1e-6)

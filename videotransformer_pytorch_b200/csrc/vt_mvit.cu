@@ -1073,7 +1073,7 @@ static int xa_strides_ok(const long long* s, int n) {
 
 extern "C" int vt_xattn_fwd(const vt_xattn_fwd_params* p, void* stream) {
   VT_REQUIRE(p && p->q && p->k && p->v && p->o && p->lse, "vt_xattn_fwd: null pointer");
-  VT_REQUIRE(p->hd == 96, "vt_xattn_fwd: head dim %d unsupported (96 only)", p->hd);
+  VT_REQUIRE(p->hd == 96 || p->hd == 64, "vt_xattn_fwd: head dim %d unsupported (64 or 96)", p->hd);
   VT_REQUIRE(p->B > 0 && p->H > 0 && p->Nq > 0 && p->Nk > 0 && (long long)p->B * p->H <= 65535, "vt_xattn_fwd: bad dims");
   VT_REQUIRE(p->impl >= VT_XATTN_AUTO && p->impl <= VT_XATTN_TCGEN05, "vt_xattn_fwd: bad impl %d", p->impl);
   if (p->impl == VT_XATTN_TCGEN05 ||
@@ -1081,6 +1081,8 @@ extern "C" int vt_xattn_fwd(const vt_xattn_fwd_params* p, void* stream) {
                                                       p->v_hs, p->v_rs, p->B, p->H, p->Nq, p->Nk, p->hd) &&
        (p->o_rs * 2) % 16 == 0 && ((uintptr_t)p->o & 15) == 0))
     return xattn_tc_fwd_launch(p, static_cast<cudaStream_t>(stream));
+  VT_REQUIRE(p->hd == 96, "vt_xattn_fwd: the CUDA-core kernels cover head dim 96 only; head dim %d needs a layout the tcgen05 "
+             "kernels accept (token-major or head-major contiguous, 16-byte aligned rows)", p->hd);
   const long long ss[12] = {p->q_bs, p->q_hs, p->q_rs, p->k_bs, p->k_hs, p->k_rs, p->v_bs, p->v_hs, p->v_rs, p->o_bs, p->o_hs, p->o_rs};
   VT_REQUIRE(xa_strides_ok(ss, 12), "vt_xattn_fwd: strides must be even (4-byte aligned bf16 pairs)");
   VT_REQUIRE(((uintptr_t)p->q | (uintptr_t)p->k | (uintptr_t)p->v | (uintptr_t)p->o) % 4 == 0, "vt_xattn_fwd: pointers must be 4-byte aligned");
@@ -1094,7 +1096,7 @@ extern "C" int vt_xattn_fwd(const vt_xattn_fwd_params* p, void* stream) {
 
 extern "C" int vt_xattn_bwd(const vt_xattn_bwd_params* p, void* stream) {
   VT_REQUIRE(p && p->q && p->k && p->v && p->o && p->dout && p->lse && p->delta && p->dq && p->dk && p->dv, "vt_xattn_bwd: null pointer");
-  VT_REQUIRE(p->hd == 96, "vt_xattn_bwd: head dim %d unsupported (96 only)", p->hd);
+  VT_REQUIRE(p->hd == 96 || p->hd == 64, "vt_xattn_bwd: head dim %d unsupported (64 or 96)", p->hd);
   VT_REQUIRE(p->B > 0 && p->H > 0 && p->Nq > 0 && p->Nk > 0 && (long long)p->B * p->H <= 65535, "vt_xattn_bwd: bad dims");
   VT_REQUIRE(p->impl >= VT_XATTN_AUTO && p->impl <= VT_XATTN_TCGEN05, "vt_xattn_bwd: bad impl %d", p->impl);
   if (p->impl == VT_XATTN_TCGEN05 ||
@@ -1103,6 +1105,7 @@ extern "C" int vt_xattn_bwd(const vt_xattn_bwd_params* p, void* stream) {
        (p->o_rs * 2) % 16 == 0 && (p->dq_rs * 2) % 16 == 0 && (p->dq_hs * 2) % 16 == 0 && (p->dq_bs * 2) % 16 == 0 &&
        (((uintptr_t)p->o | (uintptr_t)p->dout | (uintptr_t)p->dq) & 15) == 0))
     return xattn_tc_bwd_launch(p, static_cast<cudaStream_t>(stream));
+  VT_REQUIRE(p->hd == 96, "vt_xattn_bwd: the CUDA-core kernels cover head dim 96 only (got %d)", p->hd);
   const long long ss[15] = {p->q_bs, p->q_hs, p->q_rs, p->k_bs, p->k_hs, p->k_rs, p->v_bs, p->v_hs, p->v_rs, p->o_bs, p->o_hs, p->o_rs,
                             p->dq_bs, p->dq_hs, p->dq_rs};
   VT_REQUIRE(xa_strides_ok(ss, 15), "vt_xattn_bwd: strides must be even");

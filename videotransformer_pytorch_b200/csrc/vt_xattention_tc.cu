@@ -19,10 +19,8 @@ namespace vt {
 
 int make_tmap_bf16_2d(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows);
 
-constexpr int XT_HD = 96;
 constexpr int XT_BLK = 128 * 128;      // one swizzled block: 128 rows x 64 bf16 = 16 KiB
 constexpr int XT_TILE = 2 * XT_BLK;    // 128 rows x 128 (padded) columns
-constexpr int XT_KSTEPS_HD = XT_HD / 16;
 constexpr float XT_LOG2E = 1.4426950408889634f;
 constexpr float XT_LN2 = 0.6931471805599453f;
 constexpr int XT_THREADS = 320;        // warps 0-3 / 4-7: two warpgroups; warp 8: MMA issuer; warp 9: TMA producer
@@ -44,10 +42,11 @@ __device__ __forceinline__ void xt_load_tile(uint8_t* dst, const CUtensorMap* ma
   tma_load_2d(dst, map, bar, col, row);
   tma_load_2d(dst + XT_BLK, map, bar, col + 64, row);
 }
-// D[128 x 128] (+)= A[128 x 96] B[128 x 96]^T, both K-major tiles (contraction over the head dim)
+// D[128 x 128] (+)= A[128 x HD] B[128 x HD]^T, both K-major tiles (contraction over the head dim: HD/16 K-steps)
+template <int HD>
 __device__ __forceinline__ void xt_mma_hd(uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr, uint32_t idesc) {
 #pragma unroll
-  for (int k = 0; k < XT_KSTEPS_HD; ++k)
+  for (int k = 0; k < HD / 16; ++k)
     umma_bf16_ss(d_tmem, sdesc_kmajor(a_addr + (k >> 2) * XT_BLK + (k & 3) * 32),
                  sdesc_kmajor(b_addr + (k >> 2) * XT_BLK + (k & 3) * 32), idesc, k > 0);
 }
@@ -59,10 +58,11 @@ __device__ __forceinline__ uint4 xt_pack8(const float* e) {
   o.w = pack_bf16x2(e[6], e[7]);
   return o;
 }
-__device__ __forceinline__ void xt_store_row96(__nv_bfloat16* dst, const float* v, float mul) {
+template <int HD>
+__device__ __forceinline__ void xt_store_row(__nv_bfloat16* dst, const float* v, float mul) {
   uint4* d = reinterpret_cast<uint4*>(dst);
 #pragma unroll
-  for (int g = 0; g < 12; ++g) {
+  for (int g = 0; g < HD / 8; ++g) {
     uint4 o;
     o.x = pack_bf16x2(v[g * 8 + 0] * mul, v[g * 8 + 1] * mul);
     o.y = pack_bf16x2(v[g * 8 + 2] * mul, v[g * 8 + 3] * mul);
@@ -84,6 +84,7 @@ struct XtFwd {
   float scale;
 };
 
+template <int XT_HD>
 __global__ void __launch_bounds__(XT_THREADS, 1)
 xattn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const XtFwd p) {
@@ -149,7 +150,7 @@ xattn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const int s = j & 1;
         mbar_wait(&bar_kv_full[s], (j >> 1) & 1);
         tc_fence_after();
-        xt_mma_hd(tmem_base + s * 128, qa, smem_u32(sK + s * XT_TILE), idesc_s);
+        xt_mma_hd<XT_HD>(tmem_base + s * 128, qa, smem_u32(sK + s * XT_TILE), idesc_s);
         umma_commit(&bar_s[s]);
       };
       issue_qk(0);
@@ -223,7 +224,7 @@ xattn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       mbar_wait(&bar_pv[wg], ph);
       tc_fence_after();
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
+      for (int c = 0; c < XT_HD / 32; ++c) {
         uint32_t v[32];
         tmem_ld32(tlane + 256 + wg * 128 + c * 32, v);
         tmem_ld_wait();
@@ -234,12 +235,13 @@ xattn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     // merge the two warpgroups' partial softmax states (all P.V MMAs have completed: each group waited for its last)
     tc_fence_before();
     xt_bar_sync(1, 256);
-    float* stash = reinterpret_cast<float*>(sP);               // [128][97] O rows, then m[128], l[128]
-    float* stash_m = stash + 128 * 97;
+    constexpr int PITCH = XT_HD + 1;                           // odd pitch: conflict-free row-per-thread access
+    float* stash = reinterpret_cast<float*>(sP);               // [128][PITCH] O rows, then m[128], l[128]
+    float* stash_m = stash + 128 * PITCH;
     float* stash_l = stash_m + 128;
     if (wg == 1) {
 #pragma unroll
-      for (int d = 0; d < XT_HD; ++d) stash[r * 97 + d] = acc[d];
+      for (int d = 0; d < XT_HD; ++d) stash[r * PITCH + d] = acc[d];
       stash_m[r] = m;
       stash_l[r] = l;
     }
@@ -252,8 +254,8 @@ xattn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const int q = qt * 128 + r;
       if (q < p.Nq) {
 #pragma unroll
-        for (int d = 0; d < XT_HD; ++d) acc[d] = acc[d] * f0 + stash[r * 97 + d] * f1;
-        xt_store_row96(p.o + (long long)b * p.o_bs + (long long)h * p.o_hs + (long long)q * p.o_rs, acc, 1.0f / lt);
+        for (int d = 0; d < XT_HD; ++d) acc[d] = acc[d] * f0 + stash[r * PITCH + d] * f1;
+        xt_store_row<XT_HD>(p.o + (long long)b * p.o_bs + (long long)h * p.o_hs + (long long)q * p.o_rs, acc, 1.0f / lt);
         p.lse[(long long)bh * p.Nq + q] = (mm + log2f(lt)) * XT_LN2;
       }
     }
@@ -281,6 +283,7 @@ struct XtDq {
   float scale;
 };
 
+template <int XT_HD>
 __global__ void __launch_bounds__(XT_THREADS, 1)
 xattn_tc_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmD, const XtDq p) {
@@ -352,8 +355,8 @@ xattn_tc_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const uint32_t ka = smem_u32(sK + s * XT_TILE), va = smem_u32(sV + s * XT_TILE);
         mbar_wait(&bar_kv_full[s], (j >> 1) & 1);
         tc_fence_after();
-        xt_mma_hd(tmem_base + COL_S, qa, ka, idesc_s);
-        xt_mma_hd(tmem_base + COL_DP, doa, va, idesc_s);
+        xt_mma_hd<XT_HD>(tmem_base + COL_S, qa, ka, idesc_s);
+        xt_mma_hd<XT_HD>(tmem_base + COL_DP, doa, va, idesc_s);
         umma_commit(bar_sdp);
         mbar_wait(bar_ds, j & 1);
         tc_fence_after();
@@ -378,7 +381,7 @@ xattn_tc_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const uint4* o4 = reinterpret_cast<const uint4*>(p.o + off);
         const uint4* g4 = reinterpret_cast<const uint4*>(p.dout + off);
 #pragma unroll
-        for (int i = 0; i < 12; ++i) {
+        for (int i = 0; i < XT_HD / 8; ++i) {
           const uint4 a = o4[i], g = g4[i];
           const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z), a3 = unpack_bf16x2(a.w);
           const float2 g0 = unpack_bf16x2(g.x), g1 = unpack_bf16x2(g.y), g2 = unpack_bf16x2(g.z), g3 = unpack_bf16x2(g.w);
@@ -423,7 +426,7 @@ xattn_tc_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if (half == 0) {
       float out[XT_HD];
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
+      for (int c = 0; c < XT_HD / 32; ++c) {
         uint32_t v[32];
         tmem_ld32(tlane + COL_DQ + c * 32, v);
         tmem_ld_wait();
@@ -431,7 +434,7 @@ xattn_tc_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         for (int jj = 0; jj < 32; ++jj) out[c * 32 + jj] = __uint_as_float(v[jj]);
       }
       if (qok)
-        xt_store_row96(p.dq + (long long)b * p.dq_bs + (long long)h * p.dq_hs + (long long)q * p.dq_rs, out, 1.0f);
+        xt_store_row<XT_HD>(p.dq + (long long)b * p.dq_bs + (long long)h * p.dq_hs + (long long)q * p.dq_rs, out, 1.0f);
     }
   }
   tc_fence_before();
@@ -455,6 +458,7 @@ struct XtDkv {
   float scale;
 };
 
+template <int XT_HD>
 __global__ void __launch_bounds__(XT_THREADS, 1)
 xattn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmD, const XtDkv p) {
@@ -522,8 +526,8 @@ xattn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       for (int it = 0; it < n_it; ++it) {
         mbar_wait(bar_qdo_full, it & 1);
         tc_fence_after();
-        xt_mma_hd(tmem_base + COL_S, qa, ka, idesc_s);       // S [query x key]
-        xt_mma_hd(tmem_base + COL_DP, doa, va, idesc_s);     // dP
+        xt_mma_hd<XT_HD>(tmem_base + COL_S, qa, ka, idesc_s);       // S [query x key]
+        xt_mma_hd<XT_HD>(tmem_base + COL_DP, doa, va, idesc_s);     // dP
         umma_commit(bar_sdp);
         mbar_wait(bar_pds, it & 1);
         tc_fence_after();
@@ -584,7 +588,7 @@ xattn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     float* dst = (half == 0 ? p.dk : p.dv) + ((long long)bh * p.Nk + key) * XT_HD;
     const uint32_t col = half == 0 ? COL_DK : COL_DV;
 #pragma unroll 1
-    for (int c = 0; c < 3; ++c) {
+    for (int c = 0; c < XT_HD / 32; ++c) {
       uint32_t v[32];
       tmem_ld32(tlane + col + c * 32, v);
       tmem_ld_wait();
@@ -608,28 +612,28 @@ xattn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 // Classify an operand addressed as (b, h, n, c) -> b*bs + h*hs + n*rs + c into a 2-D TMA view.
 //   token-major  (hs == hd):           rows = B*N, row = b*N + n, col = h*hd + c, ld = rs   (needs bs == N*rs)
 //   head-major   (rs == hd, contiguous): rows = B*H*N, row = (b*H + h)*N + n, col = c, ld = hd
-static bool xt_classify(long long bs, long long hs, long long rs, int B, int H, int N, XtOp* op, long long* rows,
+static bool xt_classify(long long bs, long long hs, long long rs, int B, int H, int N, int hd, XtOp* op, long long* rows,
                         long long* cols, long long* ld) {
-  if (hs == XT_HD && bs == (long long)N * rs && rs >= (long long)H * XT_HD) {
-    *op = XtOp{N, 0, XT_HD};
+  if (hs == hd && bs == (long long)N * rs && rs >= (long long)H * hd) {
+    *op = XtOp{N, 0, hd};
     *rows = (long long)B * N;
-    *cols = (long long)H * XT_HD;
+    *cols = (long long)H * hd;
     *ld = rs;
     return true;
   }
-  if (rs == XT_HD && hs == (long long)N * XT_HD && bs == (long long)H * N * XT_HD) {
+  if (rs == hd && hs == (long long)N * hd && bs == (long long)H * N * hd) {
     *op = XtOp{H * N, N, 0};
     *rows = (long long)B * H * N;
-    *cols = XT_HD;
-    *ld = XT_HD;
+    *cols = hd;
+    *ld = hd;
     return true;
   }
   return false;
 }
 
-static int xt_map(CUtensorMap* m, const void* base, long long bs, long long hs, long long rs, int B, int H, int N, XtOp* op) {
+static int xt_map(CUtensorMap* m, const void* base, long long bs, long long hs, long long rs, int B, int H, int N, int hd, XtOp* op) {
   long long rows, cols, ld;
-  if (!xt_classify(bs, hs, rs, B, H, N, op, &rows, &cols, &ld)) return -1;
+  if (!xt_classify(bs, hs, rs, B, H, N, hd, op, &rows, &cols, &ld)) return -1;
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld * 2) % 16 != 0) return -1;
   return make_tmap_bf16_2d(m, base, rows, cols, ld, 128);
 }
@@ -637,11 +641,11 @@ static int xt_map(CUtensorMap* m, const void* base, long long bs, long long hs, 
 bool xattn_tc_supported(const void* q, long long q_bs, long long q_hs, long long q_rs, const void* k, long long k_bs,
                         long long k_hs, long long k_rs, const void* v, long long v_bs, long long v_hs, long long v_rs, int B,
                         int H, int Nq, int Nk, int hd) {
-  if (hd != XT_HD) return false;
+  if (hd != 96 && hd != 64) return false;
   XtOp op;
   long long a, b2, c;
   auto ok = [&](const void* p, long long bs, long long hs, long long rs, int N) {
-    return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && xt_classify(bs, hs, rs, B, H, N, &op, &a, &b2, &c) && (c * 2) % 16 == 0;
+    return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && xt_classify(bs, hs, rs, B, H, N, hd, &op, &a, &b2, &c) && (c * 2) % 16 == 0;
   };
   return ok(q, q_bs, q_hs, q_rs, Nq) && ok(k, k_bs, k_hs, k_rs, Nk) && ok(v, v_bs, v_hs, v_rs, Nk);
 }
@@ -664,20 +668,23 @@ int xattn_tc_fwd_launch(const vt_xattn_fwd_params* q, cudaStream_t st) {
   static_assert(XT_SMEM_FWD <= 232448 && XT_SMEM_DQ <= 232448 && XT_SMEM_DKV <= 232448, "shared memory budget");
   XtFwd p;
   CUtensorMap tmQ, tmK, tmV;
-  VT_REQUIRE(xt_map(&tmQ, q->q, q->q_bs, q->q_hs, q->q_rs, q->B, q->H, q->Nq, &p.q) == 0, "xattn_tc_fwd: unsupported q layout");
-  VT_REQUIRE(xt_map(&tmK, q->k, q->k_bs, q->k_hs, q->k_rs, q->B, q->H, q->Nk, &p.k) == 0, "xattn_tc_fwd: unsupported k layout");
-  VT_REQUIRE(xt_map(&tmV, q->v, q->v_bs, q->v_hs, q->v_rs, q->B, q->H, q->Nk, &p.v) == 0, "xattn_tc_fwd: unsupported v layout");
+  VT_REQUIRE(xt_map(&tmQ, q->q, q->q_bs, q->q_hs, q->q_rs, q->B, q->H, q->Nq, q->hd, &p.q) == 0, "xattn_tc_fwd: unsupported q layout");
+  VT_REQUIRE(xt_map(&tmK, q->k, q->k_bs, q->k_hs, q->k_rs, q->B, q->H, q->Nk, q->hd, &p.k) == 0, "xattn_tc_fwd: unsupported k layout");
+  VT_REQUIRE(xt_map(&tmV, q->v, q->v_bs, q->v_hs, q->v_rs, q->B, q->H, q->Nk, q->hd, &p.v) == 0, "xattn_tc_fwd: unsupported v layout");
   VT_REQUIRE((q->o_rs * 2) % 16 == 0 && (q->o_hs * 2) % 16 == 0 && (q->o_bs * 2) % 16 == 0 && ((uintptr_t)q->o & 15) == 0,
              "xattn_tc_fwd: output rows must be 16-byte aligned");
   p.o = static_cast<__nv_bfloat16*>(q->o);
   p.lse = q->lse;
   p.o_bs = q->o_bs; p.o_hs = q->o_hs; p.o_rs = q->o_rs;
   p.H = q->H; p.Nq = q->Nq; p.Nk = q->Nk; p.nkt = (q->Nk + 127) / 128; p.scale = q->scale;
-  static bool attr = false;
-  int rc = xt_set_smem(xattn_tc_fwd_kernel, XT_SMEM_FWD, &attr, "xattn_tc_fwd");
+  VT_REQUIRE(q->hd == 96 || q->hd == 64, "xattn_tc_fwd: head dim %d unsupported (64 or 96)", q->hd);
+  static bool attr96 = false, attr64 = false;
+  int rc = q->hd == 96 ? xt_set_smem(xattn_tc_fwd_kernel<96>, XT_SMEM_FWD, &attr96, "xattn_tc_fwd")
+                       : xt_set_smem(xattn_tc_fwd_kernel<64>, XT_SMEM_FWD, &attr64, "xattn_tc_fwd");
   if (rc) return rc;
   dim3 grid((q->Nq + 127) / 128, q->B * q->H);
-  xattn_tc_fwd_kernel<<<grid, XT_THREADS, XT_SMEM_FWD, st>>>(tmQ, tmK, tmV, p);
+  if (q->hd == 96) xattn_tc_fwd_kernel<96><<<grid, XT_THREADS, XT_SMEM_FWD, st>>>(tmQ, tmK, tmV, p);
+  else xattn_tc_fwd_kernel<64><<<grid, XT_THREADS, XT_SMEM_FWD, st>>>(tmQ, tmK, tmV, p);
   return check_launch("xattn_tc_fwd_kernel");
 }
 
@@ -685,10 +692,10 @@ int xattn_tc_bwd_launch(const vt_xattn_bwd_params* q, cudaStream_t st) {
   XtDq a;
   XtDkv c;
   CUtensorMap tmQ, tmK, tmV, tmD;
-  VT_REQUIRE(xt_map(&tmQ, q->q, q->q_bs, q->q_hs, q->q_rs, q->B, q->H, q->Nq, &a.q) == 0, "xattn_tc_bwd: unsupported q layout");
-  VT_REQUIRE(xt_map(&tmK, q->k, q->k_bs, q->k_hs, q->k_rs, q->B, q->H, q->Nk, &a.k) == 0, "xattn_tc_bwd: unsupported k layout");
-  VT_REQUIRE(xt_map(&tmV, q->v, q->v_bs, q->v_hs, q->v_rs, q->B, q->H, q->Nk, &a.v) == 0, "xattn_tc_bwd: unsupported v layout");
-  VT_REQUIRE(xt_map(&tmD, q->dout, q->o_bs, q->o_hs, q->o_rs, q->B, q->H, q->Nq, &a.d) == 0, "xattn_tc_bwd: unsupported dout layout");
+  VT_REQUIRE(xt_map(&tmQ, q->q, q->q_bs, q->q_hs, q->q_rs, q->B, q->H, q->Nq, q->hd, &a.q) == 0, "xattn_tc_bwd: unsupported q layout");
+  VT_REQUIRE(xt_map(&tmK, q->k, q->k_bs, q->k_hs, q->k_rs, q->B, q->H, q->Nk, q->hd, &a.k) == 0, "xattn_tc_bwd: unsupported k layout");
+  VT_REQUIRE(xt_map(&tmV, q->v, q->v_bs, q->v_hs, q->v_rs, q->B, q->H, q->Nk, q->hd, &a.v) == 0, "xattn_tc_bwd: unsupported v layout");
+  VT_REQUIRE(xt_map(&tmD, q->dout, q->o_bs, q->o_hs, q->o_rs, q->B, q->H, q->Nq, q->hd, &a.d) == 0, "xattn_tc_bwd: unsupported dout layout");
   VT_REQUIRE((q->o_rs * 2) % 16 == 0 && (q->o_hs * 2) % 16 == 0 && (q->o_bs * 2) % 16 == 0 && ((uintptr_t)q->o & 15) == 0 &&
                  ((uintptr_t)q->dout & 15) == 0, "xattn_tc_bwd: o / dout rows must be 16-byte aligned");
   VT_REQUIRE((q->dq_rs * 2) % 16 == 0 && (q->dq_hs * 2) % 16 == 0 && (q->dq_bs * 2) % 16 == 0 && ((uintptr_t)q->dq & 15) == 0,
@@ -706,13 +713,17 @@ int xattn_tc_bwd_launch(const vt_xattn_bwd_params* q, cudaStream_t st) {
   a.o_bs = q->o_bs; a.o_hs = q->o_hs; a.o_rs = q->o_rs;
   a.dq_bs = q->dq_bs; a.dq_hs = q->dq_hs; a.dq_rs = q->dq_rs;
   a.H = q->H; a.Nq = q->Nq; a.Nk = q->Nk; a.nkt = (q->Nk + 127) / 128; a.scale = q->scale;
-  static bool attr_dq = false, attr_dkv = false;
-  int rc = xt_set_smem(xattn_tc_dq_kernel, XT_SMEM_DQ, &attr_dq, "xattn_tc_dq");
+  VT_REQUIRE(q->hd == 96 || q->hd == 64, "xattn_tc_bwd: head dim %d unsupported (64 or 96)", q->hd);
+  static bool attr_dq96 = false, attr_dkv96 = false, attr_dq64 = false, attr_dkv64 = false;
+  int rc = q->hd == 96 ? xt_set_smem(xattn_tc_dq_kernel<96>, XT_SMEM_DQ, &attr_dq96, "xattn_tc_dq")
+                       : xt_set_smem(xattn_tc_dq_kernel<64>, XT_SMEM_DQ, &attr_dq64, "xattn_tc_dq");
   if (rc) return rc;
-  rc = xt_set_smem(xattn_tc_dkv_kernel, XT_SMEM_DKV, &attr_dkv, "xattn_tc_dkv");
+  rc = q->hd == 96 ? xt_set_smem(xattn_tc_dkv_kernel<96>, XT_SMEM_DKV, &attr_dkv96, "xattn_tc_dkv")
+                   : xt_set_smem(xattn_tc_dkv_kernel<64>, XT_SMEM_DKV, &attr_dkv64, "xattn_tc_dkv");
   if (rc) return rc;
   dim3 gq((q->Nq + 127) / 128, q->B * q->H);
-  xattn_tc_dq_kernel<<<gq, XT_THREADS, XT_SMEM_DQ, st>>>(tmQ, tmK, tmV, tmD, a);
+  if (q->hd == 96) xattn_tc_dq_kernel<96><<<gq, XT_THREADS, XT_SMEM_DQ, st>>>(tmQ, tmK, tmV, tmD, a);
+  else xattn_tc_dq_kernel<64><<<gq, XT_THREADS, XT_SMEM_DQ, st>>>(tmQ, tmK, tmV, tmD, a);
   rc = check_launch("xattn_tc_dq_kernel");
   if (rc) return rc;
   c.lse = q->lse;
@@ -724,7 +735,8 @@ int xattn_tc_bwd_launch(const vt_xattn_bwd_params* q, cudaStream_t st) {
   const int chunks = (c.nqt + XT_QTILES_PER_CHUNK - 1) / XT_QTILES_PER_CHUNK;
   VT_REQUIRE(chunks <= 65535 && q->B * q->H <= 65535, "xattn_tc_bwd: grid too large");
   dim3 gk(a.nkt, chunks, q->B * q->H);
-  xattn_tc_dkv_kernel<<<gk, XT_THREADS, XT_SMEM_DKV, st>>>(tmQ, tmK, tmV, tmD, c);
+  if (q->hd == 96) xattn_tc_dkv_kernel<96><<<gk, XT_THREADS, XT_SMEM_DKV, st>>>(tmQ, tmK, tmV, tmD, c);
+  else xattn_tc_dkv_kernel<64><<<gk, XT_THREADS, XT_SMEM_DKV, st>>>(tmQ, tmK, tmV, tmD, c);
   return check_launch("xattn_tc_dkv_kernel");
 }
 

@@ -118,6 +118,15 @@ def _dgrad(dout, w, m_tok, k_in, n_out, **kw):
     return K().gemm(dout, w, m_tok, k_in, n_out, b_mn=True, **kw)
 
 
+ATTN_SINGLE_PASS_MAX = 256      # vt_attn_*: whole score row in TMEM / registers; longer sequences stream K/V (vt_xattn_*)
+
+
+def _packed_heads(qkv, Bp, N, H, hd):
+    """q, k, v of a packed [Bp*N, 3*H*hd] projection as [Bp, H, N, hd] views (token-major, no copy)."""
+    v5 = qkv.view(Bp, N, 3, H, hd)
+    return tuple(v5[:, :, s].permute(0, 2, 1, 3) for s in range(3))
+
+
 def _mul_opt(a, b):
     if a is None:
         return b
@@ -246,7 +255,14 @@ class JointAttnFn(torch.autograd.Function):
         hd = D // H
         xn, mean, rstd = k.ln_fwd(x2, ln_w, ln_b, eps)
         qkv = k.gemm(xn, qkv_wh, M, 3 * D, D, bias=qkv_b, epi='bf16')
-        cx, lse, _ = k.attn_fwd(qkv, Bp, N, H, hd, hd ** -0.5)
+        if N <= ATTN_SINGLE_PASS_MAX:
+            cx, lse, _ = k.attn_fwd(qkv, Bp, N, H, hd, hd ** -0.5)
+        else:
+            # long sequences (joint space-time attention: 1 + P*T = 1569 tokens): streaming tcgen05 kernel, q/k/v read in
+            # place from the packed projection
+            q4, k4, v4 = _packed_heads(qkv, Bp, N, H, hd)
+            cx, lse = k.xattn_fwd(q4, k4, v4, hd ** -0.5)
+            cx = cx.view(M, D)
         y = torch.empty_like(x)
         k.gemm(cx, proj_wh, M, D, D, bias=proj_b, epi='f32', aux=x2, out=y.view(M, D), row_scale=dp)
         ctx.save_for_backward(x, ln_w, mean, rstd, xn, qkv, cx, lse, qkv_wh, proj_wh, dp)
@@ -267,7 +283,15 @@ class JointAttnFn(torch.autograd.Function):
         d_proj_w = _wgrad(g, cx, D, D, M)
         d_proj_b = k.colsum(g)
         dcx = _dgrad(g, proj_wh, M, D, D, epi='bf16')
-        dqkv = k.attn_bwd(qkv, cx, dcx, lse, Bp, N, H, hd, hd ** -0.5)
+        if N <= ATTN_SINGLE_PASS_MAX:
+            dqkv = k.attn_bwd(qkv, cx, dcx, lse, Bp, N, H, hd, hd ** -0.5)
+        else:
+            q4, k4, v4 = _packed_heads(qkv, Bp, N, H, hd)
+            dqkv = torch.empty_like(qkv)
+            dq4, dk4, dv4 = _packed_heads(dqkv, Bp, N, H, hd)
+            dk, dv = k.xattn_bwd(q4, k4, v4, cx.view(Bp, N, D), dcx.view(Bp, N, D), lse, hd ** -0.5, dq4)
+            dk4.copy_(dk)           # fp32 [Bp,H,N,hd] accumulators -> their bf16 slots of the packed gradient
+            dv4.copy_(dv)
         d_qkv_w = _wgrad(dqkv, xn, 3 * D, D, M)
         d_qkv_b = k.colsum(dqkv)
         dxn = _dgrad(dqkv, qkv_wh, M, D, 3 * D, epi='bf16')

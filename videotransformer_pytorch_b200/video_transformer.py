@@ -2,9 +2,9 @@
 and state-dict keys (reference video_transformer.py:20-268 and :270-557), forward/backward on the
 sm_100a kernels.
 
-Covered hot-path configurations: TimeSformer `divided_space_time`, ViViT `fact_encoder`.
-`space_only` / `joint_space_time` (sequence 197 / 1569 joint attention) are the "next" rows of §8f and
-raise NotImplementedError rather than falling back to eager PyTorch.
+Covered configurations: TimeSformer `divided_space_time`, `space_only` (197-token joint
+attention per frame) and `joint_space_time` (one 1569-token attention per clip, streaming tcgen05 kernel); ViViT
+`fact_encoder`.  Nothing falls back to eager PyTorch.
 """
 from __future__ import annotations
 
@@ -34,9 +34,6 @@ class TimeSformer(nn.Module):
                  use_learnable_pos_emb=True, return_cls_token=True, **kwargs):
         super().__init__()
         assert attention_type in self.supported_attention_types, f'Unsupported Attention Type {attention_type}!'
-        if attention_type == 'joint_space_time':
-            raise NotImplementedError('joint_space_time (one 1569-token attention per clip) is not on the B200 hot path yet '
-                                      '(SURVEY §8f rank 4); divided_space_time and space_only are')
         if dropout_p:
             raise NotImplementedError('dropout_p > 0 is not on the reference hot path (always 0.)')
         self.num_frames = num_frames
@@ -110,7 +107,7 @@ class TimeSformer(nn.Module):
             raise NotImplementedError('input size must match img_size (no pos-embed interpolation on the hot path)')
         pos, tim = self._embeds(x)
         pe = self.patch_embed
-        mode = 'timesformer' if self.attention_type == 'divided_space_time' else 'frames'   # space_only: per-frame tokens
+        mode = 'frames' if self.attention_type == 'space_only' else 'timesformer'   # space_only: per-frame tokens
         tok = ops.PatchTokensFn.apply(x, _f32(pe.projection.weight), _f32(pe.projection.bias), self.cls_token, pos, tim,
                                       pe.shadow(), mode, 1)
         return tok, b
