@@ -191,6 +191,10 @@ int vt_debug_buffer(void* device_ptr);
  * ------------------------------------------------------------------------------------------- */
 typedef struct { const float* x; void* cols; int32_t B, T, C, H, W, tube, ph, pw; } vt_im2col_params;
 int vt_im2col_bf16(const vt_im2col_params* p, void* stream);
+/* Same operand from the decoder's uint8 clip (data_transform.py:52-64 ToTensor + :534-539 Normalize fused in):
+ *   x u8 [B, T, H, W, C] (channels last) -> cols[row, k] = bf16(x * scale[c] + shift[c]),  scale = 1/(255 std), shift = -mean/std */
+typedef struct { const uint8_t* x; const float* scale; const float* shift; void* cols; int32_t B, T, C, H, W, tube, ph, pw; } vt_im2col_u8_params;
+int vt_im2col_u8_bf16(const vt_im2col_u8_params* p, void* stream);
 typedef struct { const float* cols; float* dx; int32_t B, T, C, H, W, tube, ph, pw; } vt_col2im_params;
 int vt_col2im_f32(const vt_col2im_params* p, void* stream);
 

@@ -177,6 +177,10 @@ class EmuKernels:
         xx = self._up(x).reshape(B, Tp, tube, C, Hp, ph, Wp, pw).permute(0, 1, 4, 6, 3, 2, 5, 7)
         return self._h(xx.reshape(B * Tp * Hp * Wp, C * tube * ph * pw))
 
+    def im2col_u8(self, x, scale, shift, tube, ph, pw):
+        xf = x.to(self.f).permute(0, 1, 4, 2, 3) * self._up(scale).view(1, 1, -1, 1, 1) + self._up(shift).view(1, 1, -1, 1, 1)
+        return self.im2col(xf, tube, ph, pw)
+
     def col2im(self, cols, shape, tube, ph, pw):
         B, T, C, H, W = shape
         Tp, Hp, Wp = T // tube, H // ph, W // pw

@@ -53,7 +53,7 @@ def test_ctypes_structs_match_the_header(tmp_path):
              'vt_reduce_params': _lib.ReduceParams, 'vt_colsum_params': _lib.ColsumParams, 'vt_cast_params': _lib.CastParams,
              'vt_gather_cast_params': _lib.GatherCastParams, 'vt_gelu_params': _lib.GeluParams,
              'vt_attn_fwd_params': _lib.AttnFwdParams, 'vt_attn_bwd_params': _lib.AttnBwdParams,
-             'vt_im2col_params': _lib.Im2colParams, 'vt_hog_params': _lib.HogParams,
+             'vt_im2col_params': _lib.Im2colParams, 'vt_im2col_u8_params': _lib.Im2colU8Params, 'vt_hog_params': _lib.HogParams,
              'vt_pool_fwd_params': _lib.PoolFwdParams, 'vt_pool_bwd_params': _lib.PoolBwdParams,
              'vt_xattn_fwd_params': _lib.XattnFwdParams, 'vt_xattn_bwd_params': _lib.XattnBwdParams,
              'vt_maxpool_fwd_params': _lib.MaxpoolFwdParams, 'vt_maxpool_bwd_params': _lib.MaxpoolBwdParams,

@@ -79,3 +79,18 @@ def test_im2col_col2im(tube):
     assert torch.equal(cols, ref.bfloat16())
     back = K().col2im(ref.contiguous(), (B, T, C, H, W), tube, 16, 16)
     assert torch.equal(back, x)
+
+
+def test_im2col_u8_normalised():
+    from tests.emu_kernels import EmuKernels
+    from videotransformer_pytorch_b200 import _lib
+    g = torch.Generator().manual_seed(0)
+    x = torch.randint(0, 256, (2, 4, 32, 48, 3), dtype=torch.uint8, generator=g)
+    scale = torch.tensor([1 / (255 * 0.229), 1 / (255 * 0.224), 1 / (255 * 0.225)])
+    shift = torch.tensor([-0.485 / 0.229, -0.456 / 0.224, -0.406 / 0.225])
+    for tube in (1, 2):
+        ref = EmuKernels(exact=True).im2col_u8(x, scale, shift, tube, 16, 16)
+        got = _lib.K.im2col_u8(x.cuda(), scale.cuda(), shift.cuda(), tube, 16, 16)
+        assert got.shape == ref.shape
+        assert float((got.float().cpu() - ref).abs().max()) < 2e-2          # bf16 rounding of values in [-2.2, 2.7]
+        assert float((got.float().cpu() - ref.bfloat16().float()).abs().max()) < 1.6e-2

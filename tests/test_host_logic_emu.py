@@ -142,3 +142,28 @@ def test_timesformer_joint_space_time(golden, emu, name):
     check_grads({n: p.grad for n, p in m.named_parameters()}, g, 2e-4)
     used = {c_[0] for c_ in emu.calls if isinstance(c_, tuple)}
     assert ('xattn' in used) == (name == 'timesformer_joint_n289')
+
+
+def test_timesformer_accepts_uint8_clip(golden, emu):
+    """the decoder's uint8 clip [B,T,H,W,3] with ToTensor + Normalize folded into the patch operand
+    gives what the reference computes from the CPU-normalised float clip."""
+    from videotransformer_pytorch_b200 import TimeSformer
+    g = golden('timesformer_tiny')
+    c = g.cfg
+    m = TimeSformer(num_frames=c['num_frames'], img_size=c['img_size'], patch_size=c['patch_size'],
+                    embed_dims=c['embed_dims'], num_heads=c['num_heads'],
+                    num_transformer_layers=c['num_transformer_layers'], attention_type='divided_space_time')
+    m.load_state_dict(g.sd, strict=True)
+    m.eval()
+    mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+    m.set_input_normalization(mean, std)
+    u8 = torch.randint(0, 256, (2, c['num_frames'], c['img_size'], c['img_size'], 3), dtype=torch.uint8,
+                       generator=torch.Generator().manual_seed(0))
+    xf = (u8.float() / 255.0 - torch.tensor(mean)) / torch.tensor(std)          # ToTensor + Normalize
+    with torch.no_grad():
+        y8 = m(u8)
+        yf = m(xf.permute(0, 1, 4, 2, 3).contiguous())
+    assert rel_err(y8, yf) < 1e-5
+    m.train()
+    m(u8).sum().backward()                        # parameters still get gradients; the byte clip has none
+    assert all(p.grad is not None for p in m.parameters())

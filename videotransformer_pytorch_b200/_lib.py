@@ -81,6 +81,11 @@ class Im2colParams(C.Structure):
                 ('W', c_i32), ('tube', c_i32), ('ph', c_i32), ('pw', c_i32)]
 
 
+class Im2colU8Params(C.Structure):
+    _fields_ = [('x', c_vp), ('scale', c_vp), ('shift', c_vp), ('cols', c_vp), ('B', c_i32), ('T', c_i32), ('C', c_i32),
+                ('H', c_i32), ('W', c_i32), ('tube', c_i32), ('ph', c_i32), ('pw', c_i32)]
+
+
 class HogParams(C.Structure):
     _fields_ = [('frames', c_vp), ('lut', c_vp), ('feat', c_vp), ('bins', c_vp),
                 ('F', c_i32), ('H', c_i32), ('W', c_i32)]
@@ -163,7 +168,7 @@ class OptParams(C.Structure):
 
 EXPORTS = ['vt_version', 'vt_last_error', 'vt_sm_count', 'vt_set_reserved_sms', 'vt_launch_count', 'vt_gemm', 'vt_layernorm_fwd', 'vt_ln_bwd_blocks',
            'vt_layernorm_bwd', 'vt_reduce_rows', 'vt_colsum_chunks', 'vt_colsum_bf16', 'vt_cast_f32_bf16',
-           'vt_gather_cast_bf16', 'vt_gelu_fwd_bf16', 'vt_gelu_bwd_bf16', 'vt_attn_fwd', 'vt_attn_bwd', 'vt_debug_buffer', 'vt_im2col_bf16', 'vt_col2im_f32', 'vt_hog',
+           'vt_gather_cast_bf16', 'vt_gelu_fwd_bf16', 'vt_gelu_bwd_bf16', 'vt_attn_fwd', 'vt_attn_bwd', 'vt_debug_buffer', 'vt_im2col_bf16', 'vt_im2col_u8_bf16', 'vt_col2im_f32', 'vt_hog',
            'vt_pool_fwd', 'vt_pool_bwd_scratch', 'vt_pool_bwd', 'vt_xattn_fwd', 'vt_xattn_bwd', 'vt_maxpool_fwd',
            'vt_maxpool_bwd', 'vt_im2col3d_bf16', 'vt_mvit_tokens_fwd', 'vt_mvit_tokens_bwd', 'vt_mse_blocks',
            'vt_mse_fwd', 'vt_mse_bwd', 'vt_opt_norm2', 'vt_opt_sgd', 'vt_opt_adamw']
@@ -432,6 +437,20 @@ class CudaKernels:
         p.x, p.cols = x.data_ptr(), cols.data_ptr()
         p.B, p.T, p.C, p.H, p.W, p.tube, p.ph, p.pw = B, T, Cc, H, W, tube, ph, pw
         _check(lib.vt_im2col_bf16(C.byref(p), _stream()), 'vt_im2col_bf16')
+        return cols
+
+    def im2col_u8(self, x, scale, shift, tube, ph, pw):
+        """x u8 [B,T,H,W,C] -> normalised bf16 patch rows [B*(T/tube)*(H/ph)*(W/pw), C*tube*ph*pw]"""
+        lib = load_library()
+        x = _req(x, torch.uint8, 'im2col_u8.x').contiguous()
+        B, T, H, W, Cc = x.shape
+        rows = B * (T // tube) * (H // ph) * (W // pw)
+        cols = torch.empty((rows, Cc * tube * ph * pw), dtype=torch.bfloat16, device=x.device)
+        p = Im2colU8Params()
+        p.x, p.cols = x.data_ptr(), cols.data_ptr()
+        p.scale, p.shift = _req(scale, torch.float32, 'im2col_u8.scale').data_ptr(), _req(shift, torch.float32, 'im2col_u8.shift').data_ptr()
+        p.B, p.T, p.C, p.H, p.W, p.tube, p.ph, p.pw = B, T, Cc, H, W, tube, ph, pw
+        _check(lib.vt_im2col_u8_bf16(C.byref(p), _stream()), 'vt_im2col_u8_bf16')
         return cols
 
     def col2im(self, cols, shape, tube, ph, pw):

@@ -333,6 +333,37 @@ __global__ void im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __rest
   }
 }
 
+// uint8 clip straight from the decoder ([B, T, H, W, C], channels last) -> normalised bf16 patch rows: fuses ToTensor
+// (/255), Normalize(mean, std) and the patch regrouping, so the clip crosses PCIe and HBM as bytes.
+// one thread = 8 consecutive j of one (row, c, dt, i)
+__global__ void im2col_u8_kernel(const uint8_t* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
+                                 __nv_bfloat16* __restrict__ cols, int B, int T, int C, int H, int W, int tube, int ph,
+                                 int pw, long long total8) {
+  const int Kc = C * tube * ph * pw;
+  const int Hp = H / ph, Wp = W / pw, Tp = T / tube;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total8; idx += (long long)gridDim.x * blockDim.x) {
+    const long long e = idx * 8;
+    const long long row = e / Kc;
+    int k = (int)(e - row * Kc);
+    const int j = k % pw; k /= pw;
+    const int i = k % ph; k /= ph;
+    const int dt = k % tube; const int c = k / tube;
+    long long rr = row;
+    const int wp = (int)(rr % Wp); rr /= Wp;
+    const int hp = (int)(rr % Hp); rr /= Hp;
+    const int tp = (int)(rr % Tp); const int b = (int)(rr / Tp);
+    const uint8_t* src = x + ((((long long)b * T + (tp * tube + dt)) * H + (hp * ph + i)) * W + wp * pw + j) * C + c;
+    const float sc = scale[c], sh = shift[c];
+    float v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = fmaf((float)src[(long long)q * C], sc, sh);
+    uint4 o;
+    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+    o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(cols + e) = o;
+  }
+}
+
 __global__ void col2im_kernel(const float* __restrict__ cols, float* __restrict__ dx, int B, int T, int C, int H, int W,
                               int tube, int ph, int pw, long long total4) {
   const int Kc = C * tube * ph * pw;
@@ -504,6 +535,16 @@ extern "C" int vt_im2col_bf16(const vt_im2col_params* p, void* stream) {
   im2col_kernel<<<grid_for(total8, 256), 256, 0, st>>>(p->x, static_cast<__nv_bfloat16*>(p->cols), p->B, p->T, p->C, p->H,
                                                        p->W, p->tube, p->ph, p->pw, total8);
   return check_launch("im2col_kernel");
+}
+
+extern "C" int vt_im2col_u8_bf16(const vt_im2col_u8_params* p, void* stream) {
+  VT_REQUIRE(p && p->x && p->scale && p->shift && p->cols, "vt_im2col_u8_bf16: null pointer");
+  VT_REQUIRE(p->pw % 8 == 0 && p->W % p->pw == 0 && p->H % p->ph == 0 && p->T % p->tube == 0, "vt_im2col_u8_bf16: unsupported geometry");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long total8 = (long long)p->B * p->T * p->C * p->H * p->W / 8;
+  im2col_u8_kernel<<<grid_for(total8, 256), 256, 0, st>>>(p->x, p->scale, p->shift, static_cast<__nv_bfloat16*>(p->cols), p->B,
+                                                          p->T, p->C, p->H, p->W, p->tube, p->ph, p->pw, total8);
+  return check_launch("im2col_u8_kernel");
 }
 
 extern "C" int vt_col2im_f32(const vt_col2im_params* p, void* stream) {

@@ -358,15 +358,20 @@ class PatchTokensFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x, w, b, cls_token, pos_embed, time_embed, wh, mode, tube):
+    def forward(ctx, x, w, b, cls_token, pos_embed, time_embed, wh, mode, tube, norm=None):
         k = K()
-        B, T, C, Himg, Wimg = x.shape
         D = w.shape[0]
         ph, pw = w.shape[-2], w.shape[-1]
+        if x.dtype == torch.uint8:
+            # decoder output [B, T, H, W, C]: ToTensor + Normalize are folded into the operand kernel (norm = (scale, shift))
+            B, T, Himg, Wimg, C = x.shape
+            cols = k.im2col_u8(x, norm[0], norm[1], tube, ph, pw)
+        else:
+            B, T, C, Himg, Wimg = x.shape
+            cols = k.im2col(x.float(), tube, ph, pw)
         Tp = T // tube
         P = (Himg // ph) * (Wimg // pw)
         Kc = C * tube * ph * pw
-        cols = k.im2col(x.float(), tube, ph, pw)
         M = B * Tp * P
         pos = pos_embed.reshape(-1, D).float()
         if mode == 'timesformer':
@@ -385,8 +390,9 @@ class PatchTokensFn(torch.autograd.Function):
                out=out.view(-1, D), out_row=out_row)
         out[:, 0] = cls_token.reshape(D).float() + pos[0]
         ctx.save_for_backward(cols, wh)
-        ctx.meta = (mode, tube, tuple(x.shape), tuple(w.shape), tuple(cls_token.shape), tuple(pos_embed.shape),
-                    None if time_embed is None else tuple(time_embed.shape), P, Tp, ctx.needs_input_grad[0])
+        ctx.meta = (mode, tube, (B, T, C, Himg, Wimg), tuple(w.shape), tuple(cls_token.shape), tuple(pos_embed.shape),
+                    None if time_embed is None else tuple(time_embed.shape), P, Tp,
+                    ctx.needs_input_grad[0] and x.dtype != torch.uint8)
         return out
 
     @staticmethod
@@ -420,7 +426,7 @@ class PatchTokensFn(torch.autograd.Function):
             dcols = _dgrad(g, wh.reshape(D, Kc), M, Kc, D, epi='f32')
             dx = k.col2im(dcols, xshape, tube, wshape[-2], wshape[-1])
         # small grads are returned as fresh contiguous tensors (not views) so autograd can adopt them in place
-        return dx, dw.contiguous(), db, dcls.reshape(cshape).clone(), dpos.contiguous(), dtime, None, None, None
+        return dx, dw.contiguous(), db, dcls.reshape(cshape).clone(), dpos.contiguous(), dtime, None, None, None, None
 
 
 # --------------------------------------------------------------------------------------------------

@@ -100,8 +100,28 @@ class TimeSformer(nn.Module):
             tim = None if tim is None else tim.to(x.device).detach()
         return pos, tim
 
+    def set_input_normalization(self, mean, std):
+        """Normalisation applied when the model is fed the decoder's uint8 clip [B, T, H, W, 3] directly (the reference
+        does it on the CPU: data_transform.py ToTensor + Normalize with data_trainer.py:69-73's mean / std)."""
+        self._input_norm = (tuple(float(m) for m in mean), tuple(float(s) for s in std))
+        self._input_norm_dev = None
+
+    def _norm_tensors(self, device):
+        cached = getattr(self, '_input_norm_dev', None)
+        if cached is None or cached[0].device != device:
+            mean, std = getattr(self, '_input_norm', ((0.45, 0.45, 0.45), (0.225, 0.225, 0.225)))
+            scale = torch.tensor([1.0 / (255.0 * s) for s in std], dtype=torch.float32, device=device)
+            shift = torch.tensor([-m / s for m, s in zip(mean, std)], dtype=torch.float32, device=device)
+            cached = self._input_norm_dev = (scale, shift)
+        return cached
+
     def prepare_tokens(self, x):
-        b, t, c, h, w = x.shape
+        if x.dtype == torch.uint8:          # [B, T, H, W, C] bytes: normalisation is fused into the patch operand kernel
+            b, t, h, w, c = x.shape
+            norm = self._norm_tensors(x.device)
+        else:
+            b, t, c, h, w = x.shape
+            norm = None
         P = self.patch_embed.num_patches
         if (h // self.patch_embed.patch_size[0]) * (w // self.patch_embed.patch_size[1]) != P or w != h:
             raise NotImplementedError('input size must match img_size (no pos-embed interpolation on the hot path)')
@@ -109,7 +129,7 @@ class TimeSformer(nn.Module):
         pe = self.patch_embed
         mode = 'frames' if self.attention_type == 'space_only' else 'timesformer'   # space_only: per-frame tokens
         tok = ops.PatchTokensFn.apply(x, _f32(pe.projection.weight), _f32(pe.projection.bias), self.cls_token, pos, tim,
-                                      pe.shadow(), mode, 1)
+                                      pe.shadow(), mode, 1, norm)
         return tok, b
 
     def forward(self, x):
