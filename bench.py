@@ -84,6 +84,9 @@ def host_threads():
     return n
 
 
+WORKLOAD = 'TimeSformer-B divided_space_time 8x224x224 fwd+bwd (+cls head, CE), train mode, DropPath 0..0.1'
+
+
 def run_cpu(steps, warmup, batch=1):
     cores = host_threads()
     torch.set_num_threads(cores)
@@ -113,7 +116,9 @@ def main_reference(args):
         'metric': METRIC, 'value': r['value'], 'unit': UNIT, 'n_gpus': args.gpus, 'steps': steps, 'warmup': warm,
         'ms_per_step': r['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic', 'impl': 'reference',
-        'config': {'workload': 'TimeSformer-B divided_space_time 8x224x224 fwd+bwd (cls head + CE), CPU', 'batch_per_step': 1},
+        'config': {'workload': WORKLOAD, 'batch_per_gpu': 1, 'global_batch': 1, 'parallelism': 'cpu',
+                   'arm': 'oracle port of the reference TimeSformer on the host cores (fp32, torch CPU kernels); each step is a '
+                          '1-clip sample of the 8-clip workload'},
         'cpu_baseline': {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': 'port', 'sample': r['sample']},
         'e2e': {'value': r['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
@@ -372,8 +377,7 @@ def main_gpu(args):
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': max(args.warmup, 3), 'ms_per_step': ms_dev / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
-            'config': {'workload': 'TimeSformer-B divided_space_time 8x224x224 fwd+bwd (+cls head, CE), train mode, '
-                                   'DropPath 0..0.1', 'batch_per_gpu': B, 'global_batch': B * world,
+            'config': {'workload': WORKLOAD, 'batch_per_gpu': B, 'global_batch': B * world,
                        'parallelism': f'dp{world}', 'residual_stream': 'fp32', 'gemm_operands': 'bf16/fp32-accum',
                        'optimizer': 'excluded (metric is fwd+bwd)', 'launch': 'eager' if args.no_graph else 'cuda-graph replay (fwd+bwd captured once)', 'grad_allreduce': f'fp32 buckets, NCCL AVG, overlapped with backward inside the graph, {args.reserve_sms} SMs reserved' if world > 1 else 'n/a',
                        'l2': 'per-step working set ~5 GB >> 126 MB L2 (no flush needed)'},
