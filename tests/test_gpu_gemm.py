@@ -1,5 +1,4 @@
 """tcgen05 GEMM (vt_gemm) vs torch fp32 matmul on the same bf16-rounded operands.  -m gpu"""
-import math
 
 import pytest
 import torch

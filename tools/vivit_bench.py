@@ -1,5 +1,5 @@
 """ViViT-B fact_encoder 16x224 batch 8 fwd+bwd timing (BASELINE config 3) + HOG kernel throughput."""
-import os, sys, time
+import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from videotransformer_pytorch_b200 import ViViT, ClassificationHead

@@ -15,9 +15,6 @@ mvit_ops.py -> libvt_b200.so.  No eager / CPU fallback.
 """
 from __future__ import annotations
 
-import math
-from typing import List, Optional, Sequence
-
 import torch
 import torch.nn as nn
 
