@@ -92,13 +92,28 @@ def test_gemm_gelu_and_dgelu():
     assert rel(out, ref_mm(g, b, False, False) * zz.grad) < 4e-3
 
 
+@pytest.mark.parametrize('path', ['tma-reduce-add', 'workspace'])
+@pytest.mark.parametrize('cluster', [1, 3], ids=['single-cta', 'cta-pair'])
 @pytest.mark.parametrize('splits', [2, 5, 16])
-def test_gemm_splitk_wgrad(splits):
+def test_gemm_splitk_wgrad(splits, cluster, path, monkeypatch):
+    """split-K partial tiles: reduce-added into the zeroed output by TMA (default) or summed from an fp32 workspace."""
+    if path == 'workspace':
+        monkeypatch.setenv('VT_SPLITK_WORKSPACE', '1')
     Mtok, Nout, Kin = 2048 + 64, 384, 256
     dy, x = mk((Mtok, Nout), 16).bfloat16(), mk((Mtok, Kin), 17).bfloat16()
-    out = K().gemm(dy, x, Nout, Kin, Mtok, a_mn=True, b_mn=True, epi='f32', split_ok=True, force_splits=splits)
+    out = torch.full((Nout, Kin), 7.0, device='cuda')            # stale contents must not leak into the result
+    K().gemm(dy, x, Nout, Kin, Mtok, a_mn=True, b_mn=True, epi='f32', split_ok=True, force_splits=splits,
+             force_cluster=cluster, out=out)
     r = dy.float().t() @ x.float()
     assert rel(out, r) < 1e-5
+
+
+def test_gemm_splitk_odd_tile_edges():
+    """in-place split-K on a shape whose tiles hang over both output edges (TMA clips the reduce-add box)."""
+    Mtok, Nout, Kin = 1000, 200, 136
+    dy, x = mk((Mtok, Nout), 26).bfloat16(), mk((Mtok, Kin), 27).bfloat16()
+    out = K().gemm(dy, x, Nout, Kin, Mtok, a_mn=True, b_mn=True, epi='f32', split_ok=True, force_splits=4)
+    assert rel(out, dy.float().t() @ x.float()) < 1e-5
 
 
 def test_gemm_wgrad_heuristic_split_big():

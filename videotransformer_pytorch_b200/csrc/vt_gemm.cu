@@ -242,16 +242,30 @@ int make_tmap_out_3d(CUtensorMap* map, const void* base, int fp32, long long M, 
   return 0;
 }
 
+// Split-K partials can be reduce-added straight into the output by TMA (cp.reduce.async.bulk.tensor ... add) instead of
+// going through the fp32 workspace + reduce_rows: needs the plain fp32 TMA epilogue and a dense output.
+bool splitk_in_place(const vt_gemm_params* q) {
+  return q->ldo == q->N && !getenv("VT_NO_TMA_STORE") && !getenv("VT_SPLITK_WORKSPACE");
+}
+
 // Decide whether the plain TMA-store epilogue applies and build its map (called after the split decision).
-int setup_out_map(const vt_gemm_params* q, GemmDev& d, CUtensorMap* tmC) {
+// in_place: d.out is the final output and the d.splits partial tiles of every output tile are reduce-added into it.
+int setup_out_map(const vt_gemm_params* q, GemmDev& d, CUtensorMap* tmC, bool in_place) {
   d.tma_store = 0;
   memset(tmC, 0, sizeof(*tmC));
   const bool plain = (q->epilogue == VT_EPI_BF16 || q->epilogue == VT_EPI_F32) && !q->out_row && !q->aux;
   if (!plain || getenv("VT_NO_TMA_STORE")) return 0;
   const int fp32 = q->epilogue == VT_EPI_F32;
-  int rc = make_tmap_out_3d(tmC, d.out, fp32, q->M, q->N, d.ldo, d.splits, d.split_stride);
+  int rc = make_tmap_out_3d(tmC, d.out, fp32, q->M, q->N, d.ldo, in_place ? 1 : d.splits, in_place ? 0 : d.split_stride);
   if (rc) return rc;
-  d.tma_store = 1;
+  d.tma_store = in_place ? 2 : 1;
+  return 0;
+}
+
+// zero the output ahead of an in-place split-K launch
+int splitk_zero(const vt_gemm_params* q, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(q->out, 0, (size_t)q->M * q->N * sizeof(float), st);
+  VT_REQUIRE(e == cudaSuccess, "vt_gemm: split-K output memset: %s", cudaGetErrorString(e));
   return 0;
 }
 
@@ -359,15 +373,18 @@ static int launch_gemm(const vt_gemm_params* q, GemmDev& d, cudaStream_t st) {
   }
   d.splits = splits;
   void* final_out = d.out;
-  if (splits > 1) {
+  const bool in_place = splits > 1 && splitk_in_place(q);
+  d.split_stride = 0;
+  if (in_place) {
+    rc = splitk_zero(q, st);
+    if (rc) return rc;
+  } else if (splits > 1) {
     d.out = q->workspace;
     d.ldo = q->N;
     d.split_stride = tile_out;
-  } else {
-    d.split_stride = 0;
   }
   CUtensorMap tmC;
-  rc = setup_out_map(q, d, &tmC);
+  rc = setup_out_map(q, d, &tmC, in_place);
   if (rc) return rc;
   const int units = tiles * splits;
   const int max_clusters = sms / csize;
@@ -391,7 +408,7 @@ static int launch_gemm(const vt_gemm_params* q, GemmDev& d, cudaStream_t st) {
   }
   rc = check_launch("gemm_tcgen05_kernel");
   if (rc) return rc;
-  if (splits > 1) {
+  if (splits > 1 && !in_place) {
     // partials [splits, M, N] -> out [M, ldo]
     if (q->ldo == q->N) {
       return launch_reduce_rows(static_cast<const float*>(q->workspace), static_cast<float*>(final_out), tile_out, splits,

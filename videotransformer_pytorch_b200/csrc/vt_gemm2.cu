@@ -19,7 +19,9 @@ namespace vt {
 int make_tmap_bf16_2d(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows);
 int launch_reduce_rows(const float* in, float* out, long long stride, int S, long long n, int accumulate, float scale,
                        cudaStream_t st);
-int setup_out_map(const vt_gemm_params* q, GemmDev& d, CUtensorMap* tmC);
+int setup_out_map(const vt_gemm_params* q, GemmDev& d, CUtensorMap* tmC, bool in_place);
+bool splitk_in_place(const vt_gemm_params* q);
+int splitk_zero(const vt_gemm_params* q, cudaStream_t st);
 
 template <int BN>
 struct Gemm2Cfg {
@@ -246,16 +248,19 @@ static int launch_gemm2_t(const vt_gemm_params* q, GemmDev& d, cudaStream_t st) 
   }
   d.splits = splits;
   void* final_out = d.out;
-  if (splits > 1) {
+  const bool in_place = splits > 1 && splitk_in_place(q);
+  d.split_stride = 0;
+  if (in_place) {
+    rc = splitk_zero(q, st);
+    if (rc) return rc;
+  } else if (splits > 1) {
     VT_REQUIRE(q->ldo == q->N, "vt_gemm: split-K requires ldo == N");
     d.out = q->workspace;
     d.ldo = q->N;
     d.split_stride = tile_out;
-  } else {
-    d.split_stride = 0;
   }
   CUtensorMap tmC;
-  rc = setup_out_map(q, d, &tmC);
+  rc = setup_out_map(q, d, &tmC, in_place);
   if (rc) return rc;
   const int units = tiles * splits;
   const int grid = 2 * (units < pairs ? units : pairs);
@@ -278,7 +283,7 @@ static int launch_gemm2_t(const vt_gemm_params* q, GemmDev& d, cudaStream_t st) 
   }
   rc = check_launch("gemm2_tcgen05_kernel");
   if (rc) return rc;
-  if (splits > 1)
+  if (splits > 1 && !in_place)
     return launch_reduce_rows(static_cast<const float*>(q->workspace), static_cast<float*>(final_out), tile_out, splits,
                               tile_out, 0, 1.0f, st);
   return 0;

@@ -28,7 +28,8 @@ struct GemmDev {
   const float* row_scale;
   long long split_stride;  // elements between split partials (EPI_F32 only)
   long long* dbg;          // optional diagnostics: per-CTA clock64 stamps [cta][16] (NULL in production)
-  int tma_store;           // 1: plain row-major output written by TMA bulk stores (epilogue_tile_tma)
+  int tma_store;           // 1: plain row-major output written by TMA bulk stores (epilogue_tile_tma); 2: split-K partials
+                           //    reduce-added into the (pre-zeroed) output by TMA
 };
 
 // Drain accumulator tile (m_blk, n_blk) of this CTA: TMEM columns [t_base, t_base + BN) of lane quadrant q.
@@ -136,6 +137,14 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void*
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
+// same box, but added into global memory (fp32 reduction performed by the L2): split-K partial tiles accumulate straight
+// into the output, no workspace round trip and no second kernel
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() {
@@ -195,7 +204,8 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmDev& p, const CUtens
     fence_proxy_async();
     __syncwarp();
     if (lane == 0) {
-      tma_store_3d(tmC, buf, n0, m_blk * BM + q * 32, split);
+      if (p.tma_store == 2) tma_reduce_add_3d(tmC, buf, n0, m_blk * BM + q * 32, 0);
+      else tma_store_3d(tmC, buf, n0, m_blk * BM + q * 32, split);
       bulk_commit();
     }
   }
