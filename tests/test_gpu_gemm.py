@@ -141,14 +141,16 @@ def test_gemm_bn192_and_auto_config(M, N, Kd):
         assert rel(out, r) < 1e-5, bn
 
 
-def test_gelu_kernels():
+@pytest.mark.parametrize('shape', [(1000, 3072), (12552, 3072), (2344, 3072), (5, 8), (1, 8)])
+def test_gelu_kernels(shape):
+    """sizes below, between and above one / two grid strides (the kernels take two vectors per thread per iteration)"""
     torch.manual_seed(3)
-    z = (torch.randn(1000, 3072) * 1.5).cuda().bfloat16()
+    z = (torch.randn(*shape) * 1.5).cuda().bfloat16()
     h = K().gelu(z)
     zf = z.float().requires_grad_(True)
     ref = torch.nn.functional.gelu(zf)
     assert rel(h, ref) < 3e-3
-    dh = torch.randn(1000, 3072).cuda().bfloat16()
+    dh = torch.randn(*shape).cuda().bfloat16()
     ref.backward(dh.float())
     assert rel(K().dgelu(dh, z), zf.grad) < 3e-3
 
