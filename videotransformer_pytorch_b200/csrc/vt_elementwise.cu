@@ -387,49 +387,30 @@ __global__ void col2im_kernel(const float* __restrict__ cols, float* __restrict_
 // ------------------------------------------------------------------------------------------------
 // exact-erf GELU on bf16 rows, forward (h = gelu(z)) and backward (dz = dh * gelu'(z)); 8 elements per thread
 // ------------------------------------------------------------------------------------------------
-// two 16-byte vectors per thread per iteration: both loads are issued before the erf math of either (the kernels sit at the
-// balance point of HBM bandwidth and MUFU/FMA throughput, so memory latency has to overlap the arithmetic)
-__device__ __forceinline__ uint4 gelu8(const uint4 v) {
-  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-  uint32_t o[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const float2 f = unpack_bf16x2(w[k]);
-    o[k] = pack_bf16x2(gelu_fast(f.x), gelu_fast(f.y));
-  }
-  return make_uint4(o[0], o[1], o[2], o[3]);
-}
-__device__ __forceinline__ uint4 dgelu8(const uint4 g, const uint4 v) {
-  const uint32_t gw[4] = {g.x, g.y, g.z, g.w}, zw[4] = {v.x, v.y, v.z, v.w};
-  uint32_t o[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const float2 a = unpack_bf16x2(gw[k]), f = unpack_bf16x2(zw[k]);
-    o[k] = pack_bf16x2(a.x * dgelu_fast(f.x), a.y * dgelu_fast(f.y));
-  }
-  return make_uint4(o[0], o[1], o[2], o[3]);
-}
-
 __global__ void gelu_fwd_kernel(const uint4* __restrict__ z, uint4* __restrict__ h, long long n8) {
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += 2 * stride) {
-    const long long j = i + stride;
-    const bool two = j < n8;
-    const uint4 v0 = z[i];
-    const uint4 v1 = two ? z[j] : make_uint4(0u, 0u, 0u, 0u);
-    h[i] = gelu8(v0);
-    if (two) h[j] = gelu8(v1);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 v = z[i];
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = unpack_bf16x2(w[k]);
+      o[k] = pack_bf16x2(gelu_fast(f.x), gelu_fast(f.y));
+    }
+    h[i] = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
 __global__ void gelu_bwd_kernel(const uint4* __restrict__ dh, const uint4* __restrict__ z, uint4* __restrict__ dz, long long n8) {
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += 2 * stride) {
-    const long long j = i + stride;
-    const bool two = j < n8;
-    const uint4 g0 = dh[i], v0 = z[i];
-    const uint4 g1 = two ? dh[j] : make_uint4(0u, 0u, 0u, 0u), v1 = two ? z[j] : make_uint4(0u, 0u, 0u, 0u);
-    dz[i] = dgelu8(g0, v0);
-    if (two) dz[j] = dgelu8(g1, v1);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 g = dh[i], v = z[i];
+    const uint32_t gw[4] = {g.x, g.y, g.z, g.w}, zw[4] = {v.x, v.y, v.z, v.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 a = unpack_bf16x2(gw[k]), f = unpack_bf16x2(zw[k]);
+      o[k] = pack_bf16x2(a.x * dgelu_fast(f.x), a.y * dgelu_fast(f.y));
+    }
+    dz[i] = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
 
