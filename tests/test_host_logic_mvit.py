@@ -64,3 +64,35 @@ def test_forward_backward(maskfeat_golden, emu, name):
     loss.backward()
     grads = {k: (p.grad if p.grad is not None else torch.zeros_like(p)) for k, p in m.named_parameters()}
     check_grads(grads, g, 2e-3)
+
+
+@pytest.mark.parametrize('case', ['zero_mask', 'full_mask', 'batch3_shared_centres'])
+def test_loss_edge_cases_vs_oracle(maskfeat_golden, emu, case):
+    """Edge cases of MaskFeat.forward (video_transformer.py:889-901) against the oracle: nothing masked (loss 0 through the
+    1e-5 guard), everything masked, an odd batch whose cubes share a centre frame."""
+    from oracle import mvit_oracle as mo
+    g = maskfeat_golden('maskfeat_s32')
+    m = build(g).train()
+    cfg = g.cfg
+    t, h, w = cfg['thw'][0], cfg['thw'][1] // cfg['downsample_rate'], cfg['thw'][2] // cfg['downsample_rate']
+    gen = torch.Generator().manual_seed(5)
+    B = 3 if case == 'batch3_shared_centres' else 2
+    x = torch.randn(B, cfg['num_frames'], 3, cfg['img_size'], cfg['img_size'], generator=gen)
+    target = torch.randn(B, cfg['num_frames'], h, w, cfg['feature_dim'] // cfg['stride'][0], generator=gen)
+    if case == 'zero_mask':
+        mask = torch.zeros(B, t, h, w)
+    elif case == 'full_mask':
+        mask = torch.ones(B, t, h, w)
+    else:
+        mask = (torch.rand(B, t, h, w, generator=gen) < 0.5).float()
+    markers = [[[0, 1], [0, 1]], [[t - 1, 1]], [[1, 2], [0, 3]]][:B]         # duplicated and overlapping cubes
+    pred, loss = m(x, target, mask, markers)
+    sd = {k: v.double() for k, v in g.state(torch.float32).items()}
+    with torch.no_grad():
+        pred_o, loss_o = mo.maskfeat_forward(sd, x.double(), target.double(), mask.double(), markers, cfg)
+    assert rel_err(pred.detach(), pred_o) < 5e-5
+    assert abs(float(loss) - float(loss_o)) < 1e-5 * max(1.0, abs(float(loss_o)))
+    if case == 'zero_mask':
+        assert float(loss) == 0.0
+    loss.backward()                                    # gradients exist and are finite even when the loss is identically 0
+    assert all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for p in m.parameters())
