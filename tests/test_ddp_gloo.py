@@ -66,3 +66,69 @@ def test_gradient_buckets_average_across_ranks():
         ref = cur if ref is None else [a + b for a, b in zip(ref, cur)]
     for a, r in zip(g0, ref):
         assert np.allclose(a, (r / 2).numpy(), atol=1e-6)
+
+
+def _train_worker(rank, world, port, q):
+    """Two data-parallel ranks: bucketed gradient mean + fused clip/SGD step (kernel table = CPU emulation)."""
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from tests.emu_kernels import EmuKernels
+    from videotransformer_pytorch_b200 import _lib
+    from videotransformer_pytorch_b200.ddp import GradientBuckets
+    from videotransformer_pytorch_b200.optim import FusedSGD
+    _lib.K = EmuKernels(exact=True)
+    torch.manual_seed(7)
+    net = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.GELU(), torch.nn.Linear(32, 4))
+    red = GradientBuckets(net, bucket_bytes=256)
+    opt = FusedSGD(net.parameters(), lr=0.1, momentum=0.9, nesterov=True, weight_decay=1e-3)
+    norms = []
+    for step in range(3):
+        red.zero_grad()
+        g = torch.Generator().manual_seed(10 * step + rank)
+        net(torch.randn(6, 16, generator=g)).square().mean().backward()
+        red.finish()
+        norms.append(float(opt.step(clip_grad=0.05)))      # p.grad are views of the flat buckets
+    q.put((rank, [p.detach().numpy().copy() for p in net.parameters()], norms))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_data_parallel_step_with_fused_optimizer():
+    import numpy as np
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_train_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, w0, n0), (_, w1, n1) = res
+    for a, b in zip(w0, w1):
+        assert np.allclose(a, b, atol=1e-7)                  # replicas stay in lock-step
+    assert np.allclose(n0, n1, rtol=1e-6)
+    # single-process reference: mean of the two ranks' gradients, reference clip flow, torch SGD
+    torch.manual_seed(7)
+    net = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.GELU(), torch.nn.Linear(32, 4))
+    ref = torch.optim.SGD(net.parameters(), lr=0.1, momentum=0.9, nesterov=True, weight_decay=1e-3)
+    for step in range(3):
+        acc = None
+        for rank in range(2):
+            for p in net.parameters():
+                p.grad = None
+            g = torch.Generator().manual_seed(10 * step + rank)
+            net(torch.randn(6, 16, generator=g)).square().mean().backward()
+            cur = [p.grad.clone() for p in net.parameters()]
+            acc = cur if acc is None else [a + b for a, b in zip(acc, cur)]
+        for p, gsum in zip(net.parameters(), acc):
+            p.grad = gsum / 2
+            nrm = torch.norm(p.grad, 2)
+            coef = 0.05 / (nrm + 1e-6)
+            if coef < 1:
+                p.grad.mul_(coef)
+        ref.step()
+    for a, p in zip(w0, net.parameters()):
+        assert np.allclose(a, p.detach().numpy(), atol=2e-6)
