@@ -444,3 +444,108 @@ def test_xattn_tile_algorithm(Nq, Nk):
     sdq, sdk, sdv = sim_xattn_bwd(q, k, v, o, do, lse, scale)
     for mine, ref in ((sdq, dq), (sdk, dk), (sdv, dv)):      # one key => dq, dk are exactly 0: compare absolutely
         assert np.abs(mine - ref).max() < 1e-12 * max(1.0, np.abs(ref).max())
+
+
+# ---- tcgen05 pooling attention (vt_xattention_tc.cu): tile walk, two-warpgroup split + merge, garbage padding ---------
+def sim_xattn_tc_fwd(q, k, v, scale, garbage):
+    """128-query CTA tiles, 128-key tiles taken alternately by two warpgroups with private (m, l, O) states that are merged
+    at the end; rows / columns past Nq / Nk hold `garbage` (what TMA brings in from the neighbouring head or batch) and
+    must not influence the result."""
+    Nq, Nk = q.shape[0], k.shape[0]
+    nqt, nkt = -(-Nq // 128), -(-Nk // 128)
+    qp = np.concatenate([q, garbage((nqt * 128 - Nq, HD))])
+    kp = np.concatenate([k, garbage((nkt * 128 - Nk, HD))])
+    vp = np.concatenate([v, garbage((nkt * 128 - Nk, HD))])
+    sl2 = scale * LOG2E
+    out, lse = np.zeros((Nq, HD)), np.zeros(Nq)
+    for qt in range(nqt):
+        Q = qp[qt * 128:(qt + 1) * 128]
+        state = []
+        for wg in range(2):
+            m, l, acc = np.full(128, -np.inf), np.zeros(128), np.zeros((128, HD))
+            for j in range(wg, nkt, 2):
+                S = Q @ kp[j * 128:(j + 1) * 128].T
+                nvalid = min(128, Nk - j * 128)
+                mx = np.where(np.arange(128)[None, :] < nvalid, S, -np.inf).max(1)
+                mn = np.maximum(m, mx * sl2)
+                corr = np.exp2(m - mn)
+                e = np.where(np.arange(128)[None, :] < nvalid, np.exp2(S * sl2 - mn[:, None]), 0.0)
+                l = l * corr + e.sum(1)
+                acc = acc * corr[:, None] + e @ vp[j * 128:(j + 1) * 128]
+                m = mn
+            state.append((m, l, acc))
+        (m0, l0, a0), (m1, l1, a1) = state
+        mm = np.maximum(m0, m1)
+        f0, f1 = np.exp2(m0 - mm), np.exp2(m1 - mm)              # m1 = -inf when the second group had no tile
+        lt = l0 * f0 + l1 * f1
+        o = (a0 * f0[:, None] + a1 * f1[:, None]) / lt[:, None]
+        n = min(128, Nq - qt * 128)
+        out[qt * 128:qt * 128 + n] = o[:n]
+        lse[qt * 128:qt * 128 + n] = ((mm + np.log2(lt)) * LN2)[:n]
+    return out, lse
+
+
+def sim_xattn_tc_bwd(q, k, v, o, do, lse, scale, garbage, qtiles_per_chunk=2):
+    Nq, Nk = q.shape[0], k.shape[0]
+    nqt, nkt = -(-Nq // 128), -(-Nk // 128)
+    pad = lambda a, n: np.concatenate([a, garbage((n - a.shape[0], HD))])
+    qp, dop = pad(q, nqt * 128), pad(do, nqt * 128)
+    kp, vp = pad(k, nkt * 128), pad(v, nkt * 128)
+    sl2 = scale * LOG2E
+    lse2 = np.full(nqt * 128, np.inf)
+    lse2[:Nq] = lse * LOG2E                                      # rows past Nq: +inf => P = 0
+    delta = np.zeros(nqt * 128)
+    delta[:Nq] = (do * o).sum(1)
+    kcol = np.arange(128)[None, :]
+    # dQ kernel: one CTA per query tile, key tiles streamed
+    dq = np.zeros((Nq, HD))
+    for qt in range(nqt):
+        rows = slice(qt * 128, (qt + 1) * 128)
+        acc = np.zeros((128, HD))
+        for j in range(nkt):
+            K_, V_ = kp[j * 128:(j + 1) * 128], vp[j * 128:(j + 1) * 128]
+            S, dP = qp[rows] @ K_.T, dop[rows] @ V_.T
+            P = np.where(j * 128 + kcol < Nk, np.exp2(S * sl2 - lse2[rows, None]), 0.0)
+            dS = P * (dP - delta[rows, None]) * scale
+            acc += dS @ K_
+        n = min(128, Nq - qt * 128)
+        dq[qt * 128:qt * 128 + n] = acc[:n]
+    # dK/dV kernel: CTA = key tile x chunk of query tiles, chunks merged by atomics
+    dk, dv = np.zeros((Nk, HD)), np.zeros((Nk, HD))
+    for kt in range(nkt):
+        K_, V_ = kp[kt * 128:(kt + 1) * 128], vp[kt * 128:(kt + 1) * 128]
+        for c0 in range(0, nqt, qtiles_per_chunk):
+            dK, dV = np.zeros((128, HD)), np.zeros((128, HD))
+            for qt in range(c0, min(nqt, c0 + qtiles_per_chunk)):
+                rows = slice(qt * 128, (qt + 1) * 128)
+                S, dP = qp[rows] @ K_.T, dop[rows] @ V_.T
+                P = np.where(kt * 128 + kcol < Nk, np.exp2(S * sl2 - lse2[rows, None]), 0.0)
+                dS = P * (dP - delta[rows, None]) * scale
+                dK += dS.T @ qp[rows]
+                dV += P.T @ dop[rows]
+            n = min(128, Nk - kt * 128)
+            dk[kt * 128:kt * 128 + n] += dK[:n]
+            dv[kt * 128:kt * 128 + n] += dV[:n]
+    return dq, dk, dv
+
+
+@pytest.mark.parametrize('Nq,Nk', [(70, 37), (300, 393), (129, 128), (5, 1), (520, 260)])
+def test_xattn_tensor_core_tile_walk(Nq, Nk):
+    rng = np.random.default_rng(9)
+    garbage = lambda shape: rng.standard_normal(shape) * 7.0      # finite junk in every padded row
+    q, k, v = rng.standard_normal((Nq, HD)), rng.standard_normal((Nk, HD)), rng.standard_normal((Nk, HD))
+    scale = HD ** -0.5
+    s = (q @ k.T) * scale
+    mx = s.max(1, keepdims=True)
+    lse = (mx + np.log(np.exp(s - mx).sum(1, keepdims=True)))[:, 0]
+    p = np.exp(s - lse[:, None])
+    o = p @ v
+    so, slse = sim_xattn_tc_fwd(q, k, v, scale, garbage)
+    assert rel(so, o) < 1e-12 and rel(slse, lse) < 1e-12
+    do = rng.standard_normal((Nq, HD))
+    dv = p.T @ do
+    ds = p * (do @ v.T - (do * o).sum(1, keepdims=True)) * scale
+    dq, dk = ds @ k, ds.T @ q
+    sdq, sdk, sdv = sim_xattn_tc_bwd(q, k, v, o, do, lse, scale, garbage)
+    for mine, ref in ((sdq, dq), (sdk, dk), (sdv, dv)):
+        assert np.abs(mine - ref).max() < 1e-11 * max(1.0, np.abs(ref).max())
