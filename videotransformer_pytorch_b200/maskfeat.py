@@ -205,9 +205,6 @@ class MaskFeat(nn.Module):
                  pool_q_stride_size=[[1, 1, 2, 2], [3, 1, 2, 2], [14, 1, 2, 2]], pool_kv_stride_adaptive=[1, 8, 8],
                  pool_kvq_kernel=[3, 3, 3], head=None, pretrain_pth=None, **kwargs):
         super().__init__()
-        if pretrain_pth is not None:
-            raise NotImplementedError('pretrain_pth: checkpoint remapping is control-plane code; load the state dict '
-                                      '(keys are identical to the reference) instead')
         self.num_frames = num_frames
         self.img_size = img_size
         self.stride = tuple(conv_patch_embed_stride)
@@ -232,6 +229,13 @@ class MaskFeat(nn.Module):
         nn.init.constant_(self.decoder_pred.bias, 0)
         nn.init.trunc_normal_(self.mask_token, std=.02)
         self._shadow = ShadowWeights()
+        if pretrain_pth is not None:
+            self.init_weights(pretrain_pth)
+
+    def init_weights(self, pretrain_pth):
+        """reference video_transformer.py:866-870"""
+        from .weight_init import init_from_kinetics_pretrain_
+        init_from_kinetics_pretrain_(self, pretrain_pth)
 
     @torch.jit.ignore
     def no_weight_decay_keywords(self):

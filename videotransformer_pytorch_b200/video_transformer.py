@@ -13,14 +13,20 @@ import torch.nn as nn
 
 from . import ops
 from .transformer import PatchEmbed, TransformerContainer, get_sine_cosine_pos_emb, _f32
-from .weight_init import trunc_normal_
+from .weight_init import init_from_kinetics_pretrain_, init_from_vit_pretrain_, trunc_normal_
 
 
-def _no_pretrain(pth):
-    if pth is not None:
-        raise NotImplementedError(
-            'pretrain_pth: checkpoint key remapping is control-plane code outside the hot path; apply the '
-            "reference's weight_init.init_from_*_pretrain_ to this module (state-dict keys are identical).")
+def _load_pretrained(module, **vit_kwargs):
+    """reference video_transformer.py:154-165 / :434-451: image (ViT) or kinetics checkpoint by `weights_from`."""
+    if module.pretrain_pth is None:
+        return
+    if module.weights_from == 'imagenet':
+        init_from_vit_pretrain_(module, module.pretrain_pth, module.conv_type, module.attention_type, module.copy_strategy,
+                                **vit_kwargs)
+    elif module.weights_from == 'kinetics':
+        init_from_kinetics_pretrain_(module, module.pretrain_pth)
+    else:
+        raise TypeError(f'not support the pretrained weight {module.pretrain_pth}')
 
 
 class TimeSformer(nn.Module):
@@ -79,7 +85,7 @@ class TimeSformer(nn.Module):
             if self.attention_type != 'space_only':
                 nn.init.trunc_normal_(self.time_embed, std=.02)
         trunc_normal_(self.cls_token, std=.02)
-        _no_pretrain(self.pretrain_pth)
+        _load_pretrained(self)
 
     @torch.jit.ignore
     def no_weight_decay_keywords(self):
@@ -219,7 +225,8 @@ class ViViT(nn.Module):
             nn.init.trunc_normal_(self.pos_embed, std=.02)
             nn.init.trunc_normal_(self.time_embed, std=.02)
         trunc_normal_(self.cls_token, std=.02)
-        _no_pretrain(self.pretrain_pth)
+        _load_pretrained(self, extend_strategy=self.extend_strategy, tube_size=self.tube_size,
+                         num_time_transformer_layers=self.num_time_transformer_layers)
 
     @torch.jit.ignore
     def no_weight_decay_keywords(self):
