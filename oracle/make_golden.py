@@ -229,6 +229,49 @@ def space_only_case(vt, name, cfg, B, seed, attention_type='space_only'):
     np.savez_compressed(os.path.join(GOLD, name + '.npz'), **save)
 
 
+def vivit_variant_case(vt, name, cfg, B, seed, attention_type):
+    """ViViT 'joint_space_time' / 'divided_space_time' (video_transformer.py:349-373) vs the oracle."""
+    from oracle import vt_oracle as O
+    torch.manual_seed(seed)
+    m = vt.ViViT(num_frames=cfg['num_frames_in'], img_size=cfg['img_size'], patch_size=cfg['patch_size'],
+                 embed_dims=cfg['embed_dims'], num_heads=cfg['num_heads'],
+                 num_transformer_layers=cfg['num_transformer_layers'], attention_type=attention_type)
+    randomize(m, seed + 1)
+    m = m.double()
+    sd = {k: v.detach().clone().float().double() for k, v in m.state_dict().items()}
+    m.load_state_dict(sd)
+    x = torch.randn(B, cfg['num_frames_in'], 3, cfg['img_size'], cfg['img_size'], dtype=torch.float64).float().double()
+    m.eval()
+    with torch.no_grad():
+        y_eval = m(x)
+        assert rel(O.vivit_variant_forward(sd, x, cfg, attention_type), y_eval) < 1e-12
+    m.train()
+    torch.manual_seed(4000 + seed)
+    y_tr = m(x)
+    w = torch.linspace(-1, 1, y_tr.numel(), dtype=torch.float64).reshape(y_tr.shape)
+    (y_tr * w).sum().backward()
+    grads = {n: p.grad.detach().clone() for n, p in m.named_parameters()}
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    torch.manual_seed(4000 + seed)
+    yo = O.vivit_variant_forward(sdg, x, cfg, attention_type, training=True)
+    (yo * w).sum().backward()
+    assert rel(yo.detach(), y_tr.detach()) < 1e-12
+    for n, g in grads.items():
+        assert rel(sdg[n].grad, g) < 1e-9, n
+    print(f'[{name}] oracle == reference (eval, train fwd, all {len(grads)} grads)')
+    save = {'x': x.float().numpy(), 'train_seed': np.int64(4000 + seed), 'B': np.int64(B)}
+    for k, v in cfg.items():
+        if isinstance(v, int):
+            save['cfg_' + k] = np.int64(v)
+    for k, v in sd.items():
+        save['sd::' + k] = v.float().numpy()
+    save['out::y_eval'] = y_eval.numpy()
+    save['out::y_train'] = y_tr.detach().numpy()
+    save['out::loss_w'] = w.numpy()
+    pack_grads(save, grads)
+    np.savez_compressed(os.path.join(GOLD, name + '.npz'), **save)
+
+
 def mask_cases(mg):
     from oracle.mask_oracle import CubeMaskOracle
     rows = {}
@@ -324,6 +367,10 @@ def maskfeat_case(vt, name, kwargs, B, seed, with_grads=True):
 def main():
     os.makedirs(GOLD, exist_ok=True)
     tr, vt, mg = import_reference()
+    only = set(sys.argv[1:])          # optional: names of the cases to (re)generate; default all
+    if only:
+        return main_selected(tr, vt, mg, only)
+    main_selected(tr, vt, mg, None)
     tiny = dict(num_frames=4, img_size=32, patch_size=16, embed_dims=32, num_heads=4,
                 num_transformer_layers=2)
     timesformer_case(vt, 'timesformer_tiny', tiny, B=2, seed=0)
@@ -347,6 +394,16 @@ def main():
     maskfeat_case(vt, 'maskfeat_s64_3stage',
                   dict(img_size=64, num_frames=4, feature_dim=2 * 108,
                        pool_q_stride_size=((1, 1, 2, 2), (3, 1, 2, 2), (14, 1, 2, 2))), B=1, seed=9, with_grads=False)
+
+
+def main_selected(tr, vt, mg, only):
+    """Cases added after round 1 (run alone with `python oracle/make_golden.py <name> ...`)."""
+    want = lambda n: only is None or n in only
+    vv = dict(num_frames_in=8, img_size=32, patch_size=16, embed_dims=32, num_heads=4, num_transformer_layers=2)
+    if want('vivit_joint_tiny'):
+        vivit_variant_case(vt, 'vivit_joint_tiny', vv, B=2, seed=11, attention_type='joint_space_time')
+    if want('vivit_divided_tiny'):
+        vivit_variant_case(vt, 'vivit_divided_tiny', vv, B=2, seed=12, attention_type='divided_space_time')
 
 
 if __name__ == '__main__':

@@ -182,9 +182,10 @@ def patch_embed(x: Tensor, w: Tensor, b: Tensor) -> Tensor:
 # ----------------------------------------------------------------------------
 def timesformer_tokens(sd, x, cfg):
     """TimeSformer.prepare_tokens (divided_space_time), video_transformer.py:193-240."""
-    B, T = x.shape[0], x.shape[1]
+    B = x.shape[0]
     tok = patch_embed(x, sd['patch_embed.projection.weight'], sd['patch_embed.projection.bias'])
     BT, P, D = tok.shape
+    T = BT // B                                                           # frames, or tubelets for a Conv3d embedding
     cls = sd['cls_token'].expand(BT, 1, D)
     tok = torch.cat((cls, tok), dim=1) + sd['pos_embed']                  # :207-209
     cls_tokens = tok[:B, 0, :].unsqueeze(1)                               # :216
@@ -257,6 +258,18 @@ def vivit_forward(sd, x, cfg, training=False):
                   cfg['num_heads'], training)                             # :525, 4 layers :377
     t = layer_norm(t, sd['norm.weight'], sd['norm.bias'], 1e-6)           # :527
     return t[:, 0]                                                        # :530
+
+
+def vivit_variant_forward(sd, x, cfg, attention_type, training=False):
+    """ViViT.forward with attention_type 'joint_space_time' (model 1) or 'divided_space_time' (model 3),
+    video_transformer.py:349-373, :455-510, :527-532.  With `use_cls_token_temporal` False for both (:405-411) the token
+    assembly (:461-499) is TimeSformer's, on tubelets: cls + pos_embed(1+P), time_embed(T') per patch, tokens 'b (p t) d'."""
+    tok = timesformer_tokens(sd, x, cfg)
+    Tp = (tok.shape[1] - 1) // ((cfg['img_size'] // cfg['patch_size']) ** 2)
+    order = ['self_attn', 'ffn'] if attention_type == 'joint_space_time' else ['time_attn', 'space_attn', 'ffn']
+    tok = container(tok, sd, 'transformer_layers.', cfg['num_transformer_layers'], order, Tp, cfg['num_heads'], training)
+    tok = layer_norm(tok, sd['norm.weight'], sd['norm.bias'], 1e-6)
+    return tok[:, 0]
 
 
 def classification_head(sd, x, pre='cls_head.'):

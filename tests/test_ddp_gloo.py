@@ -132,3 +132,121 @@ def test_data_parallel_step_with_fused_optimizer():
         ref.step()
     for a, p in zip(w0, net.parameters()):
         assert np.allclose(a, p.detach().numpy(), atol=2e-6)
+
+
+def _none_grad_worker(rank, world, port, q):
+    """A foreign `zero_grad(set_to_none=True)` (torch / Lightning default) between steps must not lose the exchange."""
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from videotransformer_pytorch_b200.ddp import GradientBuckets
+    torch.manual_seed(3)
+    net = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.GELU(), torch.nn.Linear(32, 4))
+    red = GradientBuckets(net, bucket_bytes=128)
+    opt = torch.optim.SGD(net.parameters(), lr=0.1)
+    for step in range(2):
+        opt.zero_grad()                      # set_to_none=True: p.grad is no longer the bucket view
+        assert all(p.grad is None for p in net.parameters())
+        red._pending = [len(ps) for ps in red._bucket_params]
+        g = torch.Generator().manual_seed(10 * step + rank)
+        net(torch.randn(6, 16, generator=g)).square().mean().backward()
+        red.finish()
+        for p in net.parameters():           # re-attached to the flat buckets, holding the MEAN gradient
+            assert any(b.data_ptr() <= p.grad.data_ptr() < b.data_ptr() + b.numel() * 4 for b in red.buckets)
+    q.put((rank, [p.grad.detach().numpy().copy() for p in net.parameters()]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_buckets_survive_set_to_none_zero_grad():
+    import numpy as np
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_none_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, g0), (_, g1) = res
+    torch.manual_seed(3)
+    net = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.GELU(), torch.nn.Linear(32, 4))
+    acc = None
+    for rank in range(2):
+        for p in net.parameters():
+            p.grad = None
+        g = torch.Generator().manual_seed(10 + rank)
+        net(torch.randn(6, 16, generator=g)).square().mean().backward()
+        cur = [p.grad.clone() for p in net.parameters()]
+        acc = cur if acc is None else [a + b for a, b in zip(acc, cur)]
+    for a, b, r in zip(g0, g1, acc):
+        assert np.allclose(a, b, atol=1e-7)
+        assert np.allclose(a, (r / 2).numpy(), atol=1e-6)
+
+
+def _stock_ddp_worker(rank, world, port, q):
+    """The package's modules under the stock torch DistributedDataParallel wrapper, as Lightning's DDPPlugin applies it
+    to the reference (model_pretrain.py:200-204): every gradient flows through ordinary autograd, so the stock reducer's
+    hooks fire.  Kernel table = CPU emulation (host logic only)."""
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from tests.emu_kernels import EmuKernels
+    from videotransformer_pytorch_b200 import TimeSformer, _lib
+    _lib.K = EmuKernels(exact=True)
+    cfg = dict(num_frames=2, img_size=32, patch_size=16, embed_dims=32, num_heads=2, num_transformer_layers=1)
+    torch.manual_seed(5 + rank)                    # DDP broadcasts rank 0's parameters
+    net = TimeSformer(**cfg).eval()
+    with torch.no_grad():
+        for n, p in net.named_parameters():
+            if 'temporal_fc' in n:
+                p.normal_(std=0.05)
+    ddp = torch.nn.parallel.DistributedDataParallel(net)
+    g = torch.Generator().manual_seed(50 + rank)
+    x = torch.randn(2, 2, 3, 32, 32, generator=g)
+    ddp(x).square().mean().backward()
+    q.put((rank, {n: p.grad.detach().numpy().copy() for n, p in net.named_parameters()},
+           {n: p.detach().numpy().copy() for n, p in net.named_parameters()}))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_modules_work_under_stock_distributed_data_parallel():
+    import numpy as np
+    from tests.emu_kernels import EmuKernels
+    from videotransformer_pytorch_b200 import TimeSformer, _lib
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_stock_ddp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=180) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, g0, w0), (_, g1, w1) = res
+    for n in g0:
+        assert np.array_equal(w0[n], w1[n]), n
+        assert np.allclose(g0[n], g1[n], atol=1e-7), n
+    # single-process reference with rank 0's weights: mean of the two ranks' gradients
+    old = _lib.K
+    _lib.K = EmuKernels(exact=True)
+    try:
+        cfg = dict(num_frames=2, img_size=32, patch_size=16, embed_dims=32, num_heads=2, num_transformer_layers=1)
+        net = TimeSformer(**cfg).eval()
+        net.load_state_dict({k: torch.from_numpy(v) for k, v in w0.items()}, strict=False)
+        acc = None
+        for rank in range(2):
+            for p in net.parameters():
+                p.grad = None
+            g = torch.Generator().manual_seed(50 + rank)
+            net(torch.randn(2, 2, 3, 32, 32, generator=g)).square().mean().backward()
+            cur = {n: p.grad.clone() for n, p in net.named_parameters()}
+            acc = cur if acc is None else {n: acc[n] + cur[n] for n in cur}
+    finally:
+        _lib.K = old
+    for n in g0:
+        assert np.allclose(g0[n], (acc[n] / 2).numpy(), atol=1e-6, rtol=1e-5), n

@@ -209,3 +209,46 @@ def test_joint_space_time_vs_golden(golden):
             worst = max(worst, abs(p.grad.double().norm().item() - ref[1]) / ref[1])
     print(f'joint_space_time n289 train: worst grad rel err {worst:.2e}')
     assert worst < 5e-2
+
+
+@pytest.mark.parametrize('name,attention_type', [('vivit_joint_tiny', 'joint_space_time'),
+                                                 ('vivit_divided_tiny', 'divided_space_time')])
+def test_vivit_joint_and_divided_variants_vs_golden(golden, name, attention_type):
+    """ViViT models 1 / 3 (reference video_transformer.py:349-373) on the kernels vs goldens from the real reference."""
+    from videotransformer_pytorch_b200 import ViViT
+    g = golden(name)
+    c = g.cfg
+    m = ViViT(num_frames=c['num_frames_in'], img_size=c['img_size'], patch_size=c['patch_size'],
+              embed_dims=c['embed_dims'], num_heads=c['num_heads'],
+              num_transformer_layers=c['num_transformer_layers'], attention_type=attention_type)
+    m.load_state_dict(g.sd, strict=True)
+    m = m.cuda().eval()
+    with torch.no_grad():
+        e = rel_err(m(g.x.cuda()).cpu(), g.out['y_eval'])
+    print(f'ViViT {attention_type} eval: {e:.2e}')
+    assert e < 1.5e-2
+    m.train()
+    torch.manual_seed(g.train_seed)
+    y = m(g.x.cuda())
+    assert rel_err(y.detach().cpu(), g.out['y_train']) < 1.5e-2
+    (y.double() * g.out['loss_w'].cuda()).sum().backward()
+    worst = check_grads({n: p.grad for n, p in m.named_parameters()}, g, 5e-2)
+    print(f'ViViT {attention_type} train: worst small-grad rel err {worst:.2e}')
+
+
+def test_vivit_b_joint_space_time_1569_tokens_vs_oracle():
+    """ViViT-B model 1 at 16x224 (1 + 196*8 = 1569 tokens per clip, streaming tcgen05 attention), one layer, B=1."""
+    from oracle import vt_oracle as O
+    from videotransformer_pytorch_b200 import ViViT
+    torch.manual_seed(8)
+    kw = dict(num_frames=16, img_size=224, patch_size=16, embed_dims=768, num_heads=12, num_transformer_layers=1)
+    m = ViViT(attention_type='joint_space_time', **kw)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    cfg = dict(img_size=224, patch_size=16, embed_dims=768, num_heads=12, num_transformer_layers=1)
+    x = torch.randn(1, 16, 3, 224, 224)
+    with torch.no_grad():
+        ref = O.vivit_variant_forward({k: v.double() for k, v in sd.items()}, x.double(), cfg, 'joint_space_time')
+        got = m.cuda().eval()(x.cuda())
+    e = rel_err(got.cpu(), ref)
+    print(f'ViViT-B joint_space_time 1569 tokens: {e:.2e}')
+    assert e < 5e-3

@@ -66,3 +66,40 @@ def test_fused_sgd_on_a_model_with_static_grads():
         mo.step(clip_grad=1.0)
     for p, q in zip(ref.parameters(), net.parameters()):
         assert rel_err(q.detach().cpu(), p.detach()) < 5e-6
+
+
+def test_eager_training_with_fused_sgd_tracks_torch_sgd():
+    """Eager (non-graph) training of a package model: the fused optimizer updates parameters through raw pointers, the
+    bf16 weight shadows must follow (stale-shadow bug).  Two identical TimeSformers, one stepped by
+    FusedSGD and one by torch.optim.SGD, stay together for 3 steps and both move away from the initial weights."""
+    from videotransformer_pytorch_b200 import TimeSformer
+    from videotransformer_pytorch_b200.optim import FusedSGD
+    cfg = dict(num_frames=4, img_size=48, patch_size=16, embed_dims=128, num_heads=2, num_transformer_layers=2)
+    torch.manual_seed(0)
+    a = TimeSformer(**cfg)
+    with torch.no_grad():
+        for n, p in a.named_parameters():
+            if 'temporal_fc' in n:
+                p.normal_(std=0.05)
+    b = TimeSformer(**cfg)
+    b.load_state_dict(a.state_dict())
+    a, b = a.cuda().eval(), b.cuda().eval()          # eval: no DropPath randomness between the two copies
+    oa = FusedSGD(a.parameters(), lr=0.05, momentum=0.9, nesterov=True, weight_decay=1e-4)
+    ob = torch.optim.SGD(b.parameters(), lr=0.05, momentum=0.9, nesterov=True, weight_decay=1e-4)
+    x = torch.randn(2, 4, 3, 48, 48, generator=torch.Generator().manual_seed(1)).cuda()
+    losses = []
+    for step in range(3):
+        for m, o in ((a, oa), (b, ob)):
+            for p in m.parameters():
+                p.grad = None
+            loss = m(x).square().mean()
+            loss.backward()
+            o.step()
+            losses.append(float(loss))
+    la, lb = losses[0::2], losses[1::2]
+    assert abs(la[0] - lb[0]) < 1e-6 * abs(lb[0])
+    assert la[2] < la[0]                                              # the model really trains
+    for i in range(3):
+        assert abs(la[i] - lb[i]) < 2e-3 * abs(lb[i]), (la, lb)      # stale bf16 shadows would freeze la at la[0]
+    for (n, p), q in zip(a.named_parameters(), b.parameters()):
+        assert rel_err(p.detach(), q.detach()) < 1e-3, n

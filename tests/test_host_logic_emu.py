@@ -167,3 +167,27 @@ def test_timesformer_accepts_uint8_clip(golden, emu):
     m.train()
     m(u8).sum().backward()                        # parameters still get gradients; the byte clip has none
     assert all(p.grad is not None for p in m.parameters())
+
+
+@pytest.mark.parametrize('name,attention_type', [('vivit_joint_tiny', 'joint_space_time'),
+                                                 ('vivit_divided_tiny', 'divided_space_time')])
+def test_vivit_joint_and_divided_variants(golden, emu, name, attention_type):
+    """ViViT models 1 and 3 (reference video_transformer.py:349-373): state-dict surface, eval and train-mode forward and
+    all gradients against goldens generated by the real reference class."""
+    from videotransformer_pytorch_b200 import ViViT
+    g = golden(name)
+    c = g.cfg
+    m = ViViT(num_frames=c['num_frames_in'], img_size=c['img_size'], patch_size=c['patch_size'],
+              embed_dims=c['embed_dims'], num_heads=c['num_heads'],
+              num_transformer_layers=c['num_transformer_layers'], attention_type=attention_type)
+    assert list(m.state_dict().keys()) == list(g.sd.keys())
+    m.load_state_dict(g.sd, strict=True)
+    m.eval()
+    with torch.no_grad():
+        assert rel_err(m(g.x), g.out['y_eval']) < 2e-5
+    m.train()
+    torch.manual_seed(g.train_seed)
+    y = m(g.x)
+    assert rel_err(y, g.out['y_train']) < 2e-5
+    (y.double() * g.out['loss_w']).sum().backward()
+    check_grads({n: p.grad for n, p in m.named_parameters()}, g, 2e-4)

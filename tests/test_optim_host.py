@@ -67,3 +67,87 @@ def test_step_without_clipping_and_missing_grad(emu):
     qs[0].grad = None
     with pytest.raises(RuntimeError, match='no gradient'):
         mine.step()
+
+
+@pytest.mark.parametrize('kind', ['sgd', 'adamw'])
+def test_state_dict_round_trip_resumes_identically(emu, kind):
+    """Momentum / Adam moments and the step count live in torch.optim.Optimizer.state: a checkpointed and restored
+    optimizer continues exactly like the uninterrupted one (Lightning resume)."""
+    import copy
+    from videotransformer_pytorch_b200.optim import FusedAdamW, FusedSGD
+    mk = (lambda ps: FusedSGD(ps, lr=0.05, momentum=0.9, nesterov=True, weight_decay=0.01)) if kind == 'sgd' else \
+         (lambda ps: FusedAdamW(ps, lr=1e-2, weight_decay=0.05))
+    a_p, b_p = make_params(3), make_params(3)
+    a, b = mk(a_p), mk(b_p)
+
+    def grads(step, ps):
+        gg = torch.Generator().manual_seed(200 + step)
+        for p in ps:
+            p.grad = torch.randn(p.shape, generator=gg)
+
+    for step in range(3):
+        grads(step, a_p); grads(step, b_p)
+        a.step(clip_grad=1.0); b.step(clip_grad=1.0)
+    sd = copy.deepcopy(b.state_dict())
+    assert len(sd['state']) == len(b_p)
+    names = ('momentum_buffer',) if kind == 'sgd' else ('exp_avg', 'exp_avg_sq')
+    assert all(n in sd['state'][0] for n in names) and float(sd['state'][0]['step']) == 3.0
+    c_p = [torch.nn.Parameter(p.detach().clone()) for p in b_p]
+    c = mk(c_p)
+    c.load_state_dict(sd)
+    for step in range(3, 6):
+        grads(step, a_p); grads(step, c_p)
+        a.step(clip_grad=1.0); c.step(clip_grad=1.0)
+    for p, q in zip(a_p, c_p):
+        assert torch.equal(p.detach(), q.detach())
+    # a torch.optim.SGD checkpoint (momentum buffers, no step counter) is accepted: not treated as a first step
+    if kind == 'sgd':
+        t_p = make_params(4)
+        t = torch.optim.SGD(t_p, lr=0.05, momentum=0.9, nesterov=True, weight_decay=0.01)
+        f_p = make_params(4)
+        for step in range(2):
+            grads(step, t_p)
+            t.step()
+        f = mk([torch.nn.Parameter(p.detach().clone()) for p in t_p])
+        f.load_state_dict(copy.deepcopy(t.state_dict()))
+        f_p = [p for g in f.param_groups for p in g['params']]
+        grads(5, t_p); grads(5, f_p)
+        t.step(); f.step()
+        for p, q in zip(t_p, f_p):
+            assert rel_err(q.detach(), p.detach()) < 1e-6
+
+
+def test_step_bumps_parameter_versions(emu):
+    """The CUDA kernels write parameters through raw pointers; step() must still advance `param._version` so the bf16
+    weight shadows (transformer.ShadowWeights, keyed on the version) are re-cast in eager training."""
+    from videotransformer_pytorch_b200.optim import FusedSGD
+    from videotransformer_pytorch_b200.transformer import ShadowWeights
+
+    class RawWrites(type(emu)):
+        """emulation that, like the real kernels, does not touch the version counters"""
+        def opt_sgd(self, tbl, clip, momentum, nesterov, first_step):
+            params = tbl['_params']
+            saved = [p._version for p in params]
+            for p in params:
+                p.data.add_(-0.1)          # .data writes do not bump the version
+            assert [p._version for p in params] == saved
+
+        def cast_bf16(self, x):
+            return x.bfloat16()
+
+    from videotransformer_pytorch_b200 import _lib
+    old = _lib.K
+    _lib.K = RawWrites(exact=True)
+    try:
+        p = torch.nn.Parameter(torch.randn(8, 4))
+        sh = ShadowWeights()
+        w0 = sh.get('w', p)
+        opt = FusedSGD([p], lr=0.1)
+        p.grad = torch.ones_like(p)
+        v0 = p._version
+        opt.step()
+        assert p._version > v0
+        w1 = sh.get('w', p)
+        assert not torch.equal(w0, w1) and torch.equal(w1, p.detach().bfloat16())
+    finally:
+        _lib.K = old

@@ -57,12 +57,14 @@ class GradientBuckets:
         if cur:
             self._bucket_params.append(cur)
         self._owner = {}
+        self._view = {}
         for bi, ps in enumerate(self._bucket_params):
             n = sum(p.numel() for p in ps)
             flat = torch.zeros(n, dtype=torch.float32, device=self.device)
             off = 0
             for p in ps:
                 p.grad = flat[off:off + p.numel()].view_as(p)
+                self._view[p] = p.grad
                 off += p.numel()
                 self._owner[p] = bi
                 p.register_post_accumulate_grad_hook(self._hook)
@@ -75,9 +77,13 @@ class GradientBuckets:
 
     # -- per step -------------------------------------------------------------------------------
     def zero_grad(self):
-        """Gradients live in the buckets: zero them in place (keeps the p.grad views valid)."""
+        """Gradients live in the buckets: zero them in place and make sure every p.grad is its bucket view again
+        (a foreign zero_grad(set_to_none=True) is tolerated: see _hook)."""
         for b in self.buckets:
             b.zero_()
+        for p, view in self._view.items():
+            if p.grad is not view:
+                p.grad = view
         self._pending = [len(ps) for ps in self._bucket_params]
 
     def reset_counters(self):
@@ -87,6 +93,14 @@ class GradientBuckets:
 
     def _hook(self, p):
         bi = self._owner[p]
+        view = self._view[p]
+        if p.grad is not view and (p.grad is None or p.grad.data_ptr() != view.data_ptr()):
+            # something replaced p.grad (optimizer.zero_grad(set_to_none=True), Lightning's default): autograd then
+            # accumulated into a fresh tensor.  Move it into the bucket and re-attach the view, otherwise the bucket
+            # would be all-reduced without this rank's gradient and the optimizer would consume the unsynchronised one.
+            with torch.no_grad():
+                view.copy_(p.grad)
+            p.grad = view
         self._pending[bi] -= 1
         if self._pending[bi] == 0:
             self._launch(bi)

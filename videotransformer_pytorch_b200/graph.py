@@ -26,7 +26,13 @@ class MaskArena:
     def __init__(self, device, capacity: int = 1 << 20):
         self.device = device
         self.dev = torch.ones(capacity, dtype=torch.float32, device=device)
-        self.host = torch.ones(capacity, dtype=torch.float32).pin_memory() if device.type == 'cuda' else torch.ones(capacity)
+        # pinned staging is rotated over three buffers, each guarded by an event recorded after its upload: the host may
+        # run ahead of the GPU (back-to-back replays without a sync) and must not rewrite a buffer whose copy is pending
+        cuda = device.type == 'cuda'
+        self.hosts = [torch.ones(capacity, dtype=torch.float32).pin_memory() if cuda else torch.ones(capacity)
+                      for _ in range(3 if cuda else 1)]
+        self.uploaded = [torch.cuda.Event() if cuda else None for _ in self.hosts]
+        self._slot = 0
         self.entries = []      # (offset, n0, keep)
         self.used = 0
         self.recording = False
@@ -42,11 +48,18 @@ class MaskArena:
     def refill(self):
         """Draw this step's masks exactly like the reference does (one torch.rand((n0,1,1)) per active DropPath,
         in forward order) and upload them with one copy."""
+        slot = self._slot
+        self._slot = (slot + 1) % len(self.hosts)
+        host, ev = self.hosts[slot], self.uploaded[slot]
+        if ev is not None:
+            ev.synchronize()          # no-op unless this buffer's previous upload (3 steps ago) is still in flight
         for off, n0, keep in self.entries:
             r = (keep + torch.rand((n0, 1, 1))).floor_().reshape(n0) / keep
-            self.host[off:off + n0] = r
+            host[off:off + n0] = r
         if self.used:
-            self.dev[:self.used].copy_(self.host[:self.used], non_blocking=True)
+            self.dev[:self.used].copy_(host[:self.used], non_blocking=True)
+            if ev is not None:
+                ev.record(torch.cuda.current_stream(self.device))
 
 
 class GraphedTrainStep:

@@ -22,9 +22,11 @@ CHUNK = 1 << 16
 
 
 class TensorTable:
-    """Device-side description of a list of (param, grad, state...) tensors for the multi-tensor kernels."""
+    """Device-side description of a list of (param, grad, state...) tensors for the multi-tensor kernels.
+    `state` = one list of tensors per state slot (momentum | exp_avg, exp_avg_sq), owned by the optimizer's
+    torch.optim.Optimizer.state so that state_dict() / load_state_dict() round-trip them."""
 
-    def __init__(self, params, n_state):
+    def __init__(self, params, state):
         self.params = list(params)
         dev = self.params[0].device
         self.device = dev
@@ -38,7 +40,11 @@ class TensorTable:
         # rows of {int32 tensor, int32 len, int64 offset} = 16 bytes, built as int64 pairs (little endian)
         tbl = torch.tensor([[(ln << 32) | i, off] for i, ln, off in rows], dtype=torch.int64)
         n = len(self.params)
-        self.state = [[torch.zeros_like(p, memory_format=torch.contiguous_format) for p in self.params] for _ in range(n_state)]
+        self.state = [list(slot) for slot in state]
+        for slot in self.state:
+            for p, s_ in zip(self.params, slot):
+                if s_.dtype != torch.float32 or not s_.is_contiguous() or s_.device != p.device or s_.shape != p.shape:
+                    raise RuntimeError('fused optimizer: state tensors must be contiguous fp32 like their parameter')
         self.t = {
             'chunks': tbl.to(dev), 'n_chunks': len(rows), 'n_tensors': n,
             'pptr': torch.tensor([p.data_ptr() for p in self.params], dtype=torch.int64, device=dev),
@@ -51,7 +57,7 @@ class TensorTable:
         # python-side handles (used by the CPU emulation of the kernel table in tests; the CUDA path reads the pointer arrays)
         self.t['_params'], self.t['_state'] = self.params, self.state
         self.t['_grads'] = lambda: [p.grad for p in self.params]
-        if n_state > 1:
+        if len(self.state) > 1:
             self.t['s2ptr'] = torch.tensor([s.data_ptr() for s in self.state[1]], dtype=torch.int64, device=dev)
         self._gptr_host = None
         self._hp_host = None
@@ -79,14 +85,37 @@ class TensorTable:
 
 
 class _FusedBase(torch.optim.Optimizer):
-    n_state = 1
+    state_names = ('momentum_buffer',)       # keys in self.state[p], same names as torch.optim.SGD / AdamW
 
     def _table(self):
         params = [p for g in self.param_groups for p in g['params'] if p.requires_grad]
         tab = getattr(self, '_tab', None)
         if tab is None or [id(p) for p in tab.params] != [id(p) for p in params]:
-            tab = self._tab = TensorTable(params, self.n_state)
-            self._steps = 0
+            # (re)bind: the per-parameter buffers live in torch.optim.Optimizer.state, so they survive
+            # state_dict()/load_state_dict() (checkpoint resume) and changes of the parameter list (add_param_group)
+            had_all = True
+            slots = [[] for _ in self.state_names]
+            steps = 0
+            for p in params:
+                st = self.state[p]
+                for si, name in enumerate(self.state_names):
+                    buf = st.get(name)
+                    if buf is None:
+                        had_all = False
+                        buf = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                    elif buf.dtype != torch.float32 or buf.device != p.device or not buf.is_contiguous():
+                        buf = buf.to(device=p.device, dtype=torch.float32).contiguous()
+                    st[name] = buf
+                    slots[si].append(buf)
+                if 'step' in st:
+                    steps = max(steps, int(float(st['step'])))
+            tab = self._tab = TensorTable(params, slots)
+            # fresh buffers start the count at 0; restored buffers without a counter (torch.optim.SGD keeps none) are
+            # past their first step
+            self._steps = steps if steps > 0 else (1 if had_all else 0)
+            self._step_tensor = torch.tensor(float(self._steps))
+            for p in params:
+                self.state[p]['step'] = self._step_tensor        # one shared host scalar (torch keeps one per tensor)
         lrs, wds = [], []
         for g in self.param_groups:
             for p in g['params']:
@@ -96,6 +125,10 @@ class _FusedBase(torch.optim.Optimizer):
         tab.bind_hyper(lrs, wds)
         tab.bind_grads()
         return tab
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self._tab = None              # pointer tables are rebuilt from the restored self.state on the next step
 
     @torch.no_grad()
     def step(self, closure=None, clip_grad=None):
@@ -110,6 +143,11 @@ class _FusedBase(torch.optim.Optimizer):
             total = n2.sum().sqrt()
         self._update(tab, float(clip_grad or 0.0))
         self._steps += 1
+        self._step_tensor.fill_(float(self._steps))
+        # the kernels wrote the parameters through raw pointers: bump the autograd version counters so everything keyed
+        # on them (the bf16 weight shadows of transformer.ShadowWeights, saved-tensor checks) sees the update
+        for p in tab.params:
+            torch.autograd.graph.increment_version(p)
         return total
 
 
@@ -131,7 +169,7 @@ class FusedSGD(_FusedBase):
 
 class FusedAdamW(_FusedBase):
     """torch.optim.AdamW(betas, eps, weight_decay) with the reference's per-parameter clipping."""
-    n_state = 2
+    state_names = ('exp_avg', 'exp_avg_sq')
 
     def __init__(self, params, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))

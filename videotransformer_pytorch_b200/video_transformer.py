@@ -4,7 +4,8 @@ sm_100a kernels.
 
 Covered configurations: TimeSformer `divided_space_time`, `space_only` (197-token joint
 attention per frame) and `joint_space_time` (one 1569-token attention per clip, streaming tcgen05 kernel); ViViT
-`fact_encoder`.  Nothing falls back to eager PyTorch.
+`fact_encoder` (model 2), `joint_space_time` (model 1) and `divided_space_time` (model 3).  Nothing falls back to eager
+PyTorch.
 """
 from __future__ import annotations
 
@@ -179,8 +180,6 @@ class ViViT(nn.Module):
                  extend_strategy='temporal_avg', use_learnable_pos_emb=True, return_cls_token=True, **kwargs):
         super().__init__()
         assert attention_type in self.supported_attention_types, f'Unsupported Attention Type {attention_type}!'
-        if attention_type != 'fact_encoder':
-            raise NotImplementedError(f'{attention_type}: only fact_encoder is on the B200 hot path (SURVEY §8f)')
         if dropout_p:
             raise NotImplementedError('dropout_p > 0 is not on the reference hot path (always 0.)')
         if conv_type != 'Conv3d':
@@ -196,26 +195,34 @@ class ViViT(nn.Module):
         self.copy_strategy = copy_strategy
         self.extend_strategy = extend_strategy
         self.tube_size = tube_size
-        self.num_time_transformer_layers = 4
+        self.num_time_transformer_layers = 4 if attention_type == 'fact_encoder' else 0
         self.use_learnable_pos_emb = use_learnable_pos_emb
         self.return_cls_token = return_cls_token
 
         self.patch_embed = PatchEmbed(img_size=img_size, patch_size=patch_size, in_channels=in_channels,
                                       embed_dims=embed_dims, tube_size=tube_size, conv_type=conv_type)
         num_patches = self.patch_embed.num_patches
-        mk = lambda n: TransformerContainer(
+        mk = lambda n, order: TransformerContainer(
             num_transformer_layers=n, embed_dims=embed_dims, num_heads=num_heads, num_frames=num_frames,
-            norm_layer=norm_layer, hidden_channels=embed_dims * 4, operator_order=['self_attn', 'ffn'])
-        self.transformer_layers = nn.ModuleList([mk(num_transformer_layers), mk(self.num_time_transformer_layers)])
+            norm_layer=norm_layer, hidden_channels=embed_dims * 4, operator_order=order)
+        if attention_type == 'divided_space_time':          # model 3 (reference :349-360)
+            self.transformer_layers = mk(num_transformer_layers, ['time_attn', 'space_attn', 'ffn'])
+        elif attention_type == 'joint_space_time':          # model 1 (:361-373): one 1+P*T' token attention per clip
+            self.transformer_layers = mk(num_transformer_layers, ['self_attn', 'ffn'])
+        else:                                               # model 2, factorised encoder (:374-400)
+            self.transformer_layers = nn.ModuleList([mk(num_transformer_layers, ['self_attn', 'ffn']),
+                                                     mk(self.num_time_transformer_layers, ['self_attn', 'ffn'])])
         self.norm = norm_layer(embed_dims, eps=1e-6)
         self.cls_token = nn.Parameter(torch.zeros(1, 1, embed_dims))
+        # reference :405-416: only fact_encoder has a cls slot in time_embed; operator_order[-2] is never 'time_attn'
         self.use_cls_token_temporal = False
+        n_time = num_frames + 1 if attention_type == 'fact_encoder' else num_frames
         if use_learnable_pos_emb:
             self.pos_embed = nn.Parameter(torch.zeros(1, num_patches + 1, embed_dims))
-            self.time_embed = nn.Parameter(torch.zeros(1, num_frames + 1, embed_dims))
+            self.time_embed = nn.Parameter(torch.zeros(1, n_time, embed_dims))
         else:
             self.pos_embed = get_sine_cosine_pos_emb(num_patches + 1, embed_dims)
-            self.time_embed = get_sine_cosine_pos_emb(num_frames + 1, embed_dims)
+            self.time_embed = get_sine_cosine_pos_emb(n_time, embed_dims)
         self.drop_after_pos = nn.Dropout(p=dropout_p)
         self.drop_after_time = nn.Dropout(p=dropout_p)
         self.init_weights()
@@ -236,8 +243,15 @@ class ViViT(nn.Module):
         b = x.shape[0]
         pos = self.pos_embed if self.use_learnable_pos_emb else self.pos_embed.to(x.device).detach()
         pe = self.patch_embed
-        tok = ops.PatchTokensFn.apply(x, _f32(pe.projection.weight), _f32(pe.projection.bias), self.cls_token, pos, None,
-                                      pe.shadow(), 'frames', self.tube_size)
+        if self.attention_type == 'fact_encoder':
+            tok = ops.PatchTokensFn.apply(x, _f32(pe.projection.weight), _f32(pe.projection.bias), self.cls_token, pos, None,
+                                          pe.shadow(), 'frames', self.tube_size)
+        else:
+            # reference :476-499 with use_cls_token_temporal False == TimeSformer's assembly on tubelets: one cls,
+            # tokens 'b (p t) d', pos_embed per patch + time_embed per tubelet (fused into the patch GEMM epilogue)
+            tim = self.time_embed if self.use_learnable_pos_emb else self.time_embed.to(x.device).detach()
+            tok = ops.PatchTokensFn.apply(x, _f32(pe.projection.weight), _f32(pe.projection.bias), self.cls_token, pos, tim,
+                                          pe.shadow(), 'timesformer', self.tube_size)
         cls_tokens = self.cls_token.expand(tok.shape[0], -1, -1)
         return tok, cls_tokens, b
 
@@ -251,10 +265,13 @@ class ViViT(nn.Module):
 
     def forward(self, x):
         x, cls_tokens, b = self.prepare_tokens(x)
-        spatial, temporal = self.transformer_layers
-        x = spatial(x)
-        x = self._temporal_tokens(x, b)
-        x = temporal(x)
+        if self.attention_type != 'fact_encoder':
+            x = self.transformer_layers(x)
+        else:
+            spatial, temporal = self.transformer_layers
+            x = spatial(x)
+            x = self._temporal_tokens(x, b)
+            x = temporal(x)
         if self.return_cls_token:
             S = x.shape[1]
             rows = (torch.arange(b, device=x.device, dtype=torch.int32) * S).contiguous()
@@ -264,6 +281,8 @@ class ViViT(nn.Module):
 
     def get_last_selfattention(self, x):
         x, cls_tokens, b = self.prepare_tokens(x)
+        if self.attention_type != 'fact_encoder':
+            return self.transformer_layers(x, return_attention=True)
         spatial, temporal = self.transformer_layers
         x = spatial(x)
         x = self._temporal_tokens(x, b)

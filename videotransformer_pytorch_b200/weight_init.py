@@ -50,13 +50,16 @@ _LAYER_IDX = re.compile(r'(?<=layers\.)\d+')
 
 
 def _inflate_patch_filter(weight, tube_size, extend_strategy):
-    """Conv2d filter [D,C,h,w] -> Conv3d filter [D,C,tube,h,w] (weight_init.py:130-139)."""
+    """Conv2d filter [D,C,h,w] -> Conv3d filter [D,C,tube,h,w] (weight_init.py:130-139).
+
+    Quirk reproduced, not fixed: for 'center_frame' the reference zeroes `new_weight` in place, but einops.repeat returned
+    an expanded VIEW of `weight`, so the 2-D filter is zeroed with it and the "centre frame" it then copies in is all
+    zeros — the inflated filter is identically zero (checked against the reference function, tests/test_checkpoint_loaders.py)."""
     w3 = weight.unsqueeze(2).repeat(1, 1, tube_size, 1, 1)
     if extend_strategy == 'temporal_avg':
         w3 = w3 / tube_size
     elif extend_strategy == 'center_frame':
         w3 = torch.zeros_like(w3)
-        w3[:, :, tube_size // 2] = weight
     return w3
 
 
