@@ -348,6 +348,45 @@ int vt_opt_norm2(const vt_opt_params* p, void* stream);
 int vt_opt_sgd(const vt_opt_params* p, void* stream);
 int vt_opt_adamw(const vt_opt_params* p, void* stream);
 
+/* =============================================================================================
+ * Classification head + loss, long-sequence attention maps, Mixup/CutMix operand.
+ * ============================================================================================= */
+
+/* Skinny fp32 linear layer  y[M,N] = x[M,K] W[N,K]^T + b  (ClassificationHead.forward, transformer.py:78-80: 8 x 768 -> 400)
+ * and its adjoints  dW = dy^T x, db = colsum(dy), dx = dy W  (dw / dx may be NULL to skip).  Warp-per-output GEMV on
+ * the fp32 parameters themselves (no bf16 shadow); M <= 4096, K % 4 == 0. */
+typedef struct { const float* x; const float* w; const float* b; float* y; int32_t M, N, K; } vt_linear_small_params;
+int vt_linear_small_fwd(const vt_linear_small_params* p, void* stream);
+typedef struct { const float* dy; const float* x; const float* w; float* dw; float* db; float* dx; int32_t M, N, K; } vt_linear_small_bwd_params;
+int vt_linear_small_bwd(const vt_linear_small_bwd_params* p, void* stream);
+
+/* Softmax cross-entropy, mean over rows: nn.CrossEntropyLoss (model_trainer.py:91, :208) with int64 `labels`, or timm's
+ * SoftTargetCrossEntropy (:89) with fp32 `soft_targets` [M,N] (exactly one of the two).  One launch writes loss[0],
+ * optional per-row losses and dlogits = d loss / d logits. */
+typedef struct {
+  const float* logits; const int64_t* labels; const float* soft_targets;
+  float* loss; float* row_loss; float* dlogits; int32_t M, N;
+} vt_softmax_ce_params;
+int vt_softmax_ce(const vt_softmax_ce_params* p, void* stream);
+/* out[i] = in[i] * scalar[0] (device scalar: chain rule through the loss inside a captured graph) */
+typedef struct { const float* in; const float* scalar; float* out; int64_t n; } vt_scale_params;
+int vt_scale_by_scalar(const vt_scale_params* p, void* stream);
+
+/* probs[bp,h,i,j] = softmax_j(q_i . k_j * scale) for any N that fits 8 rows of scores in shared memory (N <= ~6000),
+ * q/k read in place from the packed projection bf16 [Bp, N, 3, H, 64].  Serves get_last_selfattention
+ * (video_transformer.py:258-261, transformer.py:560-561) for the 1569-token joint space-time variants. */
+typedef struct { const void* qkv; float* probs; int32_t Bp, N, H, hd; float scale; } vt_attn_probs_params;
+int vt_attn_probs(const vt_attn_probs_params* p, void* stream);
+
+/* vt_im2col_u8_bf16 with the batch-level Mixup / CutMix of mixup.py:102-114 folded in: sample b is blended with (mode 1,
+ * lam*x + (1-lam)*x.flip(0)) or patched from (mode 2, box rows [yl,yh) x cols [xl,xh)) sample B-1-b after normalisation.
+ * plan = device float[6] {mode, lam, yl, yh, xl, xh}. */
+typedef struct {
+  const uint8_t* x; const float* scale; const float* shift; const float* plan; void* cols;
+  int32_t B, T, C, H, W, tube, ph, pw;
+} vt_im2col_u8_mix_params;
+int vt_im2col_u8_mix_bf16(const vt_im2col_u8_mix_params* p, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

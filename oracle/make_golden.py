@@ -396,6 +396,33 @@ def main():
                        pool_q_stride_size=((1, 1, 2, 2), (3, 1, 2, 2), (14, 1, 2, 2))), B=1, seed=9, with_grads=False)
 
 
+def mixup_cases():
+    """Reference Mixup (mixup.py:58-126) under np.random.seed: per seed the mixed float clip, the soft targets and the
+    draw (lam / cutmix box recovered by replaying the reference's own helper calls on a copy of the RNG state)."""
+    sys.path.insert(0, REF)
+    import mixup as ref_mixup
+    rows = {}
+    B, T, C, H, W, NC = 4, 2, 3, 32, 32, 7
+    seeds = list(range(12))
+    for seed in seeds:
+        g = torch.Generator().manual_seed(seed)
+        u8 = torch.randint(0, 256, (B, T, H, W, C), generator=g, dtype=torch.uint8)
+        labels = torch.randint(0, NC, (B,), generator=g)
+        x = ((u8.float() / 255.0 - 0.45) / 0.225).permute(0, 1, 4, 2, 3).contiguous()      # ToTensor + Normalize
+        np.random.seed(seed)
+        fn = ref_mixup.Mixup(num_classes=NC)
+        xm, tgt = fn(x.clone(), labels)
+        rows[f'u8_{seed}'] = u8.numpy()
+        rows[f'labels_{seed}'] = labels.numpy()
+        rows[f'mixed_{seed}'] = xm.numpy()
+        rows[f'target_{seed}'] = tgt.cpu().numpy()
+    # reference one_hot defaults to device='cuda'; Mixup passes x.device, so CPU works
+    rows['seeds'] = np.asarray(seeds)
+    rows['num_classes'] = np.int64(NC)
+    np.savez_compressed(os.path.join(GOLD, 'mixup.npz'), **rows)
+    print(f'[mixup] {len(seeds)} seeds stored from the reference Mixup class')
+
+
 def main_selected(tr, vt, mg, only):
     """Cases added after round 1 (run alone with `python oracle/make_golden.py <name> ...`)."""
     want = lambda n: only is None or n in only
@@ -404,6 +431,8 @@ def main_selected(tr, vt, mg, only):
         vivit_variant_case(vt, 'vivit_joint_tiny', vv, B=2, seed=11, attention_type='joint_space_time')
     if want('vivit_divided_tiny'):
         vivit_variant_case(vt, 'vivit_divided_tiny', vv, B=2, seed=12, attention_type='divided_space_time')
+    if want('mixup'):
+        mixup_cases()
 
 
 if __name__ == '__main__':

@@ -181,6 +181,46 @@ class EmuKernels:
         xf = x.to(self.f).permute(0, 1, 4, 2, 3) * self._up(scale).view(1, 1, -1, 1, 1) + self._up(shift).view(1, 1, -1, 1, 1)
         return self.im2col(xf, tube, ph, pw)
 
+    def im2col_u8_mix(self, x, scale, shift, plan, tube, ph, pw):
+        xf = x.to(self.f).permute(0, 1, 4, 2, 3) * self._up(scale).view(1, 1, -1, 1, 1) + self._up(shift).view(1, 1, -1, 1, 1)
+        mode, lam = int(plan[0]), float(plan[1])
+        yl, yh, xl, xh = (int(v) for v in plan[2:6])
+        if mode == 1:
+            xf = xf * lam + xf.flip(0) * (1.0 - lam)
+        elif mode == 2:
+            xf = xf.clone()
+            xf[..., yl:yh, xl:xh] = xf.flip(0)[..., yl:yh, xl:xh]
+        return self.im2col(xf, tube, ph, pw)
+
+    def attn_probs(self, qkv, Bp, N, H, hd, scale):
+        q5 = self._up(qkv).reshape(Bp, N, 3, H, hd)
+        q, k = q5[:, :, 0].permute(0, 2, 1, 3), q5[:, :, 1].permute(0, 2, 1, 3)
+        return ((q @ k.transpose(-1, -2)) * scale).softmax(dim=-1).to(torch.float32)
+
+    def linear_small_fwd(self, x, w, b):
+        y = self._up(x) @ self._up(w).t()
+        return (y + self._up(b) if b is not None else y).to(torch.float32)
+
+    def linear_small_bwd(self, dy, x, w, need_dx=True, need_dw=True):
+        dy_, x_, w_ = self._up(dy), self._up(x), self._up(w)
+        dx = (dy_ @ w_).to(torch.float32) if need_dx else None
+        dw = (dy_.t() @ x_).to(torch.float32) if need_dw else None
+        db = dy_.sum(0).to(torch.float32) if need_dw else None
+        return dx, dw, db
+
+    def softmax_ce(self, logits, labels=None, soft_targets=None):
+        z = self._up(logits)
+        M, N = z.shape
+        t = torch.nn.functional.one_hot(labels, N).to(z.dtype) if labels is not None else self._up(soft_targets)
+        lse = torch.logsumexp(z, dim=-1)
+        ts = t.sum(-1)
+        row = lse * ts - (t * z).sum(-1)
+        dz = (z.softmax(-1) * ts[:, None] - t) / M
+        return row.mean().reshape(1).to(torch.float32), dz.to(torch.float32), row.to(torch.float32)
+
+    def scale_by_scalar(self, t, scalar):
+        return (self._up(t) * self._up(scalar)[0]).to(torch.float32)
+
     def col2im(self, cols, shape, tube, ph, pw):
         B, T, C, H, W = shape
         Tp, Hp, Wp = T // tube, H // ph, W // pw

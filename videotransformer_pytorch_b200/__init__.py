@@ -12,5 +12,7 @@ from .transformer import (Attention, BasicTransformerBlock, ClassificationHead, 
                           get_sine_cosine_pos_emb)
 from .video_transformer import TimeSformer, ViViT, get_vit_base_patch16_224  # noqa: F401
 from .maskfeat import MaskFeat  # noqa: F401
+from .mixup import MixedClip, Mixup  # noqa: F401
+from .ops import cross_entropy  # noqa: F401
 
 __version__ = '0.1.0'

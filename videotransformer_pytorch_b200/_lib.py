@@ -166,12 +166,41 @@ class OptParams(C.Structure):
                 ('bc2', c_f32), ('nesterov', c_i32), ('first_step', c_i32)]
 
 
+class LinearSmallParams(C.Structure):
+    _fields_ = [('x', c_vp), ('w', c_vp), ('b', c_vp), ('y', c_vp), ('M', c_i32), ('N', c_i32), ('K', c_i32)]
+
+
+class LinearSmallBwdParams(C.Structure):
+    _fields_ = [('dy', c_vp), ('x', c_vp), ('w', c_vp), ('dw', c_vp), ('db', c_vp), ('dx', c_vp),
+                ('M', c_i32), ('N', c_i32), ('K', c_i32)]
+
+
+class SoftmaxCeParams(C.Structure):
+    _fields_ = [('logits', c_vp), ('labels', c_vp), ('soft_targets', c_vp), ('loss', c_vp), ('row_loss', c_vp),
+                ('dlogits', c_vp), ('M', c_i32), ('N', c_i32)]
+
+
+class ScaleParams(C.Structure):
+    _fields_ = [('inp', c_vp), ('scalar', c_vp), ('out', c_vp), ('n', c_i64)]
+
+
+class AttnProbsParams(C.Structure):
+    _fields_ = [('qkv', c_vp), ('probs', c_vp), ('Bp', c_i32), ('N', c_i32), ('H', c_i32), ('hd', c_i32), ('scale', c_f32)]
+
+
+class Im2colU8MixParams(C.Structure):
+    _fields_ = [('x', c_vp), ('scale', c_vp), ('shift', c_vp), ('plan', c_vp), ('cols', c_vp), ('B', c_i32), ('T', c_i32),
+                ('C', c_i32), ('H', c_i32), ('W', c_i32), ('tube', c_i32), ('ph', c_i32), ('pw', c_i32)]
+
+
 EXPORTS = ['vt_version', 'vt_last_error', 'vt_sm_count', 'vt_set_reserved_sms', 'vt_launch_count', 'vt_gemm', 'vt_layernorm_fwd', 'vt_ln_bwd_blocks',
            'vt_layernorm_bwd', 'vt_reduce_rows', 'vt_colsum_chunks', 'vt_colsum_bf16', 'vt_cast_f32_bf16',
            'vt_gather_cast_bf16', 'vt_gelu_fwd_bf16', 'vt_gelu_bwd_bf16', 'vt_attn_fwd', 'vt_attn_bwd', 'vt_debug_buffer', 'vt_im2col_bf16', 'vt_im2col_u8_bf16', 'vt_col2im_f32', 'vt_hog',
            'vt_pool_fwd', 'vt_pool_bwd_scratch', 'vt_pool_bwd', 'vt_xattn_fwd', 'vt_xattn_bwd', 'vt_maxpool_fwd',
            'vt_maxpool_bwd', 'vt_im2col3d_bf16', 'vt_mvit_tokens_fwd', 'vt_mvit_tokens_bwd', 'vt_mse_blocks',
-           'vt_mse_fwd', 'vt_mse_bwd', 'vt_opt_norm2', 'vt_opt_sgd', 'vt_opt_adamw']
+           'vt_mse_fwd', 'vt_mse_bwd', 'vt_opt_norm2', 'vt_opt_sgd', 'vt_opt_adamw',
+           'vt_linear_small_fwd', 'vt_linear_small_bwd', 'vt_softmax_ce', 'vt_scale_by_scalar', 'vt_attn_probs',
+           'vt_im2col_u8_mix_bf16']
 
 _dll = None
 
@@ -426,6 +455,98 @@ class CudaKernels:
         _check(lib.vt_attn_bwd(C.byref(p), _stream()), 'vt_attn_bwd')
         return dqkv
 
+    def attn_probs(self, qkv, Bp, N, H, hd, scale):
+        """softmax(q k^T * scale) of a packed projection [Bp, N, 3, H, hd] -> fp32 [Bp, H, N, N] (any N; head dim 64)"""
+        lib = load_library()
+        _req(qkv, torch.bfloat16, 'attn_probs.qkv')
+        if not qkv.is_contiguous() or qkv.numel() != Bp * N * 3 * H * hd:
+            raise RuntimeError('attn_probs: qkv must be contiguous [Bp, N, 3, H, hd]')
+        probs = torch.empty((Bp, H, N, N), dtype=torch.float32, device=qkv.device)
+        p = AttnProbsParams()
+        p.qkv, p.probs = qkv.data_ptr(), probs.data_ptr()
+        p.Bp, p.N, p.H, p.hd, p.scale = Bp, N, H, hd, scale
+        _check(lib.vt_attn_probs(C.byref(p), _stream()), 'vt_attn_probs')
+        return probs
+
+    # -- classification head + loss -----------------------------------------------------------
+    def linear_small_fwd(self, x, w, b):
+        lib = load_library()
+        for t, n in ((x, 'x'), (w, 'w')):
+            _rows2d(_req(t, torch.float32, 'linear_small.' + n), 'linear_small.' + n)
+            if not t.is_contiguous():
+                raise RuntimeError(f'linear_small: {n} must be contiguous')
+        M, Kd = x.shape
+        N = w.shape[0]
+        if w.shape[1] != Kd:
+            raise RuntimeError('linear_small: shape mismatch')
+        y = torch.empty((M, N), dtype=torch.float32, device=x.device)
+        p = LinearSmallParams()
+        p.x, p.w, p.b, p.y = x.data_ptr(), w.data_ptr(), _ptr(None if b is None else _req(b, torch.float32, 'linear_small.b')), y.data_ptr()
+        p.M, p.N, p.K = M, N, Kd
+        _check(lib.vt_linear_small_fwd(C.byref(p), _stream()), 'vt_linear_small_fwd')
+        return y
+
+    def linear_small_bwd(self, dy, x, w, need_dx=True, need_dw=True):
+        """-> (dx | None, dw | None, db | None)"""
+        lib = load_library()
+        for t, n in ((dy, 'dy'), (x, 'x'), (w, 'w')):
+            _req(t, torch.float32, 'linear_small_bwd.' + n)
+            if not t.is_contiguous():
+                raise RuntimeError(f'linear_small_bwd: {n} must be contiguous')
+        M, Kd = x.shape
+        N = w.shape[0]
+        dev = x.device
+        dx = torch.empty((M, Kd), dtype=torch.float32, device=dev) if need_dx else None
+        dw = torch.empty((N, Kd), dtype=torch.float32, device=dev) if need_dw else None
+        db = torch.empty(N, dtype=torch.float32, device=dev) if need_dw else None
+        p = LinearSmallBwdParams()
+        p.dy, p.x, p.w = dy.data_ptr(), x.data_ptr(), w.data_ptr()
+        p.dw, p.db, p.dx = _ptr(dw), _ptr(db), _ptr(dx)
+        p.M, p.N, p.K = M, N, Kd
+        _check(lib.vt_linear_small_bwd(C.byref(p), _stream()), 'vt_linear_small_bwd')
+        return dx, dw, db
+
+    def softmax_ce(self, logits, labels=None, soft_targets=None):
+        """mean cross-entropy over rows -> (loss fp32 [1], dlogits fp32 [M,N], row_loss fp32 [M])"""
+        lib = load_library()
+        logits = _req(logits, torch.float32, 'softmax_ce.logits')
+        if logits.dim() != 2 or not logits.is_contiguous():
+            raise RuntimeError('softmax_ce: logits must be contiguous [M, N]')
+        M, N = logits.shape
+        dev = logits.device
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        row = torch.empty(M, dtype=torch.float32, device=dev)
+        dz = torch.empty_like(logits)
+        p = SoftmaxCeParams()
+        p.logits, p.loss, p.row_loss, p.dlogits = logits.data_ptr(), loss.data_ptr(), row.data_ptr(), dz.data_ptr()
+        if (labels is None) == (soft_targets is None):
+            raise RuntimeError('softmax_ce: give labels or soft_targets')
+        if labels is not None:
+            labels = _req(labels, torch.int64, 'softmax_ce.labels').contiguous()
+            if labels.numel() != M:
+                raise RuntimeError('softmax_ce: one label per row expected')
+            p.labels = labels.data_ptr()
+        else:
+            soft_targets = _req(soft_targets, torch.float32, 'softmax_ce.soft_targets').contiguous()
+            if tuple(soft_targets.shape) != (M, N):
+                raise RuntimeError('softmax_ce: soft_targets must be [M, N]')
+            p.soft_targets = soft_targets.data_ptr()
+        p.M, p.N = M, N
+        _check(lib.vt_softmax_ce(C.byref(p), _stream()), 'vt_softmax_ce')
+        return loss, dz, row
+
+    def scale_by_scalar(self, t, scalar):
+        lib = load_library()
+        t = _req(t, torch.float32, 'scale.t')
+        if not t.is_contiguous():
+            raise RuntimeError('scale_by_scalar: tensor must be contiguous')
+        scalar = _req(scalar, torch.float32, 'scale.scalar')
+        out = torch.empty_like(t)
+        p = ScaleParams()
+        p.inp, p.scalar, p.out, p.n = t.data_ptr(), scalar.data_ptr(), out.data_ptr(), t.numel()
+        _check(lib.vt_scale_by_scalar(C.byref(p), _stream()), 'vt_scale_by_scalar')
+        return out
+
     # -- patch embedding operand -------------------------------------------------------------
     def im2col(self, x, tube, ph, pw):
         lib = load_library()
@@ -451,6 +572,23 @@ class CudaKernels:
         p.scale, p.shift = _req(scale, torch.float32, 'im2col_u8.scale').data_ptr(), _req(shift, torch.float32, 'im2col_u8.shift').data_ptr()
         p.B, p.T, p.C, p.H, p.W, p.tube, p.ph, p.pw = B, T, Cc, H, W, tube, ph, pw
         _check(lib.vt_im2col_u8_bf16(C.byref(p), _stream()), 'vt_im2col_u8_bf16')
+        return cols
+
+    def im2col_u8_mix(self, x, scale, shift, plan, tube, ph, pw):
+        """im2col_u8 with Mixup / CutMix against the flipped batch; plan: fp32 [6] device tensor {mode, lam, yl, yh, xl, xh}"""
+        lib = load_library()
+        x = _req(x, torch.uint8, 'im2col_u8_mix.x').contiguous()
+        B, T, H, W, Cc = x.shape
+        rows = B * (T // tube) * (H // ph) * (W // pw)
+        cols = torch.empty((rows, Cc * tube * ph * pw), dtype=torch.bfloat16, device=x.device)
+        p = Im2colU8MixParams()
+        p.x, p.cols = x.data_ptr(), cols.data_ptr()
+        p.scale, p.shift = _req(scale, torch.float32, 'im2col_u8_mix.scale').data_ptr(), _req(shift, torch.float32, 'im2col_u8_mix.shift').data_ptr()
+        if plan.numel() < 6:
+            raise RuntimeError('im2col_u8_mix: plan must hold 6 floats {mode, lam, yl, yh, xl, xh}')
+        p.plan = _req(plan, torch.float32, 'im2col_u8_mix.plan').data_ptr()
+        p.B, p.T, p.C, p.H, p.W, p.tube, p.ph, p.pw = B, T, Cc, H, W, tube, ph, pw
+        _check(lib.vt_im2col_u8_mix_bf16(C.byref(p), _stream()), 'vt_im2col_u8_mix_bf16')
         return cols
 
     def col2im(self, cols, shape, tube, ph, pw):

@@ -127,6 +127,18 @@ def _packed_heads(qkv, Bp, N, H, hd):
     return tuple(v5[:, :, s].permute(0, 2, 1, 3) for s in range(3))
 
 
+def _streaming_attn_bwd(k, qkv, cx, dcx, lse, Bp, N, H, hd):
+    """dqkv of a long-sequence attention through the streaming tcgen05 kernels (q/k/v and dq in place in the packed layout)."""
+    q4, k4, v4 = _packed_heads(qkv, Bp, N, H, hd)
+    dqkv = torch.empty_like(qkv)
+    dq4, dk4, dv4 = _packed_heads(dqkv, Bp, N, H, hd)
+    D = H * hd
+    dk, dv = k.xattn_bwd(q4, k4, v4, cx.view(Bp, N, D), dcx.view(Bp, N, D), lse, hd ** -0.5, dq4)
+    dk4.copy_(dk)           # fp32 [Bp,H,N,hd] accumulators -> their bf16 slots of the packed gradient
+    dv4.copy_(dv)
+    return dqkv
+
+
 def _mul_opt(a, b):
     if a is None:
         return b
@@ -286,12 +298,7 @@ class JointAttnFn(torch.autograd.Function):
         if N <= ATTN_SINGLE_PASS_MAX:
             dqkv = k.attn_bwd(qkv, cx, dcx, lse, Bp, N, H, hd, hd ** -0.5)
         else:
-            q4, k4, v4 = _packed_heads(qkv, Bp, N, H, hd)
-            dqkv = torch.empty_like(qkv)
-            dq4, dk4, dv4 = _packed_heads(dqkv, Bp, N, H, hd)
-            dk, dv = k.xattn_bwd(q4, k4, v4, cx.view(Bp, N, D), dcx.view(Bp, N, D), lse, hd ** -0.5, dq4)
-            dk4.copy_(dk)           # fp32 [Bp,H,N,hd] accumulators -> their bf16 slots of the packed gradient
-            dv4.copy_(dv)
+            dqkv = _streaming_attn_bwd(k, qkv, cx, dcx, lse, Bp, N, H, hd)
         d_qkv_w = _wgrad(dqkv, xn, 3 * D, D, M)
         d_qkv_b = k.colsum(dqkv)
         dxn = _dgrad(dqkv, qkv_wh, M, D, 3 * D, epi='bf16')
@@ -358,14 +365,18 @@ class PatchTokensFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x, w, b, cls_token, pos_embed, time_embed, wh, mode, tube, norm=None):
+    def forward(ctx, x, w, b, cls_token, pos_embed, time_embed, wh, mode, tube, norm=None, mix_plan=None):
         k = K()
         D = w.shape[0]
         ph, pw = w.shape[-2], w.shape[-1]
         if x.dtype == torch.uint8:
-            # decoder output [B, T, H, W, C]: ToTensor + Normalize are folded into the operand kernel (norm = (scale, shift))
+            # decoder output [B, T, H, W, C]: ToTensor + Normalize are folded into the operand kernel (norm = (scale, shift)),
+            # and with a mix plan (mixup.Mixup) the batch-level Mixup / CutMix of mixup.py:102-114 as well
             B, T, Himg, Wimg, C = x.shape
-            cols = k.im2col_u8(x, norm[0], norm[1], tube, ph, pw)
+            if mix_plan is not None:
+                cols = k.im2col_u8_mix(x, norm[0], norm[1], mix_plan, tube, ph, pw)
+            else:
+                cols = k.im2col_u8(x, norm[0], norm[1], tube, ph, pw)
         else:
             B, T, C, Himg, Wimg = x.shape
             cols = k.im2col(x.float(), tube, ph, pw)
@@ -426,7 +437,7 @@ class PatchTokensFn(torch.autograd.Function):
             dcols = _dgrad(g, wh.reshape(D, Kc), M, Kc, D, epi='f32')
             dx = k.col2im(dcols, xshape, tube, wshape[-2], wshape[-1])
         # small grads are returned as fresh contiguous tensors (not views) so autograd can adopt them in place
-        return dx, dw.contiguous(), db, dcls.reshape(cshape).clone(), dpos.contiguous(), dtime, None, None, None, None
+        return dx, dw.contiguous(), db, dcls.reshape(cshape).clone(), dpos.contiguous(), dtime, None, None, None, None, None
 
 
 # --------------------------------------------------------------------------------------------------
@@ -471,7 +482,15 @@ class AttentionCoreFn(torch.autograd.Function):
         hd = C // H
         xh = k.gather_cast(x.reshape(M, C).float().contiguous())
         qkv = k.gemm(xh, qkv_wh, M, 3 * C, C, bias=qkv_b, epi='bf16')
-        cx, lse, probs = k.attn_fwd(qkv, Bp, N, H, hd, hd ** -0.5, want_probs=want_probs)
+        if N <= ATTN_SINGLE_PASS_MAX:
+            cx, lse, probs = k.attn_fwd(qkv, Bp, N, H, hd, hd ** -0.5, want_probs=want_probs)
+        else:
+            # long sequences (joint space-time: 1569 tokens): context by the streaming tcgen05 kernel; the probability
+            # maps the reference returns (transformer.py:171-177) by a row-tile softmax kernel, 8 query rows per CTA
+            q4, k4, v4 = _packed_heads(qkv, Bp, N, H, hd)
+            cx, lse = k.xattn_fwd(q4, k4, v4, hd ** -0.5)
+            cx = cx.view(M, C)
+            probs = k.attn_probs(qkv, Bp, N, H, hd, hd ** -0.5) if want_probs else None
         out = k.gemm(cx, proj_wh, M, C, C, bias=proj_b, epi='f32').view(Bp, N, C)
         ctx.save_for_backward(xh, qkv, cx, lse, qkv_wh, proj_wh)
         ctx.geom = (Bp, N, C, H)
@@ -491,8 +510,61 @@ class AttentionCoreFn(torch.autograd.Function):
         d_proj_w = _wgrad(g, cx, C, C, M)
         d_proj_b = k.colsum(g)
         dcx = _dgrad(g, proj_wh, M, C, C, epi='bf16')
-        dqkv = k.attn_bwd(qkv, cx, dcx, lse, Bp, N, H, hd, hd ** -0.5)
+        if N <= ATTN_SINGLE_PASS_MAX:
+            dqkv = k.attn_bwd(qkv, cx, dcx, lse, Bp, N, H, hd, hd ** -0.5)
+        else:
+            dqkv = _streaming_attn_bwd(k, qkv, cx, dcx, lse, Bp, N, H, hd)
         d_qkv_w = _wgrad(dqkv, xh, 3 * C, C, M)
         d_qkv_b = k.colsum(dqkv)
         dx = _dgrad(dqkv, qkv_wh, M, C, 3 * C, epi='f32').view(Bp, N, C)
         return dx, d_qkv_w, d_qkv_b, d_proj_w, d_proj_b, None, None, None, None
+
+
+# --------------------------------------------------------------------------------------------------
+class LinearSmallFn(torch.autograd.Function):
+    """y = x W^T + b for a handful of rows (ClassificationHead.forward, transformer.py:78-80), fp32 GEMV kernels."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        k = K()
+        x2 = x.reshape(-1, x.shape[-1]).float().contiguous()
+        y = k.linear_small_fwd(x2, w.contiguous(), b)
+        ctx.save_for_backward(x2, w)
+        ctx.has_bias = b is not None
+        ctx.xshape = tuple(x.shape)
+        return y.view(*x.shape[:-1], w.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        k = K()
+        x2, w = ctx.saved_tensors
+        dy2 = dy.reshape(-1, dy.shape[-1]).float().contiguous()
+        dx, dw, db = k.linear_small_bwd(dy2, x2, w.contiguous(), need_dx=ctx.needs_input_grad[0],
+                                        need_dw=ctx.needs_input_grad[1] or ctx.needs_input_grad[2])
+        return (None if dx is None else dx.view(ctx.xshape)), dw, (db if ctx.has_bias else None)
+
+
+class SoftmaxCEFn(torch.autograd.Function):
+    """Mean softmax cross-entropy over rows: hard int64 labels (nn.CrossEntropyLoss, model_trainer.py:91) or soft fp32
+    targets (timm SoftTargetCrossEntropy, :89).  Forward also produces d loss / d logits (one launch)."""
+
+    @staticmethod
+    def forward(ctx, logits, target):
+        k = K()
+        z = logits.float().contiguous()
+        if target.dtype == torch.int64:
+            loss, dz, _ = k.softmax_ce(z, labels=target)
+        else:
+            loss, dz, _ = k.softmax_ce(z, soft_targets=target.float())
+        ctx.save_for_backward(dz)
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, dloss):
+        (dz,) = ctx.saved_tensors
+        return K().scale_by_scalar(dz, dloss.reshape(1).float().contiguous()), None
+
+
+def cross_entropy(logits, target):
+    """F.cross_entropy(logits, target) (mean reduction) / SoftTargetCrossEntropy()(logits, target) on the repo's kernel."""
+    return SoftmaxCEFn.apply(logits, target)

@@ -120,7 +120,8 @@ def _dp_scale(layer_drop, n0, repeat, device):
 
 
 class ClassificationHead(nn.Module):
-    """Linear classifier on the cls feature (8 x 768 -> num_classes: left to torch.nn.Linear)."""
+    """Linear classifier on the cls feature (reference transformer.py:45-80).  `cls_head` holds the parameters under the
+    reference's names; forward is the fp32 skinny-GEMV kernel (ops.LinearSmallFn), `loss` adds the fused softmax-CE kernel."""
 
     def __init__(self, num_classes, in_channels, init_std=0.02, eval_metrics='finetune', **kwargs):
         super().__init__()
@@ -139,7 +140,12 @@ class ClassificationHead(nn.Module):
             constant_init_(module.bias, constant_value=0)
 
     def forward(self, x):
-        return self.cls_head(x)
+        return ops.LinearSmallFn.apply(x, _f32(self.cls_head.weight), None if self.cls_head.bias is None else _f32(self.cls_head.bias))
+
+    def loss(self, x, target):
+        """mean cross-entropy of the head's logits: int64 labels (nn.CrossEntropyLoss, model_trainer.py:91, :207-208) or
+        soft targets from Mixup (SoftTargetCrossEntropy, :89)."""
+        return ops.cross_entropy(self.forward(x), target)
 
 
 class PatchEmbed(nn.Module):

@@ -13,6 +13,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
+from .mixup import MixedClip
 from .transformer import PatchEmbed, TransformerContainer, get_sine_cosine_pos_emb, _f32
 from .weight_init import init_from_kinetics_pretrain_, init_from_vit_pretrain_, trunc_normal_
 
@@ -30,7 +31,37 @@ def _load_pretrained(module, **vit_kwargs):
         raise TypeError(f'not support the pretrained weight {module.pretrain_pth}')
 
 
-class TimeSformer(nn.Module):
+class _ByteClipInput:
+    """Models fed the decoder's uint8 clip [B, T, H, W, 3] (optionally wrapped in a mixup.MixedClip): ToTensor + Normalize
+    (+ Mixup / CutMix) are folded into the patch-operand kernel."""
+
+    def set_input_normalization(self, mean, std):
+        """Normalisation applied when the model is fed the decoder's uint8 clip [B, T, H, W, 3] directly (the reference
+        does it on the CPU: data_transform.py ToTensor + Normalize with data_trainer.py:69-73's mean / std)."""
+        self._input_norm = (tuple(float(m) for m in mean), tuple(float(s) for s in std))
+        self._input_norm_dev = None
+
+    def _norm_tensors(self, device):
+        cached = getattr(self, '_input_norm_dev', None)
+        if cached is None or cached[0].device != device:
+            mean, std = getattr(self, '_input_norm', ((0.45, 0.45, 0.45), (0.225, 0.225, 0.225)))
+            scale = torch.tensor([1.0 / (255.0 * s) for s in std], dtype=torch.float32, device=device)
+            shift = torch.tensor([-m / s for m, s in zip(mean, std)], dtype=torch.float32, device=device)
+            cached = self._input_norm_dev = (scale, shift)
+        return cached
+
+    def _unwrap_clip(self, x):
+        """-> (tensor, (scale, shift) | None, mix plan | None)"""
+        plan = None
+        if isinstance(x, MixedClip):
+            x, plan = x.clip, x.plan
+        norm = self._norm_tensors(x.device) if x.dtype == torch.uint8 else None
+        if plan is not None and norm is None:
+            raise RuntimeError('MixedClip must wrap a uint8 clip (float clips are mixed by Mixup.__call__ itself)')
+        return x, norm, plan
+
+
+class TimeSformer(_ByteClipInput, nn.Module):
     """TimeSformer (divided space-time attention).  forward(x[B,T,3,H,W]) -> [B, embed_dims]."""
 
     supported_attention_types = ['divided_space_time', 'space_only', 'joint_space_time']
@@ -107,28 +138,12 @@ class TimeSformer(nn.Module):
             tim = None if tim is None else tim.to(x.device).detach()
         return pos, tim
 
-    def set_input_normalization(self, mean, std):
-        """Normalisation applied when the model is fed the decoder's uint8 clip [B, T, H, W, 3] directly (the reference
-        does it on the CPU: data_transform.py ToTensor + Normalize with data_trainer.py:69-73's mean / std)."""
-        self._input_norm = (tuple(float(m) for m in mean), tuple(float(s) for s in std))
-        self._input_norm_dev = None
-
-    def _norm_tensors(self, device):
-        cached = getattr(self, '_input_norm_dev', None)
-        if cached is None or cached[0].device != device:
-            mean, std = getattr(self, '_input_norm', ((0.45, 0.45, 0.45), (0.225, 0.225, 0.225)))
-            scale = torch.tensor([1.0 / (255.0 * s) for s in std], dtype=torch.float32, device=device)
-            shift = torch.tensor([-m / s for m, s in zip(mean, std)], dtype=torch.float32, device=device)
-            cached = self._input_norm_dev = (scale, shift)
-        return cached
-
     def prepare_tokens(self, x):
-        if x.dtype == torch.uint8:          # [B, T, H, W, C] bytes: normalisation is fused into the patch operand kernel
+        x, norm, plan = self._unwrap_clip(x)
+        if norm is not None:                # [B, T, H, W, C] bytes
             b, t, h, w, c = x.shape
-            norm = self._norm_tensors(x.device)
         else:
             b, t, c, h, w = x.shape
-            norm = None
         P = self.patch_embed.num_patches
         if (h // self.patch_embed.patch_size[0]) * (w // self.patch_embed.patch_size[1]) != P or w != h:
             raise NotImplementedError('input size must match img_size (no pos-embed interpolation on the hot path)')
@@ -136,7 +151,7 @@ class TimeSformer(nn.Module):
         pe = self.patch_embed
         mode = 'frames' if self.attention_type == 'space_only' else 'timesformer'   # space_only: per-frame tokens
         tok = ops.PatchTokensFn.apply(x, _f32(pe.projection.weight), _f32(pe.projection.bias), self.cls_token, pos, tim,
-                                      pe.shadow(), mode, 1, norm)
+                                      pe.shadow(), mode, 1, norm, plan)
         return tok, b
 
     def forward(self, x):
@@ -168,7 +183,7 @@ def get_vit_base_patch16_224(**kwargs):
                        return_cls_token=True)
 
 
-class ViViT(nn.Module):
+class ViViT(_ByteClipInput, nn.Module):
     """ViViT factorised encoder (model 2): tubelet embed -> 12 spatial layers per frame ->
     frame tokens (+ the reference's `x[:b,0,:]` cls gather) -> 4 temporal layers."""
 
@@ -240,18 +255,19 @@ class ViViT(nn.Module):
         return {'pos_embed', 'cls_token', 'mask_token'}
 
     def prepare_tokens(self, x):
+        x, norm, plan = self._unwrap_clip(x)
         b = x.shape[0]
         pos = self.pos_embed if self.use_learnable_pos_emb else self.pos_embed.to(x.device).detach()
         pe = self.patch_embed
         if self.attention_type == 'fact_encoder':
             tok = ops.PatchTokensFn.apply(x, _f32(pe.projection.weight), _f32(pe.projection.bias), self.cls_token, pos, None,
-                                          pe.shadow(), 'frames', self.tube_size)
+                                          pe.shadow(), 'frames', self.tube_size, norm, plan)
         else:
             # reference :476-499 with use_cls_token_temporal False == TimeSformer's assembly on tubelets: one cls,
             # tokens 'b (p t) d', pos_embed per patch + time_embed per tubelet (fused into the patch GEMM epilogue)
             tim = self.time_embed if self.use_learnable_pos_emb else self.time_embed.to(x.device).detach()
             tok = ops.PatchTokensFn.apply(x, _f32(pe.projection.weight), _f32(pe.projection.bias), self.cls_token, pos, tim,
-                                          pe.shadow(), 'timesformer', self.tube_size)
+                                          pe.shadow(), 'timesformer', self.tube_size, norm, plan)
         cls_tokens = self.cls_token.expand(tok.shape[0], -1, -1)
         return tok, cls_tokens, b
 
