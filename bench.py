@@ -188,7 +188,7 @@ class Trainee(torch.nn.Module):
                     p.normal_(std=0.02)
 
     def forward(self, x, y):
-        return torch.nn.functional.cross_entropy(self.cls_head(self.model(x)), y)
+        return self.cls_head.loss(self.model(x), y)          # skinny-GEMV head + fused softmax-CE kernels
 
 
 def main_gpu(args):

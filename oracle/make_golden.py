@@ -431,6 +431,11 @@ def main_selected(tr, vt, mg, only):
         vivit_variant_case(vt, 'vivit_joint_tiny', vv, B=2, seed=11, attention_type='joint_space_time')
     if want('vivit_divided_tiny'):
         vivit_variant_case(vt, 'vivit_divided_tiny', vv, B=2, seed=12, attention_type='divided_space_time')
+    vv128 = dict(num_frames_in=8, img_size=48, patch_size=16, embed_dims=128, num_heads=2, num_transformer_layers=1)
+    if want('vivit_joint_hd64'):        # D = 128: the width the GPU row-map LayerNorm needs (D % 128 == 0)
+        vivit_variant_case(vt, 'vivit_joint_hd64', vv128, B=2, seed=13, attention_type='joint_space_time')
+    if want('vivit_divided_hd64'):
+        vivit_variant_case(vt, 'vivit_divided_hd64', vv128, B=2, seed=14, attention_type='divided_space_time')
     if want('mixup'):
         mixup_cases()
 

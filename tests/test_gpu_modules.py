@@ -211,8 +211,8 @@ def test_joint_space_time_vs_golden(golden):
     assert worst < 5e-2
 
 
-@pytest.mark.parametrize('name,attention_type', [('vivit_joint_tiny', 'joint_space_time'),
-                                                 ('vivit_divided_tiny', 'divided_space_time')])
+@pytest.mark.parametrize('name,attention_type', [('vivit_joint_hd64', 'joint_space_time'),
+                                                 ('vivit_divided_hd64', 'divided_space_time')])
 def test_vivit_joint_and_divided_variants_vs_golden(golden, name, attention_type):
     """ViViT models 1 / 3 (reference video_transformer.py:349-373) on the kernels vs goldens from the real reference."""
     from videotransformer_pytorch_b200 import ViViT

@@ -129,7 +129,7 @@ def test_masked_mse_vs_oracle_loss():
     num = K().mse_fwd(pred_rows.detach().reshape(B * L1, dt * dc).cuda(), target.cuda(), m.cuda(), dims)
     loss = num[0].item() / (m.sum().item() + 1e-5)
     assert abs(loss - loss_o.item()) < 1e-5 * abs(loss_o.item())
-    coef = torch.tensor([1.0 / (m.sum().item() + 1e-5)])
+    coef = torch.tensor([(2.0 / dc) / (m.sum().item() + 1e-5)])       # d loss / d (pred - target)^2-sum, as MaskedMSEFn passes it
     dp = K().mse_bwd(pred_rows.detach().reshape(B * L1, dt * dc).cuda(), target.cuda(), m.cuda(), coef.cuda(), dims)
     assert rel_err(dp.float().cpu(), pred_rows.grad.reshape(B * L1, dt * dc)) < 4e-3
 
