@@ -86,6 +86,18 @@ typedef struct {
   int32_t force_cluster;   /* 0/1 = single CTAs, 2 = clusters of 2 CTAs along M sharing each B tile by TMA multicast,
                               3 = CTA pairs issuing tcgen05.mma.cta_group::2 (256 x BN tiles, half of B per SM) */
   void* debug;             /* diagnostics only: int64 [grid][16] clock64 stamps of the kernel's phases, or NULL */
+  /* Affine description of out_row / aux_row for VT_EPI_F32 with aux (the residual scatter of the divided space-time blocks),
+   * map_period = 0: none.  GEMM row m -> outer = m / map_period, inner = m % map_period.  Rows with inner < map_skip are
+   * "special" (the per-frame cls replicas of the spatial pass): no addend, written to out + map_special_base +
+   * outer * map_special_stride (dropped when map_special_base < 0).  Every other row reads its addend from / writes its
+   * result to element offset  map_base + (outer % map_tcount) * map_stride_t + (inner - map_skip) * map_stride_p +
+   * (outer / map_tcount) * map_stride_b  of aux / out.  With it the epilogue moves whole 32 x 32 boxes by TMA through a
+   * 4-D tensor map (reference einops: transformer.py:250, :279-280, :352-356, :375-377) instead of per-thread rows; the
+   * out_row / aux_row arrays, when also given, must describe the same mapping (they serve the generic epilogue). */
+  int32_t map_period, map_skip, map_tcount;
+  int32_t force_tail;      /* 0 = heuristic, 1 = never cut the partial last row of tiles into narrow units, 2 = prefer to */
+  int64_t map_stride_t, map_stride_p, map_stride_b, map_base;
+  int64_t map_special_base, map_special_stride;
 } vt_gemm_params;
 
 int vt_gemm(const vt_gemm_params* p, void* stream);

@@ -37,8 +37,24 @@ class EmuKernels:
 
     def gemm(self, a, b, M, N, Kdim, *, a_mn=False, b_mn=False, epi='bf16', bias=None, out=None, out2=None,
              aux=None, out_row=None, aux_row=None, row_scale=None, out_rows=None, split_ok=False,
-             force_splits=0, force_bn=0, force_cluster=0, debug=None):
+             force_splits=0, force_bn=0, force_cluster=0, debug=None, row_map=None, force_tail=0):
         self.calls.append(('gemm', M, N, Kdim, a_mn, b_mn, epi))
+        if row_map is not None:
+            # the affine description handed to the TMA residual epilogue must be the out_row / aux_row arrays in closed form
+            assert epi == 'f32' and aux is not None and out_row is not None and aux_row is not None
+            ld = out.stride(0)
+            m = torch.arange(M, dtype=torch.int64)
+            outer, inner = m // row_map['period'], m % row_map['period']
+            special = inner < row_map['skip']
+            elem = (row_map['base'] + (outer % row_map['tcount']) * row_map['stride_t'] +
+                    (inner - row_map['skip']) * row_map['stride_p'] + (outer // row_map['tcount']) * row_map['stride_b'])
+            assert bool((elem % ld == 0).all()) and M % row_map['period'] == 0
+            rows = elem // ld
+            exp_out = torch.where(special, (row_map.get('special_base', -1) + outer * row_map.get('special_stride', 0)) // ld, rows)
+            exp_aux = torch.where(special, torch.full_like(rows, -1), rows)
+            assert torch.equal(exp_out, out_row.cpu().to(torch.int64)), 'row_map does not reproduce out_row'
+            assert torch.equal(exp_aux, aux_row.cpu().to(torch.int64)), 'row_map does not reproduce aux_row'
+            assert aux.stride(0) == ld
         A = self._up(a).t() if a_mn else self._up(a)
         Bm = self._up(b) if b_mn else self._up(b).t()
         assert A.shape == (M, Kdim) and Bm.shape == (Kdim, N), (A.shape, Bm.shape, M, N, Kdim)

@@ -198,3 +198,91 @@ def test_gemm_pair_kernel_epilogues(epi):
         zz = z.float().requires_grad_(True)
         torch.nn.functional.gelu(zz).sum().backward()
         assert rel(out, r * zz.grad) < 4e-3
+
+
+# ---- round 2: fp32 residual epilogue on TMA (affine row maps through a 4-D tensor map) and narrow tail units -------------
+def _ops():
+    from videotransformer_pytorch_b200 import ops
+    return ops
+
+
+@pytest.mark.parametrize('cluster', [1, 3], ids=['single-cta', 'cta-pair'])
+@pytest.mark.parametrize('bn', [0, 128, 192, 256])
+@pytest.mark.parametrize('M,N,Kd', [(1000, 768, 256), (12552, 768, 768), (130, 96, 192), (4096, 256, 64)])
+def test_residual_epilogue_tma_plain_rows(M, N, Kd, bn, cluster, monkeypatch):
+    """y = s(m) (A B^T + bias) + aux without row maps (FC2, joint proj): TMA residual path == generic per-thread path."""
+    if cluster == 3 and bn == 192:
+        pytest.skip('the pair kernel has no 192-wide tile')
+    a, b = mk((M, Kd), 30).bfloat16(), mk((N, Kd), 31).bfloat16()
+    bias, rs, aux = mk((N,), 32), mk((M,), 33), mk((M, N), 34)
+    out = torch.full((M, N), 55.0, device='cuda')
+    K().gemm(a, b, M, N, Kd, epi='f32', bias=bias, row_scale=rs, aux=aux, out=out, force_bn=bn, force_cluster=cluster)
+    r = (ref_mm(a, b, False, False) + bias) * rs[:, None] + aux
+    assert rel(out, r) < 1e-5
+    monkeypatch.setenv('VT_NO_TMA_RES', '1')
+    old = torch.empty_like(out)
+    K().gemm(a, b, M, N, Kd, epi='f32', bias=bias, row_scale=rs, aux=aux, out=old, force_bn=bn, force_cluster=cluster)
+    assert rel(out, old) < 1e-6
+
+
+@pytest.mark.parametrize('cluster', [1, 3], ids=['single-cta', 'cta-pair'])
+@pytest.mark.parametrize('B,T,P,D', [(2, 8, 196, 768), (3, 4, 9, 128), (1, 2, 50, 256), (2, 8, 196, 96)])
+def test_residual_epilogue_tma_temporal_and_spatial_maps(B, T, P, D, cluster, monkeypatch):
+    """The divided space-time scatters as 4-D TMA boxes (temporal '(b p) t', spatial '(b t) (1+p)' with the per-frame cls
+    replicas going to side rows) against the same GEMM driven by the out_row / aux_row arrays (generic epilogue)."""
+    ops = _ops()
+    maps = ops.token_maps(B, T, P, 'cuda:0')
+    aff = ops.affine_row_maps(B, T, P, D)
+    S = 1 + P * T
+    R = B * S
+    Kd = 128
+    x2 = mk((R, D), 40)
+    w, bias = mk((D, Kd), 41).bfloat16(), mk((D,), 42)
+    for name, Mrows, out_rows, out_row, aux_row in (('temporal', B * P * T, R, maps['temporal'], maps['temporal']),
+                                                    ('spatial', B * T * (P + 1), R + B * T, maps['sp_out'], maps['sp_aux'])):
+        a = mk((Mrows, Kd), 43).bfloat16()
+        rs = mk((Mrows,), 44)
+        got = torch.full((out_rows, D), -7.0, device='cuda')
+        K().gemm(a, w, Mrows, D, Kd, epi='f32', bias=bias, row_scale=rs, aux=x2, aux_row=aux_row, out=got, out_row=out_row,
+                 row_map=aff[name], force_cluster=cluster)
+        monkeypatch.setenv('VT_NO_TMA_RES', '1')
+        exp = torch.full((out_rows, D), -7.0, device='cuda')
+        K().gemm(a, w, Mrows, D, Kd, epi='f32', bias=bias, row_scale=rs, aux=x2, aux_row=aux_row, out=exp, out_row=out_row,
+                 force_cluster=cluster)
+        monkeypatch.delenv('VT_NO_TMA_RES')
+        assert rel(got, exp) < 1e-6, name
+        # rows the map never names (the cls row of every sample) keep their old contents
+        assert bool((got[torch.arange(B, device='cuda') * S] == -7.0).all()), name
+        r = (a.float() @ w.float().t() + bias) * rs[:, None]
+        add = x2[aux_row.long().clamp(min=0)] * (aux_row >= 0)[:, None]
+        full = torch.full((out_rows, D), -7.0, device='cuda')
+        full[out_row.long()] = r + add
+        assert rel(got, full) < 1e-5, name
+
+
+@pytest.mark.parametrize('cluster', [0, 1, 3], ids=['auto', 'single-cta', 'cta-pair'])
+@pytest.mark.parametrize('M,N,Kd', [(12552, 768, 768), (12608, 2304, 256), (12552, 3072, 128), (136, 512, 192), (264, 256, 64)])
+@pytest.mark.parametrize('form', ['fwd_bf16', 'dgrad_bf16', 'fwd_f32_residual'])
+def test_narrow_tail_units(M, N, Kd, form, cluster, monkeypatch):
+    """A last row of tiles with <= 64 valid rows runs as narrow units (M = 12552 / 12608 of the FFN / spatial pass): same
+    results as with the feature off, and against fp32 torch."""
+    a = mk((M, Kd), 50).bfloat16()
+    bias, rs = mk((N,), 51), mk((M,), 52)
+    if form == 'dgrad_bf16':
+        b = mk((Kd, N), 53).bfloat16()                       # W [n_out = Kd, k_in = N] read MN-major
+        kw = dict(b_mn=True, epi='bf16', row_scale=rs)
+        r = (a.float() @ b.float()) * rs[:, None]
+    elif form == 'fwd_bf16':
+        b = mk((N, Kd), 53).bfloat16()
+        kw = dict(epi='bf16', bias=bias)
+        r = a.float() @ b.float().t() + bias
+    else:
+        b = mk((N, Kd), 53).bfloat16()
+        aux = mk((M, N), 54)
+        kw = dict(epi='f32', bias=bias, row_scale=rs, aux=aux)
+        r = (a.float() @ b.float().t() + bias) * rs[:, None] + aux
+    got = K().gemm(a, b, M, N, Kd, force_cluster=cluster, force_tail=2, **kw)
+    off = K().gemm(a, b, M, N, Kd, force_cluster=cluster, force_tail=1, **kw)
+    tol = 1e-5 if form == 'fwd_f32_residual' else 4e-3
+    assert rel(got, r) < tol
+    assert torch.equal(got, off)

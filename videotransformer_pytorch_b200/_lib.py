@@ -28,7 +28,10 @@ class GemmParams(C.Structure):
                 ('ldo', c_i64), ('ldo2', c_i64), ('ldaux', c_i64),
                 ('out_row', c_vp), ('aux_row', c_vp), ('row_scale', c_vp),
                 ('workspace', c_vp), ('workspace_bytes', c_i64),
-                ('force_splits', c_i32), ('force_bn', c_i32), ('force_cluster', c_i32), ('debug', c_vp)]
+                ('force_splits', c_i32), ('force_bn', c_i32), ('force_cluster', c_i32), ('debug', c_vp),
+                ('map_period', c_i32), ('map_skip', c_i32), ('map_tcount', c_i32), ('force_tail', c_i32),
+                ('map_stride_t', c_i64), ('map_stride_p', c_i64), ('map_stride_b', c_i64), ('map_base', c_i64),
+                ('map_special_base', c_i64), ('map_special_stride', c_i64)]
 
 
 class LnFwdParams(C.Structure):
@@ -272,7 +275,9 @@ class CudaKernels:
     # -- GEMM ---------------------------------------------------------------------------------
     def gemm(self, a, b, M, N, Kdim, *, a_mn=False, b_mn=False, epi='bf16', bias=None, out=None, out2=None,
              aux=None, out_row=None, aux_row=None, row_scale=None, out_rows=None, split_ok=False,
-             force_splits=0, force_bn=0, force_cluster=0, debug=None):
+             force_splits=0, force_bn=0, force_cluster=0, debug=None, row_map=None, force_tail=0):
+        """row_map: affine description of out_row / aux_row (ops.affine_row_maps) for the fp32 residual epilogue — lets the
+        kernel move 32 x 32 boxes by TMA through a 4-D tensor map instead of per-thread rows."""
         lib = load_library()
         _rows2d(_req(a, torch.bfloat16, 'gemm.a'), 'gemm.a')
         _rows2d(_req(b, torch.bfloat16, 'gemm.b'), 'gemm.b')
@@ -315,7 +320,16 @@ class CudaKernels:
             ws = self.workspace(a.device, 16 * M * N * 4)
             p.workspace, p.workspace_bytes = ws.data_ptr(), ws.numel() * 4
         p.force_splits, p.force_bn, p.force_cluster = force_splits, force_bn, force_cluster
+        p.force_tail = force_tail
         p.debug = _ptr(debug)
+        p.map_special_base = -1
+        if row_map is not None:
+            if epi != 'f32' or aux is None:
+                raise RuntimeError('gemm.row_map: only for the fp32 residual epilogue (epi="f32" with aux)')
+            p.map_period, p.map_skip, p.map_tcount = row_map['period'], row_map['skip'], row_map['tcount']
+            p.map_stride_t, p.map_stride_p, p.map_stride_b = row_map['stride_t'], row_map['stride_p'], row_map['stride_b']
+            p.map_base = row_map['base']
+            p.map_special_base, p.map_special_stride = row_map.get('special_base', -1), row_map.get('special_stride', 0)
         _check(lib.vt_gemm(C.byref(p), _stream()), 'vt_gemm')
         return (out, out2) if epi == 'gelu' else out
 

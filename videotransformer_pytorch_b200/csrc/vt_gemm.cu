@@ -12,29 +12,36 @@
 
 namespace vt {
 
-template <int BN>
+// RES: instantiation for the fp32 residual epilogue on TMA (epilogue_tile_tma_res): 8 KiB of staging per epilogue warp
+// instead of 4.1 KiB, paid for with one pipeline stage where shared memory is full.
+template <int BN, bool RES>
 struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 192 ? 4 : 6);
+  static constexpr int STAGES = RES ? ((BN == 256) ? 3 : (BN == 192 ? 4 : 5)) : ((BN == 256) ? 4 : (BN == 192 ? 4 : 6));
   static constexpr int TMEM_COLS = (BN == 128) ? 256 : 512;  // two accumulator stages, power of two
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_WARPS * 32 * EPI_PITCH * 4 /*epilogue staging*/;
+  static constexpr int STAGING_BYTES = RES ? EPI_WARPS * RES_SLOT_BYTES : EPI_WARPS * 32 * EPI_PITCH * 4;
+  static constexpr int BAR_BYTES = 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + BAR_BYTES + STAGING_BYTES;
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
 
-template <int BN>
+template <int BN, bool RES>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const __grid_constant__ CUtensorMap tmC, const GemmDev p) {
-  using Cfg = GemmCfg<BN>;
+                    const __grid_constant__ CUtensorMap tmBt, const __grid_constant__ CUtensorMap tmC,
+                    const __grid_constant__ CUtensorMap tmX, const GemmDev p) {
+  using Cfg = GemmCfg<BN, RES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* staging = smem + Cfg::STAGES * Cfg::STAGE_BYTES;                       // 1024-aligned epilogue staging
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + EPI_WARPS * 32 * EPI_PITCH * 4);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + Cfg::STAGING_BYTES);
   uint64_t* empty_bar = full_bar + Cfg::STAGES;
   uint64_t* tfull_bar = empty_bar + Cfg::STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* aux_bar = tempty_bar + 2;                      // [EPI_WARPS][2] residual-box barriers (RES only)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 2 * EPI_WARPS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -50,7 +57,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.tail_bn) tma_prefetch_desc(&tmBt);
     if (p.tma_store) tma_prefetch_desc(&tmC);
+    if (RES) tma_prefetch_desc(&tmX);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < Cfg::STAGES; ++i) {
@@ -60,6 +69,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], EPI_WARPS);  // one arrive per epilogue warp
+    }
+    if (RES) {
+      for (int i = 0; i < 2 * EPI_WARPS; ++i) mbar_init(&aux_bar[i], 1);
     }
     fence_barrier_init();
   }
@@ -71,22 +83,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
   if (dbg && threadIdx.x == 0) dbg[1] = clock64();   // setup done
 
-  const int total_units = p.num_mp * p.num_n * p.splits;
+  const int total_units = p.full_units + p.tail_units;
   const int unit0 = blockIdx.x / csize, unit_step = gridDim.x / csize;
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0, phase = 0;
       for (int unit = unit0; unit < total_units; unit += unit_step) {
-        const int tile = unit / p.splits, split = unit - tile * p.splits;
-        const int m_blk = (tile / p.num_n) * (int)csize + (int)crank, n_blk = tile % p.num_n;   // n fastest: the A row-block stays hot in L2
-        const int kb0 = (int)(((long long)p.kblocks * split) / p.splits);
-        const int kb1 = (int)(((long long)p.kblocks * (split + 1)) / p.splits);
+        const GemmUnit u = decode_unit<BN>(p, unit);
+        const int m_blk = u.mp * (int)csize + (int)crank;
+        const bool narrow = u.bn != BN;          // tail unit (single CTAs only): own B map with a tail_bn-row box
+        const int kb0 = u.kb0, kb1 = u.kb1;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sB = sA + Cfg::A_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::A_BYTES + u.bn * BK * 2);
           if (!p.a_mn) {
             tma_load_2d(sA, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
           } else {
@@ -96,22 +108,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
           if (csize == 1) {
             if (!p.b_mn) {
-              tma_load_2d(sB, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
+              tma_load_2d(sB, narrow ? &tmBt : &tmB, &full_bar[stage], kb * BK, u.n0);
             } else {
-#pragma unroll
-              for (int c = 0; c < BN / 64; ++c)
-                tma_load_2d(sB + c * CHUNK_BYTES, &tmB, &full_bar[stage], n_blk * BN + c * 64, kb * BK);
+              for (int c = 0; c < u.bn / 64; ++c)
+                tma_load_2d(sB + c * CHUNK_BYTES, &tmB, &full_bar[stage], u.n0 + c * 64, kb * BK);
             }
           } else {
             // my half of the B tile, delivered to both CTAs (the peer sends the other half)
             if (!p.b_mn) {
               const int r0 = (int)crank * (BN / 2);
-              tma_load_2d_mc(sB + r0 * 128, &tmB, &full_bar[stage], kb * BK, n_blk * BN + r0, cmask);
+              tma_load_2d_mc(sB + r0 * 128, &tmB, &full_bar[stage], kb * BK, u.n0 + r0, cmask);
             } else {
               constexpr int NCH = BN / 64;
               const int c0 = crank == 0 ? 0 : (NCH + 1) / 2, c1 = crank == 0 ? (NCH + 1) / 2 : NCH;
               for (int c = c0; c < c1; ++c)
-                tma_load_2d_mc(sB + c * CHUNK_BYTES, &tmB, &full_bar[stage], n_blk * BN + c * 64, kb * BK, cmask);
+                tma_load_2d_mc(sB + c * CHUNK_BYTES, &tmB, &full_bar[stage], u.n0 + c * 64, kb * BK, cmask);
             }
           }
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -120,12 +131,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(BM, BN, (uint32_t)p.a_mn, (uint32_t)p.b_mn);
       int stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (int unit = unit0; unit < total_units; unit += unit_step) {
-        const int tile = unit / p.splits, split = unit - tile * p.splits;
-        const int kb0 = (int)(((long long)p.kblocks * split) / p.splits);
-        const int kb1 = (int)(((long long)p.kblocks * (split + 1)) / p.splits);
+        const GemmUnit u = decode_unit<BN>(p, unit);
+        const uint32_t idesc = make_idesc_bf16(BM, (uint32_t)u.bn, (uint32_t)p.a_mn, (uint32_t)p.b_mn);
+        const int kb0 = u.kb0, kb1 = u.kb1;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -162,14 +172,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int q = warp & 3;             // TMEM lane quadrant this warp may access
     const int half = (warp - 4) >> 2;   // which warpgroup
     float* stg = reinterpret_cast<float*>(staging) + (warp - 4) * (32 * EPI_PITCH);
-    uint8_t* slot = staging + (warp - 4) * 4096;
+    uint8_t* slot = staging + (warp - 4) * (RES ? RES_SLOT_BYTES : 4096);
+    uint32_t aux_use[2] = {0u, 0u};
     int acc = 0, acc_phase = 0;
     for (int unit = unit0; unit < total_units; unit += unit_step) {
-      const int tile = unit / p.splits, split = unit - tile * p.splits;
-      const int m_blk = (tile / p.num_n) * (int)csize + (int)crank, n_blk = tile % p.num_n;   // n fastest: the A row-block stays hot in L2
+      const GemmUnit u = decode_unit<BN>(p, unit);
+      const int m_blk = u.mp * (int)csize + (int)crank;
       const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-      if (p.tma_store) epilogue_tile_tma<BN>(p, &tmC, slot, t_base, m_blk, n_blk, split, q, half, lane, &tfull_bar[acc], (uint32_t)acc_phase);
-      else epilogue_tile<BN>(p, stg, t_base, m_blk, n_blk, split, q, half, lane, &tfull_bar[acc], (uint32_t)acc_phase);
+      if constexpr (RES) {
+        epilogue_tile_tma_res<BN>(p, &tmC, &tmX, slot, aux_bar + 2 * (warp - 4), aux_use, t_base, m_blk, u.n0, u.bn, q, half, lane,
+                                  &tfull_bar[acc], (uint32_t)acc_phase);
+      } else {
+        if (p.tma_store) epilogue_tile_tma<BN>(p, &tmC, slot, t_base, m_blk, u.n0, u.bn, u.split, q, half, lane, &tfull_bar[acc], (uint32_t)acc_phase);
+        else epilogue_tile<BN>(p, stg, t_base, m_blk, u.n0, u.bn, u.split, q, half, lane, &tfull_bar[acc], (uint32_t)acc_phase);
+      }
       if (dbg && warp == 4 && lane == 0) { if (unit == unit0) dbg[5] = clock64(); dbg[6] = clock64(); }   // first / last tile drained
       tc_fence_before();
       __syncwarp();
@@ -240,6 +256,101 @@ int make_tmap_out_3d(CUtensorMap* map, const void* base, int fp32, long long M, 
                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   VT_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(out) failed (%d) M=%lld N=%lld ld=%lld", (int)r, M, N, ld);
   return 0;
+}
+
+// 4-D fp32 map (col, t, p, b) of the residual epilogue (epilogue_tile_tma_res): box {32, 1, 32, 1}, 128B swizzle.
+//   element (n, t, p, b) at base + n + t*stride_t + p*stride_p + b*stride_b   (strides in elements, multiples of 4)
+int make_tmap_rows_4d(CUtensorMap* map, const void* base, long long cols, long long tcount, long long pcount, long long bcount,
+                      long long stride_t, long long stride_p, long long stride_b) {
+  EncodeTiledFn fn = get_encode_fn();
+  VT_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
+  VT_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base pointer must be 16-byte aligned");
+  VT_REQUIRE(stride_t % 4 == 0 && stride_p % 4 == 0 && stride_b % 4 == 0 && stride_t > 0 && stride_p > 0 && stride_b > 0,
+             "row-map strides must be positive multiples of 4 elements (%lld %lld %lld)", stride_t, stride_p, stride_b);
+  cuuint64_t gdim[4] = {(cuuint64_t)cols, (cuuint64_t)tcount, (cuuint64_t)pcount, (cuuint64_t)bcount};
+  cuuint64_t gstr[3] = {(cuuint64_t)(stride_t * 4), (cuuint64_t)(stride_p * 4), (cuuint64_t)(stride_b * 4)};
+  cuuint32_t box[4] = {32u, 1u, 32u, 1u};
+  cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  VT_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(rows 4d) failed (%d) dims %lld %lld %lld %lld strides %lld %lld %lld", (int)r,
+             cols, tcount, pcount, bcount, stride_t, stride_p, stride_b);
+  return 0;
+}
+
+// Residual epilogue on TMA (GemmDev::tma_store = 3): fp32 output with an fp32 addend whose rows — and the output's — follow
+// either no map or the affine map described in vt_gemm_params (map_period ...).  Fills tmC / tmX and the map fields of d.
+bool res_tma_applicable(const vt_gemm_params* q) {
+  if (q->epilogue != VT_EPI_F32 || !q->aux || getenv("VT_NO_TMA_STORE") || getenv("VT_NO_TMA_RES")) return false;
+  if (q->N % 4 != 0) return false;
+  if (q->map_period > 0) return q->map_period >= 32 && q->map_tcount >= 1 && q->M % q->map_period == 0;
+  return !q->out_row && !q->aux_row && q->ldo % 4 == 0 && q->ldaux % 4 == 0;
+}
+
+int setup_res_maps(const vt_gemm_params* q, GemmDev& d, CUtensorMap* tmC, CUtensorMap* tmX) {
+  d.tma_store = 3;
+  if (q->map_period > 0) {
+    d.map_period = q->map_period; d.map_skip = q->map_skip; d.map_tcount = q->map_tcount;
+    const long long outers = q->M / q->map_period;
+    const long long bcount = (outers + q->map_tcount - 1) / q->map_tcount;
+    const long long pcount = q->map_period - q->map_skip;
+    // a dimension of extent 1 still needs a legal stride: reuse the next one
+    const long long st = q->map_tcount > 1 ? q->map_stride_t : q->map_stride_p;
+    int rc = make_tmap_rows_4d(tmC, static_cast<float*>(q->out) + q->map_base, q->N, q->map_tcount, pcount, bcount, st,
+                               q->map_stride_p, q->map_stride_b);
+    if (rc) return rc;
+    rc = make_tmap_rows_4d(tmX, static_cast<const float*>(q->aux) + q->map_base, q->N, q->map_tcount, pcount, bcount, st,
+                           q->map_stride_p, q->map_stride_b);
+    if (rc) return rc;
+    d.special_out = q->map_special_base >= 0 ? static_cast<float*>(q->out) + q->map_special_base : nullptr;
+    d.special_ld = q->map_special_stride;
+    return 0;
+  }
+  d.map_period = q->M; d.map_skip = 0; d.map_tcount = 1;
+  d.special_out = nullptr; d.special_ld = 0;
+  int rc = make_tmap_rows_4d(tmC, q->out, q->N, 1, q->M, 1, q->ldo, q->ldo, q->ldo);
+  if (rc) return rc;
+  return make_tmap_rows_4d(tmX, q->aux, q->N, 1, q->M, 1, q->ldaux, q->ldaux, q->ldaux);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Unit schedule.  Regular units = (macro row, n tile, K split); if the last macro row holds only a few valid rows
+// (M = 12 552 = 98 x 128 + 8: TimeSformer's FFN; 12 608 = 98 x 128 + 64: its spatial pass) it is cut into narrow units of
+// `tail_bn` columns instead, which cost a fraction of a tile (their A rows are mostly TMA zero fill, their MMAs N = tail_bn
+// wide) and spread over the CTAs that would otherwise idle in a whole extra round.
+//   makespan model (in units of one full tile): units are dealt round-robin to `slots` CTAs / CTA pairs.
+// ------------------------------------------------------------------------------------------------
+struct Schedule { int full_units, tail_units, tail_bn, tail_mp; double makespan; };
+
+Schedule plan_units(int M, int N, int bn, int rows_per_macro, int splits, int slots, int tail_bn_cand, bool allow_tail) {
+  const int num_mp = (M + rows_per_macro - 1) / rows_per_macro;
+  const int num_n = (N + bn - 1) / bn;
+  Schedule best;
+  best.full_units = num_mp * num_n * splits; best.tail_units = 0; best.tail_bn = 0; best.tail_mp = 0;
+  best.makespan = (double)((best.full_units + slots - 1) / slots);
+  const int valid_tail = M - (num_mp - 1) * rows_per_macro;       // rows in the last macro row
+  if (!allow_tail || splits != 1 || num_mp < 2 || valid_tail == rows_per_macro || valid_tail > 64 || tail_bn_cand <= 0 ||
+      tail_bn_cand >= bn || N % 8 != 0)
+    return best;
+  Schedule t;
+  t.full_units = (num_mp - 1) * num_n; t.tail_bn = tail_bn_cand; t.tail_mp = num_mp - 1;
+  t.tail_units = (N + tail_bn_cand - 1) / tail_bn_cand;
+  // cost of a tail unit relative to a full tile: operand bytes that really come from L2 (valid A rows + narrow B) vs a full
+  // stage, floored by the MMA time ratio, plus the fixed per-unit overhead share
+  const double bytes = (double)(valid_tail + tail_bn_cand) / (double)(rows_per_macro > 128 ? 128 + bn / 2 : 128 + bn);
+  const double mma = (double)tail_bn_cand / bn;
+  const double tcost = (bytes > mma ? bytes : mma) + 0.08;
+  const int total = t.full_units + t.tail_units;
+  double worst = 0.0;
+  for (int sl = 0; sl < slots; ++sl) {            // the kernel deals unit u to slot u % slots
+    const int nf = sl < t.full_units ? (t.full_units - 1 - sl) / slots + 1 : 0;
+    const int nall = sl < total ? (total - 1 - sl) / slots + 1 : 0;
+    const double load = nf + (nall - nf) * tcost;
+    if (load > worst) worst = load;
+  }
+  t.makespan = worst;
+  return t.makespan < best.makespan - 1e-9 ? t : best;
 }
 
 // Split-K partials can be reduce-added straight into the output by TMA (cp.reduce.async.bulk.tensor ... add) instead of
@@ -331,17 +442,19 @@ int launch_reduce_rows(const float* in, float* out, long long stride, int S, lon
   return check_launch("reduce_rows_kernel");
 }
 
-template <int BN>
+template <int BN, bool RES>
 static int launch_gemm(const vt_gemm_params* q, GemmDev& d, cudaStream_t st) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, RES>;
   static bool attr_set = false;  // benign race: idempotent
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     VT_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
     attr_set = true;
   }
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmBt, tmC, tmX;
+  memset(&tmBt, 0, sizeof(tmBt));
+  memset(&tmX, 0, sizeof(tmX));
   int rc;
   if (!q->a_mn_major) rc = make_tmap_bf16_2d(&tmA, q->a, q->M, q->K, q->lda, BM);
   else rc = make_tmap_bf16_2d(&tmA, q->a, q->K, q->M, q->lda, BK);
@@ -358,7 +471,6 @@ static int launch_gemm(const vt_gemm_params* q, GemmDev& d, cudaStream_t st) {
 
   d.num_n = (q->N + BN - 1) / BN;
   d.kblocks = (q->K + BK - 1) / BK;
-  const int tiles = d.num_mp * d.num_n;     // macro tiles (one per cluster)
   const int sms = persistent_sm_count();
 
   int splits = 1;
@@ -383,11 +495,19 @@ static int launch_gemm(const vt_gemm_params* q, GemmDev& d, cudaStream_t st) {
     d.ldo = q->N;
     d.split_stride = tile_out;
   }
-  CUtensorMap tmC;
-  rc = setup_out_map(q, d, &tmC, in_place);
+  if (RES) rc = setup_res_maps(q, d, &tmC, &tmX);
+  else rc = setup_out_map(q, d, &tmC, in_place);
   if (rc) return rc;
-  const int units = tiles * splits;
+  // unit schedule (narrow tail units only for single CTAs here; CTA pairs have their own in vt_gemm2.cu)
   const int max_clusters = sms / csize;
+  const Schedule sch = plan_units(q->M, q->N, BN, BM * csize, splits, max_clusters, 64,
+                                  csize == 1 && q->force_tail != 1 && !getenv("VT_NO_TAIL_UNITS"));
+  d.full_units = sch.full_units; d.tail_units = sch.tail_units; d.tail_bn = sch.tail_bn; d.tail_mp = sch.tail_mp;
+  if (d.tail_bn && !q->b_mn_major) {
+    rc = make_tmap_bf16_2d(&tmBt, q->b, q->N, q->K, q->ldb, d.tail_bn);
+    if (rc) return rc;
+  }
+  const int units = d.full_units + d.tail_units;
   const int grid = (units < max_clusters ? units : max_clusters) * csize;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
@@ -401,7 +521,7 @@ static int launch_gemm(const vt_gemm_params* q, GemmDev& d, cudaStream_t st) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN>, tmA, tmB, tmC, d);
+  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, RES>, tmA, tmB, tmBt, tmC, tmX, d);
   if (le != cudaSuccess) {
     set_error("gemm_tcgen05_kernel: cudaLaunchKernelEx failed: %s", cudaGetErrorString(le));
     return 2;
@@ -420,7 +540,7 @@ static int launch_gemm(const vt_gemm_params* q, GemmDev& d, cudaStream_t st) {
   return 0;
 }
 
-int launch_gemm2(const vt_gemm_params* q, GemmDev& d, int bn, cudaStream_t st);
+int launch_gemm2(const vt_gemm_params* q, GemmDev& d, int bn, bool res, cudaStream_t st);
 
 }  // namespace vt
 
@@ -451,17 +571,35 @@ extern "C" int vt_gemm(const vt_gemm_params* q, void* stream) {
   d.dbg = static_cast<long long*>(q->debug);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 
+  d.tma_store = 0;
+  d.map_period = q->M > 0 ? q->M : 1; d.map_skip = 0; d.map_tcount = 1;
+  d.special_out = nullptr; d.special_ld = 0;
+  d.tail_bn = 0; d.full_units = 0; d.tail_units = 0; d.tail_mp = 0;
+  if (q->map_period > 0) {
+    VT_REQUIRE(q->epilogue == VT_EPI_F32 && q->aux, "vt_gemm: the affine row map applies to the fp32 residual epilogue only");
+    VT_REQUIRE(q->map_period >= 32 && q->M % q->map_period == 0 && q->map_tcount >= 1 && q->map_skip >= 0 &&
+                   q->map_skip < q->map_period,
+               "vt_gemm: bad affine row map (period %d, skip %d, tcount %d, M %d)", q->map_period, q->map_skip, q->map_tcount, q->M);
+  }
+  const bool res = res_tma_applicable(q);
+  if (q->map_period > 0 && !res) {
+    VT_REQUIRE(q->out_row && q->aux_row, "vt_gemm: affine row map given but the TMA residual epilogue is unavailable and no "
+                                         "out_row / aux_row arrays were supplied for the generic epilogue");
+  }
+
   int bn = q->force_bn;
   d.splits = 0;
   {
-    // Wave-quantisation aware configuration: cost ~ rounds over the SMs x per-unit time, where a unit (tile x
+    // Wave-quantisation aware configuration: cost ~ makespan over the SMs x per-unit time, where a unit (tile x
     // K-split) costs (its k-blocks + a fixed prologue/epilogue overhead) x BN, with a small penalty for narrower
     // tiles (they re-read A more often and leave less slack on the smem port).  Splitting K is only possible for
-    // plain fp32 outputs with a workspace (weight gradients).
+    // plain fp32 outputs with a workspace (weight gradients).  A partial last macro row may run as narrow tail units
+    // (plan_units).
     const int sms = persistent_sm_count();
     const int num_m = (q->M + BM - 1) / BM;
     const int kblocks = (q->K + BK - 1) / BK;
     const bool can_split = q->epilogue == VT_EPI_F32 && q->workspace && !q->out_row && !q->aux && !q->row_scale && !q->bias;
+    const bool allow_tail = q->force_tail != 1 && !getenv("VT_NO_TAIL_UNITS");
     // kernel variants: 0 = one CTA per 128 x BN tile (optionally clusters with multicast B), 1 = CTA pairs with
     // tcgen05.mma.cta_group::2 (256 x BN macro tiles, half of B per SM, 6-8 stages).  The pair kernel's unit time is
     // ~8% shorter (measured, profiles/) but its macro tiles quantise worse and it has no BN = 192; it is skipped
@@ -470,7 +608,8 @@ extern "C" int vt_gemm(const vt_gemm_params* q, void* stream) {
     const bool pair_ok = pair_forced || (q->force_cluster == 0 && num_m >= 2 &&
                                          (!q->a_mn_major || (long long)q->M * q->N >= 2000000LL));
     const int cand[3] = {256, 192, 128};
-    const double penalty[3] = {1.0, 1.04, 1.10};
+    // the residual instantiation of the single-CTA 256-wide kernel runs on 3 pipeline stages: penalised
+    const double penalty[3] = {res ? 1.12 : 1.0, 1.04, 1.10};
     double best = 1e30;
     int best_bn = 256, best_s = 1, best_pair = 0;
     for (int variant = 0; variant < 2; ++variant) {
@@ -480,26 +619,30 @@ extern "C" int vt_gemm(const vt_gemm_params* q, void* stream) {
         if (q->force_bn && cand[i] != q->force_bn) continue;
         if (variant == 1 && cand[i] == 192) continue;
         const int cs = (q->force_cluster == 2 || variant == 1) ? 2 : 1;
-        const int tiles = ((num_m + cs - 1) / cs) * ((q->N + cand[i] - 1) / cand[i]);   // (macro) tiles, one per cluster
         const int slots = sms / cs;
         const int smax = can_split ? 16 : 1;
         for (int sp = 1; sp <= smax; ++sp) {
           if (sp > 1 && (kblocks / sp < 4 || (long long)sp * q->M * q->N * 4 > q->workspace_bytes)) break;
-          const long long units = (long long)tiles * sp;
-          const long long rounds = (units + slots - 1) / slots;
-          const double cost = (double)rounds * ((double)kblocks / sp + 8.0) * cand[i] * penalty[i] * (variant == 1 ? 0.92 : 1.0);
+          const Schedule sch = plan_units(q->M, q->N, cand[i], BM * cs, sp, slots, variant == 1 ? 128 : 64,
+                                          allow_tail && (variant == 1 || q->force_cluster != 2));
+          const double cost = sch.makespan * ((double)kblocks / sp + 8.0) * cand[i] * penalty[i] * (variant == 1 ? 0.92 : 1.0);
           if (cost < best - 1e-9) { best = cost; best_bn = cand[i]; best_s = sp; best_pair = variant; }
         }
       }
     }
     if (bn == 0 || best_pair) bn = best_bn;
     d.splits = best_s;
-    if (best_pair) return launch_gemm2(q, d, bn, st);
+    if (best_pair) return launch_gemm2(q, d, bn, res, st);
   }
   VT_REQUIRE(bn == 128 || bn == 192 || bn == 256, "vt_gemm: force_bn must be 128, 192 or 256");
-  if (bn == 256) return launch_gemm<256>(q, d, st);
-  if (bn == 192) return launch_gemm<192>(q, d, st);
-  return launch_gemm<128>(q, d, st);
+  if (res) {
+    if (bn == 256) return launch_gemm<256, true>(q, d, st);
+    if (bn == 192) return launch_gemm<192, true>(q, d, st);
+    return launch_gemm<128, true>(q, d, st);
+  }
+  if (bn == 256) return launch_gemm<256, false>(q, d, st);
+  if (bn == 192) return launch_gemm<192, false>(q, d, st);
+  return launch_gemm<128, false>(q, d, st);
 }
 
 extern "C" int vt_reduce_rows(const vt_reduce_params* p, void* stream) {

@@ -12,6 +12,9 @@
 //     .multicast::cluster to the "empty" (stage free) and "tmem full" barriers of BOTH CTAs;
 //   * each CTA's 8 epilogue warps drain their own TMEM (128 lanes x BN columns) and arrive on the leader's
 //     "tmem empty" barrier (the peer through a mapa-translated remote arrive).
+#include <stdlib.h>
+#include <string.h>
+
 #include "vt_gemm_common.cuh"
 
 namespace vt {
@@ -20,17 +23,23 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* base, long long rows, long l
 int launch_reduce_rows(const float* in, float* out, long long stride, int S, long long n, int accumulate, float scale,
                        cudaStream_t st);
 int setup_out_map(const vt_gemm_params* q, GemmDev& d, CUtensorMap* tmC, bool in_place);
+int setup_res_maps(const vt_gemm_params* q, GemmDev& d, CUtensorMap* tmC, CUtensorMap* tmX);
+struct Schedule { int full_units, tail_units, tail_bn, tail_mp; double makespan; };
+Schedule plan_units(int M, int N, int bn, int rows_per_macro, int splits, int slots, int tail_bn_cand, bool allow_tail);
 bool splitk_in_place(const vt_gemm_params* q);
 int splitk_zero(const vt_gemm_params* q, cudaStream_t st);
 
-template <int BN>
+template <int BN, bool RES>
 struct Gemm2Cfg {
   static constexpr int A_BYTES = BM * BK * 2;             // this CTA's 128 rows
   static constexpr int B_BYTES = (BN / 2) * BK * 2;       // this CTA's half of the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 6 : 8;
+  static constexpr int STAGES = RES ? ((BN == 256) ? 5 : 6) : ((BN == 256) ? 6 : 8);
   static constexpr int TMEM_COLS = (BN == 128) ? 256 : 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + EPI_WARPS * 32 * EPI_PITCH * 4;
+  static constexpr int STAGING_BYTES = RES ? EPI_WARPS * RES_SLOT_BYTES : EPI_WARPS * 32 * EPI_PITCH * 4;
+  static constexpr int BAR_BYTES = 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + BAR_BYTES + STAGING_BYTES;
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
 
 constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;   // clears the CTA-in-pair bit of a shared::cluster address
@@ -78,19 +87,21 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank)
       : "memory");
 }
 
-template <int BN>
+template <int BN, bool RES>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                     const __grid_constant__ CUtensorMap tmC, const GemmDev p) {
-  using Cfg = Gemm2Cfg<BN>;
+                     const __grid_constant__ CUtensorMap tmBt, const __grid_constant__ CUtensorMap tmC,
+                     const __grid_constant__ CUtensorMap tmX, const GemmDev p) {
+  using Cfg = Gemm2Cfg<BN, RES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* staging = smem + Cfg::STAGES * Cfg::STAGE_BYTES;                       // 1024-aligned epilogue staging
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + EPI_WARPS * 32 * EPI_PITCH * 4);   // used in the leader
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + Cfg::STAGING_BYTES);              // used in the leader
   uint64_t* empty_bar = full_bar + Cfg::STAGES;                                              // local
   uint64_t* tfull_bar = empty_bar + Cfg::STAGES;                                             // local
   uint64_t* tempty_bar = tfull_bar + 2;                                                      // used in the leader
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* aux_bar = tempty_bar + 2;                      // [EPI_WARPS][2] residual-box barriers (RES only), local
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 2 * EPI_WARPS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t crank = cluster_ctarank();
@@ -99,7 +110,9 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.tail_bn) tma_prefetch_desc(&tmBt);
     if (p.tma_store) tma_prefetch_desc(&tmC);
+    if (RES) tma_prefetch_desc(&tmX);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < Cfg::STAGES; ++i) {
@@ -110,6 +123,9 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 2 * EPI_WARPS);   // epilogue warps of both CTAs
     }
+    if (RES) {
+      for (int i = 0; i < 2 * EPI_WARPS; ++i) mbar_init(&aux_bar[i], 1);
+    }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc_2cta<Cfg::TMEM_COLS>(tmem_slot);
@@ -119,35 +135,34 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int total_units = p.num_mp * p.num_n * p.splits;
+  const int total_units = p.full_units + p.tail_units;
   const int unit0 = blockIdx.x >> 1, unit_step = gridDim.x >> 1;
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0, phase = 0;
       for (int unit = unit0; unit < total_units; unit += unit_step) {
-        const int tile = unit / p.splits, split = unit - tile * p.splits;
-        const int m_blk = (tile / p.num_n) * 2 + (int)crank, n_blk = tile % p.num_n;   // n fastest: the A row-block stays hot in L2
-        const int kb0 = (int)(((long long)p.kblocks * split) / p.splits);
-        const int kb1 = (int)(((long long)p.kblocks * (split + 1)) / p.splits);
+        const GemmUnit u = decode_unit<BN>(p, unit);
+        const int m_blk = u.mp * 2 + (int)crank;
+        const bool narrow = u.bn != BN;          // tail unit: own B map with a (tail_bn / 2)-row box
+        const int kb0 = u.kb0, kb1 = u.kb1;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sB = sA + Cfg::A_BYTES;
           const uint32_t lbar = smem_u32(&full_bar[stage]) & PEER_BIT_MASK;
-          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * (Cfg::A_BYTES + (u.bn / 2) * BK * 2));
           if (!p.a_mn) {
             tma_load_2d_2cta(sA, &tmA, lbar, kb * BK, m_blk * BM);
           } else {
 #pragma unroll
             for (int c = 0; c < BM / 64; ++c) tma_load_2d_2cta(sA + c * CHUNK_BYTES, &tmA, lbar, m_blk * BM + c * 64, kb * BK);
           }
-          const int nb0 = n_blk * BN + (int)crank * (BN / 2);   // first B row (= output column) of my half
+          const int nb0 = u.n0 + (int)crank * (u.bn / 2);   // first B row (= output column) of my half
           if (!p.b_mn) {
-            tma_load_2d_2cta(sB, &tmB, lbar, kb * BK, nb0);
+            tma_load_2d_2cta(sB, narrow ? &tmBt : &tmB, lbar, kb * BK, nb0);
           } else {
-#pragma unroll
-            for (int c = 0; c < BN / 128; ++c) tma_load_2d_2cta(sB + c * CHUNK_BYTES, &tmB, lbar, nb0 + c * 64, kb * BK);
+            for (int c = 0; c < u.bn / 128; ++c) tma_load_2d_2cta(sB + c * CHUNK_BYTES, &tmB, lbar, nb0 + c * 64, kb * BK);
           }
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -155,12 +170,11 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
   } else if (warp == 1) {
     if (leader && lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(2 * BM, BN, (uint32_t)p.a_mn, (uint32_t)p.b_mn);
       int stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (int unit = unit0; unit < total_units; unit += unit_step) {
-        const int tile = unit / p.splits, split = unit - tile * p.splits;
-        const int kb0 = (int)(((long long)p.kblocks * split) / p.splits);
-        const int kb1 = (int)(((long long)p.kblocks * (split + 1)) / p.splits);
+        const GemmUnit u = decode_unit<BN>(p, unit);
+        const uint32_t idesc = make_idesc_bf16(2 * BM, (uint32_t)u.bn, (uint32_t)p.a_mn, (uint32_t)p.b_mn);
+        const int kb0 = u.kb0, kb1 = u.kb1;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -186,14 +200,20 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const int q = warp & 3;
     const int half = (warp - 4) >> 2;
     float* stg = reinterpret_cast<float*>(staging) + (warp - 4) * (32 * EPI_PITCH);
-    uint8_t* slot = staging + (warp - 4) * 4096;
+    uint8_t* slot = staging + (warp - 4) * (RES ? RES_SLOT_BYTES : 4096);
+    uint32_t aux_use[2] = {0u, 0u};
     int acc = 0, acc_phase = 0;
     for (int unit = unit0; unit < total_units; unit += unit_step) {
-      const int tile = unit / p.splits, split = unit - tile * p.splits;
-      const int m_blk = (tile / p.num_n) * 2 + (int)crank, n_blk = tile % p.num_n;   // n fastest: the A row-block stays hot in L2
+      const GemmUnit u = decode_unit<BN>(p, unit);
+      const int m_blk = u.mp * 2 + (int)crank;
       const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-      if (p.tma_store) epilogue_tile_tma<BN>(p, &tmC, slot, t_base, m_blk, n_blk, split, q, half, lane, &tfull_bar[acc], (uint32_t)acc_phase);
-      else epilogue_tile<BN>(p, stg, t_base, m_blk, n_blk, split, q, half, lane, &tfull_bar[acc], (uint32_t)acc_phase);
+      if constexpr (RES) {
+        epilogue_tile_tma_res<BN>(p, &tmC, &tmX, slot, aux_bar + 2 * (warp - 4), aux_use, t_base, m_blk, u.n0, u.bn, q, half, lane,
+                                  &tfull_bar[acc], (uint32_t)acc_phase);
+      } else {
+        if (p.tma_store) epilogue_tile_tma<BN>(p, &tmC, slot, t_base, m_blk, u.n0, u.bn, u.split, q, half, lane, &tfull_bar[acc], (uint32_t)acc_phase);
+        else epilogue_tile<BN>(p, stg, t_base, m_blk, u.n0, u.bn, u.split, q, half, lane, &tfull_bar[acc], (uint32_t)acc_phase);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -213,16 +233,18 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   }
 }
 
-template <int BN>
+template <int BN, bool RES>
 static int launch_gemm2_t(const vt_gemm_params* q, GemmDev& d, cudaStream_t st) {
-  using Cfg = Gemm2Cfg<BN>;
+  using Cfg = Gemm2Cfg<BN, RES>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm2_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm2_tcgen05_kernel<BN, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     VT_REQUIRE(e == cudaSuccess, "gemm2: cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
     attr_set = true;
   }
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmBt, tmX;
+  memset(&tmBt, 0, sizeof(tmBt));
+  memset(&tmX, 0, sizeof(tmX));
   int rc;
   if (!q->a_mn_major) rc = make_tmap_bf16_2d(&tmA, q->a, q->M, q->K, q->lda, BM);
   else rc = make_tmap_bf16_2d(&tmA, q->a, q->K, q->M, q->lda, BK);
@@ -235,7 +257,6 @@ static int launch_gemm2_t(const vt_gemm_params* q, GemmDev& d, cudaStream_t st) 
   d.num_mp = (d.num_m + 1) / 2;
   d.num_n = (q->N + BN - 1) / BN;
   d.kblocks = (q->K + BK - 1) / BK;
-  const int tiles = d.num_mp * d.num_n;
   const int pairs = persistent_sm_count() / 2;
   const long long tile_out = (long long)q->M * q->N;
   int splits = 1;
@@ -260,9 +281,16 @@ static int launch_gemm2_t(const vt_gemm_params* q, GemmDev& d, cudaStream_t st) 
     d.split_stride = tile_out;
   }
   CUtensorMap tmC;
-  rc = setup_out_map(q, d, &tmC, in_place);
+  if (RES) rc = setup_res_maps(q, d, &tmC, &tmX);
+  else rc = setup_out_map(q, d, &tmC, in_place);
   if (rc) return rc;
-  const int units = tiles * splits;
+  const Schedule sch = plan_units(q->M, q->N, BN, 2 * BM, splits, pairs, 128, q->force_tail != 1 && !getenv("VT_NO_TAIL_UNITS"));
+  d.full_units = sch.full_units; d.tail_units = sch.tail_units; d.tail_bn = sch.tail_bn; d.tail_mp = sch.tail_mp;
+  if (d.tail_bn && !q->b_mn_major) {
+    rc = make_tmap_bf16_2d(&tmBt, q->b, q->N, q->K, q->ldb, d.tail_bn / 2);
+    if (rc) return rc;
+  }
+  const int units = d.full_units + d.tail_units;
   const int grid = 2 * (units < pairs ? units : pairs);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
@@ -276,7 +304,7 @@ static int launch_gemm2_t(const vt_gemm_params* q, GemmDev& d, cudaStream_t st) 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm2_tcgen05_kernel<BN>, tmA, tmB, tmC, d);
+  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm2_tcgen05_kernel<BN, RES>, tmA, tmB, tmBt, tmC, tmX, d);
   if (le != cudaSuccess) {
     set_error("gemm2_tcgen05_kernel: cudaLaunchKernelEx failed: %s", cudaGetErrorString(le));
     return 2;
@@ -290,9 +318,13 @@ static int launch_gemm2_t(const vt_gemm_params* q, GemmDev& d, cudaStream_t st) 
 }
 
 // entry used by vt_gemm(): bn in {128, 256}
-int launch_gemm2(const vt_gemm_params* q, GemmDev& d, int bn, cudaStream_t st) {
-  if (bn == 256) return launch_gemm2_t<256>(q, d, st);
-  return launch_gemm2_t<128>(q, d, st);
+int launch_gemm2(const vt_gemm_params* q, GemmDev& d, int bn, bool res, cudaStream_t st) {
+  if (res) {
+    if (bn == 256) return launch_gemm2_t<256, true>(q, d, st);
+    return launch_gemm2_t<128, true>(q, d, st);
+  }
+  if (bn == 256) return launch_gemm2_t<256, false>(q, d, st);
+  return launch_gemm2_t<128, false>(q, d, st);
 }
 
 }  // namespace vt

@@ -29,13 +29,55 @@ struct GemmDev {
   long long split_stride;  // elements between split partials (EPI_F32 only)
   long long* dbg;          // optional diagnostics: per-CTA clock64 stamps [cta][16] (NULL in production)
   int tma_store;           // 1: plain row-major output written by TMA bulk stores (epilogue_tile_tma); 2: split-K partials
-                           //    reduce-added into the (pre-zeroed) output by TMA
+                           //    reduce-added into the (pre-zeroed) output by TMA; 3: fp32 residual epilogue, residual
+                           //    boxes TMA-loaded into the staging slot, result TMA-stored (epilogue_tile_tma_res)
+  // affine row map of the residual epilogue: GEMM row m -> outer = m / map_period, inner = m % map_period;
+  // inner < map_skip: "special" row (replicated cls token), else tensor coordinates
+  // (col, t = outer % map_tcount, p = inner - map_skip, b = outer / map_tcount) of the 4-D out / aux maps
+  int map_period, map_skip, map_tcount;
+  float* special_out;      // special rows go to special_out + outer * special_ld (plain per-thread stores), or are dropped
+  long long special_ld;
+  // narrow tail units: the last (partial) macro row of tiles is cut into units of tail_bn columns so that its few valid
+  // rows do not cost a whole extra round of full tiles
+  int tail_bn;             // 0 = none
+  int full_units;          // units [0, full_units) are regular tiles x splits; [full_units, full_units + tail_units) are tail units
+  int tail_units;
+  int tail_mp;             // macro row index of the tail units
 };
+
+// One unit of work of the persistent loop.
+struct GemmUnit {
+  int mp;        // macro row (x cluster size + cluster rank = m block)
+  int n0;        // first output column
+  int bn;        // width of the unit (BN, or tail_bn)
+  int split, kb0, kb1;
+};
+template <int BN>
+__device__ __forceinline__ GemmUnit decode_unit(const GemmDev& p, int unit) {
+  GemmUnit u;
+  if (unit < p.full_units) {
+    const int tile = unit / p.splits;
+    u.split = unit - tile * p.splits;
+    u.mp = tile / p.num_n;                     // n fastest: the A row-block stays hot in L2
+    u.n0 = (tile - u.mp * p.num_n) * BN;
+    u.bn = BN;
+    u.kb0 = (int)(((long long)p.kblocks * u.split) / p.splits);
+    u.kb1 = (int)(((long long)p.kblocks * (u.split + 1)) / p.splits);
+  } else {
+    u.split = 0;
+    u.mp = p.tail_mp;
+    u.n0 = (unit - p.full_units) * p.tail_bn;
+    u.bn = p.tail_bn;
+    u.kb0 = 0;
+    u.kb1 = p.kblocks;
+  }
+  return u;
+}
 
 // Drain accumulator tile (m_blk, n_blk) of this CTA: TMEM columns [t_base, t_base + BN) of lane quadrant q.
 // Called by the 8 epilogue warps; waits on `tfull` (parity `ph`) after issuing the first operand prefetch.
 template <int BN>
-__device__ __forceinline__ void epilogue_tile(const GemmDev& p, float* stg, uint32_t t_base, int m_blk, int n_blk, int split,
+__device__ __forceinline__ void epilogue_tile(const GemmDev& p, float* stg, uint32_t t_base, int m_blk, int n_base, int bn, int split,
                                               int q, int half, int lane, uint64_t* tfull, uint32_t ph) {
   const int rsub = lane >> 3, cg = lane & 7;
   const bool f32_aux = p.epi == VT_EPI_F32 && p.aux != nullptr;
@@ -55,7 +97,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, float* stg, uint
 #pragma unroll
   for (int it = 0; it < 8; ++it) pre[it] = make_uint4(0u, 0u, 0u, 0u);   // no epilogue operand => adds 0
   auto prefetch = [&](int c) {
-    const int n = n_blk * BN + c * 32 + cg * 4;
+    const int n = n_base + c * 32 + cg * 4;
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
       pre[it] = make_uint4(0u, 0u, 0u, 0u);
@@ -73,18 +115,18 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, float* stg, uint
   mbar_wait(tfull, ph);
   tc_fence_after();
 #pragma unroll 1
-  for (int c = half; c < BN / 32; c += 2) {
+  for (int c = half; c < bn / 32; c += 2) {
     uint32_t r[32];
     tmem_ld32(t_base + c * 32, r);
     tmem_ld_wait();
-    const int n = n_blk * BN + c * 32 + cg * 4;
-    if (n_blk * BN + c * 32 >= p.N) break;   // warp-uniform
+    const int n = n_base + c * 32 + cg * 4;
+    if (n_base + c * 32 >= p.N) break;   // warp-uniform
 #pragma unroll
     for (int j = 0; j < 32; ++j) stg[lane * EPI_PITCH + j] = __uint_as_float(r[j]);
     uint4 cur[8];
 #pragma unroll
     for (int it = 0; it < 8; ++it) cur[it] = pre[it];
-    if ((f32_aux || z_aux) && c + 2 < BN / 32) prefetch(c + 2);
+    if ((f32_aux || z_aux) && c + 2 < bn / 32) prefetch(c + 2);
     __syncwarp();
     float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (p.bias && n < p.N) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
@@ -153,7 +195,7 @@ __device__ __forceinline__ void bulk_wait_read() {
 
 template <int BN>
 __device__ __forceinline__ void epilogue_tile_tma(const GemmDev& p, const CUtensorMap* tmC, uint8_t* slot, uint32_t t_base,
-                                                  int m_blk, int n_blk, int split, int q, int half, int lane, uint64_t* tfull,
+                                                  int m_blk, int n_base, int bn, int split, int q, int half, int lane, uint64_t* tfull,
                                                   uint32_t ph) {
   const int row = m_blk * BM + q * 32 + lane;
   const float s = (row < p.M && p.row_scale) ? p.row_scale[row] : 1.0f;
@@ -162,8 +204,8 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmDev& p, const CUtens
   tc_fence_after();
   int it = 0;
 #pragma unroll 1
-  for (int c = half; c < BN / 32; c += 2, ++it) {
-    const int n0 = n_blk * BN + c * 32;
+  for (int c = half; c < bn / 32; c += 2, ++it) {
+    const int n0 = n_base + c * 32;
     float4 b[8];
 #pragma unroll
     for (int g = 0; g < 8; ++g) b[g] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -210,6 +252,146 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmDev& p, const CUtens
     }
   }
   if (lane == 0) bulk_wait_read<0>();   // staging slot is reused by the next tile
+  __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 residual epilogue on TMA:   out[map(m), n] = s(m) * (acc + bias[n]) + aux[map(m), n]
+// The residual box (32 rows x 32 fp32) is TMA-loaded into the warp's staging buffer — requested before the accumulator
+// is even waited for, the next chunk's one chunk ahead — added to in place (thread = row, same swizzled 16-byte slots
+// the load wrote), and leaves through a TMA store from the same buffer.  Rows reach memory through a 4-D tensor map
+// (col, t, p, b), so the temporal ('b (p t)') and spatial ('(b t) p' + replicated cls) regroupings cost nothing:
+// a 32-row group that crosses a period boundary is served by two boxes (out-of-range rows are clipped by the TMA unit;
+// for the loads the two segments land in the two buffers and every row reads the one its segment wrote).
+// Per warp: 2 buffers of 4 KiB + 2 mbarriers.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+
+constexpr int RES_SLOT_BYTES = 8192;      // per epilogue warp: two 32 x 32 fp32 boxes
+
+// aux_use[j]: how often buffer j's mbarrier has completed so far (its wait parity); carried across tiles by the caller
+template <int BN>
+__device__ __forceinline__ void epilogue_tile_tma_res(const GemmDev& p, const CUtensorMap* tmC, const CUtensorMap* tmX,
+                                                      uint8_t* slot, uint64_t* aux_bar, uint32_t (&aux_use)[2], uint32_t t_base,
+                                                      int m_blk, int n_base, int bn, int q, int half, int lane, uint64_t* tfull,
+                                                      uint32_t ph) {
+  const int m0 = m_blk * BM + q * 32;
+  const int row = m0 + lane;
+  const float s = (row < p.M && p.row_scale) ? p.row_scale[row] : 1.0f;
+  // segments of this 32-row group
+  const int outer0 = m0 / p.map_period, inner0 = m0 - outer0 * p.map_period;
+  const bool two = inner0 + 32 > p.map_period;
+  int seg_t[2], seg_b[2], seg_p[2];
+#pragma unroll
+  for (int sgm = 0; sgm < 2; ++sgm) {
+    const int outer = outer0 + sgm;
+    seg_b[sgm] = outer / p.map_tcount;
+    seg_t[sgm] = outer - seg_b[sgm] * p.map_tcount;
+    seg_p[sgm] = inner0 - sgm * p.map_period - p.map_skip;
+  }
+  // this lane's row: which segment, special?
+  const int my_seg = (inner0 + lane >= p.map_period) ? 1 : 0;
+  const int my_inner = inner0 + lane - my_seg * p.map_period;
+  const bool special = row < p.M && my_inner < p.map_skip;
+  const int nchunks = (bn / 32 - half + 1) / 2;          // chunks c = half, half + 2, ... of this warpgroup
+  auto chunk_cols_ok = [&](int it) { return n_base + (half + 2 * it) * 32 < p.N; };
+  auto request = [&](int it, int buf, int sgm) {        // lane 0: residual box of chunk `it`, segment sgm -> buffer buf
+    tma_load_4d(slot + buf * 4096, tmX, &aux_bar[buf], n_base + (half + 2 * it) * 32, seg_t[sgm], seg_p[sgm], seg_b[sgm]);
+  };
+  // Normal groups: chunk `it` lives in buffer it & 1 and chunk it + 1 is prefetched into the other buffer.
+  // Groups with two segments use both buffers for one chunk (segment k -> buffer k), without prefetch.
+  if (lane == 0) {
+    if (!two) {
+      if (nchunks > 0 && chunk_cols_ok(0)) { mbar_arrive_expect_tx(&aux_bar[0], 4096); request(0, 0, 0); }
+      if (nchunks > 1 && chunk_cols_ok(1)) { mbar_arrive_expect_tx(&aux_bar[1], 4096); request(1, 1, 0); }
+    } else if (nchunks > 0 && chunk_cols_ok(0)) {
+      mbar_arrive_expect_tx(&aux_bar[0], 4096); request(0, 0, 0);
+      mbar_arrive_expect_tx(&aux_bar[1], 4096); request(0, 1, 1);
+    }
+  }
+  mbar_wait(tfull, ph);
+  tc_fence_after();
+#pragma unroll 1
+  for (int it = 0; it < nchunks; ++it) {
+    const int c = half + 2 * it;
+    const int n0 = n_base + c * 32;
+    if (n0 >= p.N) break;   // warp-uniform
+    float4 b[8];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) b[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.bias) {
+#pragma unroll
+      for (int g = 0; g < 8; ++g) b[g] = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + g);   // warp-uniform address
+    }
+    uint32_t r[32];
+    tmem_ld32(t_base + c * 32, r);
+    tmem_ld_wait();
+    const int cur = two ? 0 : (it & 1);
+    // residual box(es) of this chunk have landed
+    if (!two) {
+      if (cur == 0) { mbar_wait(&aux_bar[0], aux_use[0] & 1); ++aux_use[0]; }
+      else { mbar_wait(&aux_bar[1], aux_use[1] & 1); ++aux_use[1]; }
+    } else {
+      mbar_wait(&aux_bar[0], aux_use[0] & 1);
+      mbar_wait(&aux_bar[1], aux_use[1] & 1);
+      ++aux_use[0]; ++aux_use[1];
+    }
+    uint8_t* out_buf = slot + cur * 4096;                                  // result box (segment-0 buffer when two)
+    const uint8_t* my_aux = slot + (two ? my_seg : cur) * 4096;           // where this row's residual landed
+    float4 v[8];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const float4 a = *reinterpret_cast<const float4*>(my_aux + lane * 128 + ((g ^ (lane & 7)) << 4));    // SWIZZLE_128B
+      v[g].x = fmaf(s, __uint_as_float(r[4 * g + 0]) + b[g].x, a.x);
+      v[g].y = fmaf(s, __uint_as_float(r[4 * g + 1]) + b[g].y, a.y);
+      v[g].z = fmaf(s, __uint_as_float(r[4 * g + 2]) + b[g].z, a.z);
+      v[g].w = fmaf(s, __uint_as_float(r[4 * g + 3]) + b[g].w, a.w);
+    }
+    if (special) {
+      // replicated-cls rows have no residual (their box row was clipped to zeros) and go to the side buffer
+      if (p.special_out) {
+        float* dst = p.special_out + (long long)(outer0 + my_seg) * p.special_ld + n0;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) *reinterpret_cast<float4*>(dst + 4 * g) = v[g];
+      }
+    }
+    __syncwarp();      // every lane has read its residual (possibly from the other buffer) before the box is overwritten
+#pragma unroll
+    for (int g = 0; g < 8; ++g) *reinterpret_cast<float4*>(out_buf + lane * 128 + ((g ^ (lane & 7)) << 4)) = v[g];
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_4d(tmC, out_buf, n0, seg_t[0], seg_p[0], seg_b[0]);
+      if (two) tma_store_4d(tmC, out_buf, n0, seg_t[1], seg_p[1], seg_b[1]);
+      bulk_commit();
+      // refill: the buffer just stored from must have been read out by its store first
+      if (!two) {
+        if (it + 2 < nchunks && chunk_cols_ok(it + 2)) {
+          bulk_wait_read<0>();
+          mbar_arrive_expect_tx(&aux_bar[cur], 4096);
+          request(it + 2, cur, 0);
+        }
+      } else if (it + 1 < nchunks && chunk_cols_ok(it + 1)) {
+        bulk_wait_read<0>();
+        mbar_arrive_expect_tx(&aux_bar[0], 4096); request(it + 1, 0, 0);
+        mbar_arrive_expect_tx(&aux_bar[1], 4096); request(it + 1, 1, 1);
+      }
+    }
+    __syncwarp();
+  }
+  if (lane == 0) bulk_wait_read<0>();   // both buffers are reused by the next tile
   __syncwarp();
 }
 

@@ -80,6 +80,18 @@ def token_maps(B: int, T: int, P: int, device: str):
                 cls_rows=i32(ar(B) * S))
 
 
+def affine_row_maps(B: int, T: int, P: int, D: int):
+    """The temporal / spatial row maps of token_maps() in closed form (vt_gemm_params.map_*): GEMM row m has outer = m // period,
+    inner = m % period and lands at element  base + (outer % tcount) * stride_t + (inner - skip) * stride_p +
+    (outer // tcount) * stride_b  of the [B*(1+P*T) (+B*T), D] residual stream; `skip` leading rows of every period are the
+    replicated cls rows of the spatial pass, written to the B*T side rows after the stream."""
+    S = 1 + P * T
+    temporal = dict(period=P * T, skip=0, tcount=1, stride_t=D, stride_p=D, stride_b=S * D, base=D)
+    spatial = dict(period=P + 1, skip=1, tcount=T, stride_t=D, stride_p=T * D, stride_b=S * D, base=D,
+                   special_base=B * S * D, special_stride=D)
+    return dict(temporal=temporal, spatial=spatial)
+
+
 @functools.lru_cache(maxsize=64)
 def frame_maps(BT: int, P: int, device: str):
     """ViViT spatial encoder tokens: rows (bt, n); patch-embed GEMM rows (bt, p) -> bt*(P+1)+1+p."""
@@ -167,7 +179,7 @@ class TemporalAttnFn(torch.autograd.Function):
         y = torch.empty_like(x)
         y2 = y.view(B * S, D)
         k.gemm(a, fc_wh, Mt, D, D, bias=fc_b, epi='f32', aux=x2, aux_row=maps['temporal'], out=y2,
-               out_row=maps['temporal'])
+               out_row=maps['temporal'], row_map=affine_row_maps(B, T, P, D)['temporal'])
         y[:, 0] = x[:, 0]
         ctx.save_for_backward(x, ln_w, mean, rstd, xn, qkv, cx, lse, a, qkv_wh, proj_wh, fc_wh, dp)
         ctx.geom = (B, S, D, T, H, P)
@@ -221,7 +233,7 @@ class SpatialAttnFn(torch.autograd.Function):
         cx, lse, _ = k.attn_fwd(qkv, B * T, P + 1, H, hd, hd ** -0.5)
         ybig = torch.empty((R + B * T, D), dtype=torch.float32, device=x.device)
         k.gemm(cx, proj_wh, Ms, D, D, bias=proj_b, epi='f32', aux=x2, aux_row=maps['sp_aux'], out=ybig,
-               out_row=maps['sp_out'], row_scale=dp)
+               out_row=maps['sp_out'], row_scale=dp, row_map=affine_row_maps(B, T, P, D)['spatial'])
         y = ybig[:R].view(B, S, D)
         y[:, 0] = x[:, 0] + ybig[R:].view(B, T, D).mean(dim=1)
         ctx.save_for_backward(x, ln_w, mean, rstd, xn, qkv, cx, lse, qkv_wh, proj_wh, dp)
