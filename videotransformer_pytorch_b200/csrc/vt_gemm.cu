@@ -323,14 +323,15 @@ int setup_res_maps(const vt_gemm_params* q, GemmDev& d, CUtensorMap* tmC, CUtens
 // ------------------------------------------------------------------------------------------------
 struct Schedule { int full_units, tail_units, tail_bn, tail_mp; double makespan; };
 
-Schedule plan_units(int M, int N, int bn, int rows_per_macro, int splits, int slots, int tail_bn_cand, bool allow_tail) {
+Schedule plan_units(int M, int N, int bn, int rows_per_macro, int splits, int slots, int tail_bn_cand, int tail_mode) {
   const int num_mp = (M + rows_per_macro - 1) / rows_per_macro;
   const int num_n = (N + bn - 1) / bn;
   Schedule best;
   best.full_units = num_mp * num_n * splits; best.tail_units = 0; best.tail_bn = 0; best.tail_mp = 0;
   best.makespan = (double)((best.full_units + slots - 1) / slots);
   const int valid_tail = M - (num_mp - 1) * rows_per_macro;       // rows in the last macro row
-  if (!allow_tail || splits != 1 || num_mp < 2 || valid_tail == rows_per_macro || valid_tail > 64 || tail_bn_cand <= 0 ||
+  // tail_mode: 0 = take the narrow tail when the model says it is faster, 1 = never, 2 = whenever the shape allows (tests)
+  if (tail_mode == 1 || splits != 1 || num_mp < 2 || valid_tail == rows_per_macro || valid_tail > 64 || tail_bn_cand <= 0 ||
       tail_bn_cand >= bn || N % 8 != 0)
     return best;
   Schedule t;
@@ -350,7 +351,7 @@ Schedule plan_units(int M, int N, int bn, int rows_per_macro, int splits, int sl
     if (load > worst) worst = load;
   }
   t.makespan = worst;
-  return t.makespan < best.makespan - 1e-9 ? t : best;
+  return (tail_mode == 2 || t.makespan < best.makespan - 1e-9) ? t : best;
 }
 
 // Split-K partials can be reduce-added straight into the output by TMA (cp.reduce.async.bulk.tensor ... add) instead of
@@ -501,7 +502,7 @@ static int launch_gemm(const vt_gemm_params* q, GemmDev& d, cudaStream_t st) {
   // unit schedule (narrow tail units only for single CTAs here; CTA pairs have their own in vt_gemm2.cu)
   const int max_clusters = sms / csize;
   const Schedule sch = plan_units(q->M, q->N, BN, BM * csize, splits, max_clusters, 64,
-                                  csize == 1 && q->force_tail != 1 && !getenv("VT_NO_TAIL_UNITS"));
+                                  (csize != 1 || getenv("VT_NO_TAIL_UNITS")) ? 1 : q->force_tail);
   d.full_units = sch.full_units; d.tail_units = sch.tail_units; d.tail_bn = sch.tail_bn; d.tail_mp = sch.tail_mp;
   if (d.tail_bn && !q->b_mn_major) {
     rc = make_tmap_bf16_2d(&tmBt, q->b, q->N, q->K, q->ldb, d.tail_bn);
@@ -599,7 +600,7 @@ extern "C" int vt_gemm(const vt_gemm_params* q, void* stream) {
     const int num_m = (q->M + BM - 1) / BM;
     const int kblocks = (q->K + BK - 1) / BK;
     const bool can_split = q->epilogue == VT_EPI_F32 && q->workspace && !q->out_row && !q->aux && !q->row_scale && !q->bias;
-    const bool allow_tail = q->force_tail != 1 && !getenv("VT_NO_TAIL_UNITS");
+    const int tail_mode = getenv("VT_NO_TAIL_UNITS") ? 1 : q->force_tail;
     // kernel variants: 0 = one CTA per 128 x BN tile (optionally clusters with multicast B), 1 = CTA pairs with
     // tcgen05.mma.cta_group::2 (256 x BN macro tiles, half of B per SM, 6-8 stages).  The pair kernel's unit time is
     // ~8% shorter (measured, profiles/) but its macro tiles quantise worse and it has no BN = 192; it is skipped
@@ -624,7 +625,7 @@ extern "C" int vt_gemm(const vt_gemm_params* q, void* stream) {
         for (int sp = 1; sp <= smax; ++sp) {
           if (sp > 1 && (kblocks / sp < 4 || (long long)sp * q->M * q->N * 4 > q->workspace_bytes)) break;
           const Schedule sch = plan_units(q->M, q->N, cand[i], BM * cs, sp, slots, variant == 1 ? 128 : 64,
-                                          allow_tail && (variant == 1 || q->force_cluster != 2));
+                                          (variant == 0 && q->force_cluster == 2) ? 1 : tail_mode);
           const double cost = sch.makespan * ((double)kblocks / sp + 8.0) * cand[i] * penalty[i] * (variant == 1 ? 0.92 : 1.0);
           if (cost < best - 1e-9) { best = cost; best_bn = cand[i]; best_s = sp; best_pair = variant; }
         }
