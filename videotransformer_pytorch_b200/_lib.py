@@ -275,9 +275,10 @@ class CudaKernels:
     # -- GEMM ---------------------------------------------------------------------------------
     def gemm(self, a, b, M, N, Kdim, *, a_mn=False, b_mn=False, epi='bf16', bias=None, out=None, out2=None,
              aux=None, out_row=None, aux_row=None, row_scale=None, out_rows=None, split_ok=False,
-             force_splits=0, force_bn=0, force_cluster=0, debug=None, row_map=None, force_tail=0):
+             force_splits=0, force_bn=0, force_cluster=0, debug=None, row_map=None, force_tail=0, tag=None):
         """row_map: affine description of out_row / aux_row (ops.affine_row_maps) for the fp32 residual epilogue — lets the
-        kernel move 32 x 32 boxes by TMA through a 4-D tensor map instead of per-thread rows."""
+        kernel move 32 x 32 boxes by TMA through a 4-D tensor map instead of per-thread rows.  tag: role label of the launch
+        ('qkv', 'proj', ...) for profilers that wrap this method (bench.py); ignored here."""
         lib = load_library()
         _rows2d(_req(a, torch.bfloat16, 'gemm.a'), 'gemm.a')
         _rows2d(_req(b, torch.bfloat16, 'gemm.b'), 'gemm.b')

@@ -578,8 +578,7 @@ extern "C" int vt_gemm(const vt_gemm_params* q, void* stream) {
   d.tail_bn = 0; d.full_units = 0; d.tail_units = 0; d.tail_mp = 0;
   if (q->map_period > 0) {
     VT_REQUIRE(q->epilogue == VT_EPI_F32 && q->aux, "vt_gemm: the affine row map applies to the fp32 residual epilogue only");
-    VT_REQUIRE(q->map_period >= 32 && q->M % q->map_period == 0 && q->map_tcount >= 1 && q->map_skip >= 0 &&
-                   q->map_skip < q->map_period,
+    VT_REQUIRE(q->M % q->map_period == 0 && q->map_tcount >= 1 && q->map_skip >= 0 && q->map_skip < q->map_period,
                "vt_gemm: bad affine row map (period %d, skip %d, tcount %d, M %d)", q->map_period, q->map_skip, q->map_tcount, q->M);
   }
   const bool res = res_tma_applicable(q);

@@ -53,3 +53,17 @@ def hog_targets(video_u8: torch.Tensor, cube_marker, dtype=torch.float32) -> tor
         feat, _ = hog_features(video_u8.index_select(0, sel).contiguous())
         out[sel] = feat.to(dtype)
     return out
+
+
+def hog_targets_batch(video_u8: torch.Tensor, cube_markers, dtype=torch.float32) -> torch.Tensor:
+    """hog_targets for a whole batch with ONE kernel launch: video_u8 uint8 [B, T, H, W, 3] (CUDA), cube_markers = one
+    [[start, span], ...] list per sample -> [B, T, H/16, W/16, 108], zero except on every cube's centre frame."""
+    B, T, H, W, _ = video_u8.shape
+    out = torch.zeros((B, T, H // 16, W // 16, 108), dtype=dtype, device=video_u8.device)
+    flat_idx = sorted({b * T + s * 2 + n * 2 // 2 for b, cm in enumerate(cube_markers) for s, n in cm})
+    if flat_idx:
+        sel = torch.as_tensor(flat_idx, device=video_u8.device, dtype=torch.long)
+        frames = video_u8.reshape(B * T, H, W, 3).index_select(0, sel).contiguous()
+        feat, _ = hog_features(frames)
+        out.view(B * T, H // 16, W // 16, 108)[sel] = feat.to(dtype)
+    return out

@@ -120,9 +120,9 @@ def drop_path_scale(p: float, training: bool, n0: int, repeat: int, device):
     return r.repeat_interleave(repeat).contiguous() if repeat > 1 else r.contiguous()
 
 
-def _wgrad(dout, act, n_out, k_in, m_tok):
+def _wgrad(dout, act, n_out, k_in, m_tok, tag=None):
     """dW[n_out, k_in] = dout[m_tok, n_out]^T @ act[m_tok, k_in]  (both operands MN-major, split-K)."""
-    return K().gemm(dout, act, n_out, k_in, m_tok, a_mn=True, b_mn=True, epi='f32', split_ok=True)
+    return K().gemm(dout, act, n_out, k_in, m_tok, a_mn=True, b_mn=True, epi='f32', split_ok=True, tag=tag)
 
 
 def _dgrad(dout, w, m_tok, k_in, n_out, **kw):
@@ -172,10 +172,10 @@ class TemporalAttnFn(torch.autograd.Function):
         x2 = x.reshape(B * S, D)
         Mt = B * P * T
         xn, mean, rstd = k.ln_fwd(x2, ln_w, ln_b, eps, in_row=maps['temporal'], rows=Mt)
-        qkv = k.gemm(xn, qkv_wh, Mt, 3 * D, D, bias=qkv_b, epi='bf16')
+        qkv = k.gemm(xn, qkv_wh, Mt, 3 * D, D, bias=qkv_b, epi='bf16', tag='qkv')
         hd = D // H
         cx, lse, _ = k.attn_fwd(qkv, B * P, T, H, hd, hd ** -0.5)
-        a = k.gemm(cx, proj_wh, Mt, D, D, bias=proj_b, epi='bf16', row_scale=dp)
+        a = k.gemm(cx, proj_wh, Mt, D, D, bias=proj_b, epi='bf16', row_scale=dp, tag='proj')
         y = torch.empty_like(x)
         y2 = y.view(B * S, D)
         k.gemm(a, fc_wh, Mt, D, D, bias=fc_b, epi='f32', aux=x2, aux_row=maps['temporal'], out=y2,
@@ -200,13 +200,13 @@ class TemporalAttnFn(torch.autograd.Function):
         d_fc_w = _wgrad(g, a, D, D, Mt)
         d_fc_b = k.colsum(g)
         da = _dgrad(g, fc_wh, Mt, D, D, epi='bf16', row_scale=dp)
-        d_proj_w = _wgrad(da, cx, D, D, Mt)
+        d_proj_w = _wgrad(da, cx, D, D, Mt, tag='proj')
         d_proj_b = k.colsum(da)
-        dcx = _dgrad(da, proj_wh, Mt, D, D, epi='bf16')
+        dcx = _dgrad(da, proj_wh, Mt, D, D, epi='bf16', tag='proj')
         dqkv = k.attn_bwd(qkv, cx, dcx, lse, B * P, T, H, hd, hd ** -0.5)
-        d_qkv_w = _wgrad(dqkv, xn, 3 * D, D, Mt)
+        d_qkv_w = _wgrad(dqkv, xn, 3 * D, D, Mt, tag='qkv')
         d_qkv_b = k.colsum(dqkv)
-        dxn = _dgrad(dqkv, qkv_wh, Mt, D, 3 * D, epi='bf16')
+        dxn = _dgrad(dqkv, qkv_wh, Mt, D, 3 * D, epi='bf16', tag='qkv')
         dx = torch.empty_like(x)
         _, _, d_ln_w, d_ln_b = k.ln_bwd(dxn, x2, mean, rstd, ln_w, in_row=maps['temporal'], out_row=maps['temporal'],
                                         dres=dy2, dx=dx.view(B * S, D))
@@ -229,11 +229,11 @@ class SpatialAttnFn(torch.autograd.Function):
         x2 = x.reshape(R, D)
         hd = D // H
         xn, mean, rstd = k.ln_fwd(x2, ln_w, ln_b, eps, in_row=maps['sp_in'], rows=Ms)
-        qkv = k.gemm(xn, qkv_wh, Ms, 3 * D, D, bias=qkv_b, epi='bf16')
+        qkv = k.gemm(xn, qkv_wh, Ms, 3 * D, D, bias=qkv_b, epi='bf16', tag='qkv')
         cx, lse, _ = k.attn_fwd(qkv, B * T, P + 1, H, hd, hd ** -0.5)
         ybig = torch.empty((R + B * T, D), dtype=torch.float32, device=x.device)
         k.gemm(cx, proj_wh, Ms, D, D, bias=proj_b, epi='f32', aux=x2, aux_row=maps['sp_aux'], out=ybig,
-               out_row=maps['sp_out'], row_scale=dp, row_map=affine_row_maps(B, T, P, D)['spatial'])
+               out_row=maps['sp_out'], row_scale=dp, row_map=affine_row_maps(B, T, P, D)['spatial'], tag='proj')
         y = ybig[:R].view(B, S, D)
         y[:, 0] = x[:, 0] + ybig[R:].view(B, T, D).mean(dim=1)
         ctx.save_for_backward(x, ln_w, mean, rstd, xn, qkv, cx, lse, qkv_wh, proj_wh, dp)
@@ -252,13 +252,13 @@ class SpatialAttnFn(torch.autograd.Function):
         dy2 = dy.view(R, D)
         x2 = x.reshape(R, D)
         g = k.gather_cast(dy2, in_row=maps['sp_in'], row_scale=_mul_opt(dp, maps['sp_cls_scale']), rows=Ms)
-        d_proj_w = _wgrad(g, cx, D, D, Ms)
+        d_proj_w = _wgrad(g, cx, D, D, Ms, tag='proj')
         d_proj_b = k.colsum(g)
-        dcx = _dgrad(g, proj_wh, Ms, D, D, epi='bf16')
+        dcx = _dgrad(g, proj_wh, Ms, D, D, epi='bf16', tag='proj')
         dqkv = k.attn_bwd(qkv, cx, dcx, lse, B * T, P + 1, H, hd, hd ** -0.5)
-        d_qkv_w = _wgrad(dqkv, xn, 3 * D, D, Ms)
+        d_qkv_w = _wgrad(dqkv, xn, 3 * D, D, Ms, tag='qkv')
         d_qkv_b = k.colsum(dqkv)
-        dxn = _dgrad(dqkv, qkv_wh, Ms, D, 3 * D, epi='bf16')
+        dxn = _dgrad(dqkv, qkv_wh, Ms, D, 3 * D, epi='bf16', tag='qkv')
         dx = torch.empty_like(x)
         _, aux, d_ln_w, d_ln_b = k.ln_bwd(dxn, x2, mean, rstd, ln_w, in_row=maps['sp_in'], out_row=maps['sp_bwd'],
                                           dres=dy2, dx=dx.view(R, D), n_aux=B * T)
@@ -278,7 +278,7 @@ class JointAttnFn(torch.autograd.Function):
         x2 = x.reshape(M, D)
         hd = D // H
         xn, mean, rstd = k.ln_fwd(x2, ln_w, ln_b, eps)
-        qkv = k.gemm(xn, qkv_wh, M, 3 * D, D, bias=qkv_b, epi='bf16')
+        qkv = k.gemm(xn, qkv_wh, M, 3 * D, D, bias=qkv_b, epi='bf16', tag='qkv')
         if N <= ATTN_SINGLE_PASS_MAX:
             cx, lse, _ = k.attn_fwd(qkv, Bp, N, H, hd, hd ** -0.5)
         else:
@@ -288,7 +288,7 @@ class JointAttnFn(torch.autograd.Function):
             cx, lse = k.xattn_fwd(q4, k4, v4, hd ** -0.5)
             cx = cx.view(M, D)
         y = torch.empty_like(x)
-        k.gemm(cx, proj_wh, M, D, D, bias=proj_b, epi='f32', aux=x2, out=y.view(M, D), row_scale=dp)
+        k.gemm(cx, proj_wh, M, D, D, bias=proj_b, epi='f32', aux=x2, out=y.view(M, D), row_scale=dp, tag='proj')
         ctx.save_for_backward(x, ln_w, mean, rstd, xn, qkv, cx, lse, qkv_wh, proj_wh, dp)
         ctx.geom = (Bp, N, D, H)
         return y
@@ -304,16 +304,16 @@ class JointAttnFn(torch.autograd.Function):
         dy2 = dy.view(M, D)
         x2 = x.reshape(M, D)
         g = k.gather_cast(dy2, row_scale=dp)
-        d_proj_w = _wgrad(g, cx, D, D, M)
+        d_proj_w = _wgrad(g, cx, D, D, M, tag='proj')
         d_proj_b = k.colsum(g)
-        dcx = _dgrad(g, proj_wh, M, D, D, epi='bf16')
+        dcx = _dgrad(g, proj_wh, M, D, D, epi='bf16', tag='proj')
         if N <= ATTN_SINGLE_PASS_MAX:
             dqkv = k.attn_bwd(qkv, cx, dcx, lse, Bp, N, H, hd, hd ** -0.5)
         else:
             dqkv = _streaming_attn_bwd(k, qkv, cx, dcx, lse, Bp, N, H, hd)
-        d_qkv_w = _wgrad(dqkv, xn, 3 * D, D, M)
+        d_qkv_w = _wgrad(dqkv, xn, 3 * D, D, M, tag='qkv')
         d_qkv_b = k.colsum(dqkv)
-        dxn = _dgrad(dqkv, qkv_wh, M, D, 3 * D, epi='bf16')
+        dxn = _dgrad(dqkv, qkv_wh, M, D, 3 * D, epi='bf16', tag='qkv')
         dx = torch.empty_like(x)
         _, _, d_ln_w, d_ln_b = k.ln_bwd(dxn, x2, mean, rstd, ln_w, dres=dy2, dx=dx.view(M, D))
         return dx, d_ln_w, d_ln_b, d_qkv_w, d_qkv_b, d_proj_w, d_proj_b, None, None, None, None, None
