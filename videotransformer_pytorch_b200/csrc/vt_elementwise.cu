@@ -117,43 +117,46 @@ ln_fwd_kernel(const float* __restrict__ x, long long ldx, const int* __restrict_
 // the CTA's rows, reduced across warps through shared memory, one partial row per CTA.
 // ------------------------------------------------------------------------------------------------
 template <int V>
-__global__ void __launch_bounds__(LN_WARPS * 32)
+__global__ void __launch_bounds__(LN_WARPS * 32, (V <= 6 ? 2 : 1))
 ln_bwd_kernel(const void* __restrict__ dy, int dy_fp32, const float* __restrict__ x, long long ldx,
               const int* __restrict__ in_row, const float* __restrict__ mean, const float* __restrict__ rstd,
               const float* __restrict__ gamma, const float* __restrict__ dres, float* __restrict__ dx, long long lddx,
               float* __restrict__ dx_aux, const int* __restrict__ out_row, float* __restrict__ partials, int rows) {
   constexpr int D = V * 128;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float4 g[V], dg[V], db[V];
+  // Register budget: two CTAs (16 warps) per SM need <= 128 registers per thread.  Only the dgamma / dbeta partial sums
+  // live across rows; gamma is re-read per row (3 KiB, L1-resident) and dy*gamma is recomputed in the second pass
+  // instead of being held (the first version kept gamma, xhat and dy*gamma: 162 registers, one CTA per SM, ~0.6 of HBM).
+  float4 dg[V], db[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) {
-    g[i] = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * i);
     dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
   for (int m = blockIdx.x * LN_WARPS + warp; m < rows; m += gridDim.x * LN_WARPS) {
     const int src = in_row ? in_row[m] : m;
     const float4* xr = reinterpret_cast<const float4*>(x + (long long)src * ldx);
     const float mu = mean[m], rs = rstd[m];
-    float4 xh[V], gy[V];
+    float4 xh[V];
     float s1 = 0.f, s2 = 0.f;
+    auto load_dy = [&](int i) {
+      if (dy_fp32) return reinterpret_cast<const float4*>(static_cast<const float*>(dy) + (long long)m * D)[lane + 32 * i];
+      const uint2 u = reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(dy) + (long long)m * D)[lane + 32 * i];
+      const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+      return make_float4(a.x, a.y, b.x, b.y);
+    };
 #pragma unroll
     for (int i = 0; i < V; ++i) {
-      float4 d;
-      if (dy_fp32) {
-        d = reinterpret_cast<const float4*>(static_cast<const float*>(dy) + (long long)m * D)[lane + 32 * i];
-      } else {
-        const uint2 u = reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(dy) + (long long)m * D)[lane + 32 * i];
-        const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
-        d = make_float4(a.x, a.y, b.x, b.y);
-      }
+      const float4 d = load_dy(i);
       const float4 xv = xr[lane + 32 * i];
+      const float4 g = __ldg(g4 + lane + 32 * i);
       xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
       dg[i].x += d.x * xh[i].x; dg[i].y += d.y * xh[i].y; dg[i].z += d.z * xh[i].z; dg[i].w += d.w * xh[i].w;
       db[i].x += d.x; db[i].y += d.y; db[i].z += d.z; db[i].w += d.w;
-      gy[i] = make_float4(d.x * g[i].x, d.y * g[i].y, d.z * g[i].z, d.w * g[i].w);
-      s1 += (gy[i].x + gy[i].y) + (gy[i].z + gy[i].w);
-      s2 += (gy[i].x * xh[i].x + gy[i].y * xh[i].y) + (gy[i].z * xh[i].z + gy[i].w * xh[i].w);
+      const float4 gy = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
+      s1 += (gy.x + gy.y) + (gy.z + gy.w);
+      s2 += (gy.x * xh[i].x + gy.y * xh[i].y) + (gy.z * xh[i].z + gy.w * xh[i].w);
     }
     const float m1 = warp_sum(s1) * (1.0f / D);
     const float m2 = warp_sum(s2) * (1.0f / D);
@@ -168,11 +171,13 @@ ln_bwd_kernel(const void* __restrict__ dy, int dy_fp32, const float* __restrict_
     }
 #pragma unroll
     for (int i = 0; i < V; ++i) {
+      const float4 g = __ldg(g4 + lane + 32 * i);
+      const float4 d = load_dy(i);          // second read of the row's dy: an L1 hit (1.5 - 3 KiB per warp)
       float4 o;
-      o.x = rs * (gy[i].x - m1 - xh[i].x * m2);
-      o.y = rs * (gy[i].y - m1 - xh[i].y * m2);
-      o.z = rs * (gy[i].z - m1 - xh[i].z * m2);
-      o.w = rs * (gy[i].w - m1 - xh[i].w * m2);
+      o.x = rs * (d.x * g.x - m1 - xh[i].x * m2);
+      o.y = rs * (d.y * g.y - m1 - xh[i].y * m2);
+      o.z = rs * (d.z * g.z - m1 - xh[i].z * m2);
+      o.w = rs * (d.w * g.w - m1 - xh[i].w * m2);
       if (res) {
         const float4 r = reinterpret_cast<const float4*>(res)[lane + 32 * i];
         o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
