@@ -68,6 +68,22 @@ def test_casts_and_colsum():
     assert rel(K().colsum(xb), xb.float().sum(0)) < 1e-5
 
 
+@pytest.mark.parametrize('M,N', [(12544, 768), (12608, 2304), (12552, 3072), (1, 8), (255, 264), (257, 1000), (3000, 96),
+                                 (513, 100)])
+def test_colsum_shapes_and_views(M, N, monkeypatch):
+    """bias-gradient column sums: wide 16-byte-load kernel (N % 8 == 0) and the narrow fallback, contiguous and as a column
+    slice of a wider buffer; twice in a row (the last-CTA counters clean up after themselves)."""
+    g = torch.Generator().manual_seed(M + N)
+    wide = torch.randn(M, N + 16, generator=g).cuda().bfloat16()
+    for x in (wide[:, :N].contiguous(), wide[:, 8:8 + N]):
+        ref = x.float().sum(0)
+        for _ in range(2):
+            assert rel(K().colsum(x), ref) < 1e-5
+        monkeypatch.setenv('VT_COLSUM_NARROW', '1')
+        assert rel(K().colsum(x), ref) < 1e-5
+        monkeypatch.delenv('VT_COLSUM_NARROW')
+
+
 @pytest.mark.parametrize('tube', [1, 2])
 def test_im2col_col2im(tube):
     torch.manual_seed(2)

@@ -2,6 +2,7 @@
 // fp32->bf16 casts (+row gather, +DropPath scale), bias-gradient column sums, im2col / col2im for the
 // non-overlapping patch / tubelet embedding.  All loads/stores are 16-byte vectors on contiguous rows.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "vt_common.cuh"
@@ -308,6 +309,70 @@ colsum_kernel(const __nv_bfloat16* __restrict__ in, long long ld, int M, int N, 
   }
 }
 
+// Wide form (N % 8 == 0): CTA = 256 columns x 256 rows; a lane owns 8 adjacent columns (one 16-byte load per row), the 8
+// warps are row lanes with 4 rows in flight each, so an SM holds ~32 KiB of loads in flight instead of ~8 KiB with the
+// 4-byte loads above (which ran at ~0.3 of the HBM rate).  Partials per row chunk, summed by the last CTA of each
+// column block in chunk order (deterministic).
+constexpr int COLSUM_WROWS = 256;
+
+__global__ void __launch_bounds__(256)
+colsum_wide_kernel(const __nv_bfloat16* __restrict__ in, long long ld, int M, int N, float* __restrict__ ws,
+                   float* __restrict__ out, int* __restrict__ counters) {
+  const int lane = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int col = blockIdx.x * 256 + lane * 8;
+  const int r0 = blockIdx.y * COLSUM_WROWS;
+  const int r1 = min(M, r0 + COLSUM_WROWS);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  auto add = [&](const uint4& u) {
+    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y; acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
+  };
+  if (col < N) {
+    const __nv_bfloat16* base = in + col;
+    int r = r0 + rl;
+    for (; r + 24 < r1; r += 32) {          // 4 rows of this row lane in flight
+      const uint4 u0 = *reinterpret_cast<const uint4*>(base + (long long)r * ld);
+      const uint4 u1 = *reinterpret_cast<const uint4*>(base + (long long)(r + 8) * ld);
+      const uint4 u2 = *reinterpret_cast<const uint4*>(base + (long long)(r + 16) * ld);
+      const uint4 u3 = *reinterpret_cast<const uint4*>(base + (long long)(r + 24) * ld);
+      add(u0); add(u1); add(u2); add(u3);
+    }
+    for (; r < r1; r += 8) add(*reinterpret_cast<const uint4*>(base + (long long)r * ld));
+  }
+  __shared__ float sh[8][32][9];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sh[rl][lane][j] = acc[j];
+  __syncthreads();
+  {
+    // thread t finalises column t of the block: lane t / 8, slot t % 8
+    const int l = threadIdx.x >> 3, j = threadIdx.x & 7;
+    float sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) sum += sh[w][l][j];
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c < N) ws[(long long)blockIdx.y * N + c] = sum;
+  }
+  __shared__ int is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int done = atomicAdd(&counters[blockIdx.x], 1);
+    is_last = (done == (int)gridDim.y - 1);
+    if (is_last) counters[blockIdx.x] = 0;   // self-cleaning for the next call
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < N) {
+    float t = 0.f;
+    for (int k = 0; k < (int)gridDim.y; ++k) t += __ldcg(ws + (long long)k * N + c);
+    out[c] = t;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // im2col for non-overlapping patches / tubelets, and its adjoint
 //   cols[(b,t',hp,wp), ((c*tube+dt)*ph+i)*pw+j] = x[b, t'*tube+dt, c, hp*ph+i, wp*pw+j]
@@ -514,7 +579,7 @@ extern "C" int vt_gather_cast_bf16(const vt_gather_cast_params* p, void* stream)
   return check_launch("gather_cast_kernel");
 }
 
-extern "C" int vt_colsum_chunks(int32_t M) { return (M + COLSUM_ROWS - 1) / COLSUM_ROWS; }
+extern "C" int vt_colsum_chunks(int32_t M) { return (M + COLSUM_WROWS - 1) / COLSUM_WROWS; }   // rows of the partial-sum workspace
 
 namespace vt { int launch_reduce_rows(const float*, float*, long long, int, long long, int, float, cudaStream_t); }
 
@@ -522,7 +587,13 @@ extern "C" int vt_colsum_bf16(const vt_colsum_params* p, void* stream) {
   VT_REQUIRE(p && p->in && p->out && p->workspace && p->M > 0 && p->N > 0, "vt_colsum_bf16: bad params");
   VT_REQUIRE(p->N % 4 == 0 && p->ld % 2 == 0, "vt_colsum_bf16: N %% 4 and ld %% 2 required");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int chunks = vt_colsum_chunks(p->M);
+  if (p->counters && p->N % 8 == 0 && p->ld % 8 == 0 && (reinterpret_cast<uintptr_t>(p->in) & 15) == 0 && !getenv("VT_COLSUM_NARROW")) {
+    dim3 wgrid((p->N + 255) / 256, (p->M + COLSUM_WROWS - 1) / COLSUM_WROWS);
+    colsum_wide_kernel<<<wgrid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(p->in), p->ld, p->M, p->N, p->workspace, p->out,
+                                             p->counters);
+    return check_launch("colsum_wide_kernel");
+  }
+  const int chunks = (p->M + COLSUM_ROWS - 1) / COLSUM_ROWS;
   dim3 grid((p->N + 63) / 64, chunks);
   colsum_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(p->in), p->ld, p->M, p->N, p->workspace, p->out,
                                       p->counters);
