@@ -33,10 +33,27 @@ try:
 except Exception as e:
     print('cgroup cpu.max: n/a', e)
 if mode == 'ncu':
+    # log every GEMM call of the profiled step (one kernel launch each, in order) so that tools/ncu_summarize.py can put the
+    # algorithmic bytes of each shape next to the measured DRAM traffic
+    import json
+    from videotransformer_pytorch_b200 import _lib
+    calls = []
+    real = _lib.K.gemm
+
+    def logged(a_, b_, M, N, Kd, **kw):
+        calls.append(dict(M=M, N=N, K=Kd, a_mn=bool(kw.get('a_mn')), b_mn=bool(kw.get('b_mn')), epi=kw.get('epi', 'bf16'),
+                          aux=kw.get('aux') is not None, split=bool(kw.get('split_ok')), tag=kw.get('tag')))
+        return real(a_, b_, M, N, Kd, **kw)
+
+    _lib.K.gemm = logged
     torch.cuda.cudart().cudaProfilerStart()
     step()
     torch.cuda.synchronize()
     torch.cuda.cudart().cudaProfilerStop()
+    _lib.K.gemm = real
+    os.makedirs('gpurun_out', exist_ok=True)
+    with open('gpurun_out/r2_gemm_calls.json', 'w') as fh:
+        json.dump(calls, fh)
 else:
     t0 = time.perf_counter()
     for _ in range(3):
