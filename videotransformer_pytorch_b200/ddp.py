@@ -136,6 +136,26 @@ class GradientBuckets:
             self._arrived[bi] = []
             self._launch(bi)
 
+    def backward_into_buckets(self, loss, params):
+        """Backward of `loss` with the gradients landing in the flat buckets and every bucket's all-reduce issued as soon as
+        it is complete (the body of a captured data-parallel step, graph.GraphedTrainStep; also usable eagerly after
+        zero_grad()).  Uses torch.autograd.grad, so nothing is ACCUMULATED: weight-gradient GEMMs may therefore write
+        directly into their bucket slice (ops.GRAD_DEST), other gradients are copied in by grad_ready()."""
+        from . import ops
+        params = list(params)
+        self._pending = [len(ps) for ps in self._bucket_params]
+        self._arrived = [[] for _ in self._bucket_params]
+        handles = [p.register_hook(lambda g, p=p: self.grad_ready(p, g)) for p in params]
+        ops.set_grad_destinations({p.data_ptr(): v for p, v in self._view.items()})
+        try:
+            grads = torch.autograd.grad(loss, params)
+        finally:
+            ops.set_grad_destinations(None)
+            for h in handles:
+                h.remove()
+        self.finish()
+        return grads
+
     def reduce_into_buckets(self, params, grads):
         """Graph-capture path: gradients arrive as a list (torch.autograd.grad); copy them into the flat buckets
         (p.grad stays the bucket view) and all-reduce bucket by bucket on the communication stream."""

@@ -112,16 +112,10 @@ class GraphedTrainStep:
                 if reducer is None:
                     grads = torch.autograd.grad(self.static_loss, self.params)
                 else:
-                    # per-parameter tensor hooks fire as soon as a gradient is final: it is copied into its flat
-                    # bucket and completed buckets are all-reduced on the side stream while backward continues
-                    reducer._pending = [len(ps) for ps in reducer._bucket_params]
-                    handles = [p_.register_hook(lambda g_, p_=p_: reducer.grad_ready(p_, g_)) for p_ in self.params]
-                    try:
-                        grads = torch.autograd.grad(self.static_loss, self.params)
-                    finally:
-                        for h_ in handles:
-                            h_.remove()
-                    reducer.finish()
+                    # per-parameter tensor hooks fire as soon as a gradient is final: weight gradients are written by
+                    # their GEMM straight into the flat buckets, the rest is copied there, and completed buckets are
+                    # all-reduced on the side stream while backward continues
+                    grads = reducer.backward_into_buckets(self.static_loss, self.params)
         finally:
             self.arena.recording = False
             ops.set_mask_arena(None)

@@ -120,9 +120,27 @@ def drop_path_scale(p: float, training: bool, n0: int, repeat: int, device):
     return r.repeat_interleave(repeat).contiguous() if repeat > 1 else r.contiguous()
 
 
-def _wgrad(dout, act, n_out, k_in, m_tok, tag=None):
-    """dW[n_out, k_in] = dout[m_tok, n_out]^T @ act[m_tok, k_in]  (both operands MN-major, split-K)."""
-    return K().gemm(dout, act, n_out, k_in, m_tok, a_mn=True, b_mn=True, epi='f32', split_ok=True, tag=tag)
+# While a data-parallel step is being captured (graph.GraphedTrainStep with ddp.GradientBuckets) this maps the address of a
+# weight parameter to its slice of the flat gradient bucket: the weight-gradient GEMM then writes (zero + split-K TMA
+# reduce-add) straight into the bucket and no gather copy precedes the all-reduce.  Never set in eager mode,
+# where autograd ACCUMULATES the returned gradient into p.grad — returning p.grad's own storage would double it.
+GRAD_DEST = None
+
+
+def set_grad_destinations(table):
+    global GRAD_DEST
+    GRAD_DEST = table
+
+
+def _wgrad(dout, act, n_out, k_in, m_tok, tag=None, wptr=None):
+    """dW[n_out, k_in] = dout[m_tok, n_out]^T @ act[m_tok, k_in]  (both operands MN-major, split-K).
+    wptr: data_ptr() of the fp32 parameter this is the gradient of (see GRAD_DEST)."""
+    out = None
+    if GRAD_DEST is not None and wptr is not None:
+        dest = GRAD_DEST.get(wptr)
+        if dest is not None and dest.numel() == n_out * k_in and dest.is_contiguous():
+            out = dest.view(n_out, k_in)
+    return K().gemm(dout, act, n_out, k_in, m_tok, a_mn=True, b_mn=True, epi='f32', split_ok=True, tag=tag, out=out)
 
 
 def _dgrad(dout, w, m_tok, k_in, n_out, **kw):
@@ -183,6 +201,7 @@ class TemporalAttnFn(torch.autograd.Function):
         y[:, 0] = x[:, 0]
         ctx.save_for_backward(x, ln_w, mean, rstd, xn, qkv, cx, lse, a, qkv_wh, proj_wh, fc_wh, dp)
         ctx.geom = (B, S, D, T, H, P)
+        ctx.wptrs = (qkv_w.data_ptr(), proj_w.data_ptr(), fc_w.data_ptr())
         return y
 
     @staticmethod
@@ -197,14 +216,14 @@ class TemporalAttnFn(torch.autograd.Function):
         dy2 = dy.view(B * S, D)
         x2 = x.reshape(B * S, D)
         g = k.gather_cast(dy2, in_row=maps['temporal'], rows=Mt)
-        d_fc_w = _wgrad(g, a, D, D, Mt)
+        d_fc_w = _wgrad(g, a, D, D, Mt, wptr=ctx.wptrs[2])
         d_fc_b = k.colsum(g)
         da = _dgrad(g, fc_wh, Mt, D, D, epi='bf16', row_scale=dp)
-        d_proj_w = _wgrad(da, cx, D, D, Mt, tag='proj')
+        d_proj_w = _wgrad(da, cx, D, D, Mt, tag='proj', wptr=ctx.wptrs[1])
         d_proj_b = k.colsum(da)
         dcx = _dgrad(da, proj_wh, Mt, D, D, epi='bf16', tag='proj')
         dqkv = k.attn_bwd(qkv, cx, dcx, lse, B * P, T, H, hd, hd ** -0.5)
-        d_qkv_w = _wgrad(dqkv, xn, 3 * D, D, Mt, tag='qkv')
+        d_qkv_w = _wgrad(dqkv, xn, 3 * D, D, Mt, tag='qkv', wptr=ctx.wptrs[0])
         d_qkv_b = k.colsum(dqkv)
         dxn = _dgrad(dqkv, qkv_wh, Mt, D, 3 * D, epi='bf16', tag='qkv')
         dx = torch.empty_like(x)
@@ -238,6 +257,7 @@ class SpatialAttnFn(torch.autograd.Function):
         y[:, 0] = x[:, 0] + ybig[R:].view(B, T, D).mean(dim=1)
         ctx.save_for_backward(x, ln_w, mean, rstd, xn, qkv, cx, lse, qkv_wh, proj_wh, dp)
         ctx.geom = (B, S, D, T, H, P)
+        ctx.wptrs = (qkv_w.data_ptr(), proj_w.data_ptr())
         return y
 
     @staticmethod
@@ -252,11 +272,11 @@ class SpatialAttnFn(torch.autograd.Function):
         dy2 = dy.view(R, D)
         x2 = x.reshape(R, D)
         g = k.gather_cast(dy2, in_row=maps['sp_in'], row_scale=_mul_opt(dp, maps['sp_cls_scale']), rows=Ms)
-        d_proj_w = _wgrad(g, cx, D, D, Ms, tag='proj')
+        d_proj_w = _wgrad(g, cx, D, D, Ms, tag='proj', wptr=ctx.wptrs[1])
         d_proj_b = k.colsum(g)
         dcx = _dgrad(g, proj_wh, Ms, D, D, epi='bf16', tag='proj')
         dqkv = k.attn_bwd(qkv, cx, dcx, lse, B * T, P + 1, H, hd, hd ** -0.5)
-        d_qkv_w = _wgrad(dqkv, xn, 3 * D, D, Ms, tag='qkv')
+        d_qkv_w = _wgrad(dqkv, xn, 3 * D, D, Ms, tag='qkv', wptr=ctx.wptrs[0])
         d_qkv_b = k.colsum(dqkv)
         dxn = _dgrad(dqkv, qkv_wh, Ms, D, 3 * D, epi='bf16', tag='qkv')
         dx = torch.empty_like(x)
@@ -291,6 +311,7 @@ class JointAttnFn(torch.autograd.Function):
         k.gemm(cx, proj_wh, M, D, D, bias=proj_b, epi='f32', aux=x2, out=y.view(M, D), row_scale=dp, tag='proj')
         ctx.save_for_backward(x, ln_w, mean, rstd, xn, qkv, cx, lse, qkv_wh, proj_wh, dp)
         ctx.geom = (Bp, N, D, H)
+        ctx.wptrs = (qkv_w.data_ptr(), proj_w.data_ptr())
         return y
 
     @staticmethod
@@ -304,14 +325,14 @@ class JointAttnFn(torch.autograd.Function):
         dy2 = dy.view(M, D)
         x2 = x.reshape(M, D)
         g = k.gather_cast(dy2, row_scale=dp)
-        d_proj_w = _wgrad(g, cx, D, D, M, tag='proj')
+        d_proj_w = _wgrad(g, cx, D, D, M, tag='proj', wptr=ctx.wptrs[1])
         d_proj_b = k.colsum(g)
         dcx = _dgrad(g, proj_wh, M, D, D, epi='bf16', tag='proj')
         if N <= ATTN_SINGLE_PASS_MAX:
             dqkv = k.attn_bwd(qkv, cx, dcx, lse, Bp, N, H, hd, hd ** -0.5)
         else:
             dqkv = _streaming_attn_bwd(k, qkv, cx, dcx, lse, Bp, N, H, hd)
-        d_qkv_w = _wgrad(dqkv, xn, 3 * D, D, M, tag='qkv')
+        d_qkv_w = _wgrad(dqkv, xn, 3 * D, D, M, tag='qkv', wptr=ctx.wptrs[0])
         d_qkv_b = k.colsum(dqkv)
         dxn = _dgrad(dqkv, qkv_wh, M, D, 3 * D, epi='bf16', tag='qkv')
         dx = torch.empty_like(x)
@@ -339,6 +360,7 @@ class FFNFn(torch.autograd.Function):
         y = torch.empty_like(x)
         k.gemm(h, w2h, M, D, Dh, bias=b2, epi='f32', aux=x2, out=y.view(M, D), row_scale=dp)
         ctx.save_for_backward(x, ln_w, mean, rstd, xn, z, h, w1h, w2h, dp)
+        ctx.wptrs = (w1.data_ptr(), w2.data_ptr())
         return y
 
     @staticmethod
@@ -352,13 +374,13 @@ class FFNFn(torch.autograd.Function):
         dy2 = dy.view(M, D)
         x2 = x.reshape(M, D)
         g = k.gather_cast(dy2, row_scale=dp)
-        d_w2 = _wgrad(g, h, D, Dh, M)
+        d_w2 = _wgrad(g, h, D, Dh, M, wptr=ctx.wptrs[1])
         d_b2 = k.colsum(g)
         if FUSED_GELU_EPILOGUE:
             dz = _dgrad(g, w2h, M, Dh, D, epi='dgelu', aux=z)
         else:
             dz = k.dgelu(_dgrad(g, w2h, M, Dh, D, epi='bf16'), z)
-        d_w1 = _wgrad(dz, xn, Dh, D, M)
+        d_w1 = _wgrad(dz, xn, Dh, D, M, wptr=ctx.wptrs[0])
         d_b1 = k.colsum(dz)
         dxn = _dgrad(dz, w1h, M, D, Dh, epi='bf16')
         dx = torch.empty_like(x)
