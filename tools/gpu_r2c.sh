@@ -1,10 +1,18 @@
 #!/bin/bash
+# round-2 call C: diagnose the TMA residual epilogue (sanitizer), validate everything else with it switched off
 set -u
 mkdir -p gpurun_out
 cd "${GRAFT_REPO_ROOT:-.}"
-export CUDA_LAUNCH_BLOCKING=1
-timeout 600 compute-sanitizer --tool memcheck --print-limit 5 python -m pytest "tests/test_gpu_gemm.py::test_residual_epilogue_tma_plain_rows[1000-768-256-128-single-cta]" -q -m gpu -x > gpurun_out/sanitizer_single.log 2>&1; echo "sanitizer single rc=$?"
-grep -E "=========|Error|error" gpurun_out/sanitizer_single.log | head -n 40 | cut -c1-300
-timeout 600 python -m pytest "tests/test_gpu_gemm.py::test_residual_epilogue_tma_plain_rows[1000-768-256-256-single-cta]" -q -m gpu -x > gpurun_out/t256.log 2>&1; echo "bn256 single rc=$?"; tail -n 3 gpurun_out/t256.log | cut -c1-200
-timeout 600 python -m pytest "tests/test_gpu_gemm.py::test_residual_epilogue_tma_plain_rows[4096-256-64-128-single-cta]" -q -m gpu -x > gpurun_out/t4096.log 2>&1; echo "M4096 (no partial tiles) single rc=$?"; tail -n 3 gpurun_out/t4096.log | cut -c1-200
-timeout 600 python -m pytest tests/test_gpu_gemm.py -q -m gpu -k "narrow_tail and not residual" > gpurun_out/tail.log 2>&1; echo "tail rc=$?"; tail -n 5 gpurun_out/tail.log | cut -c1-200
+T1="tests/test_gpu_gemm.py::test_residual_epilogue_tma_plain_rows[4096-256-64-128-single-cta]"
+T2="tests/test_gpu_gemm.py::test_residual_epilogue_tma_plain_rows[1000-768-256-128-single-cta]"
+timeout 300 python -m pytest "$T1" -q -m gpu -x > gpurun_out/res_t1.log 2>&1; echo "RES M4096 (whole tiles only) single rc=$?"; tail -n 2 gpurun_out/res_t1.log | cut -c1-200
+timeout 300 python -m pytest "$T2" -q -m gpu -x > gpurun_out/res_t2.log 2>&1; echo "RES M1000 single rc=$?"; tail -n 2 gpurun_out/res_t2.log | cut -c1-200
+timeout 600 compute-sanitizer --tool memcheck --print-limit 8 python -m pytest "$T1" -q -m gpu -x > gpurun_out/sanitizer_t1.log 2>&1; echo "sanitizer T1 rc=$?"
+grep -E "=========" gpurun_out/sanitizer_t1.log | head -n 40 | cut -c1-260
+export VT_NO_TMA_RES=1
+timeout 900 python -m pytest tests/test_gpu_gemm.py -q -m gpu > gpurun_out/test_gemm_nores.log 2>&1; echo "test_gemm (no RES) rc=$?"; tail -n 12 gpurun_out/test_gemm_nores.log | cut -c1-250
+timeout 1500 python -m pytest tests -q -m gpu --deselect tests/test_gpu_gemm.py > gpurun_out/pytest_gpu_nores.log 2>&1; echo "pytest -m gpu (no RES, w/o gemm file) rc=$?"
+grep -E "passed|failed" gpurun_out/pytest_gpu_nores.log | tail -n 2 | cut -c1-300; grep -E "^FAILED|^ERROR" gpurun_out/pytest_gpu_nores.log | head -n 20 | cut -c1-250
+timeout 600 python tools/gemm_table.py quick > gpurun_out/gemm_table.log 2>&1; echo "gemm_table rc=$?"
+timeout 900 python bench.py > gpurun_out/bench.log 2>&1; echo "bench rc=$?"; tail -n 1 gpurun_out/bench.log | cut -c1-600
+timeout 300 python tools/profile_step.py torchprof > gpurun_out/torchprof.log 2>&1; echo "torchprof rc=$?"
