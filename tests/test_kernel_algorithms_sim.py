@@ -549,3 +549,89 @@ def test_xattn_tensor_core_tile_walk(Nq, Nk):
     sdq, sdk, sdv = sim_xattn_tc_bwd(q, k, v, o, do, lse, scale, garbage)
     for mine, ref in ((sdq, dq), (sdk, dk), (sdv, dv)):
         assert np.abs(mine - ref).max() < 1e-11 * max(1.0, np.abs(ref).max())
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# fp32 residual epilogue on TMA (vt_gemm_common.cuh: epilogue_tile_tma_res): box / segment arithmetic of the affine row maps
+# ---------------------------------------------------------------------------------------------------------------------
+def _tma_box(tensor4, c_t, c_p, c_b, rows=32):
+    """rows x D box of the 4-D tensor view [B, P, T, D] at (t, p.., b): out-of-range rows come back as zeros (load) and are
+    dropped (store) — what the TMA unit does in tiled mode, negative start coordinates included."""
+    import torch
+    Bc, Pc, Tc, D = tensor4.shape
+    box = torch.zeros(rows, D, dtype=tensor4.dtype)
+    valid = torch.zeros(rows, dtype=torch.bool)
+    for i in range(rows):
+        p = c_p + i
+        if 0 <= c_b < Bc and 0 <= c_t < Tc and 0 <= p < Pc:
+            box[i] = tensor4[c_b, p, c_t]
+            valid[i] = True
+    return box, valid
+
+
+@pytest.mark.parametrize('B,T,P', [(2, 8, 196), (3, 4, 9 * 4), (1, 2, 50), (2, 3, 33)])
+@pytest.mark.parametrize('kind', ['temporal', 'spatial'])
+def test_residual_epilogue_segments_cover_every_row_once(B, T, P, kind):
+    """Walks the epilogue's per-group logic (32-row groups of 128-row tiles; one or two TMA boxes per group; special rows by
+    plain stores) for the temporal and spatial maps and checks it against the out_row / aux_row arrays of ops.token_maps."""
+    import torch
+    from videotransformer_pytorch_b200 import ops
+    D = 8
+    S = 1 + P * T
+    R = B * S
+    maps = ops.token_maps(B, T, P, 'cpu')
+    aff = ops.affine_row_maps(B, T, P, D)[kind]
+    if aff['period'] < 32:
+        pytest.skip('periods below 32 rows use the generic epilogue')
+    M = B * P * T if kind == 'temporal' else B * T * (P + 1)
+    out_row = maps['temporal'] if kind == 'temporal' else maps['sp_out']
+    aux_row = maps['temporal'] if kind == 'temporal' else maps['sp_aux']
+    g = torch.Generator().manual_seed(0)
+    acc = torch.randn(M, D, generator=g)                       # s * (accumulator + bias), already in GEMM row order
+    x = torch.randn(R, D, generator=g)                         # residual stream
+    rows_total = R + (B * T if kind == 'spatial' else 0)
+    got = torch.full((rows_total, D), float('nan'))
+    writes = torch.zeros(rows_total, dtype=torch.int32)
+    # the 4-D views the tensor maps describe: element (t, p, b) at base + t*stride_t + p*stride_p + b*stride_b
+    def view4(buf):
+        flat = buf.reshape(-1)
+        pc, tc = aff['period'] - aff['skip'], aff['tcount']
+        bc = (M // aff['period'] + tc - 1) // tc
+        return torch.as_strided(flat, (bc, pc, tc, D), (aff['stride_b'], aff['stride_p'], aff['stride_t'], 1), aff['base'])
+    x4 = view4(x if kind == 'temporal' else torch.cat([x, torch.zeros(B * T, D)]))
+    out_flat = got.reshape(-1)
+    period, skip, tcount = aff['period'], aff['skip'], aff['tcount']
+    for m0 in range(0, (M + 127) // 128 * 128, 32):
+        outer0, inner0 = m0 // period, m0 % period
+        two = inner0 + 32 > period
+        segs = []
+        for sg in range(2 if two else 1):
+            outer = outer0 + sg
+            segs.append((outer % tcount, inner0 - sg * period - skip, outer // tcount))
+        boxes = [_tma_box(x4, *sgm) for sgm in segs]
+        result = torch.zeros(32, D)
+        for lane in range(32):
+            row = m0 + lane
+            my_seg = 1 if inner0 + lane >= period else 0
+            my_inner = inner0 + lane - my_seg * period
+            aux = boxes[my_seg][0][lane] if my_seg < len(boxes) else torch.zeros(D)
+            val = (acc[row] if row < M else torch.zeros(D)) + aux
+            result[lane] = val
+            if row < M and my_inner < skip:                   # special row: plain store to the side rows
+                dst = (aff['special_base'] + (outer0 + my_seg) * aff['special_stride']) // D
+                got[dst] = val
+                writes[dst] += 1
+        for (c_t, c_p, c_b), (_, valid) in zip(segs, boxes):  # TMA stores clip exactly like the loads
+            for lane in range(32):
+                p = c_p + lane
+                if valid[lane]:
+                    off = aff['base'] + c_t * aff['stride_t'] + p * aff['stride_p'] + c_b * aff['stride_b']
+                    got[off // D] = result[lane]
+                    writes[off // D] += 1
+    exp = torch.full((rows_total, D), float('nan'))
+    add = x[aux_row.long().clamp(min=0)] * (aux_row >= 0)[:, None]
+    exp[out_row.long()] = acc + add
+    named = torch.zeros(rows_total, dtype=torch.int32)
+    named[out_row.long()] = 1
+    assert torch.equal(writes, named)                           # every mapped row written exactly once, no other row touched
+    assert torch.equal(torch.nan_to_num(got, nan=-1.0), torch.nan_to_num(exp, nan=-1.0))
