@@ -327,12 +327,17 @@ int vt_mvit_tokens_bwd(const vt_mvit_tokens_bwd_params* p, void* stream);
 typedef struct {
   const float* pred; const float* target; const float* mask; float* num; float* partials;
   int32_t B, t, dt, h, w, dc;
+  /* fp64 variant (the reference's targets are fp64 numpy arrays, dataset.py:190, which makes its loss fp64,
+   * video_transformer.py:899-901): target64 != NULL replaces `target`; differences, squares and all sums are then taken in
+   * fp64 and the sum goes to num64[0]; `partials` must hold vt_mse_blocks(cells) * 4 doubles. */
+  const double* target64; double* num64;
 } vt_mse_fwd_params;
 int vt_mse_blocks(int32_t cells);
 int vt_mse_fwd(const vt_mse_fwd_params* p, void* stream);
 typedef struct {
   const float* pred; const float* target; const float* mask; const float* coef; void* dpred;
   int32_t B, t, dt, h, w, dc;
+  const double* target64;   /* fp64 targets (replaces `target`) or NULL */
 } vt_mse_bwd_params;
 int vt_mse_bwd(const vt_mse_bwd_params* p, void* stream);
 

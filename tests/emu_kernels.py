@@ -372,7 +372,7 @@ class EmuKernels:
         B, t, dt, h, w, dc = dims
         p = self._mse_pred(pred, dims)
         e = ((p - self._up(target).reshape(p.shape)) ** 2).mean(-1) * self._up(mask).reshape(B, t * dt, h, w)
-        num = torch.zeros(4, dtype=self.f)
+        num = torch.zeros(4, dtype=torch.float64 if target.dtype == torch.float64 else self.f)
         num[0] = e.sum()
         return num
 

@@ -171,3 +171,22 @@ def test_multiscale_block_vs_oracle_at_mvit_b_shapes(index, thw):
     print(f'block {index} thw {thw}: y {e_y:.2e}  dx {e_dx:.2e}  worst param grad {errs[0][0]:.2e} ({errs[0][1]})')
     assert e_y < 5e-3 and e_dx < 2e-2
     assert errs[0][0] < 5e-2, errs[:4]
+
+
+def test_masked_mse_fp64_targets():
+    """fp64 targets (the reference's numpy default): differences and sums in fp64 on the device, fp64 loss; gradient as fp32."""
+    B, t, dt, h, w, dc = 2, 8, 2, 14, 14, 108
+    L1 = 1 + t * h * w
+    pred = rn((B * L1, dt * dc), 63)
+    target = torch.randn(B, t * dt, h, w, dc, generator=torch.Generator().manual_seed(64), dtype=torch.float64)
+    mask = (torch.rand(B, t * dt, h, w, generator=torch.Generator().manual_seed(65)) < 0.2).float()
+    dims = (B, t, dt, h, w, dc)
+    num = K().mse_fwd(pred.cuda(), target.cuda(), mask.cuda(), dims)
+    assert num.dtype == torch.float64
+    p = pred.view(B, L1, dt * dc)[:, 1:].reshape(B, t, h, w, dt, dc).permute(0, 1, 4, 2, 3, 5).reshape(B, t * dt, h, w, dc)
+    ref = (((p.double() - target) ** 2).mean(-1) * mask.double()).sum()
+    assert abs(num[0].item() - ref.item()) < 1e-12 * abs(ref.item())
+    coef = torch.tensor([0.01])
+    d64 = K().mse_bwd(pred.cuda(), target.cuda(), mask.cuda(), coef.cuda(), dims)
+    d32 = K().mse_bwd(pred.cuda(), target.float().cuda(), mask.cuda(), coef.cuda(), dims)
+    assert rel_err(d64.float().cpu(), d32.float().cpu()) < 4e-3

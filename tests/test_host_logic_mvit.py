@@ -96,3 +96,23 @@ def test_loss_edge_cases_vs_oracle(maskfeat_golden, emu, case):
         assert float(loss) == 0.0
     loss.backward()                                    # gradients exist and are finite even when the loss is identically 0
     assert all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for p in m.parameters())
+
+
+def test_fp64_targets_give_an_fp64_loss_like_the_reference(maskfeat_golden, emu):
+    """dataset.py:190 builds the HOG targets as fp64 numpy arrays, so the reference's masked-MSE (video_transformer.py:899-901)
+    is an fp64 tensor; with fp64 targets this package keeps the loss in fp64 too (fp32 targets -> fp32 loss)."""
+    from videotransformer_pytorch_b200 import MaskFeat
+    g = maskfeat_golden('maskfeat_s32')
+    kw = dict(g.kwargs)
+    for k in ('pool_q_stride_size', 'embed_dim_mul', 'atten_head_mul'):
+        if k in kw:
+            kw[k] = [list(r) for r in kw[k]]
+    m = MaskFeat(**kw)
+    m.load_state_dict(g.state(torch.float32), strict=True)
+    m.train()
+    _, l64 = m(g.x, g.target.double(), g.mask, g.cube_marker)
+    _, l32 = m(g.x, g.target.float(), g.mask, g.cube_marker)
+    assert l64.dtype == torch.float64 and l32.dtype == torch.float32
+    assert abs(float(l64) - g.loss) < 2e-5 * abs(g.loss) and abs(float(l32) - g.loss) < 2e-5 * abs(g.loss)
+    l64.backward()
+    assert all(p.grad is not None for n, p in m.named_parameters())

@@ -154,11 +154,13 @@ _MSE_DIMS = [(n, c_i32) for n in ('B', 't', 'dt', 'h', 'w', 'dc')]
 
 
 class MseFwdParams(C.Structure):
-    _fields_ = [('pred', c_vp), ('target', c_vp), ('mask', c_vp), ('num', c_vp), ('partials', c_vp)] + _MSE_DIMS
+    _fields_ = [('pred', c_vp), ('target', c_vp), ('mask', c_vp), ('num', c_vp), ('partials', c_vp)] + _MSE_DIMS + \
+               [('target64', c_vp), ('num64', c_vp)]
 
 
 class MseBwdParams(C.Structure):
-    _fields_ = [('pred', c_vp), ('target', c_vp), ('mask', c_vp), ('coef', c_vp), ('dpred', c_vp)] + _MSE_DIMS
+    _fields_ = [('pred', c_vp), ('target', c_vp), ('mask', c_vp), ('coef', c_vp), ('dpred', c_vp)] + _MSE_DIMS + \
+               [('target64', c_vp)]
 
 
 class OptParams(C.Structure):
@@ -843,20 +845,28 @@ class CudaKernels:
         return dt
 
     def mse_fwd(self, pred, target, mask, dims):
-        """dims = (B, t, dt, h, w, dc) -> fp32 [4]; element 0 = sum_cells mask * mean_dc (pred-target)^2"""
+        """dims = (B, t, dt, h, w, dc) -> fp32 [4]; element 0 = sum_cells mask * mean_dc (pred-target)^2.
+        fp64 targets (the reference's numpy arrays): differences and sums in fp64 -> fp64 [4]."""
         lib = load_library()
-        for tns, n in ((pred, 'pred'), (target, 'target'), (mask, 'mask')):
+        f64 = target.dtype == torch.float64
+        for tns, n in ((pred, 'pred'), (mask, 'mask')):
             _req(tns, torch.float32, 'mse.' + n)
+        _req(target, torch.float64 if f64 else torch.float32, 'mse.target')
+        for tns, n in ((pred, 'pred'), (target, 'target'), (mask, 'mask')):
             if not tns.is_contiguous():
                 raise RuntimeError(f'mse_fwd: {n} must be contiguous')
         B, t, dt, h, w, dc = dims
         cells = B * t * dt * h * w
         if pred.numel() != B * (1 + t * h * w) * dt * dc or target.numel() != cells * dc or mask.numel() != cells:
             raise RuntimeError('mse_fwd: shape mismatch')
-        num = torch.empty(4, dtype=torch.float32, device=pred.device)
-        partials = torch.empty(lib.vt_mse_blocks(cells) * 4, dtype=torch.float32, device=pred.device)
+        num = torch.zeros(4, dtype=target.dtype, device=pred.device) if f64 else torch.empty(4, dtype=torch.float32, device=pred.device)
+        partials = torch.empty(lib.vt_mse_blocks(cells) * 4, dtype=target.dtype, device=pred.device)
         p = MseFwdParams()
-        p.pred, p.target, p.mask, p.num, p.partials = pred.data_ptr(), target.data_ptr(), mask.data_ptr(), num.data_ptr(), partials.data_ptr()
+        p.pred, p.mask, p.partials = pred.data_ptr(), mask.data_ptr(), partials.data_ptr()
+        if f64:
+            p.target64, p.num64 = target.data_ptr(), num.data_ptr()
+        else:
+            p.target, p.num = target.data_ptr(), num.data_ptr()
         p.B, p.t, p.dt, p.h, p.w, p.dc = dims
         _check(lib.vt_mse_fwd(C.byref(p), _stream()), 'vt_mse_fwd')
         return num
@@ -866,7 +876,11 @@ class CudaKernels:
         B, t, dt, h, w, dc = dims
         dpred = torch.empty((B * (1 + t * h * w), dt * dc), dtype=torch.bfloat16, device=pred.device)
         p = MseBwdParams()
-        p.pred, p.target, p.mask = pred.data_ptr(), target.data_ptr(), mask.data_ptr()
+        p.pred, p.mask = pred.data_ptr(), mask.data_ptr()
+        if target.dtype == torch.float64:
+            p.target64 = target.data_ptr()
+        else:
+            p.target = _req(target, torch.float32, 'mse.target').data_ptr()
         p.coef, p.dpred = _req(coef, torch.float32, 'mse.coef').data_ptr(), dpred.data_ptr()
         p.B, p.t, p.dt, p.h, p.w, p.dc = dims
         _check(lib.vt_mse_bwd(C.byref(p), _stream()), 'vt_mse_bwd')

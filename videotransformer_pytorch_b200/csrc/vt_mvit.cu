@@ -875,6 +875,50 @@ struct MseDims {
   int B, t, dt, h, w, dc;
 };
 
+// fp64 variant: targets, differences and sums in double (reference semantics with fp64 numpy targets)
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+mse_fwd64_kernel(const float* __restrict__ pred, const double* __restrict__ target, const float* __restrict__ mask,
+                 double* __restrict__ partials, MseDims d) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int F = d.t * d.dt, hw = d.h * d.w;
+  const long long cells = (long long)d.B * F * hw;
+  const int L1 = 1 + d.t * hw, PD = d.dt * d.dc;
+  double acc = 0.0;
+  for (long long cell = (long long)blockIdx.x * ROW_WARPS + warp; cell < cells; cell += (long long)gridDim.x * ROW_WARPS) {
+    const float m = mask[cell];
+    if (m == 0.f) continue;
+    const int p = (int)(cell % hw);
+    const int f = (int)((cell / hw) % F);
+    const int b = (int)(cell / ((long long)hw * F));
+    const float* pr = pred + ((long long)b * L1 + 1 + (long long)(f / d.dt) * hw + p) * PD + (f % d.dt) * d.dc;
+    const double* tg = target + cell * d.dc;
+    double s = 0.0;
+    for (int c = lane; c < d.dc; c += 32) {
+      const double e = (double)pr[c] - tg[c];
+      s = fma(e, e, s);
+    }
+    acc += (double)m * s / (double)d.dc;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ double sh[ROW_WARPS];
+  if (lane == 0) sh[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0;
+    for (int i = 0; i < ROW_WARPS; ++i) a += sh[i];
+    partials[blockIdx.x] = a;
+  }
+}
+__global__ void mse_sum64_kernel(const double* __restrict__ partials, int n, double* __restrict__ out) {
+  // single warp, fixed order: deterministic
+  double a = 0.0;
+  for (int i = threadIdx.x; i < n; i += 32) a += partials[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if (threadIdx.x == 0) out[0] = a;
+}
+
 __global__ void __launch_bounds__(ROW_WARPS * 32)
 mse_fwd_kernel(const float* __restrict__ pred, const float* __restrict__ target, const float* __restrict__ mask,
                float* __restrict__ partials, MseDims d) {
@@ -911,8 +955,8 @@ mse_fwd_kernel(const float* __restrict__ pred, const float* __restrict__ target,
 }
 
 __global__ void mse_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ target,
-                               const float* __restrict__ mask, const float* __restrict__ coef,
-                               __nv_bfloat16* __restrict__ dpred, MseDims d) {
+                               const double* __restrict__ target64, const float* __restrict__ mask,
+                               const float* __restrict__ coef, __nv_bfloat16* __restrict__ dpred, MseDims d) {
   const int hw = d.h * d.w, F = d.t * d.dt;
   const int L1 = 1 + d.t * hw, PD = d.dt * d.dc;
   const long long n = (long long)d.B * L1 * PD;
@@ -928,7 +972,10 @@ __global__ void mse_bwd_kernel(const float* __restrict__ pred, const float* __re
       const int f = tt * d.dt + j / d.dc, c = j % d.dc;
       const long long cell = ((long long)b * F + f) * hw + p;
       const float m = mask[cell];
-      if (m != 0.f) g = cf * m * (pred[e] - target[cell * d.dc + c]);
+      if (m != 0.f) {
+        const float tv = target64 ? (float)((double)pred[e] - target64[cell * d.dc + c]) : pred[e] - target[cell * d.dc + c];
+        g = cf * m * tv;
+      }
     }
     dpred[e] = __float2bfloat16_rn(g);
   }
@@ -1190,13 +1237,22 @@ extern "C" int vt_mvit_tokens_bwd(const vt_mvit_tokens_bwd_params* p, void* stre
 extern "C" int vt_mse_blocks(int32_t cells) { return row_blocks(cells, 2); }
 
 extern "C" int vt_mse_fwd(const vt_mse_fwd_params* p, void* stream) {
-  VT_REQUIRE(p && p->pred && p->target && p->mask && p->num && p->partials, "vt_mse_fwd: null pointer");
+  VT_REQUIRE(p && p->pred && (p->target || p->target64) && p->mask && (p->num || p->num64) && p->partials, "vt_mse_fwd: null pointer");
   VT_REQUIRE(p->B > 0 && p->t > 0 && p->dt > 0 && p->h > 0 && p->w > 0 && p->dc > 0, "vt_mse_fwd: bad dims");
   VT_REQUIRE(((uintptr_t)p->partials & 15) == 0 && ((uintptr_t)p->num & 15) == 0, "vt_mse_fwd: partials/num must be 16-byte aligned");
   const MseDims d{p->B, p->t, p->dt, p->h, p->w, p->dc};
   const long long cells = (long long)p->B * p->t * p->dt * p->h * p->w;
   VT_REQUIRE(cells < 0x7fffffffll, "vt_mse_fwd: too many cells");
   const int blocks = vt_mse_blocks((int)cells);
+  if (p->target64) {
+    VT_REQUIRE(p->num64 != nullptr, "vt_mse_fwd: fp64 targets need num64");
+    double* part = reinterpret_cast<double*>(p->partials);
+    mse_fwd64_kernel<<<blocks, ROW_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(p->pred, p->target64, p->mask, part, d);
+    int rc64 = check_launch("mse_fwd64_kernel");
+    if (rc64) return rc64;
+    mse_sum64_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(part, blocks, p->num64);
+    return check_launch("mse_sum64_kernel");
+  }
   mse_fwd_kernel<<<blocks, ROW_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(p->pred, p->target, p->mask, p->partials, d);
   int rc = check_launch("mse_fwd_kernel");
   if (rc) return rc;
@@ -1205,11 +1261,11 @@ extern "C" int vt_mse_fwd(const vt_mse_fwd_params* p, void* stream) {
 }
 
 extern "C" int vt_mse_bwd(const vt_mse_bwd_params* p, void* stream) {
-  VT_REQUIRE(p && p->pred && p->target && p->mask && p->coef && p->dpred, "vt_mse_bwd: null pointer");
+  VT_REQUIRE(p && p->pred && (p->target || p->target64) && p->mask && p->coef && p->dpred, "vt_mse_bwd: null pointer");
   VT_REQUIRE(p->B > 0 && p->t > 0 && p->dt > 0 && p->h > 0 && p->w > 0 && p->dc > 0, "vt_mse_bwd: bad dims");
   const MseDims d{p->B, p->t, p->dt, p->h, p->w, p->dc};
   const long long n = (long long)p->B * (1 + (long long)p->t * p->h * p->w) * p->dt * p->dc;
-  mse_bwd_kernel<<<flat_blocks(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p->pred, p->target, p->mask, p->coef,
-                                                                                     static_cast<__nv_bfloat16*>(p->dpred), d);
+  mse_bwd_kernel<<<flat_blocks(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p->pred, p->target, p->target64, p->mask,
+                                                                                     p->coef, static_cast<__nv_bfloat16*>(p->dpred), d);
   return check_launch("mse_bwd_kernel");
 }

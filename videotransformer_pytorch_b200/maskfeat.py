@@ -290,8 +290,10 @@ class MaskFeat(nn.Module):
         fdim = self.decoder_pred.out_features
         dc = fdim // dt
         B = x.shape[0]
-        # the reference's targets are fp64 numpy arrays (dataset.py:190); the kernels compute the loss in fp32
-        target = target_x.to(device=x.device, dtype=torch.float32).contiguous()
+        # the reference's targets are fp64 numpy arrays (dataset.py:190), which makes its loss fp64 (:899-901): fp64 targets
+        # are kept and the loss kernel then works in fp64; anything else is taken in fp32
+        tdt = torch.float64 if target_x.dtype == torch.float64 else torch.float32
+        target = target_x.to(device=x.device, dtype=tdt).contiguous()
         m = center_mask.to(device=x.device, dtype=torch.float32).contiguous()
         pred, loss = mvit_ops.MaskedMSEFn.apply(feats, _f32(self.decoder_pred.weight), _f32(self.decoder_pred.bias),
                                                 self._shadow.get('dec', self.decoder_pred.weight), target, m,

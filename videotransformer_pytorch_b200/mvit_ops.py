@@ -234,9 +234,9 @@ class MaskedMSEFn(torch.autograd.Function):
         F_out = dec_wh.shape[0]
         f = k.gather_cast(feats.contiguous().view(M, D))
         pred = k.gemm(f, dec_wh, M, F_out, D, bias=dec_b, epi='f32')
-        num = k.mse_fwd(pred, target, mask, dims)
+        num = k.mse_fwd(pred, target, mask, dims)            # fp64 when the targets are (reference: numpy fp64, dataset.py:190)
         denom = mask.sum() + 1e-5
-        loss = num[0] / denom
+        loss = num[0] / denom.to(num.dtype)
         ctx.save_for_backward(f, pred, target, mask, denom, dec_wh)
         ctx.dims = dims
         pred3 = pred.view(B, N1, F_out)
@@ -250,7 +250,7 @@ class MaskedMSEFn(torch.autograd.Function):
         dims = ctx.dims
         M, D = f.shape
         F_out = dec_wh.shape[0]
-        coef = (dloss.float() * (2.0 / dims[5]) / denom).reshape(1).contiguous()
+        coef = (dloss.float() * (2.0 / dims[5]) / denom.float()).reshape(1).contiguous()
         dp = k.mse_bwd(pred, target, mask, coef, dims)
         d_w = _wgrad(dp, f, F_out, D, M)
         d_b = k.colsum(dp)
