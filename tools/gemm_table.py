@@ -90,8 +90,7 @@ case('qkv spatial', 12608, 2304, 768, variants=tail)
 case('proj spatial (f32 resid, map)', 12608, 768, 768, epi='f32', resid='spatial', rowscale=True, variants=resv + [('auto-notail', dict(force_tail=1))])
 case('fc1 (bf16)', 12552, 3072, 768, variants=tail)
 case('fc2 (f32 resid)', 12552, 768, 3072, epi='f32', resid='plain', rowscale=True, variants=resv + [('auto-notail', dict(force_tail=1))])
-if not QUICK:
-    case('fc1 gelu epilogue', 12552, 3072, 768, epi='gelu')
+case('fc1 gelu epilogue (z,h by TMA)', 12552, 3072, 768, epi='gelu', variants=tail)
 print('== dgrad (B MN-major)')
 case('d proj / d temporal_fc', 12544, 768, 768, b_mn=True, rowscale=True)
 case('d qkv temporal', 12544, 768, 2304, b_mn=True)

@@ -59,7 +59,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tma_prefetch_desc(&tmB);
     if (p.tail_bn) tma_prefetch_desc(&tmBt);
     if (p.tma_store) tma_prefetch_desc(&tmC);
-    if (RES) tma_prefetch_desc(&tmX);
+    if (RES || p.tma_store == 4) tma_prefetch_desc(&tmX);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < Cfg::STAGES; ++i) {
@@ -183,7 +183,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         epilogue_tile_tma_res<BN>(p, &tmC, &tmX, slot, aux_bar + 2 * (warp - 4), aux_use, t_base, m_blk, u.n0, u.bn, q, half, lane,
                                   &tfull_bar[acc], (uint32_t)acc_phase);
       } else {
-        if (p.tma_store) epilogue_tile_tma<BN>(p, &tmC, slot, t_base, m_blk, u.n0, u.bn, u.split, q, half, lane, &tfull_bar[acc], (uint32_t)acc_phase);
+        if (p.tma_store) epilogue_tile_tma<BN>(p, &tmC, &tmX, slot, t_base, m_blk, u.n0, u.bn, u.split, q, half, lane, &tfull_bar[acc], (uint32_t)acc_phase);
         else epilogue_tile<BN>(p, stg, t_base, m_blk, u.n0, u.bn, u.split, q, half, lane, &tfull_bar[acc], (uint32_t)acc_phase);
       }
       if (dbg && warp == 4 && lane == 0) { if (unit == unit0) dbg[5] = clock64(); dbg[6] = clock64(); }   // first / last tile drained
@@ -362,9 +362,18 @@ bool splitk_in_place(const vt_gemm_params* q) {
 
 // Decide whether the plain TMA-store epilogue applies and build its map (called after the split decision).
 // in_place: d.out is the final output and the d.splits partial tiles of every output tile are reduce-added into it.
-int setup_out_map(const vt_gemm_params* q, GemmDev& d, CUtensorMap* tmC, bool in_place) {
+int setup_out_map(const vt_gemm_params* q, GemmDev& d, CUtensorMap* tmC, bool in_place, CUtensorMap* tmC2) {
   d.tma_store = 0;
   memset(tmC, 0, sizeof(*tmC));
+  if (q->epilogue == VT_EPI_GELU && !q->out_row && !getenv("VT_NO_TMA_STORE") && !getenv("VT_NO_TMA_GELU") && tmC2) {
+    // z and h = gelu(z) both leave through TMA stores (two bf16 boxes per chunk)
+    int rc = make_tmap_out_3d(tmC, d.out, 0, q->M, q->N, d.ldo, 1, 0);
+    if (rc) return rc;
+    rc = make_tmap_out_3d(tmC2, d.out2, 0, q->M, q->N, d.ldo2, 1, 0);
+    if (rc) return rc;
+    d.tma_store = 4;
+    return 0;
+  }
   const bool plain = (q->epilogue == VT_EPI_BF16 || q->epilogue == VT_EPI_F32) && !q->out_row && !q->aux;
   if (!plain || getenv("VT_NO_TMA_STORE")) return 0;
   const int fp32 = q->epilogue == VT_EPI_F32;
@@ -497,7 +506,7 @@ static int launch_gemm(const vt_gemm_params* q, GemmDev& d, cudaStream_t st) {
     d.split_stride = tile_out;
   }
   if (RES) rc = setup_res_maps(q, d, &tmC, &tmX);
-  else rc = setup_out_map(q, d, &tmC, in_place);
+  else rc = setup_out_map(q, d, &tmC, in_place, &tmX);
   if (rc) return rc;
   // unit schedule (narrow tail units only for single CTAs here; CTA pairs have their own in vt_gemm2.cu)
   const int max_clusters = sms / csize;

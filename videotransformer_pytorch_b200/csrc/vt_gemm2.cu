@@ -22,7 +22,7 @@ namespace vt {
 int make_tmap_bf16_2d(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows);
 int launch_reduce_rows(const float* in, float* out, long long stride, int S, long long n, int accumulate, float scale,
                        cudaStream_t st);
-int setup_out_map(const vt_gemm_params* q, GemmDev& d, CUtensorMap* tmC, bool in_place);
+int setup_out_map(const vt_gemm_params* q, GemmDev& d, CUtensorMap* tmC, bool in_place, CUtensorMap* tmC2);
 int setup_res_maps(const vt_gemm_params* q, GemmDev& d, CUtensorMap* tmC, CUtensorMap* tmX);
 struct Schedule { int full_units, tail_units, tail_bn, tail_mp; double makespan; };
 Schedule plan_units(int M, int N, int bn, int rows_per_macro, int splits, int slots, int tail_bn_cand, int tail_mode);
@@ -112,7 +112,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     tma_prefetch_desc(&tmB);
     if (p.tail_bn) tma_prefetch_desc(&tmBt);
     if (p.tma_store) tma_prefetch_desc(&tmC);
-    if (RES) tma_prefetch_desc(&tmX);
+    if (RES || p.tma_store == 4) tma_prefetch_desc(&tmX);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < Cfg::STAGES; ++i) {
@@ -211,7 +211,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         epilogue_tile_tma_res<BN>(p, &tmC, &tmX, slot, aux_bar + 2 * (warp - 4), aux_use, t_base, m_blk, u.n0, u.bn, q, half, lane,
                                   &tfull_bar[acc], (uint32_t)acc_phase);
       } else {
-        if (p.tma_store) epilogue_tile_tma<BN>(p, &tmC, slot, t_base, m_blk, u.n0, u.bn, u.split, q, half, lane, &tfull_bar[acc], (uint32_t)acc_phase);
+        if (p.tma_store) epilogue_tile_tma<BN>(p, &tmC, &tmX, slot, t_base, m_blk, u.n0, u.bn, u.split, q, half, lane, &tfull_bar[acc], (uint32_t)acc_phase);
         else epilogue_tile<BN>(p, stg, t_base, m_blk, u.n0, u.bn, u.split, q, half, lane, &tfull_bar[acc], (uint32_t)acc_phase);
       }
       tc_fence_before();
@@ -282,7 +282,7 @@ static int launch_gemm2_t(const vt_gemm_params* q, GemmDev& d, cudaStream_t st) 
   }
   CUtensorMap tmC;
   if (RES) rc = setup_res_maps(q, d, &tmC, &tmX);
-  else rc = setup_out_map(q, d, &tmC, in_place);
+  else rc = setup_out_map(q, d, &tmC, in_place, &tmX);
   if (rc) return rc;
   const Schedule sch = plan_units(q->M, q->N, BN, 2 * BM, splits, pairs, 128, getenv("VT_NO_TAIL_UNITS") ? 1 : q->force_tail);
   d.full_units = sch.full_units; d.tail_units = sch.tail_units; d.tail_bn = sch.tail_bn; d.tail_mp = sch.tail_mp;

@@ -194,12 +194,13 @@ __device__ __forceinline__ void bulk_wait_read() {
 }
 
 template <int BN>
-__device__ __forceinline__ void epilogue_tile_tma(const GemmDev& p, const CUtensorMap* tmC, uint8_t* slot, uint32_t t_base,
-                                                  int m_blk, int n_base, int bn, int split, int q, int half, int lane, uint64_t* tfull,
-                                                  uint32_t ph) {
+__device__ __forceinline__ void epilogue_tile_tma(const GemmDev& p, const CUtensorMap* tmC, const CUtensorMap* tmC2, uint8_t* slot,
+                                                  uint32_t t_base, int m_blk, int n_base, int bn, int split, int q, int half, int lane,
+                                                  uint64_t* tfull, uint32_t ph) {
   const int row = m_blk * BM + q * 32 + lane;
   const float s = (row < p.M && p.row_scale) ? p.row_scale[row] : 1.0f;
   const bool f32 = p.epi == VT_EPI_F32;
+  const bool gelu = p.epi == VT_EPI_GELU;      // two bf16 boxes per chunk: z = acc + bias (tmC) and h = gelu(z) (tmC2)
   mbar_wait(tfull, ph);
   tc_fence_after();
   int it = 0;
@@ -217,12 +218,31 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmDev& p, const CUtens
     tmem_ld32(t_base + c * 32, r);
     tmem_ld_wait();
     if (n0 >= p.N) break;   // warp-uniform
-    uint8_t* buf = slot + ((f32 || (it & 1) == 0) ? 0 : 2048);
+    uint8_t* buf = slot + ((f32 || gelu || (it & 1) == 0) ? 0 : 2048);
     if (lane == 0) {        // the box about to be overwritten must have been read by its store
-      if (f32) bulk_wait_read<0>(); else bulk_wait_read<1>();
+      if (f32 || gelu) bulk_wait_read<0>(); else bulk_wait_read<1>();
     }
     __syncwarp();
-    if (f32) {
+    if (gelu) {
+      // h is computed from the bf16-rounded z, exactly what the stand-alone GELU kernel reads back (same results either way)
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4 w, hh;
+        uint32_t* wz = reinterpret_cast<uint32_t*>(&w);
+        uint32_t* wh = reinterpret_cast<uint32_t*>(&hh);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 bb = b[2 * g + (j >> 1)];
+          const float b0 = (j & 1) ? bb.z : bb.x, b1 = (j & 1) ? bb.w : bb.y;
+          wz[j] = pack_bf16x2(__uint_as_float(r[8 * g + 2 * j]) + b0, __uint_as_float(r[8 * g + 2 * j + 1]) + b1);
+          const float2 zr = unpack_bf16x2(wz[j]);
+          wh[j] = pack_bf16x2(gelu_fast(zr.x), gelu_fast(zr.y));
+        }
+        const int off = lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4);                          // SWIZZLE_64B
+        *reinterpret_cast<uint4*>(buf + off) = w;
+        *reinterpret_cast<uint4*>(buf + 2048 + off) = hh;
+      }
+    } else if (f32) {
 #pragma unroll
       for (int g = 0; g < 8; ++g) {
         float4 v;
@@ -248,6 +268,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmDev& p, const CUtens
     if (lane == 0) {
       if (p.tma_store == 2) tma_reduce_add_3d(tmC, buf, n0, m_blk * BM + q * 32, 0);
       else tma_store_3d(tmC, buf, n0, m_blk * BM + q * 32, split);
+      if (gelu) tma_store_3d(tmC2, buf + 2048, n0, m_blk * BM + q * 32, 0);
       bulk_commit();
     }
   }

@@ -34,8 +34,11 @@ def K():
 _MASK_ARENA = None
 
 # FFN activation: fused into the FC1 / FC2-dgrad GEMM epilogues (VT_EPI_GELU / VT_EPI_DGELU) or as stand-alone
-# bandwidth kernels after a plain bf16 epilogue.  Measured on B200 (profiles/): the erf math in the 8 epilogue
-# warps costs more than the extra 150 MB of HBM traffic, so the split form is the default.
+# bandwidth kernels after a plain bf16 epilogue.  Round 1 measured the split form faster (the erf math sat in the slow
+# transposing epilogue); the forward GELU epilogue now stores z and h as two TMA boxes — VT_FUSED_GELU=1 selects it
+# for FC1 (the dGELU epilogue of the FC2 data gradient stays split).
+import os as _os
+FUSED_GELU_FWD = _os.environ.get('VT_FUSED_GELU', '0') == '1'
 FUSED_GELU_EPILOGUE = False
 
 
@@ -352,7 +355,7 @@ class FFNFn(torch.autograd.Function):
         Dh = w1h.shape[0]
         x2 = x.reshape(M, D)
         xn, mean, rstd = k.ln_fwd(x2, ln_w, ln_b, eps)
-        if FUSED_GELU_EPILOGUE:
+        if FUSED_GELU_EPILOGUE or FUSED_GELU_FWD:
             z, h = k.gemm(xn, w1h, M, Dh, D, bias=b1, epi='gelu')
         else:
             z = k.gemm(xn, w1h, M, Dh, D, bias=b1, epi='bf16')
