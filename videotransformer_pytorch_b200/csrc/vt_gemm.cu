@@ -279,6 +279,25 @@ int make_tmap_rows_4d(CUtensorMap* map, const void* base, long long cols, long l
   return 0;
 }
 
+// 3-D fp32 map (col, p, b), box {32, 32, 1}: the row maps whose period is a single run of rows (temporal, or no map at all)
+int make_tmap_rows_3d(CUtensorMap* map, const void* base, long long cols, long long pcount, long long bcount, long long stride_p,
+                      long long stride_b) {
+  EncodeTiledFn fn = get_encode_fn();
+  VT_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
+  VT_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base pointer must be 16-byte aligned");
+  VT_REQUIRE(stride_p % 4 == 0 && stride_b % 4 == 0 && stride_p > 0 && stride_b > 0, "row-map strides must be positive multiples of 4");
+  cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)pcount, (cuuint64_t)bcount};
+  cuuint64_t gstr[2] = {(cuuint64_t)(stride_p * 4), (cuuint64_t)(stride_b * 4)};
+  cuuint32_t box[3] = {32u, 32u, 1u};
+  cuuint32_t estr[3] = {1u, 1u, 1u};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  VT_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(rows 3d) failed (%d) dims %lld %lld %lld strides %lld %lld", (int)r, cols,
+             pcount, bcount, stride_p, stride_b);
+  return 0;
+}
+
 // Residual epilogue on TMA (GemmDev::tma_store = 3): fp32 output with an fp32 addend whose rows — and the output's — follow
 // either no map or the affine map described in vt_gemm_params (map_period ...).  Fills tmC / tmX and the map fields of d.
 bool res_tma_applicable(const vt_gemm_params* q) {
@@ -295,23 +314,32 @@ int setup_res_maps(const vt_gemm_params* q, GemmDev& d, CUtensorMap* tmC, CUtens
     const long long outers = q->M / q->map_period;
     const long long bcount = (outers + q->map_tcount - 1) / q->map_tcount;
     const long long pcount = q->map_period - q->map_skip;
-    // a dimension of extent 1 still needs a legal stride: reuse the next one
-    const long long st = q->map_tcount > 1 ? q->map_stride_t : q->map_stride_p;
-    int rc = make_tmap_rows_4d(tmC, static_cast<float*>(q->out) + q->map_base, q->N, q->map_tcount, pcount, bcount, st,
-                               q->map_stride_p, q->map_stride_b);
-    if (rc) return rc;
-    rc = make_tmap_rows_4d(tmX, static_cast<const float*>(q->aux) + q->map_base, q->N, q->map_tcount, pcount, bcount, st,
-                           q->map_stride_p, q->map_stride_b);
+    int rc;
+    if (q->map_tcount == 1) {
+      d.map_rank = 3;
+      rc = make_tmap_rows_3d(tmC, static_cast<float*>(q->out) + q->map_base, q->N, pcount, bcount, q->map_stride_p, q->map_stride_b);
+      if (rc) return rc;
+      rc = make_tmap_rows_3d(tmX, static_cast<const float*>(q->aux) + q->map_base, q->N, pcount, bcount, q->map_stride_p,
+                             q->map_stride_b);
+    } else {
+      d.map_rank = 4;
+      rc = make_tmap_rows_4d(tmC, static_cast<float*>(q->out) + q->map_base, q->N, q->map_tcount, pcount, bcount, q->map_stride_t,
+                             q->map_stride_p, q->map_stride_b);
+      if (rc) return rc;
+      rc = make_tmap_rows_4d(tmX, static_cast<const float*>(q->aux) + q->map_base, q->N, q->map_tcount, pcount, bcount,
+                             q->map_stride_t, q->map_stride_p, q->map_stride_b);
+    }
     if (rc) return rc;
     d.special_out = q->map_special_base >= 0 ? static_cast<float*>(q->out) + q->map_special_base : nullptr;
     d.special_ld = q->map_special_stride;
     return 0;
   }
-  d.map_period = q->M; d.map_skip = 0; d.map_tcount = 1;
+  d.map_period = q->M; d.map_skip = 0; d.map_tcount = 1; d.map_rank = 3;
   d.special_out = nullptr; d.special_ld = 0;
-  int rc = make_tmap_rows_4d(tmC, q->out, q->N, 1, q->M, 1, q->ldo, q->ldo, q->ldo);
+  // one "sample" of M rows: (col, row, 0); the third dimension only exists to clip rows >= M of a two-segment group
+  int rc = make_tmap_rows_3d(tmC, q->out, q->N, q->M, 1, q->ldo, (long long)q->M * q->ldo);
   if (rc) return rc;
-  return make_tmap_rows_4d(tmX, q->aux, q->N, 1, q->M, 1, q->ldaux, q->ldaux, q->ldaux);
+  return make_tmap_rows_3d(tmX, q->aux, q->N, q->M, 1, q->ldaux, (long long)q->M * q->ldaux);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -582,7 +610,7 @@ extern "C" int vt_gemm(const vt_gemm_params* q, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 
   d.tma_store = 0;
-  d.map_period = q->M > 0 ? q->M : 1; d.map_skip = 0; d.map_tcount = 1;
+  d.map_period = q->M > 0 ? q->M : 1; d.map_skip = 0; d.map_tcount = 1; d.map_rank = 3;
   d.special_out = nullptr; d.special_ld = 0;
   d.tail_bn = 0; d.full_units = 0; d.tail_units = 0; d.tail_mp = 0;
   if (q->map_period > 0) {

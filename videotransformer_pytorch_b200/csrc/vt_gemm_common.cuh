@@ -35,6 +35,7 @@ struct GemmDev {
   // inner < map_skip: "special" row (replicated cls token), else tensor coordinates
   // (col, t = outer % map_tcount, p = inner - map_skip, b = outer / map_tcount) of the 4-D out / aux maps
   int map_period, map_skip, map_tcount;
+  int map_rank;            // 3: tensor maps are (col, p, b) with box {32, 32, 1} (map_tcount == 1); 4: (col, t, p, b), box {32, 1, 32, 1}
   float* special_out;      // special rows go to special_out + outer * special_ld (plain per-thread stores), or are dropped
   long long special_ld;
   // narrow tail units: the last (partial) macro row of tiles is cut into units of tail_bn columns so that its few valid
@@ -328,8 +329,14 @@ __device__ __forceinline__ void epilogue_tile_tma_res(const GemmDev& p, const CU
   const bool special = row < p.M && my_inner < p.map_skip;
   const int nchunks = (bn / 32 - half + 1) / 2;          // chunks c = half, half + 2, ... of this warpgroup
   auto chunk_cols_ok = [&](int it) { return n_base + (half + 2 * it) * 32 < p.N; };
+  const bool rank3 = p.map_rank == 3;
   auto request = [&](int it, int buf, int sgm) {        // lane 0: residual box of chunk `it`, segment sgm -> buffer buf
-    tma_load_4d(slot + buf * 4096, tmX, &aux_bar[buf], n_base + (half + 2 * it) * 32, seg_t[sgm], seg_p[sgm], seg_b[sgm]);
+    if (rank3) tma_load_3d(slot + buf * 4096, tmX, &aux_bar[buf], n_base + (half + 2 * it) * 32, seg_p[sgm], seg_b[sgm]);
+    else tma_load_4d(slot + buf * 4096, tmX, &aux_bar[buf], n_base + (half + 2 * it) * 32, seg_t[sgm], seg_p[sgm], seg_b[sgm]);
+  };
+  auto store = [&](const void* src, int n0, int sgm) {
+    if (rank3) tma_store_3d(tmC, src, n0, seg_p[sgm], seg_b[sgm]);
+    else tma_store_4d(tmC, src, n0, seg_t[sgm], seg_p[sgm], seg_b[sgm]);
   };
   // Normal groups: chunk `it` lives in buffer it & 1 and chunk it + 1 is prefetched into the other buffer.
   // Groups with two segments use both buffers for one chunk (segment k -> buffer k), without prefetch.
@@ -394,8 +401,8 @@ __device__ __forceinline__ void epilogue_tile_tma_res(const GemmDev& p, const CU
     fence_proxy_async();
     __syncwarp();
     if (lane == 0) {
-      tma_store_4d(tmC, out_buf, n0, seg_t[0], seg_p[0], seg_b[0]);
-      if (two) tma_store_4d(tmC, out_buf, n0, seg_t[1], seg_p[1], seg_b[1]);
+      store(out_buf, n0, 0);
+      if (two) store(out_buf, n0, 1);
       bulk_commit();
       // refill: the buffer just stored from must have been read out by its store first
       if (!two) {
