@@ -3,6 +3,9 @@
 set -u
 mkdir -p gpurun_out
 cd "${GRAFT_REPO_ROOT:-.}"
+for c in "plain 1" "plain 3" "plain 1 1000" "temporal 1" "temporal 3" "spatial 1" "spatial 3"; do
+  timeout 120 python tools/res_probe.py $c > gpurun_out/probe.log 2>&1; echo "probe [$c] rc=$? : $(grep -E 'rel err|Error' gpurun_out/probe.log | tail -n 1 | cut -c1-160)"
+done
 T1="tests/test_gpu_gemm.py::test_residual_epilogue_tma_plain_rows[4096-256-64-128-single-cta]"
 T2="tests/test_gpu_gemm.py::test_residual_epilogue_tma_plain_rows[1000-768-256-128-single-cta]"
 timeout 300 python -m pytest "$T1" -q -m gpu -x > gpurun_out/res_t1.log 2>&1; echo "RES M4096 (whole tiles only) single rc=$?"; tail -n 2 gpurun_out/res_t1.log | cut -c1-200
