@@ -114,6 +114,12 @@ if a.profile:
     print(f'kernel time total {tot / 1e3:.2f} ms')
     for r in rows:
         print(f'{r.device_time_total / 1e3:9.3f} ms  {r.count:5d}x  {r.key[:110]}')
+    # the 30 longest individual launches (which pooling / attention launches carry the time)
+    singles = sorted((e for e in prof.events() if e.device_time_total > 0 and e.device_type.name == 'CUDA'),
+                     key=lambda e: -e.device_time_total)[:30]
+    print('longest single launches:')
+    for e in singles:
+        print(f'  {e.device_time_total:8.1f} us  {e.name[:100]}')
     # per-shape GEMM table: every K.gemm call launches exactly one *gemm*_tcgen05_kernel, in call order
     evs = sorted((e for e in prof.events() if 'tcgen05_kernel' in e.name and 'gemm' in e.name), key=lambda e: e.time_range.start)
     if len(evs) == len(shapes):
