@@ -312,24 +312,31 @@ __device__ __forceinline__ void epilogue_tile_tma_res(const GemmDev& p, const CU
   const int m0 = m_blk * BM + q * 32;
   const int row = m0 + lane;
   const float s = (row < p.M && p.row_scale) ? p.row_scale[row] : 1.0f;
-  // segments of this 32-row group
+  // segments of this 32-row group: rows [inner0, period) of period `outer0` and, when the group crosses the boundary, rows
+  // [0, ...) of period outer0 + 1.  A segment is "live" when its box overlaps the tensor at all; boxes that would lie fully
+  // outside (rows >= M, or a second segment consisting of the special row only) are never issued.
   const int outer0 = m0 / p.map_period, inner0 = m0 - outer0 * p.map_period;
-  const bool two = inner0 + 32 > p.map_period;
+  const int n_outer = p.M / p.map_period, pcount = p.map_period - p.map_skip;
   int seg_t[2], seg_b[2], seg_p[2];
+  bool live[2];
 #pragma unroll
   for (int sgm = 0; sgm < 2; ++sgm) {
     const int outer = outer0 + sgm;
     seg_b[sgm] = outer / p.map_tcount;
     seg_t[sgm] = outer - seg_b[sgm] * p.map_tcount;
     seg_p[sgm] = inner0 - sgm * p.map_period - p.map_skip;
+    live[sgm] = outer < n_outer && seg_p[sgm] + 31 >= 0 && seg_p[sgm] < pcount && (sgm == 0 || inner0 + 32 > p.map_period);
   }
+  const bool two = live[0] && live[1];
+  const int only = live[0] ? 0 : 1;                    // the segment served in single-segment mode
+  const bool any = live[0] || live[1];
   // this lane's row: which segment, special?
   const int my_seg = (inner0 + lane >= p.map_period) ? 1 : 0;
   const int my_inner = inner0 + lane - my_seg * p.map_period;
   const bool special = row < p.M && my_inner < p.map_skip;
   const int nchunks = (bn / 32 - half + 1) / 2;          // chunks c = half, half + 2, ... of this warpgroup
-  auto chunk_cols_ok = [&](int it) { return n_base + (half + 2 * it) * 32 < p.N; };
   const bool rank3 = p.map_rank == 3;
+  auto chunk_cols_ok = [&](int it) { return n_base + (half + 2 * it) * 32 < p.N; };
   auto request = [&](int it, int buf, int sgm) {        // lane 0: residual box of chunk `it`, segment sgm -> buffer buf
     if (rank3) tma_load_3d(slot + buf * 4096, tmX, &aux_bar[buf], n_base + (half + 2 * it) * 32, seg_p[sgm], seg_b[sgm]);
     else tma_load_4d(slot + buf * 4096, tmX, &aux_bar[buf], n_base + (half + 2 * it) * 32, seg_t[sgm], seg_p[sgm], seg_b[sgm]);
@@ -338,12 +345,12 @@ __device__ __forceinline__ void epilogue_tile_tma_res(const GemmDev& p, const CU
     if (rank3) tma_store_3d(tmC, src, n0, seg_p[sgm], seg_b[sgm]);
     else tma_store_4d(tmC, src, n0, seg_t[sgm], seg_p[sgm], seg_b[sgm]);
   };
-  // Normal groups: chunk `it` lives in buffer it & 1 and chunk it + 1 is prefetched into the other buffer.
-  // Groups with two segments use both buffers for one chunk (segment k -> buffer k), without prefetch.
-  if (lane == 0) {
+  // Single-segment groups: chunk `it` lives in buffer it & 1 and chunk it + 1 is prefetched into the other buffer.
+  // Groups with two live segments use both buffers for one chunk (segment k -> buffer k), without prefetch.
+  if (lane == 0 && any) {
     if (!two) {
-      if (nchunks > 0 && chunk_cols_ok(0)) { mbar_arrive_expect_tx(&aux_bar[0], 4096); request(0, 0, 0); }
-      if (nchunks > 1 && chunk_cols_ok(1)) { mbar_arrive_expect_tx(&aux_bar[1], 4096); request(1, 1, 0); }
+      if (nchunks > 0 && chunk_cols_ok(0)) { mbar_arrive_expect_tx(&aux_bar[0], 4096); request(0, 0, only); }
+      if (nchunks > 1 && chunk_cols_ok(1)) { mbar_arrive_expect_tx(&aux_bar[1], 4096); request(1, 1, only); }
     } else if (nchunks > 0 && chunk_cols_ok(0)) {
       mbar_arrive_expect_tx(&aux_bar[0], 4096); request(0, 0, 0);
       mbar_arrive_expect_tx(&aux_bar[1], 4096); request(0, 1, 1);
@@ -351,6 +358,7 @@ __device__ __forceinline__ void epilogue_tile_tma_res(const GemmDev& p, const CU
   }
   mbar_wait(tfull, ph);
   tc_fence_after();
+  if (!any) return;        // nothing of this group exists (rows >= M): the caller still releases the accumulator
 #pragma unroll 1
   for (int it = 0; it < nchunks; ++it) {
     const int c = half + 2 * it;
@@ -377,11 +385,14 @@ __device__ __forceinline__ void epilogue_tile_tma_res(const GemmDev& p, const CU
       ++aux_use[0]; ++aux_use[1];
     }
     uint8_t* out_buf = slot + cur * 4096;                                  // result box (segment-0 buffer when two)
-    const uint8_t* my_aux = slot + (two ? my_seg : cur) * 4096;           // where this row's residual landed
+    // where this row's residual landed; rows of a segment that is not live (beyond M, or special) have none
+    const bool have_aux = two || my_seg == only;
+    const uint8_t* my_aux = slot + (two ? my_seg : cur) * 4096;
     float4 v[8];
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
-      const float4 a = *reinterpret_cast<const float4*>(my_aux + lane * 128 + ((g ^ (lane & 7)) << 4));    // SWIZZLE_128B
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (have_aux) a = *reinterpret_cast<const float4*>(my_aux + lane * 128 + ((g ^ (lane & 7)) << 4));    // SWIZZLE_128B
       v[g].x = fmaf(s, __uint_as_float(r[4 * g + 0]) + b[g].x, a.x);
       v[g].y = fmaf(s, __uint_as_float(r[4 * g + 1]) + b[g].y, a.y);
       v[g].z = fmaf(s, __uint_as_float(r[4 * g + 2]) + b[g].z, a.z);
@@ -401,15 +412,15 @@ __device__ __forceinline__ void epilogue_tile_tma_res(const GemmDev& p, const CU
     fence_proxy_async();
     __syncwarp();
     if (lane == 0) {
-      store(out_buf, n0, 0);
-      if (two) store(out_buf, n0, 1);
+      if (two) { store(out_buf, n0, 0); store(out_buf, n0, 1); }
+      else store(out_buf, n0, only);
       bulk_commit();
       // refill: the buffer just stored from must have been read out by its store first
       if (!two) {
         if (it + 2 < nchunks && chunk_cols_ok(it + 2)) {
           bulk_wait_read<0>();
           mbar_arrive_expect_tx(&aux_bar[cur], 4096);
-          request(it + 2, cur, 0);
+          request(it + 2, cur, only);
         }
       } else if (it + 1 < nchunks && chunk_cols_ok(it + 1)) {
         bulk_wait_read<0>();
