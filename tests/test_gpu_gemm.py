@@ -286,3 +286,29 @@ def test_narrow_tail_units(M, N, Kd, form, cluster, monkeypatch):
     tol = 1e-5 if form == 'fwd_f32_residual' else 4e-3
     assert rel(got, r) < tol
     assert torch.equal(got, off)
+
+
+@pytest.mark.parametrize('cluster', [1, 3], ids=['single-cta', 'cta-pair'])
+@pytest.mark.parametrize('M,N,Kd', [(12552, 3072, 768), (1000, 512, 128), (130, 96, 64)])
+def test_gelu_and_dgelu_epilogues_on_tma(M, N, Kd, cluster, monkeypatch):
+    """FC1 with z / h = gelu(z) leaving as two TMA boxes, and the FC2 data gradient with gelu'(z) multiplied in from a
+    TMA-loaded z box: both equal the generic epilogues bit for bit and match torch."""
+    a, b = mk((M, Kd), 60, 0.3).bfloat16(), mk((N, Kd), 61, 0.3).bfloat16()
+    bias = mk((N,), 62)
+    z, h = K().gemm(a, b, M, N, Kd, epi='gelu', bias=bias, force_cluster=cluster)
+    zr = ref_mm(a, b, False, False) + bias
+    assert rel(z, zr) < 4e-3 and rel(h, torch.nn.functional.gelu(zr)) < 4e-3
+    monkeypatch.setenv('VT_NO_TMA_GELU', '1')
+    z0, h0 = K().gemm(a, b, M, N, Kd, epi='gelu', bias=bias, force_cluster=cluster)
+    monkeypatch.delenv('VT_NO_TMA_GELU')
+    assert torch.equal(z, z0) and torch.equal(h, h0)
+    g = mk((M, Kd), 63, 0.3).bfloat16()
+    w = mk((Kd, N), 64, 0.3).bfloat16()                       # [n_out = Kd, k_in = N], read MN-major
+    d0 = K().gemm(g, w, M, N, Kd, b_mn=True, epi='dgelu', aux=z, force_cluster=cluster)
+    monkeypatch.setenv('VT_TMA_DGELU', '1')
+    d1 = K().gemm(g, w, M, N, Kd, b_mn=True, epi='dgelu', aux=z, force_cluster=cluster)
+    monkeypatch.delenv('VT_TMA_DGELU')
+    zz = z.float().requires_grad_(True)
+    torch.nn.functional.gelu(zz).sum().backward()
+    assert rel(d1, (g.float() @ w.float()) * zz.grad) < 4e-3
+    assert torch.equal(d0, d1)

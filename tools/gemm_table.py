@@ -67,7 +67,8 @@ def case(name, M, N, Kd, a_mn=False, b_mn=False, epi='bf16', split=False, resid=
         call_kw.update(extra)
         if env:
             os.environ[env] = '1'
-            call_kw.pop('row_map', None)
+            if env == 'VT_NO_TMA_RES':
+                call_kw.pop('row_map', None)
         try:
             t = bench(lambda: K.gemm(a, b, M, N, Kd, a_mn=a_mn, b_mn=b_mn, epi=epi, bias=bias, out=out, out2=out2,
                                      split_ok=split, **call_kw))
@@ -98,8 +99,7 @@ case('d proj spatial', 12608, 768, 768, b_mn=True, variants=tail)
 case('d qkv spatial', 12608, 768, 2304, b_mn=True, variants=tail)
 case('d fc2 (bf16)', 12552, 3072, 768, b_mn=True, variants=tail)
 case('d fc1', 12552, 768, 3072, b_mn=True, variants=tail)
-if not QUICK:
-    case('d fc2 dgelu epilogue', 12552, 3072, 768, b_mn=True, epi='dgelu')
+case('d fc2 dgelu epilogue', 12552, 3072, 768, b_mn=True, epi='dgelu', variants=[('generic', {}), ('tma', dict(env='VT_TMA_DGELU'))])
 print('== wgrad (A,B MN-major, split-K)')
 case('w 768x768', 768, 768, 12544, a_mn=True, b_mn=True, epi='f32', split=True)
 case('w qkv 2304x768', 2304, 768, 12544, a_mn=True, b_mn=True, epi='f32', split=True)

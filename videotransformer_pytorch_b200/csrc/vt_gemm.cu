@@ -59,7 +59,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tma_prefetch_desc(&tmB);
     if (p.tail_bn) tma_prefetch_desc(&tmBt);
     if (p.tma_store) tma_prefetch_desc(&tmC);
-    if (RES || p.tma_store == 4) tma_prefetch_desc(&tmX);
+    if (RES || p.tma_store >= 4) tma_prefetch_desc(&tmX);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < Cfg::STAGES; ++i) {
@@ -70,7 +70,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], EPI_WARPS);  // one arrive per epilogue warp
     }
-    if (RES) {
+    if (RES || p.tma_store == 5) {
       for (int i = 0; i < 2 * EPI_WARPS; ++i) mbar_init(&aux_bar[i], 1);
     }
     fence_barrier_init();
@@ -183,7 +183,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         epilogue_tile_tma_res<BN>(p, &tmC, &tmX, slot, aux_bar + 2 * (warp - 4), aux_use, t_base, m_blk, u.n0, u.bn, q, half, lane,
                                   &tfull_bar[acc], (uint32_t)acc_phase);
       } else {
-        if (p.tma_store) epilogue_tile_tma<BN>(p, &tmC, &tmX, slot, t_base, m_blk, u.n0, u.bn, u.split, q, half, lane, &tfull_bar[acc], (uint32_t)acc_phase);
+        if (p.tma_store == 5) epilogue_tile_tma_dgelu<BN>(p, &tmC, &tmX, slot, aux_bar + 2 * (warp - 4), aux_use, t_base, m_blk, u.n0, u.bn, q, half, lane, &tfull_bar[acc], (uint32_t)acc_phase);
+        else if (p.tma_store) epilogue_tile_tma<BN>(p, &tmC, &tmX, slot, t_base, m_blk, u.n0, u.bn, u.split, q, half, lane, &tfull_bar[acc], (uint32_t)acc_phase);
         else epilogue_tile<BN>(p, stg, t_base, m_blk, u.n0, u.bn, u.split, q, half, lane, &tfull_bar[acc], (uint32_t)acc_phase);
       }
       if (dbg && warp == 4 && lane == 0) { if (unit == unit0) dbg[5] = clock64(); dbg[6] = clock64(); }   // first / last tile drained
@@ -400,6 +401,16 @@ int setup_out_map(const vt_gemm_params* q, GemmDev& d, CUtensorMap* tmC, bool in
     rc = make_tmap_out_3d(tmC2, d.out2, 0, q->M, q->N, d.ldo2, 1, 0);
     if (rc) return rc;
     d.tma_store = 4;
+    return 0;
+  }
+  if (q->epilogue == VT_EPI_DGELU && !q->out_row && !q->aux_row && q->aux && !getenv("VT_NO_TMA_STORE") && getenv("VT_TMA_DGELU") && tmC2 &&
+      q->ldo % 8 == 0 && q->ldaux % 8 == 0) {
+    // out = acc * gelu'(z): z boxes TMA-loaded into the staging buffers, product TMA-stored from there (opt-in: VT_TMA_DGELU=1)
+    int rc = make_tmap_out_3d(tmC, d.out, 0, q->M, q->N, d.ldo, 1, 0);
+    if (rc) return rc;
+    rc = make_tmap_out_3d(tmC2, q->aux, 0, q->M, q->N, q->ldaux, 1, 0);
+    if (rc) return rc;
+    d.tma_store = 5;
     return 0;
   }
   const bool plain = (q->epilogue == VT_EPI_BF16 || q->epilogue == VT_EPI_F32) && !q->out_row && !q->aux;

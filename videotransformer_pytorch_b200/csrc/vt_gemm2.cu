@@ -112,7 +112,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     tma_prefetch_desc(&tmB);
     if (p.tail_bn) tma_prefetch_desc(&tmBt);
     if (p.tma_store) tma_prefetch_desc(&tmC);
-    if (RES || p.tma_store == 4) tma_prefetch_desc(&tmX);
+    if (RES || p.tma_store >= 4) tma_prefetch_desc(&tmX);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < Cfg::STAGES; ++i) {
@@ -123,7 +123,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 2 * EPI_WARPS);   // epilogue warps of both CTAs
     }
-    if (RES) {
+    if (RES || p.tma_store == 5) {
       for (int i = 0; i < 2 * EPI_WARPS; ++i) mbar_init(&aux_bar[i], 1);
     }
     fence_barrier_init();
@@ -211,7 +211,8 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         epilogue_tile_tma_res<BN>(p, &tmC, &tmX, slot, aux_bar + 2 * (warp - 4), aux_use, t_base, m_blk, u.n0, u.bn, q, half, lane,
                                   &tfull_bar[acc], (uint32_t)acc_phase);
       } else {
-        if (p.tma_store) epilogue_tile_tma<BN>(p, &tmC, &tmX, slot, t_base, m_blk, u.n0, u.bn, u.split, q, half, lane, &tfull_bar[acc], (uint32_t)acc_phase);
+        if (p.tma_store == 5) epilogue_tile_tma_dgelu<BN>(p, &tmC, &tmX, slot, aux_bar + 2 * (warp - 4), aux_use, t_base, m_blk, u.n0, u.bn, q, half, lane, &tfull_bar[acc], (uint32_t)acc_phase);
+        else if (p.tma_store) epilogue_tile_tma<BN>(p, &tmC, &tmX, slot, t_base, m_blk, u.n0, u.bn, u.split, q, half, lane, &tfull_bar[acc], (uint32_t)acc_phase);
         else epilogue_tile<BN>(p, stg, t_base, m_blk, u.n0, u.bn, u.split, q, half, lane, &tfull_bar[acc], (uint32_t)acc_phase);
       }
       tc_fence_before();

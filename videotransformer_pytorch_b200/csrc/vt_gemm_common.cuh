@@ -303,6 +303,74 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void*
 
 constexpr int RES_SLOT_BYTES = 8192;      // per epilogue warp: two 32 x 32 fp32 boxes
 
+// ------------------------------------------------------------------------------------------------
+// dGELU epilogue on TMA (autograd of nn.GELU fused into the FC2 data-gradient GEMM):
+//   out_bf16[m, n] = acc[m, n] * gelu'(z_bf16[m, n])        plain rows, no maps
+// Same mechanics as the residual epilogue with 2 KiB bf16 boxes (64B swizzle): the z box is TMA-loaded one chunk ahead into
+// one of the warp's two buffers, multiplied into the accumulator in place and TMA-stored from the same buffer.
+// ------------------------------------------------------------------------------------------------
+template <int BN>
+__device__ __forceinline__ void epilogue_tile_tma_dgelu(const GemmDev& p, const CUtensorMap* tmC, const CUtensorMap* tmZ,
+                                                        uint8_t* slot, uint64_t* aux_bar, uint32_t (&aux_use)[2], uint32_t t_base,
+                                                        int m_blk, int n_base, int bn, int q, int half, int lane, uint64_t* tfull,
+                                                        uint32_t ph) {
+  const int m0 = m_blk * BM + q * 32;
+  const bool any = m0 < p.M;
+  const int nchunks = (bn / 32 - half + 1) / 2;
+  auto chunk_cols_ok = [&](int it) { return n_base + (half + 2 * it) * 32 < p.N; };
+  auto request = [&](int it, int buf) {
+    mbar_arrive_expect_tx(&aux_bar[buf], 2048);
+    tma_load_3d(slot + buf * 2048, tmZ, &aux_bar[buf], n_base + (half + 2 * it) * 32, m0, 0);
+  };
+  if (lane == 0 && any) {
+    if (nchunks > 0 && chunk_cols_ok(0)) request(0, 0);
+    if (nchunks > 1 && chunk_cols_ok(1)) request(1, 1);
+  }
+  mbar_wait(tfull, ph);
+  tc_fence_after();
+  if (!any) return;
+#pragma unroll 1
+  for (int it = 0; it < nchunks; ++it) {
+    const int c = half + 2 * it;
+    const int n0 = n_base + c * 32;
+    if (n0 >= p.N) break;   // warp-uniform
+    uint32_t r[32];
+    tmem_ld32(t_base + c * 32, r);
+    tmem_ld_wait();
+    const int cur = it & 1;
+    if (cur == 0) { mbar_wait(&aux_bar[0], aux_use[0] & 1); ++aux_use[0]; }
+    else { mbar_wait(&aux_bar[1], aux_use[1] & 1); ++aux_use[1]; }
+    uint8_t* buf = slot + cur * 2048;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      uint4* cell = reinterpret_cast<uint4*>(buf + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4));     // SWIZZLE_64B
+      const uint4 zz = *cell;
+      const uint32_t zw[4] = {zz.x, zz.y, zz.z, zz.w};
+      uint32_t ow[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 z2 = unpack_bf16x2(zw[j]);
+        ow[j] = pack_bf16x2(__uint_as_float(r[8 * g + 2 * j]) * dgelu_fast(z2.x),
+                            __uint_as_float(r[8 * g + 2 * j + 1]) * dgelu_fast(z2.y));
+      }
+      *cell = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_3d(tmC, buf, n0, m0, 0);
+      bulk_commit();
+      if (it + 2 < nchunks && chunk_cols_ok(it + 2)) {
+        bulk_wait_read<0>();
+        request(it + 2, cur);
+      }
+    }
+    __syncwarp();
+  }
+  if (lane == 0) bulk_wait_read<0>();
+  __syncwarp();
+}
+
 // aux_use[j]: how often buffer j's mbarrier has completed so far (its wait parity); carried across tiles by the caller
 template <int BN>
 __device__ __forceinline__ void epilogue_tile_tma_res(const GemmDev& p, const CUtensorMap* tmC, const CUtensorMap* tmX,

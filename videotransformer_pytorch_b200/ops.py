@@ -39,6 +39,7 @@ _MASK_ARENA = None
 # for FC1 (the dGELU epilogue of the FC2 data gradient stays split).
 import os as _os
 FUSED_GELU_FWD = _os.environ.get('VT_FUSED_GELU', '0') == '1'
+FUSED_DGELU_BWD = _os.environ.get('VT_TMA_DGELU', '0') == '1'      # dGELU epilogue of the FC2 data gradient on TMA
 FUSED_GELU_EPILOGUE = False
 
 
@@ -379,7 +380,7 @@ class FFNFn(torch.autograd.Function):
         g = k.gather_cast(dy2, row_scale=dp)
         d_w2 = _wgrad(g, h, D, Dh, M, wptr=ctx.wptrs[1])
         d_b2 = k.colsum(g)
-        if FUSED_GELU_EPILOGUE:
+        if FUSED_GELU_EPILOGUE or FUSED_DGELU_BWD:
             dz = _dgrad(g, w2h, M, Dh, D, epi='dgelu', aux=z)
         else:
             dz = k.dgelu(_dgrad(g, w2h, M, Dh, D, epi='bf16'), z)
