@@ -408,7 +408,17 @@ def measure(run, args, world, rank, dist, steps, with_probe):
     res = dict(ms_dev=ms_dev, ms_e2e=ms_e2e, launches=launches, loss=loss_value, reducer=reducer, graphed=graphed,
                step_inputs=step_inputs, eager_step=eager_step, kernels_per_replay=(graphed.kernels_per_replay if graphed else None))
     if with_probe:
-        res['roofline'] = gemm_probe(run, args, reducer, step_inputs, eager_step, ms_dev / steps)
+        try:
+            res['roofline'] = gemm_probe(run, args, reducer, step_inputs, eager_step, ms_dev / steps)
+        except Exception as exc:             # the probe must never cost the headline line
+            import traceback
+            traceback.print_exc()
+            pk = peaks()
+            res['roofline'] = {'kernel': 'gemm_tcgen05_kernel / gemm2_tcgen05_kernel', 'bound': 'tensor', 'achieved': None,
+                               'peak': pk['tflops'], 'unit': 'TFLOP/s', 'frac': None, 'traffic': None,
+                               'error': f'{type(exc).__name__}: {str(exc)[:200]}',
+                               'whole_step_frac_of_tensor_roofline':
+                                   (run.w['flop_per_clip'] * run.B / (ms_dev / steps * 1e-3) / 1e12) / pk['tflops']}
     return res
 
 
@@ -587,7 +597,14 @@ def main_gpu(args):
     sampler = ClockSampler(torch.cuda.current_device()) if rank == 0 else None
     res = measure(run, args, world, rank, dist, args.steps, with_probe=True)
     clocks = sampler.stop() if sampler else None
-    check = ddp_check(run, res, dist) if world > 1 else None
+    check = None
+    if world > 1:
+        try:
+            check = ddp_check(run, res, dist)
+        except Exception as exc:
+            import traceback
+            traceback.print_exc()
+            check = {'error': f'{type(exc).__name__}: {str(exc)[:200]}'}
 
     exposed = None
     if world > 1 and not args.no_graph:

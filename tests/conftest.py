@@ -13,9 +13,16 @@ GOLD = os.path.join(ROOT, 'tests', 'golden')
 
 def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box: pytest -m gpu)')
+    config.addinivalue_line('markers', 'experimental: kernel paths that ship disabled until confirmed on hardware '
+                                       '(run with VT_EXPERIMENTAL=1; the test switches the path on itself)')
 
 
 def pytest_collection_modifyitems(config, items):
+    if not os.environ.get('VT_EXPERIMENTAL'):
+        skip_exp = pytest.mark.skip(reason='experimental kernel path (set VT_EXPERIMENTAL=1)')
+        for it in items:
+            if 'experimental' in it.keywords:
+                it.add_marker(skip_exp)
     if torch.cuda.is_available():
         return
     skip = pytest.mark.skip(reason='no CUDA device')

@@ -269,7 +269,7 @@ def _captured_body_worker(rank, world, port, q):
         for n, p in net.named_parameters():
             if 'temporal_fc' in n:
                 p.normal_(std=0.05)
-    red = GradientBuckets(net, bucket_bytes=4096)
+    red = GradientBuckets(net, bucket_bytes=4096, direct_wgrad=True)
     params = [p for p in net.parameters() if p.requires_grad]
     g = torch.Generator().manual_seed(70 + rank)
     x = torch.randn(2, 2, 3, 32, 32, generator=g)

@@ -206,6 +206,7 @@ def _ops():
     return ops
 
 
+@pytest.mark.experimental
 @pytest.mark.parametrize('cluster', [1, 3], ids=['single-cta', 'cta-pair'])
 @pytest.mark.parametrize('bn', [0, 128, 192, 256])
 @pytest.mark.parametrize('M,N,Kd', [(1000, 768, 256), (12552, 768, 768), (130, 96, 192), (4096, 256, 64)])
@@ -216,15 +217,17 @@ def test_residual_epilogue_tma_plain_rows(M, N, Kd, bn, cluster, monkeypatch):
     a, b = mk((M, Kd), 30).bfloat16(), mk((N, Kd), 31).bfloat16()
     bias, rs, aux = mk((N,), 32), mk((M,), 33), mk((M, N), 34)
     out = torch.full((M, N), 55.0, device='cuda')
+    monkeypatch.setenv('VT_TMA_RES', '1')
     K().gemm(a, b, M, N, Kd, epi='f32', bias=bias, row_scale=rs, aux=aux, out=out, force_bn=bn, force_cluster=cluster)
     r = (ref_mm(a, b, False, False) + bias) * rs[:, None] + aux
     assert rel(out, r) < 1e-5
-    monkeypatch.setenv('VT_NO_TMA_RES', '1')
+    monkeypatch.setenv('VT_TMA_RES', '0')
     old = torch.empty_like(out)
     K().gemm(a, b, M, N, Kd, epi='f32', bias=bias, row_scale=rs, aux=aux, out=old, force_bn=bn, force_cluster=cluster)
     assert rel(out, old) < 1e-6
 
 
+@pytest.mark.experimental
 @pytest.mark.parametrize('cluster', [1, 3], ids=['single-cta', 'cta-pair'])
 @pytest.mark.parametrize('B,T,P,D', [(2, 8, 196, 768), (3, 4, 9, 128), (1, 2, 50, 256), (2, 8, 196, 96)])
 def test_residual_epilogue_tma_temporal_and_spatial_maps(B, T, P, D, cluster, monkeypatch):
@@ -243,13 +246,13 @@ def test_residual_epilogue_tma_temporal_and_spatial_maps(B, T, P, D, cluster, mo
         a = mk((Mrows, Kd), 43).bfloat16()
         rs = mk((Mrows,), 44)
         got = torch.full((out_rows, D), -7.0, device='cuda')
+        monkeypatch.setenv('VT_TMA_RES', '1')
         K().gemm(a, w, Mrows, D, Kd, epi='f32', bias=bias, row_scale=rs, aux=x2, aux_row=aux_row, out=got, out_row=out_row,
                  row_map=aff[name], force_cluster=cluster)
-        monkeypatch.setenv('VT_NO_TMA_RES', '1')
+        monkeypatch.setenv('VT_TMA_RES', '0')
         exp = torch.full((out_rows, D), -7.0, device='cuda')
         K().gemm(a, w, Mrows, D, Kd, epi='f32', bias=bias, row_scale=rs, aux=x2, aux_row=aux_row, out=exp, out_row=out_row,
                  force_cluster=cluster)
-        monkeypatch.delenv('VT_NO_TMA_RES')
         assert rel(got, exp) < 1e-6, name
         # rows the map never names (the cls row of every sample) keep their old contents
         assert bool((got[torch.arange(B, device='cuda') * S] == -7.0).all()), name
@@ -260,6 +263,7 @@ def test_residual_epilogue_tma_temporal_and_spatial_maps(B, T, P, D, cluster, mo
         assert rel(got, full) < 1e-5, name
 
 
+@pytest.mark.experimental
 @pytest.mark.parametrize('cluster', [0, 1, 3], ids=['auto', 'single-cta', 'cta-pair'])
 @pytest.mark.parametrize('M,N,Kd', [(12552, 768, 768), (12608, 2304, 256), (12552, 3072, 128), (136, 512, 192), (264, 256, 64)])
 @pytest.mark.parametrize('form', ['fwd_bf16', 'dgrad_bf16', 'fwd_f32_residual'])
@@ -281,6 +285,7 @@ def test_narrow_tail_units(M, N, Kd, form, cluster, monkeypatch):
         aux = mk((M, N), 54)
         kw = dict(epi='f32', bias=bias, row_scale=rs, aux=aux)
         r = (a.float() @ b.float().t() + bias) * rs[:, None] + aux
+    monkeypatch.setenv('VT_TAIL_UNITS', '1')
     got = K().gemm(a, b, M, N, Kd, force_cluster=cluster, force_tail=2, **kw)
     off = K().gemm(a, b, M, N, Kd, force_cluster=cluster, force_tail=1, **kw)
     tol = 1e-5 if form == 'fwd_f32_residual' else 4e-3
@@ -288,6 +293,7 @@ def test_narrow_tail_units(M, N, Kd, form, cluster, monkeypatch):
     assert torch.equal(got, off)
 
 
+@pytest.mark.experimental
 @pytest.mark.parametrize('cluster', [1, 3], ids=['single-cta', 'cta-pair'])
 @pytest.mark.parametrize('M,N,Kd', [(12552, 3072, 768), (1000, 512, 128), (130, 96, 64)])
 def test_gelu_and_dgelu_epilogues_on_tma(M, N, Kd, cluster, monkeypatch):
@@ -295,19 +301,19 @@ def test_gelu_and_dgelu_epilogues_on_tma(M, N, Kd, cluster, monkeypatch):
     TMA-loaded z box: both equal the generic epilogues bit for bit and match torch."""
     a, b = mk((M, Kd), 60, 0.3).bfloat16(), mk((N, Kd), 61, 0.3).bfloat16()
     bias = mk((N,), 62)
+    monkeypatch.setenv('VT_TMA_GELU', '1')
     z, h = K().gemm(a, b, M, N, Kd, epi='gelu', bias=bias, force_cluster=cluster)
     zr = ref_mm(a, b, False, False) + bias
     assert rel(z, zr) < 4e-3 and rel(h, torch.nn.functional.gelu(zr)) < 4e-3
-    monkeypatch.setenv('VT_NO_TMA_GELU', '1')
+    monkeypatch.setenv('VT_TMA_GELU', '0')
     z0, h0 = K().gemm(a, b, M, N, Kd, epi='gelu', bias=bias, force_cluster=cluster)
-    monkeypatch.delenv('VT_NO_TMA_GELU')
     assert torch.equal(z, z0) and torch.equal(h, h0)
     g = mk((M, Kd), 63, 0.3).bfloat16()
     w = mk((Kd, N), 64, 0.3).bfloat16()                       # [n_out = Kd, k_in = N], read MN-major
+    monkeypatch.setenv('VT_TMA_DGELU', '0')
     d0 = K().gemm(g, w, M, N, Kd, b_mn=True, epi='dgelu', aux=z, force_cluster=cluster)
     monkeypatch.setenv('VT_TMA_DGELU', '1')
     d1 = K().gemm(g, w, M, N, Kd, b_mn=True, epi='dgelu', aux=z, force_cluster=cluster)
-    monkeypatch.delenv('VT_TMA_DGELU')
     zz = z.float().requires_grad_(True)
     torch.nn.functional.gelu(zz).sum().backward()
     assert rel(d1, (g.float() @ w.float()) * zz.grad) < 4e-3

@@ -12,6 +12,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from videotransformer_pytorch_b200 import _lib, ops
 
+# the round-2 paths are switched on here explicitly (they ship behind environment switches until confirmed on hardware)
+for _name in ('VT_TMA_RES', 'VT_TAIL_UNITS', 'VT_TMA_GELU'):
+    os.environ.setdefault(_name, '1')
 K = _lib.K
 dev = torch.device('cuda')
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -62,19 +65,22 @@ def case(name, M, N, Kd, a_mn=False, b_mn=False, epi='bf16', split=False, resid=
     res = []
     variants = variants or [('auto', {}), ('single', dict(force_cluster=1)), ('pair', dict(force_cluster=3))]
     for label, extra in variants:
-        env = extra.pop('env', None) if isinstance(extra, dict) else None
+        env = extra.pop('env', None) if isinstance(extra, dict) else None      # (name, value) applied for this variant only
         call_kw = dict(kw)
         call_kw.update(extra)
+        saved = None
         if env:
-            os.environ[env] = '1'
-            if env == 'VT_NO_TMA_RES':
-                call_kw.pop('row_map', None)
+            saved = os.environ.get(env[0])
+            os.environ[env[0]] = env[1]
         try:
             t = bench(lambda: K.gemm(a, b, M, N, Kd, a_mn=a_mn, b_mn=b_mn, epi=epi, bias=bias, out=out, out2=out2,
                                      split_ok=split, **call_kw))
         finally:
             if env:
-                os.environ.pop(env, None)
+                if saved is None:
+                    os.environ.pop(env[0], None)
+                else:
+                    os.environ[env[0]] = saved
                 extra['env'] = env
         res.append(f'{label}: {t * 1e3:6.1f}us {fl / t / 1e9:5.0f}TF')
     print(f'{name:30s} M={M:6d} N={N:5d} K={Kd:6d} | cuBLAS {t_ref * 1e3:6.1f}us {fl / t_ref / 1e9:5.0f}TF | ' + ' | '.join(res), flush=True)
@@ -82,7 +88,7 @@ def case(name, M, N, Kd, a_mn=False, b_mn=False, epi='bf16', split=False, resid=
 
 std = [('auto', {}), ('single', dict(force_cluster=1)), ('pair', dict(force_cluster=3))]
 tail = std + [('auto-notail', dict(force_tail=1))]
-resv = std + [('generic', dict(env='VT_NO_TMA_RES'))]
+resv = std + [('generic', dict(env=('VT_TMA_RES', '0')))]
 print('== forward')
 case('qkv temporal', 12544, 2304, 768)
 case('proj temporal (bf16,rowscale)', 12544, 768, 768, rowscale=True)
@@ -91,7 +97,7 @@ case('qkv spatial', 12608, 2304, 768, variants=tail)
 case('proj spatial (f32 resid, map)', 12608, 768, 768, epi='f32', resid='spatial', rowscale=True, variants=resv + [('auto-notail', dict(force_tail=1))])
 case('fc1 (bf16)', 12552, 3072, 768, variants=tail)
 case('fc2 (f32 resid)', 12552, 768, 3072, epi='f32', resid='plain', rowscale=True, variants=resv + [('auto-notail', dict(force_tail=1))])
-case('fc1 gelu epilogue (z,h by TMA)', 12552, 3072, 768, epi='gelu', variants=tail)
+case('fc1 gelu epilogue (z,h by TMA)', 12552, 3072, 768, epi='gelu', variants=tail + [('generic', dict(env=('VT_TMA_GELU', '0')))])
 print('== dgrad (B MN-major)')
 case('d proj / d temporal_fc', 12544, 768, 768, b_mn=True, rowscale=True)
 case('d qkv temporal', 12544, 768, 2304, b_mn=True)
@@ -99,7 +105,7 @@ case('d proj spatial', 12608, 768, 768, b_mn=True, variants=tail)
 case('d qkv spatial', 12608, 768, 2304, b_mn=True, variants=tail)
 case('d fc2 (bf16)', 12552, 3072, 768, b_mn=True, variants=tail)
 case('d fc1', 12552, 768, 3072, b_mn=True, variants=tail)
-case('d fc2 dgelu epilogue', 12552, 3072, 768, b_mn=True, epi='dgelu', variants=[('generic', {}), ('tma', dict(env='VT_TMA_DGELU'))])
+case('d fc2 dgelu epilogue', 12552, 3072, 768, b_mn=True, epi='dgelu', variants=[('generic', {}), ('tma', dict(env=('VT_TMA_DGELU', '1')))])
 print('== wgrad (A,B MN-major, split-K)')
 case('w 768x768', 768, 768, 12544, a_mn=True, b_mn=True, epi='f32', split=True)
 case('w qkv 2304x768', 2304, 768, 12544, a_mn=True, b_mn=True, epi='f32', split=True)

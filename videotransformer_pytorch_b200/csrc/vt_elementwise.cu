@@ -23,6 +23,12 @@ void set_error(const char* fmt, ...) {
 
 static unsigned long long g_launches = 0;
 
+bool feature_on(const char* name, bool dflt) {
+  const char* v = getenv(name);
+  if (!v || !*v) return dflt;
+  return v[0] != '0';
+}
+
 int check_launch(const char* what) {
   __atomic_add_fetch(&g_launches, 1ull, __ATOMIC_RELAXED);
   cudaError_t e = cudaGetLastError();
@@ -118,8 +124,94 @@ ln_fwd_kernel(const float* __restrict__ x, long long ldx, const int* __restrict_
 // the CTA's rows, reduced across warps through shared memory, one partial row per CTA.
 // ------------------------------------------------------------------------------------------------
 template <int V>
-__global__ void __launch_bounds__(LN_WARPS * 32, (V <= 6 ? 2 : 1))
+__global__ void __launch_bounds__(LN_WARPS * 32)
 ln_bwd_kernel(const void* __restrict__ dy, int dy_fp32, const float* __restrict__ x, long long ldx,
+              const int* __restrict__ in_row, const float* __restrict__ mean, const float* __restrict__ rstd,
+              const float* __restrict__ gamma, const float* __restrict__ dres, float* __restrict__ dx, long long lddx,
+              float* __restrict__ dx_aux, const int* __restrict__ out_row, float* __restrict__ partials, int rows) {
+  constexpr int D = V * 128;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4 g[V], dg[V], db[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    g[i] = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * i);
+    dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int m = blockIdx.x * LN_WARPS + warp; m < rows; m += gridDim.x * LN_WARPS) {
+    const int src = in_row ? in_row[m] : m;
+    const float4* xr = reinterpret_cast<const float4*>(x + (long long)src * ldx);
+    const float mu = mean[m], rs = rstd[m];
+    float4 xh[V], gy[V];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      float4 d;
+      if (dy_fp32) {
+        d = reinterpret_cast<const float4*>(static_cast<const float*>(dy) + (long long)m * D)[lane + 32 * i];
+      } else {
+        const uint2 u = reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(dy) + (long long)m * D)[lane + 32 * i];
+        const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+        d = make_float4(a.x, a.y, b.x, b.y);
+      }
+      const float4 xv = xr[lane + 32 * i];
+      xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+      dg[i].x += d.x * xh[i].x; dg[i].y += d.y * xh[i].y; dg[i].z += d.z * xh[i].z; dg[i].w += d.w * xh[i].w;
+      db[i].x += d.x; db[i].y += d.y; db[i].z += d.z; db[i].w += d.w;
+      gy[i] = make_float4(d.x * g[i].x, d.y * g[i].y, d.z * g[i].z, d.w * g[i].w);
+      s1 += (gy[i].x + gy[i].y) + (gy[i].z + gy[i].w);
+      s2 += (gy[i].x * xh[i].x + gy[i].y * xh[i].y) + (gy[i].z * xh[i].z + gy[i].w * xh[i].w);
+    }
+    const float m1 = warp_sum(s1) * (1.0f / D);
+    const float m2 = warp_sum(s2) * (1.0f / D);
+    const int t = out_row ? out_row[m] : m;
+    float* dst;
+    const float* res = nullptr;
+    if (t >= 0) {
+      dst = dx + (long long)t * lddx;
+      if (dres) res = dres + (long long)t * lddx;
+    } else {
+      dst = dx_aux + (long long)(-t - 1) * D;
+    }
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      float4 o;
+      o.x = rs * (gy[i].x - m1 - xh[i].x * m2);
+      o.y = rs * (gy[i].y - m1 - xh[i].y * m2);
+      o.z = rs * (gy[i].z - m1 - xh[i].z * m2);
+      o.w = rs * (gy[i].w - m1 - xh[i].w * m2);
+      if (res) {
+        const float4 r = reinterpret_cast<const float4*>(res)[lane + 32 * i];
+        o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+      }
+      reinterpret_cast<float4*>(dst)[lane + 32 * i] = o;
+    }
+  }
+  // cross-warp reduction of dgamma / dbeta
+  __shared__ float4 sh[LN_WARPS][32];
+  float* pg = partials + (long long)blockIdx.x * 2 * D;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    for (int pass = 0; pass < 2; ++pass) {
+      __syncthreads();
+      sh[warp][lane] = pass == 0 ? dg[i] : db[i];
+      __syncthreads();
+      if (warp == 0) {
+        float4 a = sh[0][lane];
+        for (int w = 1; w < LN_WARPS; ++w) {
+          const float4 c = sh[w][lane];
+          a.x += c.x; a.y += c.y; a.z += c.z; a.w += c.w;
+        }
+        reinterpret_cast<float4*>(pg + pass * D)[lane + 32 * i] = a;
+      }
+    }
+  }
+}
+
+// Second version (VT_LN_BWD_V2=1): two CTAs per SM.
+template <int V>
+__global__ void __launch_bounds__(LN_WARPS * 32, (V <= 6 ? 2 : 1))
+ln_bwd2_kernel(const void* __restrict__ dy, int dy_fp32, const float* __restrict__ x, long long ldx,
               const int* __restrict__ in_row, const float* __restrict__ mean, const float* __restrict__ rstd,
               const float* __restrict__ gamma, const float* __restrict__ dres, float* __restrict__ dx, long long lddx,
               float* __restrict__ dx_aux, const int* __restrict__ out_row, float* __restrict__ partials, int rows) {
@@ -314,6 +406,7 @@ colsum_kernel(const __nv_bfloat16* __restrict__ in, long long ld, int M, int N, 
 // 4-byte loads above (which ran at ~0.3 of the HBM rate).  Partials per row chunk, summed by the last CTA of each
 // column block in chunk order (deterministic).
 constexpr int COLSUM_WROWS = 256;
+constexpr bool VT_DEFAULT_COLSUM_WIDE = false;
 
 __global__ void __launch_bounds__(256)
 colsum_wide_kernel(const __nv_bfloat16* __restrict__ in, long long ld, int M, int N, float* __restrict__ ws,
@@ -547,11 +640,17 @@ extern "C" int vt_layernorm_bwd(const vt_ln_bwd_params* p, void* stream) {
   VT_REQUIRE(p->D % 128 == 0 && p->D >= 128 && p->D <= 1024, "vt_layernorm_bwd: D=%d unsupported", p->D);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int blocks = ln_blocks(p->rows);
+  const bool v2 = feature_on("VT_LN_BWD_V2", false);
 #define VT_LN_BWD(V)                                                                                                    \
   case V:                                                                                                               \
-    ln_bwd_kernel<V><<<blocks, LN_WARPS * 32, 0, st>>>(p->dy, p->dy_fp32, p->x, p->ldx, p->in_row, p->mean, p->rstd,    \
-                                                       p->gamma, p->dres, p->dx, p->lddx, p->dx_aux, p->out_row,        \
-                                                       p->partials, p->rows);                                           \
+    if (v2)                                                                                                             \
+      ln_bwd2_kernel<V><<<blocks, LN_WARPS * 32, 0, st>>>(p->dy, p->dy_fp32, p->x, p->ldx, p->in_row, p->mean, p->rstd, \
+                                                          p->gamma, p->dres, p->dx, p->lddx, p->dx_aux, p->out_row,     \
+                                                          p->partials, p->rows);                                        \
+    else                                                                                                                \
+      ln_bwd_kernel<V><<<blocks, LN_WARPS * 32, 0, st>>>(p->dy, p->dy_fp32, p->x, p->ldx, p->in_row, p->mean, p->rstd,  \
+                                                         p->gamma, p->dres, p->dx, p->lddx, p->dx_aux, p->out_row,      \
+                                                         p->partials, p->rows);                                         \
     break;
   switch (p->D / 128) {
     VT_LN_BWD(1) VT_LN_BWD(2) VT_LN_BWD(3) VT_LN_BWD(4) VT_LN_BWD(5) VT_LN_BWD(6) VT_LN_BWD(7) VT_LN_BWD(8)
@@ -587,7 +686,8 @@ extern "C" int vt_colsum_bf16(const vt_colsum_params* p, void* stream) {
   VT_REQUIRE(p && p->in && p->out && p->workspace && p->M > 0 && p->N > 0, "vt_colsum_bf16: bad params");
   VT_REQUIRE(p->N % 4 == 0 && p->ld % 2 == 0, "vt_colsum_bf16: N %% 4 and ld %% 2 required");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (p->counters && p->N % 8 == 0 && p->ld % 8 == 0 && (reinterpret_cast<uintptr_t>(p->in) & 15) == 0 && !getenv("VT_COLSUM_NARROW")) {
+  if (p->counters && p->N % 8 == 0 && p->ld % 8 == 0 && (reinterpret_cast<uintptr_t>(p->in) & 15) == 0 &&
+      feature_on("VT_COLSUM_WIDE", VT_DEFAULT_COLSUM_WIDE)) {
     dim3 wgrid((p->N + 255) / 256, (p->M + COLSUM_WROWS - 1) / COLSUM_WROWS);
     colsum_wide_kernel<<<wgrid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(p->in), p->ld, p->M, p->N, p->workspace, p->out,
                                              p->counters);

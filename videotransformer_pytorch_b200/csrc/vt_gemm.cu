@@ -14,6 +14,13 @@ namespace vt {
 
 // RES: instantiation for the fp32 residual epilogue on TMA (epilogue_tile_tma_res): 8 KiB of staging per epilogue warp
 // instead of 4.1 KiB, paid for with one pipeline stage where shared memory is full.
+// compiled defaults of the round-2 paths (environment VT_TMA_RES / VT_TAIL_UNITS / VT_TMA_GELU / VT_TMA_DGELU = 0 | 1 override)
+constexpr bool VT_DEFAULT_TMA_RES = false;
+constexpr bool VT_DEFAULT_TAIL_UNITS = false;
+constexpr bool VT_DEFAULT_TMA_GELU = false;
+constexpr bool VT_DEFAULT_TMA_DGELU = false;
+bool tail_units_enabled() { return feature_on("VT_TAIL_UNITS", VT_DEFAULT_TAIL_UNITS); }
+
 template <int BN, bool RES>
 struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;
@@ -302,7 +309,7 @@ int make_tmap_rows_3d(CUtensorMap* map, const void* base, long long cols, long l
 // Residual epilogue on TMA (GemmDev::tma_store = 3): fp32 output with an fp32 addend whose rows — and the output's — follow
 // either no map or the affine map described in vt_gemm_params (map_period ...).  Fills tmC / tmX and the map fields of d.
 bool res_tma_applicable(const vt_gemm_params* q) {
-  if (q->epilogue != VT_EPI_F32 || !q->aux || getenv("VT_NO_TMA_STORE") || getenv("VT_NO_TMA_RES")) return false;
+  if (q->epilogue != VT_EPI_F32 || !q->aux || getenv("VT_NO_TMA_STORE") || !feature_on("VT_TMA_RES", VT_DEFAULT_TMA_RES)) return false;
   if (q->N % 4 != 0) return false;
   if (q->map_period > 0) return q->map_period >= 32 && q->map_tcount >= 1 && q->M % q->map_period == 0;
   return !q->out_row && !q->aux_row && q->ldo % 4 == 0 && q->ldaux % 4 == 0;
@@ -394,7 +401,7 @@ bool splitk_in_place(const vt_gemm_params* q) {
 int setup_out_map(const vt_gemm_params* q, GemmDev& d, CUtensorMap* tmC, bool in_place, CUtensorMap* tmC2) {
   d.tma_store = 0;
   memset(tmC, 0, sizeof(*tmC));
-  if (q->epilogue == VT_EPI_GELU && !q->out_row && !getenv("VT_NO_TMA_STORE") && !getenv("VT_NO_TMA_GELU") && tmC2) {
+  if (q->epilogue == VT_EPI_GELU && !q->out_row && !getenv("VT_NO_TMA_STORE") && feature_on("VT_TMA_GELU", VT_DEFAULT_TMA_GELU) && tmC2) {
     // z and h = gelu(z) both leave through TMA stores (two bf16 boxes per chunk)
     int rc = make_tmap_out_3d(tmC, d.out, 0, q->M, q->N, d.ldo, 1, 0);
     if (rc) return rc;
@@ -403,7 +410,8 @@ int setup_out_map(const vt_gemm_params* q, GemmDev& d, CUtensorMap* tmC, bool in
     d.tma_store = 4;
     return 0;
   }
-  if (q->epilogue == VT_EPI_DGELU && !q->out_row && !q->aux_row && q->aux && !getenv("VT_NO_TMA_STORE") && getenv("VT_TMA_DGELU") && tmC2 &&
+  if (q->epilogue == VT_EPI_DGELU && !q->out_row && !q->aux_row && q->aux && !getenv("VT_NO_TMA_STORE") &&
+      feature_on("VT_TMA_DGELU", VT_DEFAULT_TMA_DGELU) && tmC2 &&
       q->ldo % 8 == 0 && q->ldaux % 8 == 0) {
     // out = acc * gelu'(z): z boxes TMA-loaded into the staging buffers, product TMA-stored from there (opt-in: VT_TMA_DGELU=1)
     int rc = make_tmap_out_3d(tmC, d.out, 0, q->M, q->N, d.ldo, 1, 0);
@@ -550,7 +558,7 @@ static int launch_gemm(const vt_gemm_params* q, GemmDev& d, cudaStream_t st) {
   // unit schedule (narrow tail units only for single CTAs here; CTA pairs have their own in vt_gemm2.cu)
   const int max_clusters = sms / csize;
   const Schedule sch = plan_units(q->M, q->N, BN, BM * csize, splits, max_clusters, 64,
-                                  (csize != 1 || getenv("VT_NO_TAIL_UNITS")) ? 1 : q->force_tail);
+                                  (csize != 1 || !tail_units_enabled()) ? 1 : q->force_tail);
   d.full_units = sch.full_units; d.tail_units = sch.tail_units; d.tail_bn = sch.tail_bn; d.tail_mp = sch.tail_mp;
   if (d.tail_bn && !q->b_mn_major) {
     rc = make_tmap_bf16_2d(&tmBt, q->b, q->N, q->K, q->ldb, d.tail_bn);
@@ -647,7 +655,7 @@ extern "C" int vt_gemm(const vt_gemm_params* q, void* stream) {
     const int num_m = (q->M + BM - 1) / BM;
     const int kblocks = (q->K + BK - 1) / BK;
     const bool can_split = q->epilogue == VT_EPI_F32 && q->workspace && !q->out_row && !q->aux && !q->row_scale && !q->bias;
-    const int tail_mode = getenv("VT_NO_TAIL_UNITS") ? 1 : q->force_tail;
+    const int tail_mode = tail_units_enabled() ? q->force_tail : 1;
     // kernel variants: 0 = one CTA per 128 x BN tile (optionally clusters with multicast B), 1 = CTA pairs with
     // tcgen05.mma.cta_group::2 (256 x BN macro tiles, half of B per SM, 6-8 stages).  The pair kernel's unit time is
     // ~8% shorter (measured, profiles/) but its macro tiles quantise worse and it has no BN = 192; it is skipped

@@ -27,6 +27,7 @@ int setup_res_maps(const vt_gemm_params* q, GemmDev& d, CUtensorMap* tmC, CUtens
 struct Schedule { int full_units, tail_units, tail_bn, tail_mp; double makespan; };
 Schedule plan_units(int M, int N, int bn, int rows_per_macro, int splits, int slots, int tail_bn_cand, int tail_mode);
 bool splitk_in_place(const vt_gemm_params* q);
+bool tail_units_enabled();
 int splitk_zero(const vt_gemm_params* q, cudaStream_t st);
 
 template <int BN, bool RES>
@@ -285,7 +286,7 @@ static int launch_gemm2_t(const vt_gemm_params* q, GemmDev& d, cudaStream_t st) 
   if (RES) rc = setup_res_maps(q, d, &tmC, &tmX);
   else rc = setup_out_map(q, d, &tmC, in_place, &tmX);
   if (rc) return rc;
-  const Schedule sch = plan_units(q->M, q->N, BN, 2 * BM, splits, pairs, 128, getenv("VT_NO_TAIL_UNITS") ? 1 : q->force_tail);
+  const Schedule sch = plan_units(q->M, q->N, BN, 2 * BM, splits, pairs, 128, tail_units_enabled() ? q->force_tail : 1);
   d.full_units = sch.full_units; d.tail_units = sch.tail_units; d.tail_bn = sch.tail_bn; d.tail_mp = sch.tail_mp;
   if (d.tail_bn && !q->b_mn_major) {
     rc = make_tmap_bf16_2d(&tmBt, q->b, q->N, q->K, q->ldb, d.tail_bn / 2);

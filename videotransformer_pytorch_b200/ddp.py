@@ -28,11 +28,15 @@ import torch.distributed as dist
 
 class GradientBuckets:
     def __init__(self, module: torch.nn.Module, bucket_bytes: int = 32 << 20, process_group=None,
-                 broadcast_parameters: bool = True):
+                 broadcast_parameters: bool = True, direct_wgrad=None):
         if not dist.is_initialized():
             raise RuntimeError('GradientBuckets needs an initialised torch.distributed process group')
         self.group = process_group
         self.world = dist.get_world_size(process_group)
+        # weight-gradient GEMMs of a captured step write straight into the bucket slices (backward_into_buckets);
+        # VT_DDP_DIRECT=0/1 overrides
+        import os
+        self.direct_wgrad = (os.environ.get('VT_DDP_DIRECT', '0') == '1') if direct_wgrad is None else bool(direct_wgrad)
         params = [p for p in module.parameters() if p.requires_grad]
         if not params:
             raise RuntimeError('module has no trainable parameters')
@@ -146,7 +150,8 @@ class GradientBuckets:
         self._pending = [len(ps) for ps in self._bucket_params]
         self._arrived = [[] for _ in self._bucket_params]
         handles = [p.register_hook(lambda g, p=p: self.grad_ready(p, g)) for p in params]
-        ops.set_grad_destinations({p.data_ptr(): v for p, v in self._view.items()})
+        if self.direct_wgrad:
+            ops.set_grad_destinations({p.data_ptr(): v for p, v in self._view.items()})
         try:
             grads = torch.autograd.grad(loss, params)
         finally:
