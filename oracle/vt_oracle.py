@@ -48,7 +48,7 @@ def drop_path(x: Tensor, p: float, training: bool) -> Tensor:
         return x
     keep = 1.0 - p
     shape = (x.shape[0],) + (1,) * (x.ndim - 1)
-    r = (keep + torch.rand(shape).to(x.dtype)).floor()
+    r = (keep + torch.rand(shape).to(device=x.device, dtype=x.dtype)).floor()      # `.type_as(x)`: CPU draw, moved to x
     return x / keep * r
 
 
