@@ -70,6 +70,7 @@ def test_casts_and_colsum():
     assert rel(K().colsum(xb), xb.float().sum(0)) < 1e-5
 
 
+@pytest.mark.experimental      # not yet confirmed on hardware (GPU queue): run with VT_EXPERIMENTAL=1
 @pytest.mark.parametrize('M,N', [(12544, 768), (12608, 2304), (12552, 3072), (1, 8), (255, 264), (257, 1000), (3000, 96),
                                  (513, 100)])
 def test_colsum_shapes_and_views(M, N, monkeypatch):

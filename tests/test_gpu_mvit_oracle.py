@@ -112,6 +112,7 @@ def test_token_preparation_vs_oracle():
     assert rel_err(got.cpu(), ref) < 1e-6
 
 
+@pytest.mark.experimental      # not yet confirmed on hardware (GPU queue): run with VT_EXPERIMENTAL=1
 def test_masked_mse_vs_oracle_loss():
     """Loss half of mvit_oracle.maskfeat_forward (video_transformer.py:882-901) incl. the centre-frame mask."""
     from oracle import mvit_oracle as MO
