@@ -725,7 +725,28 @@ def main():
     args = ap.parse_args()
     if args.impl == 'reference':
         return main_reference(args)
-    return main_gpu(args)
+    if int(os.environ.get('WORLD_SIZE', '1')) > 1 or args.workload != 'timesformer':
+        return main_gpu(args)
+    try:
+        return main_gpu(args)
+    except SystemExit:
+        raise
+    except Exception as exc:
+        # One GPU, default workload: never lose the headline line to a bug in the newer measurement code — re-run the copy of
+        # this benchmark that was confirmed on hardware (tools/bench_v1.py) in a fresh process (fresh CUDA context).
+        import traceback
+        traceback.print_exc()
+        sys.stderr.write(f'bench.py: measurement raised {type(exc).__name__}; falling back to tools/bench_v1.py\n')
+        cmd = [sys.executable, os.path.join(ROOT, 'tools', 'bench_v1.py'), '--gpus', '1', '--steps', str(args.steps),
+               '--warmup', str(args.warmup)] + (['--no-graph'] if args.no_graph else [])
+        out = subprocess.run(cmd, capture_output=True, text=True)
+        sys.stderr.write(out.stderr[-4000:])
+        lines = [ln for ln in out.stdout.splitlines() if ln.startswith('{')]
+        if not lines:
+            raise
+        line = json.loads(lines[-1])
+        line['fallback'] = f'tools/bench_v1.py after {type(exc).__name__}: {str(exc)[:160]}'
+        print(json.dumps(line), flush=True)
 
 
 if __name__ == '__main__':
