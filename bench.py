@@ -256,6 +256,10 @@ class MaskFeatStep(torch.nn.Module):
         from videotransformer_pytorch_b200 import MaskFeat
         self.net = MaskFeat(**MASKFEAT_KW)
         self.features_only = features_only
+        if features_only:       # backbone alone: the decoder and the mask token take no part (model_trainer.py:78-79 freezes the decoder)
+            for p in self.net.decoder_pred.parameters():
+                p.requires_grad = False
+            self.net.mask_token.requires_grad = False
 
     def forward(self, x, target=None, mask=None, cmask=None):
         if self.features_only:
@@ -658,9 +662,10 @@ def main_gpu(args):
         dist.barrier()
     cpu = cpu_fwd = eager = None
     if rank == 0:
-        cpu = run_cpu(name, steps=5, warmup=1, batch=1)
-        cpu_fwd = run_cpu(name, steps=5, warmup=1, batch=1, forward_only=True)
-        if name == 'timesformer' and world == 1:
+        k_cpu = 5 if args.baselines else 1
+        cpu = run_cpu(name, steps=k_cpu, warmup=1 if args.baselines else 0, batch=1)
+        cpu_fwd = run_cpu(name, steps=k_cpu, warmup=1 if args.baselines else 0, batch=1, forward_only=True)
+        if name == 'timesformer' and world == 1 and args.baselines:
             try:
                 eager = gpu_eager_baseline(dev, B)
             except Exception as exc:
@@ -722,6 +727,7 @@ def main():
     ap.add_argument('--reserve-sms', type=int, default=0, help='SMs kept free of persistent GEMM CTAs when N > 1 (NCCL overlap)')
     ap.add_argument('--no-graph', action='store_true', help='issue the step kernel by kernel instead of replaying a CUDA graph')
     ap.add_argument('--no-others', dest='others', action='store_false', help='skip the other BASELINE configs in the default line')
+    ap.add_argument('--no-baselines', dest='baselines', action='store_false', help='skip the CPU / eager-GPU comparators (A/B runs)')
     args = ap.parse_args()
     if args.impl == 'reference':
         return main_reference(args)

@@ -70,7 +70,6 @@ def test_casts_and_colsum():
     assert rel(K().colsum(xb), xb.float().sum(0)) < 1e-5
 
 
-@pytest.mark.experimental      # not yet confirmed on hardware (GPU queue): run with VT_EXPERIMENTAL=1
 @pytest.mark.parametrize('M,N', [(12544, 768), (12608, 2304), (12552, 3072), (1, 8), (255, 264), (257, 1000), (3000, 96),
                                  (513, 100)])
 def test_colsum_shapes_and_views(M, N, monkeypatch):
@@ -81,8 +80,6 @@ def test_colsum_shapes_and_views(M, N, monkeypatch):
     for x in (wide[:, :N].contiguous(), wide[:, 8:8 + N]):
         ref = x.float().sum(0)
         for mode in ('0', '1'):
-            if mode == '1' and not os.environ.get('VT_EXPERIMENTAL'):
-                continue                      # the wide kernel ships disabled until confirmed on hardware
             monkeypatch.setenv('VT_COLSUM_WIDE', mode)
             for _ in range(2):
                 assert rel(K().colsum(x), ref) < 1e-5

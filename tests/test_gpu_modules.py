@@ -211,7 +211,6 @@ def test_joint_space_time_vs_golden(golden):
     assert worst < 5e-2
 
 
-@pytest.mark.experimental      # not yet confirmed on hardware (GPU queue): run with VT_EXPERIMENTAL=1
 @pytest.mark.parametrize('name,attention_type', [('vivit_joint_hd64', 'joint_space_time'),
                                                  ('vivit_divided_hd64', 'divided_space_time')])
 def test_vivit_joint_and_divided_variants_vs_golden(golden, name, attention_type):

@@ -112,7 +112,6 @@ def test_token_preparation_vs_oracle():
     assert rel_err(got.cpu(), ref) < 1e-6
 
 
-@pytest.mark.experimental      # not yet confirmed on hardware (GPU queue): run with VT_EXPERIMENTAL=1
 def test_masked_mse_vs_oracle_loss():
     """Loss half of mvit_oracle.maskfeat_forward (video_transformer.py:882-901) incl. the centre-frame mask."""
     from oracle import mvit_oracle as MO
@@ -174,7 +173,6 @@ def test_multiscale_block_vs_oracle_at_mvit_b_shapes(index, thw):
     assert errs[0][0] < 5e-2, errs[:4]
 
 
-@pytest.mark.experimental
 def test_masked_mse_fp64_targets():
     """fp64 targets (the reference's numpy default): differences and sums in fp64 on the device, fp64 loss; gradient as fp32."""
     B, t, dt, h, w, dc = 2, 8, 2, 14, 14, 108

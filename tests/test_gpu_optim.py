@@ -68,7 +68,6 @@ def test_fused_sgd_on_a_model_with_static_grads():
         assert rel_err(q.detach().cpu(), p.detach()) < 5e-6
 
 
-@pytest.mark.experimental      # not yet confirmed on hardware (GPU queue): run with VT_EXPERIMENTAL=1
 def test_eager_training_with_fused_sgd_tracks_torch_sgd():
     """Eager (non-graph) training of a package model: the fused optimizer updates parameters through raw pointers, the
     bf16 weight shadows must follow (stale-shadow bug).  Two identical TimeSformers, one stepped by

@@ -7,7 +7,8 @@ import sys
 import time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from bench import Trainee, T, IMG, NUM_CLASSES
+from bench import Trainee, IMG, NUM_CLASSES
+T = 8
 
 mode = sys.argv[1] if len(sys.argv) > 1 else 'torchprof'
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 8

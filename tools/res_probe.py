@@ -3,6 +3,7 @@ import os
 import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 os.environ['VT_TMA_RES'] = '1'
+os.environ.setdefault('VT_TMA_RES_SPATIAL', '1')
 import torch
 from videotransformer_pytorch_b200 import _lib, ops
 

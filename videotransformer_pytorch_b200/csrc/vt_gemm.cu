@@ -16,6 +16,7 @@ namespace vt {
 // instead of 4.1 KiB, paid for with one pipeline stage where shared memory is full.
 // compiled defaults of the round-2 paths (environment VT_TMA_RES / VT_TAIL_UNITS / VT_TMA_GELU / VT_TMA_DGELU = 0 | 1 override)
 constexpr bool VT_DEFAULT_TMA_RES = false;
+constexpr bool VT_DEFAULT_TMA_RES_SPATIAL = false;
 constexpr bool VT_DEFAULT_TAIL_UNITS = false;
 constexpr bool VT_DEFAULT_TMA_GELU = false;
 constexpr bool VT_DEFAULT_TMA_DGELU = false;
@@ -269,7 +270,7 @@ int make_tmap_out_3d(CUtensorMap* map, const void* base, int fp32, long long M, 
 // 4-D fp32 map (col, t, p, b) of the residual epilogue (epilogue_tile_tma_res): box {32, 1, 32, 1}, 128B swizzle.
 //   element (n, t, p, b) at base + n + t*stride_t + p*stride_p + b*stride_b   (strides in elements, multiples of 4)
 int make_tmap_rows_4d(CUtensorMap* map, const void* base, long long cols, long long tcount, long long pcount, long long bcount,
-                      long long stride_t, long long stride_p, long long stride_b) {
+                      long long stride_t, long long stride_p, long long stride_b, bool p_first) {
   EncodeTiledFn fn = get_encode_fn();
   VT_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
   VT_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base pointer must be 16-byte aligned");
@@ -278,6 +279,11 @@ int make_tmap_rows_4d(CUtensorMap* map, const void* base, long long cols, long l
   cuuint64_t gdim[4] = {(cuuint64_t)cols, (cuuint64_t)tcount, (cuuint64_t)pcount, (cuuint64_t)bcount};
   cuuint64_t gstr[3] = {(cuuint64_t)(stride_t * 4), (cuuint64_t)(stride_p * 4), (cuuint64_t)(stride_b * 4)};
   cuuint32_t box[4] = {32u, 1u, 32u, 1u};
+  if (p_first) {      // (col, p, t, b): the 32-row side of the box is the second dimension, like every 2-D / 3-D map in this library
+    gdim[1] = (cuuint64_t)pcount; gdim[2] = (cuuint64_t)tcount;
+    gstr[0] = (cuuint64_t)(stride_p * 4); gstr[1] = (cuuint64_t)(stride_t * 4);
+    box[1] = 32u; box[2] = 1u;
+  }
   cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), gdim, gstr, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
@@ -311,7 +317,10 @@ int make_tmap_rows_3d(CUtensorMap* map, const void* base, long long cols, long l
 bool res_tma_applicable(const vt_gemm_params* q) {
   if (q->epilogue != VT_EPI_F32 || !q->aux || getenv("VT_NO_TMA_STORE") || !feature_on("VT_TMA_RES", VT_DEFAULT_TMA_RES)) return false;
   if (q->N % 4 != 0) return false;
-  if (q->map_period > 0) return q->map_period >= 32 && q->map_tcount >= 1 && q->M % q->map_period == 0;
+  if (q->map_period > 0) {
+    if (q->map_tcount > 1 && !feature_on("VT_TMA_RES_SPATIAL", VT_DEFAULT_TMA_RES_SPATIAL)) return false;   // rank-4 maps: separate switch
+    return q->map_period >= 32 && q->map_tcount >= 1 && q->M % q->map_period == 0;
+  }
   return !q->out_row && !q->aux_row && q->ldo % 4 == 0 && q->ldaux % 4 == 0;
 }
 
@@ -330,12 +339,13 @@ int setup_res_maps(const vt_gemm_params* q, GemmDev& d, CUtensorMap* tmC, CUtens
       rc = make_tmap_rows_3d(tmX, static_cast<const float*>(q->aux) + q->map_base, q->N, pcount, bcount, q->map_stride_p,
                              q->map_stride_b);
     } else {
-      d.map_rank = 4;
+      const bool p_first = feature_on("VT_RES_4D_PFIRST", true);
+      d.map_rank = p_first ? 40 : 4;
       rc = make_tmap_rows_4d(tmC, static_cast<float*>(q->out) + q->map_base, q->N, q->map_tcount, pcount, bcount, q->map_stride_t,
-                             q->map_stride_p, q->map_stride_b);
+                             q->map_stride_p, q->map_stride_b, p_first);
       if (rc) return rc;
       rc = make_tmap_rows_4d(tmX, static_cast<const float*>(q->aux) + q->map_base, q->N, q->map_tcount, pcount, bcount,
-                             q->map_stride_t, q->map_stride_p, q->map_stride_b);
+                             q->map_stride_t, q->map_stride_p, q->map_stride_b, p_first);
     }
     if (rc) return rc;
     d.special_out = q->map_special_base >= 0 ? static_cast<float*>(q->out) + q->map_special_base : nullptr;

@@ -404,13 +404,17 @@ __device__ __forceinline__ void epilogue_tile_tma_res(const GemmDev& p, const CU
   const bool special = row < p.M && my_inner < p.map_skip;
   const int nchunks = (bn / 32 - half + 1) / 2;          // chunks c = half, half + 2, ... of this warpgroup
   const bool rank3 = p.map_rank == 3;
+  const bool p_first = p.map_rank == 40;     // rank 4 with the box-spanning dimension second: (col, p, t, b), box {32, 32, 1, 1}
   auto chunk_cols_ok = [&](int it) { return n_base + (half + 2 * it) * 32 < p.N; };
   auto request = [&](int it, int buf, int sgm) {        // lane 0: residual box of chunk `it`, segment sgm -> buffer buf
-    if (rank3) tma_load_3d(slot + buf * 4096, tmX, &aux_bar[buf], n_base + (half + 2 * it) * 32, seg_p[sgm], seg_b[sgm]);
-    else tma_load_4d(slot + buf * 4096, tmX, &aux_bar[buf], n_base + (half + 2 * it) * 32, seg_t[sgm], seg_p[sgm], seg_b[sgm]);
+    const int n = n_base + (half + 2 * it) * 32;
+    if (rank3) tma_load_3d(slot + buf * 4096, tmX, &aux_bar[buf], n, seg_p[sgm], seg_b[sgm]);
+    else if (p_first) tma_load_4d(slot + buf * 4096, tmX, &aux_bar[buf], n, seg_p[sgm], seg_t[sgm], seg_b[sgm]);
+    else tma_load_4d(slot + buf * 4096, tmX, &aux_bar[buf], n, seg_t[sgm], seg_p[sgm], seg_b[sgm]);
   };
   auto store = [&](const void* src, int n0, int sgm) {
     if (rank3) tma_store_3d(tmC, src, n0, seg_p[sgm], seg_b[sgm]);
+    else if (p_first) tma_store_4d(tmC, src, n0, seg_p[sgm], seg_t[sgm], seg_b[sgm]);
     else tma_store_4d(tmC, src, n0, seg_t[sgm], seg_p[sgm], seg_b[sgm]);
   };
   // Single-segment groups: chunk `it` lives in buffer it & 1 and chunk it + 1 is prefetched into the other buffer.
