@@ -13,5 +13,6 @@ timeout 1500 ncu --profile-from-start off --set full --clock-control none --impo
   -o gpurun_out/r2_bwd python tools/profile_step.py ncu > gpurun_out/ncu_bwd.log 2>&1; echo "full bwd rc=$?"
 for f in fwd bwd; do
   ncu -i gpurun_out/r2_$f.ncu-rep --page raw --csv > gpurun_out/r2_${f}_raw.csv 2> /dev/null
+  rm -f gpurun_out/r2_$f.ncu-rep          # ~100 MB each: gpurun only brings back 64 MiB, the raw page is what gets summarised
 done
 ls -la gpurun_out/ | tail -n 12

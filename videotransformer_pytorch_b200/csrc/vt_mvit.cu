@@ -392,6 +392,256 @@ pool_dw_kernel(const float* __restrict__ dpooled, const __nv_bfloat16* __restric
 }
 
 // ================================================================================================
+// Second generation of the three pooling kernels (head dim 96): lane l < 24 owns the four consecutive channels
+// [4l, 4l+4) of a head, so one token row of a head is ONE 8-byte load per lane (bf16) or one 16-byte load (fp32) instead
+// of three 2-byte / 4-byte ones, filter taps sit in shared memory as float4 [tap][lane], and every tap of a window is
+// in flight before the first FMA.  Lanes 24..31 carry zeros through the warp reductions.
+//   forward: warp = pooled row (b, h, l)
+//   d(input): warp = (input token, head); the <= 27 covering outputs come from the per-axis tables, nine predicated
+//             loads per valid time plane
+//   d(filter): warp = (pooled row, time tap): 9 taps x 4 channels of accumulators per lane, CTA = 4 row slots x 3 time
+//             taps; the four slots are summed in shared memory in a fixed order (deterministic), one partial row per CTA
+// Needs 8-byte aligned token rows (row / batch strides multiples of 4 elements) — the launchers check.
+// ================================================================================================
+constexpr int PV_LANES = 24;
+constexpr int PV_HD = 96;
+
+__device__ __forceinline__ void bf16x4_to_f(uint2 raw, float (&f)[4]) {
+  f[0] = __uint_as_float(raw.x << 16);
+  f[1] = __uint_as_float(raw.x & 0xffff0000u);
+  f[2] = __uint_as_float(raw.y << 16);
+  f[3] = __uint_as_float(raw.y & 0xffff0000u);
+}
+__device__ __forceinline__ uint2 f_to_bf16x4(const float (&f)[4]) {
+  const __nv_bfloat162 a = __floats2bfloat162_rn(f[0], f[1]), b = __floats2bfloat162_rn(f[2], f[3]);
+  uint2 r;
+  r.x = *reinterpret_cast<const unsigned*>(&a);
+  r.y = *reinterpret_cast<const unsigned*>(&b);
+  return r;
+}
+// filter taps as float4 [tap][lane]: element j of entry (tap, l) is w[(4l + j) * 27 + tap]
+__device__ __forceinline__ void stage_taps(float4* sw4, const float* __restrict__ w) {
+  for (int i = threadIdx.x; i < 27 * PV_LANES; i += blockDim.x) {
+    const int tap = i / PV_LANES, l = i - tap * PV_LANES;
+    sw4[i] = make_float4(w[(4 * l + 0) * 27 + tap], w[(4 * l + 1) * 27 + tap], w[(4 * l + 2) * 27 + tap], w[(4 * l + 3) * 27 + tap]);
+  }
+}
+
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+pool_ln_fwd_v2_kernel(const __nv_bfloat16* __restrict__ in, long long in_bs, long long in_rs,
+                      const float* __restrict__ w, const float* __restrict__ gamma, const float* __restrict__ beta,
+                      float* __restrict__ pooled, __nv_bfloat16* __restrict__ out, float* __restrict__ mean,
+                      float* __restrict__ rstd, PoolDims d, float eps) {
+  __shared__ float4 sw4[27 * PV_LANES];
+  stage_taps(sw4, w);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool act = lane < PV_LANES;
+  const int cl = act ? lane : 0;                                  // idle lanes shadow lane 0's addresses, contribute zeros
+  const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma) + cl);
+  const float4 b4 = __ldg(reinterpret_cast<const float4*>(beta) + cl);
+  const int Lo1 = 1 + d.To * d.Ho * d.Wo;
+  const int rows = d.B * d.H * Lo1;                               // < 2^31, checked by the launcher
+  for (int r = blockIdx.x * ROW_WARPS + warp; r < rows; r += gridDim.x * ROW_WARPS) {
+    const int bh = r / Lo1, l = r - bh * Lo1;
+    const int b = bh / d.H, h = bh - b * d.H;
+    const __nv_bfloat16* base = in + (long long)b * in_bs + (long long)h * PV_HD + 4 * cl;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (l == 0) {
+      bf16x4_to_f(__ldg(reinterpret_cast<const uint2*>(base)), acc);
+    } else {
+      const int o = l - 1;
+      const int o2 = o / d.Wo;
+      const int ow = o - o2 * d.Wo, ot = o2 / d.Ho, oh = o2 - ot * d.Ho;
+      long long off[9];
+      bool ok[9];
+#pragma unroll
+      for (int dh = 0; dh < 3; ++dh)
+#pragma unroll
+        for (int dw = 0; dw < 3; ++dw) {
+          const int hi = oh * d.sh - 1 + dh, wi = ow * d.sw - 1 + dw;
+          ok[dh * 3 + dw] = hi >= 0 && hi < d.Hin && wi >= 0 && wi < d.Win;
+          off[dh * 3 + dw] = ((long long)min(max(hi, 0), d.Hin - 1) * d.Win + min(max(wi, 0), d.Win - 1)) * in_rs;
+        }
+      uint2 x[27];
+      bool tok[3];
+#pragma unroll
+      for (int dt = 0; dt < 3; ++dt) {
+        const int ti = ot * d.st - 1 + dt;
+        tok[dt] = ti >= 0 && ti < d.T;
+        const __nv_bfloat16* plane = base + (1 + (long long)min(max(ti, 0), d.T - 1) * d.Hin * d.Win) * in_rs;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) x[dt * 9 + k] = __ldg(reinterpret_cast<const uint2*>(plane + off[k]));
+      }
+#pragma unroll
+      for (int dt = 0; dt < 3; ++dt)
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+          const float4 f = sw4[(dt * 9 + k) * PV_LANES + cl];
+          float xv[4];
+          bf16x4_to_f(x[dt * 9 + k], xv);
+          const float m = tok[dt] && ok[k] ? 1.f : 0.f;
+          acc[0] = fmaf(xv[0] * m, f.x, acc[0]);
+          acc[1] = fmaf(xv[1] * m, f.y, acc[1]);
+          acc[2] = fmaf(xv[2] * m, f.z, acc[2]);
+          acc[3] = fmaf(xv[3] * m, f.w, acc[3]);
+        }
+    }
+    if (!act) acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+    const float mu = warp_sum(acc[0] + acc[1] + acc[2] + acc[3]) * (1.0f / PV_HD);
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float c = acc[j] - mu;
+      ss += c * c;
+    }
+    const float rs = rsqrtf(warp_sum(act ? ss : 0.f) * (1.0f / PV_HD) + eps);
+    if (lane == 0) {
+      mean[r] = mu;
+      rstd[r] = rs;
+    }
+    if (act) {
+      *reinterpret_cast<float4*>(pooled + (long long)r * PV_HD + 4 * lane) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      const float y[4] = {(acc[0] - mu) * rs * g4.x + b4.x, (acc[1] - mu) * rs * g4.y + b4.y, (acc[2] - mu) * rs * g4.z + b4.z,
+                          (acc[3] - mu) * rs * g4.w + b4.w};
+      *reinterpret_cast<uint2*>(out + (long long)r * PV_HD + 4 * lane) = f_to_bf16x4(y);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+pool_din_v2_kernel(const float* __restrict__ dpooled, const float* __restrict__ w, __nv_bfloat16* __restrict__ din,
+                   long long din_bs, long long din_rs, PoolDims d) {
+  __shared__ float4 sw4[27 * PV_LANES];
+  __shared__ short tab[3][3][POOL_MAX_DIM];     // [axis t/h/w][tap][input coordinate] -> output coordinate, -1 = none
+  stage_taps(sw4, w);
+  for (int i = threadIdx.x; i < 9 * POOL_MAX_DIM; i += blockDim.x) {
+    const int axis = i / (3 * POOL_MAX_DIM), k = (i / POOL_MAX_DIM) % 3, c = i % POOL_MAX_DIM;
+    const int n_in = axis == 0 ? d.T : axis == 1 ? d.Hin : d.Win;
+    const int s = axis == 0 ? d.st : axis == 1 ? d.sh : d.sw;
+    const int n_out = axis == 0 ? d.To : axis == 1 ? d.Ho : d.Wo;
+    int v = -1;
+    if (c < n_in) {
+      const int nn = c + 1 - k;                   // o * s - 1 + k == c
+      if (nn >= 0 && nn % s == 0 && nn / s < n_out) v = nn / s;
+    }
+    tab[axis][k][c] = (short)v;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool act = lane < PV_LANES;
+  const int cl = act ? lane : 0;
+  const int L1 = 1 + d.T * d.Hin * d.Win;
+  const int Lo1 = 1 + d.To * d.Ho * d.Wo;
+  const long long items = (long long)d.B * L1 * d.H;
+  for (long long it = (long long)blockIdx.x * ROW_WARPS + warp; it < items; it += (long long)gridDim.x * ROW_WARPS) {
+    const int tok = (int)(it / d.H), h = (int)(it - (long long)tok * d.H);
+    const int b = tok / L1, n = tok - b * L1;
+    const float* dp = dpooled + ((long long)b * d.H + h) * Lo1 * PV_HD + 4 * cl;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (n == 0) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(dp));
+      acc[0] = g.x, acc[1] = g.y, acc[2] = g.z, acc[3] = g.w;
+    } else {
+      const int idx = n - 1;
+      const int t2 = idx / d.Win;
+      const int wi = idx - t2 * d.Win, ti = t2 / d.Hin, hi = t2 - ti * d.Hin;
+      int rowoff[9];                                 // (oh * Wo + ow) of the output reached through (dh, dw), -1 = none
+#pragma unroll
+      for (int dh = 0; dh < 3; ++dh)
+#pragma unroll
+        for (int dw = 0; dw < 3; ++dw) {
+          const int oh = tab[1][dh][hi], ow = tab[2][dw][wi];
+          rowoff[dh * 3 + dw] = oh >= 0 && ow >= 0 ? oh * d.Wo + ow : -1;
+        }
+#pragma unroll
+      for (int dt = 0; dt < 3; ++dt) {
+        const int ot = tab[0][dt][ti];
+        if (ot < 0) continue;                          // warp-uniform
+        const float* plane = dp + (1 + (long long)ot * d.Ho * d.Wo) * PV_HD;
+        float4 g[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k)
+          g[k] = rowoff[k] >= 0 ? __ldg(reinterpret_cast<const float4*>(plane + (long long)rowoff[k] * PV_HD)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+          const float4 f = sw4[(dt * 9 + k) * PV_LANES + cl];
+          acc[0] = fmaf(g[k].x, f.x, acc[0]);
+          acc[1] = fmaf(g[k].y, f.y, acc[1]);
+          acc[2] = fmaf(g[k].z, f.z, acc[2]);
+          acc[3] = fmaf(g[k].w, f.w, acc[3]);
+        }
+      }
+    }
+    if (act) *reinterpret_cast<uint2*>(din + (long long)b * din_bs + (long long)n * din_rs + h * PV_HD + 4 * lane) = f_to_bf16x4(acc);
+  }
+}
+
+constexpr int DW2_SLOTS = 4;                      // pooled rows in flight per CTA (x 3 time taps = 12 warps)
+constexpr int DW2_MIN_ROWS_PER_CTA = 8;
+
+__global__ void __launch_bounds__(DW2_SLOTS * 3 * 32)
+pool_dw_v2_kernel(const float* __restrict__ dpooled, const __nv_bfloat16* __restrict__ in, long long in_bs, long long in_rs,
+                  float* __restrict__ partials, PoolDims d, int rows_per_cta) {
+  __shared__ float red[DW2_SLOTS][27 * PV_HD];     // 41 KB
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slot = warp / 3, dt = warp - slot * 3;
+  const bool act = lane < PV_LANES;
+  const int cl = act ? lane : 0;
+  const int Lo = d.To * d.Ho * d.Wo;
+  const long long rows = (long long)d.B * d.H * Lo;
+  const long long r0 = (long long)blockIdx.x * rows_per_cta;
+  const long long r1 = min(rows, r0 + rows_per_cta);
+  float acc[9][4];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.f;
+  for (long long r = r0 + slot; r < r1; r += DW2_SLOTS) {
+    const int bh = (int)(r / Lo), o = (int)(r - (long long)bh * Lo);
+    const int b = bh / d.H, h = bh - b * d.H;
+    const int o2 = o / d.Wo;
+    const int ow = o - o2 * d.Wo, ot = o2 / d.Ho, oh = o2 - ot * d.Ho;
+    const int ti = ot * d.st - 1 + dt;
+    if (ti < 0 || ti >= d.T) continue;             // warp-uniform: this time tap falls outside the clip
+    const float4 g = __ldg(reinterpret_cast<const float4*>(dpooled + ((long long)bh * (Lo + 1) + 1 + o) * PV_HD + 4 * cl));
+    const __nv_bfloat16* plane = in + (long long)b * in_bs + (long long)h * PV_HD + 4 * cl + (1 + (long long)ti * d.Hin * d.Win) * in_rs;
+    uint2 x[9];
+    bool ok[9];
+#pragma unroll
+    for (int dh = 0; dh < 3; ++dh)
+#pragma unroll
+      for (int dw = 0; dw < 3; ++dw) {
+        const int hi = oh * d.sh - 1 + dh, wi = ow * d.sw - 1 + dw;
+        ok[dh * 3 + dw] = hi >= 0 && hi < d.Hin && wi >= 0 && wi < d.Win;
+        x[dh * 3 + dw] = __ldg(reinterpret_cast<const uint2*>(plane + ((long long)min(max(hi, 0), d.Hin - 1) * d.Win + min(max(wi, 0), d.Win - 1)) * in_rs));
+      }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      float xv[4];
+      bf16x4_to_f(x[k], xv);
+      const float m = ok[k] ? 1.f : 0.f;
+      acc[k][0] = fmaf(g.x * m, xv[0], acc[k][0]);
+      acc[k][1] = fmaf(g.y * m, xv[1], acc[k][1]);
+      acc[k][2] = fmaf(g.z * m, xv[2], acc[k][2]);
+      acc[k][3] = fmaf(g.w * m, xv[3], acc[k][3]);
+    }
+  }
+  if (act) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) red[slot][(4 * lane + j) * 27 + dt * 9 + k] = acc[k][j];
+  }
+  __syncthreads();
+  float* pg = partials + (long long)blockIdx.x * 27 * PV_HD;
+  for (int i = threadIdx.x; i < 27 * PV_HD; i += blockDim.x) {
+    float a = red[0][i];
+#pragma unroll
+    for (int s2 = 1; s2 < DW2_SLOTS; ++s2) a += red[s2][i];
+    pg[i] = a;
+  }
+}
+
+// ================================================================================================
 // Pooling attention, head dim HD (96): CUDA-core flash kernels.
 //   forward / dQ: two threads per query row (each owns HD/2 dims), 64 queries per CTA, K/V tiles of 16 keys in smem
 //   dK/dV: four threads per key row (each owns HD/4 dims), 32 keys per CTA, Q/dO tiles of 16 queries in smem,
@@ -1025,6 +1275,14 @@ int vt::layernorm_bwd_small(const vt_ln_bwd_params* p, void* stream) {
   return check_launch("ln_small_bwd_kernel");
 }
 
+// the 4-channels-per-lane kernels need 8-byte aligned token rows; VT_POOL_V2=0 selects the first generation
+#ifndef VT_DEFAULT_POOL_V2
+#define VT_DEFAULT_POOL_V2 false
+#endif
+static bool pool_v2(const void* ptr, long long bs, long long rs) {
+  return feature_on("VT_POOL_V2", VT_DEFAULT_POOL_V2) && ((uintptr_t)ptr & 7) == 0 && bs % 4 == 0 && rs % 4 == 0;
+}
+
 static int pool_dims_ok(int T, int Hin, int Win, int st, int sh, int sw, int To, int Ho, int Wo) {
   return st >= 1 && sh >= 1 && sw >= 1 && To == (T + 2 - 3) / st + 1 && Ho == (Hin + 2 - 3) / sh + 1 && Wo == (Win + 2 - 3) / sw + 1;
 }
@@ -1037,6 +1295,12 @@ extern "C" int vt_pool_fwd(const vt_pool_fwd_params* p, void* stream) {
   const PoolDims d{p->B, p->H, p->T, p->Hin, p->Win, p->st, p->sh, p->sw, p->To, p->Ho, p->Wo};
   const long long rows = (long long)p->B * p->H * (1 + (long long)p->To * p->Ho * p->Wo);
   VT_REQUIRE(rows < 0x7fffffffll, "vt_pool_fwd: too many rows");
+  if (pool_v2(p->in, p->in_bs, p->in_rs)) {
+    pool_ln_fwd_v2_kernel<<<row_blocks(rows, 8), ROW_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(p->in), p->in_bs, p->in_rs, p->w, p->gamma, p->beta, p->pooled,
+        static_cast<__nv_bfloat16*>(p->out), p->mean, p->rstd, d, p->eps);
+    return check_launch("pool_ln_fwd_v2_kernel");
+  }
   pool_ln_fwd_kernel<3><<<row_blocks(rows, 8), ROW_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(p->in), p->in_bs, p->in_rs, p->w, p->gamma, p->beta, p->pooled,
       static_cast<__nv_bfloat16*>(p->out), p->mean, p->rstd, d, p->eps);
@@ -1044,8 +1308,8 @@ extern "C" int vt_pool_fwd(const vt_pool_fwd_params* p, void* stream) {
 }
 
 constexpr int DW_MIN_ROWS_PER_CTA = 64;
-static int pool_dw_blocks(long long rows) {
-  long long blocks = (rows + DW_MIN_ROWS_PER_CTA - 1) / DW_MIN_ROWS_PER_CTA;
+static int pool_dw_blocks(long long rows) {                        // sized for the finer-grained second generation
+  long long blocks = (rows + DW2_MIN_ROWS_PER_CTA - 1) / DW2_MIN_ROWS_PER_CTA;
   const long long cap = (long long)sm_count() * 2;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
@@ -1095,18 +1359,33 @@ extern "C" int vt_pool_bwd(const vt_pool_bwd_params* p, void* stream) {
              p->T, p->Hin, p->Win, POOL_MAX_DIM);
   const long long tokens_in = (long long)p->B * (1 + (long long)p->T * p->Hin * p->Win);
   VT_REQUIRE(tokens_in < 0x7fffffffll, "vt_pool_bwd: too many tokens");
-  pool_din_kernel<3><<<row_blocks(tokens_in, 8), ROW_WARPS * 32, 0, st>>>(dpooled, p->w, static_cast<__nv_bfloat16*>(p->din),
-                                                                        p->din_bs, p->din_rs, d);
-  rc = check_launch("pool_din_kernel");
+  const bool v2 = pool_v2(p->in, p->in_bs, p->in_rs) && pool_v2(p->din, p->din_bs, p->din_rs);
+  if (v2) {
+    pool_din_v2_kernel<<<row_blocks(tokens_in * p->H, 8), ROW_WARPS * 32, 0, st>>>(dpooled, p->w, static_cast<__nv_bfloat16*>(p->din),
+                                                                                   p->din_bs, p->din_rs, d);
+    rc = check_launch("pool_din_v2_kernel");
+  } else {
+    pool_din_kernel<3><<<row_blocks(tokens_in, 8), ROW_WARPS * 32, 0, st>>>(dpooled, p->w, static_cast<__nv_bfloat16*>(p->din),
+                                                                          p->din_bs, p->din_rs, d);
+    rc = check_launch("pool_din_kernel");
+  }
   if (rc) return rc;
   // 3. filter gradient
   const long long rows_conv = (long long)p->B * p->H * Lo;         // pooled rows without the cls rows
   int dwb = pool_dw_blocks(rows_conv);
+  if (!v2 && dwb > (rows_conv + DW_MIN_ROWS_PER_CTA - 1) / DW_MIN_ROWS_PER_CTA)
+    dwb = (int)((rows_conv + DW_MIN_ROWS_PER_CTA - 1) / DW_MIN_ROWS_PER_CTA);
   const int rows_per_cta = (int)((rows_conv + dwb - 1) / dwb);
   dwb = (int)((rows_conv + rows_per_cta - 1) / rows_per_cta);      // no empty CTAs: every partial row is written
-  pool_dw_kernel<3><<<dwb, 27 * 32, 0, st>>>(dpooled, static_cast<const __nv_bfloat16*>(p->in), p->in_bs, p->in_rs, dw_part, d,
-                                             rows_per_cta);
-  rc = check_launch("pool_dw_kernel");
+  if (v2) {
+    pool_dw_v2_kernel<<<dwb, DW2_SLOTS * 3 * 32, 0, st>>>(dpooled, static_cast<const __nv_bfloat16*>(p->in), p->in_bs, p->in_rs, dw_part,
+                                                          d, rows_per_cta);
+    rc = check_launch("pool_dw_v2_kernel");
+  } else {
+    pool_dw_kernel<3><<<dwb, 27 * 32, 0, st>>>(dpooled, static_cast<const __nv_bfloat16*>(p->in), p->in_bs, p->in_rs, dw_part, d,
+                                               rows_per_cta);
+    rc = check_launch("pool_dw_kernel");
+  }
   if (rc) return rc;
   vt_reduce_params r3{dw_part, p->dw, 27ll * hd, dwb, 27ll * hd, 0, 1.0f};
   return vt_reduce_rows(&r3, stream);
