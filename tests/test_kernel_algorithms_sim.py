@@ -554,19 +554,22 @@ def test_xattn_tensor_core_tile_walk(Nq, Nk):
 # ---------------------------------------------------------------------------------------------------------------------
 # fp32 residual epilogue on TMA (vt_gemm_common.cuh: epilogue_tile_tma_res): box / segment arithmetic of the affine row maps
 # ---------------------------------------------------------------------------------------------------------------------
-def _tma_box(tensor4, c_t, c_p, c_b, rows=32):
-    """rows x D box of the 4-D tensor view [B, P, T, D] at (t, p.., b): out-of-range rows come back as zeros (load) and are
-    dropped (store) — what the TMA unit does in tiled mode, negative start coordinates included."""
+def _tma_box(tensor3, c_row, c_b, estride, rows=32):
+    """rows x D box of the 3-D tensor view [samples, rows in sample, D] starting at row c_row and stepping `estride` rows (the
+    map's element stride): out-of-range rows come back as zeros (load) and are dropped (store) — what the TMA unit does in
+    tiled mode, negative start coordinates included.  Returns (box, valid, row index of every box row)."""
     import torch
-    Bc, Pc, Tc, D = tensor4.shape
-    box = torch.zeros(rows, D, dtype=tensor4.dtype)
+    Bc, Rc, D = tensor3.shape
+    box = torch.zeros(rows, D, dtype=tensor3.dtype)
     valid = torch.zeros(rows, dtype=torch.bool)
+    where = []
     for i in range(rows):
-        p = c_p + i
-        if 0 <= c_b < Bc and 0 <= c_t < Tc and 0 <= p < Pc:
-            box[i] = tensor4[c_b, p, c_t]
+        r = c_row + i * estride
+        where.append(r)
+        if 0 <= c_b < Bc and 0 <= r < Rc:
+            box[i] = tensor3[c_b, r]
             valid[i] = True
-    return box, valid
+    return box, valid, where
 
 
 @pytest.mark.parametrize('B,T,P', [(2, 8, 196), (3, 4, 9 * 4), (1, 2, 50), (2, 3, 33)])
@@ -592,23 +595,25 @@ def test_residual_epilogue_segments_cover_every_row_once(B, T, P, kind):
     rows_total = R + (B * T if kind == 'spatial' else 0)
     got = torch.full((rows_total, D), float('nan'))
     writes = torch.zeros(rows_total, dtype=torch.int32)
-    # the 4-D views the tensor maps describe: element (t, p, b) at base + t*stride_t + p*stride_p + b*stride_b
-    def view4(buf):
-        flat = buf.reshape(-1)
-        pc, tc = aff['period'] - aff['skip'], aff['tcount']
-        bc = (M // aff['period'] + tc - 1) // tc
-        return torch.as_strided(flat, (bc, pc, tc, D), (aff['stride_b'], aff['stride_p'], aff['stride_t'], 1), aff['base'])
-    x4 = view4(x if kind == 'temporal' else torch.cat([x, torch.zeros(B * T, D)]))
-    out_flat = got.reshape(-1)
+    # the 3-D view the tensor maps describe: (sample, row in sample, col); the spatial regrouping walks it with element stride T
     period, skip, tcount = aff['period'], aff['skip'], aff['tcount']
+    pc = period - skip
+    bc = (M // period + tcount - 1) // tcount
+    row_stride = aff['stride_t'] if tcount > 1 else aff['stride_p']
+    if tcount > 1:
+        assert aff['stride_p'] == tcount * aff['stride_t'] and tcount <= 8      # what res_tma_applicable requires
+    def view3(buf):
+        return torch.as_strided(buf.reshape(-1), (bc, pc * tcount, D), (aff['stride_b'], row_stride, 1), aff['base'])
+    x3 = view3(x if kind == 'temporal' else torch.cat([x, torch.zeros(B * T, D)]))
     for m0 in range(0, (M + 127) // 128 * 128, 32):
         outer0, inner0 = m0 // period, m0 % period
         two = inner0 + 32 > period
         segs = []
         for sg in range(2 if two else 1):
             outer = outer0 + sg
-            segs.append((outer % tcount, inner0 - sg * period - skip, outer // tcount))
-        boxes = [_tma_box(x4, *sgm) for sgm in segs]
+            seg_t, seg_p, seg_b = outer % tcount, inner0 - sg * period - skip, outer // tcount
+            segs.append((seg_p * tcount + seg_t, seg_b))        # the kernel's box coordinates
+        boxes = [_tma_box(x3, c_row, c_b, tcount) for c_row, c_b in segs]
         result = torch.zeros(32, D)
         for lane in range(32):
             row = m0 + lane
@@ -621,11 +626,10 @@ def test_residual_epilogue_segments_cover_every_row_once(B, T, P, kind):
                 dst = (aff['special_base'] + (outer0 + my_seg) * aff['special_stride']) // D
                 got[dst] = val
                 writes[dst] += 1
-        for (c_t, c_p, c_b), (_, valid) in zip(segs, boxes):  # TMA stores clip exactly like the loads
+        for (c_row, c_b), (_, valid, where) in zip(segs, boxes):  # TMA stores clip exactly like the loads
             for lane in range(32):
-                p = c_p + lane
                 if valid[lane]:
-                    off = aff['base'] + c_t * aff['stride_t'] + p * aff['stride_p'] + c_b * aff['stride_b']
+                    off = aff['base'] + where[lane] * row_stride + c_b * aff['stride_b']
                     got[off // D] = result[lane]
                     writes[off // D] += 1
     exp = torch.full((rows_total, D), float('nan'))

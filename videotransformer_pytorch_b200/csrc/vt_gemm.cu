@@ -267,43 +267,19 @@ int make_tmap_out_3d(CUtensorMap* map, const void* base, int fp32, long long M, 
   return 0;
 }
 
-// 4-D fp32 map (col, t, p, b) of the residual epilogue (epilogue_tile_tma_res): box {32, 1, 32, 1}, 128B swizzle.
-//   element (n, t, p, b) at base + n + t*stride_t + p*stride_p + b*stride_b   (strides in elements, multiples of 4)
-int make_tmap_rows_4d(CUtensorMap* map, const void* base, long long cols, long long tcount, long long pcount, long long bcount,
-                      long long stride_t, long long stride_p, long long stride_b, bool p_first) {
-  EncodeTiledFn fn = get_encode_fn();
-  VT_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
-  VT_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base pointer must be 16-byte aligned");
-  VT_REQUIRE(stride_t % 4 == 0 && stride_p % 4 == 0 && stride_b % 4 == 0 && stride_t > 0 && stride_p > 0 && stride_b > 0,
-             "row-map strides must be positive multiples of 4 elements (%lld %lld %lld)", stride_t, stride_p, stride_b);
-  cuuint64_t gdim[4] = {(cuuint64_t)cols, (cuuint64_t)tcount, (cuuint64_t)pcount, (cuuint64_t)bcount};
-  cuuint64_t gstr[3] = {(cuuint64_t)(stride_t * 4), (cuuint64_t)(stride_p * 4), (cuuint64_t)(stride_b * 4)};
-  cuuint32_t box[4] = {32u, 1u, 32u, 1u};
-  if (p_first) {      // (col, p, t, b): the 32-row side of the box is the second dimension, like every 2-D / 3-D map in this library
-    gdim[1] = (cuuint64_t)pcount; gdim[2] = (cuuint64_t)tcount;
-    gstr[0] = (cuuint64_t)(stride_p * 4); gstr[1] = (cuuint64_t)(stride_t * 4);
-    box[1] = 32u; box[2] = 1u;
-  }
-  cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), gdim, gstr, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  VT_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(rows 4d) failed (%d) dims %lld %lld %lld %lld strides %lld %lld %lld", (int)r,
-             cols, tcount, pcount, bcount, stride_t, stride_p, stride_b);
-  return 0;
-}
-
 // 3-D fp32 map (col, p, b), box {32, 32, 1}: the row maps whose period is a single run of rows (temporal, or no map at all)
+// estride > 1: the box covers 32 rows that lie `estride` rows apart (box height 32 * estride, element stride estride <= 8)
 int make_tmap_rows_3d(CUtensorMap* map, const void* base, long long cols, long long pcount, long long bcount, long long stride_p,
-                      long long stride_b) {
+                      long long stride_b, int estride = 1) {
   EncodeTiledFn fn = get_encode_fn();
   VT_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
   VT_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base pointer must be 16-byte aligned");
   VT_REQUIRE(stride_p % 4 == 0 && stride_b % 4 == 0 && stride_p > 0 && stride_b > 0, "row-map strides must be positive multiples of 4");
+  VT_REQUIRE(estride >= 1 && estride <= 8, "row-map element stride %d outside 1..8", estride);
   cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)pcount, (cuuint64_t)bcount};
   cuuint64_t gstr[2] = {(cuuint64_t)(stride_p * 4), (cuuint64_t)(stride_b * 4)};
-  cuuint32_t box[3] = {32u, 32u, 1u};
-  cuuint32_t estr[3] = {1u, 1u, 1u};
+  cuuint32_t box[3] = {32u, 32u * (cuuint32_t)estride, 1u};
+  cuuint32_t estr[3] = {1u, (cuuint32_t)estride, 1u};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), gdim, gstr, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -318,7 +294,10 @@ bool res_tma_applicable(const vt_gemm_params* q) {
   if (q->epilogue != VT_EPI_F32 || !q->aux || getenv("VT_NO_TMA_STORE") || !feature_on("VT_TMA_RES", VT_DEFAULT_TMA_RES)) return false;
   if (q->N % 4 != 0) return false;
   if (q->map_period > 0) {
-    if (q->map_tcount > 1 && !feature_on("VT_TMA_RES_SPATIAL", VT_DEFAULT_TMA_RES_SPATIAL)) return false;   // rank-4 maps: separate switch
+    if (q->map_tcount > 1) {        // spatial regrouping: element-strided boxes, own switch
+      if (!feature_on("VT_TMA_RES_SPATIAL", VT_DEFAULT_TMA_RES_SPATIAL)) return false;
+      if (q->map_tcount > 8 || q->map_stride_p != (long long)q->map_tcount * q->map_stride_t) return false;
+    }
     return q->map_period >= 32 && q->map_tcount >= 1 && q->M % q->map_period == 0;
   }
   return !q->out_row && !q->aux_row && q->ldo % 4 == 0 && q->ldaux % 4 == 0;
@@ -331,22 +310,16 @@ int setup_res_maps(const vt_gemm_params* q, GemmDev& d, CUtensorMap* tmC, CUtens
     const long long outers = q->M / q->map_period;
     const long long bcount = (outers + q->map_tcount - 1) / q->map_tcount;
     const long long pcount = q->map_period - q->map_skip;
-    int rc;
-    if (q->map_tcount == 1) {
-      d.map_rank = 3;
-      rc = make_tmap_rows_3d(tmC, static_cast<float*>(q->out) + q->map_base, q->N, pcount, bcount, q->map_stride_p, q->map_stride_b);
-      if (rc) return rc;
-      rc = make_tmap_rows_3d(tmX, static_cast<const float*>(q->aux) + q->map_base, q->N, pcount, bcount, q->map_stride_p,
-                             q->map_stride_b);
-    } else {
-      const bool p_first = feature_on("VT_RES_4D_PFIRST", true);
-      d.map_rank = p_first ? 40 : 4;
-      rc = make_tmap_rows_4d(tmC, static_cast<float*>(q->out) + q->map_base, q->N, q->map_tcount, pcount, bcount, q->map_stride_t,
-                             q->map_stride_p, q->map_stride_b, p_first);
-      if (rc) return rc;
-      rc = make_tmap_rows_4d(tmX, static_cast<const float*>(q->aux) + q->map_base, q->N, q->map_tcount, pcount, bcount,
-                             q->map_stride_t, q->map_stride_p, q->map_stride_b, p_first);
-    }
+    // one map for both regroupings: (col, row in sample, sample).  map_tcount > 1 (spatial): the stream rows of one frame are
+    // map_tcount rows apart = element stride of the box
+    d.map_rank = 3;
+    const long long rows_in_sample = pcount * q->map_tcount;
+    const long long row_stride = q->map_tcount > 1 ? q->map_stride_t : q->map_stride_p;
+    int rc = make_tmap_rows_3d(tmC, static_cast<float*>(q->out) + q->map_base, q->N, rows_in_sample, bcount, row_stride, q->map_stride_b,
+                               q->map_tcount);
+    if (rc) return rc;
+    rc = make_tmap_rows_3d(tmX, static_cast<const float*>(q->aux) + q->map_base, q->N, rows_in_sample, bcount, row_stride,
+                           q->map_stride_b, q->map_tcount);
     if (rc) return rc;
     d.special_out = q->map_special_base >= 0 ? static_cast<float*>(q->out) + q->map_special_base : nullptr;
     d.special_ld = q->map_special_stride;
@@ -611,7 +584,44 @@ int launch_gemm2(const vt_gemm_params* q, GemmDev& d, int bn, bool res, cudaStre
 
 }  // namespace vt
 
+namespace vt {
+int launch_gemm_rows(const vt_gemm_params* q, int m0, void* stream);   // vt_gemm_rows.cu
+}
+
+// M a few rows past a multiple of 128: tensor-core kernel on the full row tiles, CUDA-core dot products for the rest
+// (vt_gemm_rows.cu).  Plain row-major calls only; anything forced by a test goes through the one-kernel path.
+#ifndef VT_DEFAULT_ROWS_SPLIT
+#define VT_DEFAULT_ROWS_SPLIT false
+#endif
+static int rows_split_point(const vt_gemm_params* q) {
+  const int r = q->M % vt::BM;
+  if (r == 0 || r > 16 || q->M < 8 * vt::BM) return 0;
+  if (!vt::feature_on("VT_ROWS_SPLIT", VT_DEFAULT_ROWS_SPLIT)) return 0;
+  if (q->a_mn_major || (q->epilogue != VT_EPI_BF16 && q->epilogue != VT_EPI_F32)) return 0;
+  if (q->out_row || q->aux_row || q->map_period > 0 || q->debug || q->force_splits || q->force_bn || q->force_cluster || q->force_tail) return 0;
+  if (q->epilogue == VT_EPI_F32 && q->workspace && !q->aux && !q->bias && !q->row_scale) return 0;   // split-K candidates
+  if (q->K % 8 != 0 || q->lda % 8 != 0 || q->ldb % 8 != 0) return 0;
+  if ((reinterpret_cast<uintptr_t>(q->a) & 15) || (reinterpret_cast<uintptr_t>(q->b) & 15)) return 0;
+  return q->M - r;
+}
+
+static int gemm_dispatch(const vt_gemm_params* q, void* stream);
+
 extern "C" int vt_gemm(const vt_gemm_params* q, void* stream) {
+  using namespace vt;
+  VT_REQUIRE(q != nullptr, "vt_gemm: null params");
+  const int m0 = (q->a && q->b && q->out && q->M > 0 && q->N > 0 && q->K > 0) ? rows_split_point(q) : 0;
+  if (m0 > 0) {
+    vt_gemm_params head = *q;
+    head.M = m0;
+    const int rc = gemm_dispatch(&head, stream);
+    if (rc) return rc;
+    return launch_gemm_rows(q, m0, stream);
+  }
+  return gemm_dispatch(q, stream);
+}
+
+static int gemm_dispatch(const vt_gemm_params* q, void* stream) {
   using namespace vt;
   VT_REQUIRE(q != nullptr, "vt_gemm: null params");
   VT_REQUIRE(q->M > 0 && q->N > 0 && q->K > 0, "vt_gemm: bad shape M=%d N=%d K=%d", q->M, q->N, q->K);

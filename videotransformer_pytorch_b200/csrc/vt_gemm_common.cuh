@@ -35,7 +35,7 @@ struct GemmDev {
   // inner < map_skip: "special" row (replicated cls token), else tensor coordinates
   // (col, t = outer % map_tcount, p = inner - map_skip, b = outer / map_tcount) of the 4-D out / aux maps
   int map_period, map_skip, map_tcount;
-  int map_rank;            // 3: tensor maps are (col, p, b) with box {32, 32, 1} (map_tcount == 1); 4: (col, t, p, b), box {32, 1, 32, 1}
+  int map_rank;            // 3: tensor maps are (col, row in sample, sample), box {32, 32 * map_tcount, 1} with element stride map_tcount
   float* special_out;      // special rows go to special_out + outer * special_ld (plain per-thread stores), or are dropped
   long long special_ld;
   // narrow tail units: the last (partial) macro row of tiles is cut into units of tail_bn columns so that its few valid
@@ -281,26 +281,15 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmDev& p, const CUtens
 // fp32 residual epilogue on TMA:   out[map(m), n] = s(m) * (acc + bias[n]) + aux[map(m), n]
 // The residual box (32 rows x 32 fp32) is TMA-loaded into the warp's staging buffer — requested before the accumulator
 // is even waited for, the next chunk's one chunk ahead — added to in place (thread = row, same swizzled 16-byte slots
-// the load wrote), and leaves through a TMA store from the same buffer.  Rows reach memory through a 4-D tensor map
-// (col, t, p, b), so the temporal ('b (p t)') and spatial ('(b t) p' + replicated cls) regroupings cost nothing:
+// the load wrote), and leaves through a TMA store from the same buffer.  Rows reach memory through a 3-D tensor map
+// (col, row in sample, sample); for the spatial regrouping the 32 rows of a box are T stream rows apart, which the map
+// expresses as box height 32*T with element stride T (a rank-4 map (col, t, p, b) is not encodable: TMA strides must nest,
+// and the sample stride (1 + P*T) * D is not a multiple of the patch stride T * D — such maps fault on the first store).
+// So the temporal ('b (p t)') and spatial ('(b t) p' + replicated cls) regroupings cost nothing:
 // a 32-row group that crosses a period boundary is served by two boxes (out-of-range rows are clipped by the TMA unit;
 // for the loads the two segments land in the two buffers and every row reads the one its segment wrote).
 // Per warp: 2 buffers of 4 KiB + 2 mbarriers.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(smem_u32(smem_dst)),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2, int c3) {
-  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
-                   reinterpret_cast<uint64_t>(map)),
-               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-               : "memory");
-}
-
 constexpr int RES_SLOT_BYTES = 8192;      // per epilogue warp: two 32 x 32 fp32 boxes
 
 // ------------------------------------------------------------------------------------------------
@@ -403,19 +392,15 @@ __device__ __forceinline__ void epilogue_tile_tma_res(const GemmDev& p, const CU
   const int my_inner = inner0 + lane - my_seg * p.map_period;
   const bool special = row < p.M && my_inner < p.map_skip;
   const int nchunks = (bn / 32 - half + 1) / 2;          // chunks c = half, half + 2, ... of this warpgroup
-  const bool rank3 = p.map_rank == 3;
-  const bool p_first = p.map_rank == 40;     // rank 4 with the box-spanning dimension second: (col, p, t, b), box {32, 32, 1, 1}
+  // row coordinate of a segment in the (col, row-in-sample, sample) map: rows of one frame sit map_tcount apart (the box
+  // walks them through the map's element stride), so segment row p of frame t starts at p * map_tcount + t
   auto chunk_cols_ok = [&](int it) { return n_base + (half + 2 * it) * 32 < p.N; };
   auto request = [&](int it, int buf, int sgm) {        // lane 0: residual box of chunk `it`, segment sgm -> buffer buf
     const int n = n_base + (half + 2 * it) * 32;
-    if (rank3) tma_load_3d(slot + buf * 4096, tmX, &aux_bar[buf], n, seg_p[sgm], seg_b[sgm]);
-    else if (p_first) tma_load_4d(slot + buf * 4096, tmX, &aux_bar[buf], n, seg_p[sgm], seg_t[sgm], seg_b[sgm]);
-    else tma_load_4d(slot + buf * 4096, tmX, &aux_bar[buf], n, seg_t[sgm], seg_p[sgm], seg_b[sgm]);
+    tma_load_3d(slot + buf * 4096, tmX, &aux_bar[buf], n, seg_p[sgm] * p.map_tcount + seg_t[sgm], seg_b[sgm]);
   };
   auto store = [&](const void* src, int n0, int sgm) {
-    if (rank3) tma_store_3d(tmC, src, n0, seg_p[sgm], seg_b[sgm]);
-    else if (p_first) tma_store_4d(tmC, src, n0, seg_p[sgm], seg_t[sgm], seg_b[sgm]);
-    else tma_store_4d(tmC, src, n0, seg_t[sgm], seg_p[sgm], seg_b[sgm]);
+    tma_store_3d(tmC, src, n0, seg_p[sgm] * p.map_tcount + seg_t[sgm], seg_b[sgm]);
   };
   // Single-segment groups: chunk `it` lives in buffer it & 1 and chunk it + 1 is prefetched into the other buffer.
   // Groups with two live segments use both buffers for one chunk (segment k -> buffer k), without prefetch.
