@@ -96,6 +96,12 @@ def alg_bytes(c):
     return b
 
 
+try:
+    BURST_TF = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['bf16_tflops']
+except Exception:
+    BURST_TF = 1682.6
+
+
 def full_summary():
     calls = []
     cj = os.path.join(OUT, 'r2_gemm_calls.json')
@@ -103,7 +109,7 @@ def full_summary():
         calls = json.load(open(cj))
     lines = ['# ncu --set full --clock-control none --import-source on: hot kernels of one eager TimeSformer-B step (batch 8)',
              '# fwd = first layers of the forward pass, bwd = backward of the last layers',
-             '# pass | kernel | grid | duration us | DRAM read MB | DRAM write MB | tensor pipe active % | DRAM throughput % | '
+             '# pass | kernel | grid | duration us | DRAM read MB | DRAM write MB | sm__pipe_tensor_cycles_active % (blind to tcgen05) | DRAM throughput % | '
              'achieved occupancy % | regs | (GEMM: M N K epilogue, algorithmic MB, DRAM/algorithmic)']
     gemm_rows = []
     for tag, skip in (('fwd', 0), ('bwd', None)):
@@ -114,6 +120,9 @@ def full_summary():
         c_name = find(hdr, 'Kernel Name')
         c_dur = find(hdr, 'gpu__time_duration.sum')
         c_rd, c_wr = find(hdr, 'dram__bytes_read.sum'), find(hdr, 'dram__bytes_write.sum')
+        # ncu 2025.2's `--set full` has no counter that sees tcgen05.mma (sm__ops_path_tensor_op_hmma_* reads 0,
+        # sm__pipe_tensor_cycles_active_realtime a few percent for a GEMM running at half of peak): the column is printed as
+        # collected, the GEMM rows add FLOP / duration against the measured burst peak instead
         c_tp = find(hdr, 'sm__pipe_tensor', 'cycles_active', 'pct') or find(hdr, 'sm__inst_executed_pipe_tensor', 'pct')
         c_dt = find(hdr, 'gpu__dram_throughput', 'pct')
         c_occ = find(hdr, 'sm__warps_active', 'pct')
@@ -147,9 +156,11 @@ def full_summary():
                 if ci is not None and ci < len(calls):
                     c = calls[ci]
                     ab = alg_bytes(c) / 1e6
-                    extra = f" | M={c['M']} N={c['N']} K={c['K']} {c['epi']}{'+aux' if c['aux'] else ''} alg {ab:.1f} MB x{(rd + wr) / ab:.2f}"
+                    tf = 2.0 * c['M'] * c['N'] * c['K'] / (dur * 1e-6) / 1e12
+                    extra = (f" | M={c['M']} N={c['N']} K={c['K']} {c['epi']}{'+aux' if c['aux'] else ''} alg {ab:.1f} MB x{(rd + wr) / ab:.2f}"
+                             f" | {tf:.0f} TFLOP/s = {100 * tf / BURST_TF:.0f}% of burst peak")
                     gemm_rows.append(dict(shape=[c['M'], c['N'], c['K']], epi=c['epi'], aux=c['aux'], dram_mb=rd + wr, alg_mb=ab,
-                                          us=dur, tensor_pct=num(r.get(c_tp, 'nan'))))
+                                          us=dur, tensor_pct=100 * tf / BURST_TF))
             lines.append(f"{tag} {name:52s} {r.get(c_grid, '?'):>7s} {dur:8.1f} {rd:8.1f} {wr:8.1f} {num(r.get(c_tp, 'nan')):6.1f} "
                          f"{num(r.get(c_dt, 'nan')):6.1f} {num(r.get(c_occ, 'nan')):6.1f} {r.get(c_reg, '?'):>4s}{extra}")
     with open(os.path.join(PROF, 'r2_ncu_full_summary.txt'), 'w') as fh:
@@ -161,7 +172,7 @@ def full_summary():
             'dram_bytes_per_launch': 1e6 * sum(g['dram_mb'] for g in gemm_rows) / len(gemm_rows),
             'algorithmic_bytes_per_launch': 1e6 * sum(g['alg_mb'] for g in gemm_rows) / len(gemm_rows),
             'launches_averaged': len(gemm_rows),
-            'time_weighted_tensor_pipe_active_pct': sum(g['us'] * g['tensor_pct'] for g in gemm_rows) / tot_us,
+            'time_weighted_pct_of_burst_bf16_peak': sum(g['us'] * g['tensor_pct'] for g in gemm_rows) / tot_us,
             'per_shape': gemm_rows[:14],
             'source': 'profiles/r2_ncu_full_summary.txt (ncu --set full, forward GEMM launches of the first layers of one step; '
                       'algorithmic bytes = operands + output + epilogue addend of the logged call)'}

@@ -401,11 +401,13 @@ colsum_kernel(const __nv_bfloat16* __restrict__ in, long long ld, int M, int N, 
   }
 }
 
-// Wide form (N % 8 == 0): CTA = 256 columns x 256 rows; a lane owns 8 adjacent columns (one 16-byte load per row), the 8
-// warps are row lanes with 4 rows in flight each, so an SM holds ~32 KiB of loads in flight instead of ~8 KiB with the
-// 4-byte loads above (which ran at ~0.3 of the HBM rate).  Partials per row chunk, summed by the last CTA of each
-// column block in chunk order (deterministic).
-constexpr int COLSUM_WROWS = 256;
+// Wide form (N % 8 == 0): CTA = 256 columns x 64 rows; a lane owns 8 adjacent columns (one 16-byte load per row), the 8
+// warps are row lanes and issue all 8 of their rows before the first add, so the whole CTA is one DRAM round trip deep
+// and a [12544 x 768] operand still spreads over 588 CTAs (with 256-row CTAs it was 150 CTAs walking 8 dependent
+// rounds: 16 us for 19 MB in the ncu capture, profiles/r2_*).  The 4-byte-load kernel above ran at ~0.3 of the HBM rate.
+// Partials per row chunk are summed by the last CTA of each column block — all 256 threads, 8 interleaved chunk lanes,
+// fixed order (deterministic).
+constexpr int COLSUM_WROWS = 64;
 constexpr bool VT_DEFAULT_COLSUM_WIDE = false;
 
 __global__ void __launch_bounds__(256)
@@ -414,25 +416,22 @@ colsum_wide_kernel(const __nv_bfloat16* __restrict__ in, long long ld, int M, in
   const int lane = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int col = blockIdx.x * 256 + lane * 8;
   const int r0 = blockIdx.y * COLSUM_WROWS;
-  const int r1 = min(M, r0 + COLSUM_WROWS);
   float acc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-  auto add = [&](const uint4& u) {
-    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
-    acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y; acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
-  };
   if (col < N) {
     const __nv_bfloat16* base = in + col;
-    int r = r0 + rl;
-    for (; r + 24 < r1; r += 32) {          // 4 rows of this row lane in flight
-      const uint4 u0 = *reinterpret_cast<const uint4*>(base + (long long)r * ld);
-      const uint4 u1 = *reinterpret_cast<const uint4*>(base + (long long)(r + 8) * ld);
-      const uint4 u2 = *reinterpret_cast<const uint4*>(base + (long long)(r + 16) * ld);
-      const uint4 u3 = *reinterpret_cast<const uint4*>(base + (long long)(r + 24) * ld);
-      add(u0); add(u1); add(u2); add(u3);
+    uint4 u[COLSUM_WROWS / 8];
+#pragma unroll
+    for (int i = 0; i < COLSUM_WROWS / 8; ++i) {
+      const int r = r0 + rl + 8 * i;
+      u[i] = r < M ? *reinterpret_cast<const uint4*>(base + (long long)r * ld) : make_uint4(0u, 0u, 0u, 0u);
     }
-    for (; r < r1; r += 8) add(*reinterpret_cast<const uint4*>(base + (long long)r * ld));
+#pragma unroll
+    for (int i = 0; i < COLSUM_WROWS / 8; ++i) {
+      const float2 a = unpack_bf16x2(u[i].x), b = unpack_bf16x2(u[i].y), c = unpack_bf16x2(u[i].z), d = unpack_bf16x2(u[i].w);
+      acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y; acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
+    }
   }
   __shared__ float sh[8][32][9];
 #pragma unroll
@@ -458,11 +457,28 @@ colsum_wide_kernel(const __nv_bfloat16* __restrict__ in, long long ld, int M, in
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  const int c = blockIdx.x * 256 + threadIdx.x;
-  if (c < N) {
-    float t = 0.f;
-    for (int k = 0; k < (int)gridDim.y; ++k) t += __ldcg(ws + (long long)k * N + c);
-    out[c] = t;
+  // chunk lane rl sums partial rows rl, rl + 8, ... of this lane's 8 columns; the 8 chunk lanes are then added in order
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (col < N) {
+    for (int k = rl; k < (int)gridDim.y; k += 8) {
+      const float4 v0 = __ldcg(reinterpret_cast<const float4*>(ws + (long long)k * N + col));
+      const float4 v1 = __ldcg(reinterpret_cast<const float4*>(ws + (long long)k * N + col + 4));
+      acc[0] += v0.x; acc[1] += v0.y; acc[2] += v0.z; acc[3] += v0.w;
+      acc[4] += v1.x; acc[5] += v1.y; acc[6] += v1.z; acc[7] += v1.w;
+    }
+  }
+  __syncthreads();        // sh is reused
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sh[rl][lane][j] = acc[j];
+  __syncthreads();
+  {
+    const int l = threadIdx.x >> 3, j = threadIdx.x & 7;
+    float sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) sum += sh[w][l][j];
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c < N) out[c] = sum;
   }
 }
 

@@ -43,28 +43,40 @@ __device__ __forceinline__ void rows_store(const RowsArgs& g, int r, int n, floa
   }
 }
 
-// B [N, K]: one warp per output column, lanes stride over K in 8-element (16-byte) pieces; the <= 8 activation rows are
-// re-read through L1 by every warp (8 x K x 2 bytes <= 48 KB)
-__global__ void __launch_bounds__(256) rows_nt_kernel(RowsArgs g) {
+// B [N, K]: one warp per output column, lanes stride over K in 8-element (16-byte) pieces, four pieces in flight; the <= 8
+// activation rows are re-read through L1 by every warp (8 x K x 2 bytes <= 48 KB)
+constexpr int NT_WARPS = 4;
+__global__ void __launch_bounds__(NT_WARPS * 32) rows_nt_kernel(RowsArgs g) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r0 = blockIdx.y * ROWS_PER_GROUP;
   const int nr = min(ROWS_PER_GROUP, g.R - r0);
   const __nv_bfloat16* a = g.a + (long long)r0 * g.lda;
-  for (int n = blockIdx.x * 8 + warp; n < g.N; n += gridDim.x * 8) {
+  for (int n = blockIdx.x * NT_WARPS + warp; n < g.N; n += gridDim.x * NT_WARPS) {
     float acc[ROWS_PER_GROUP];
 #pragma unroll
     for (int r = 0; r < ROWS_PER_GROUP; ++r) acc[r] = 0.f;
     const __nv_bfloat16* brow = g.b + (long long)n * g.ldb;
-    for (int k = lane * 8; k < g.K; k += 256) {
-      float wf[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(brow + k)), wf);
+    for (int k0 = lane * 8; k0 < g.K; k0 += 4 * 256) {
+      uint4 wv[4];
 #pragma unroll
-      for (int r = 0; r < ROWS_PER_GROUP; ++r) {
-        if (r < nr) {
-          float af[8];
-          unpack8(__ldg(reinterpret_cast<const uint4*>(a + (long long)r * g.lda + k)), af);
+      for (int u = 0; u < 4; ++u) {
+        const int k = k0 + u * 256;
+        wv[u] = k < g.K ? __ldg(reinterpret_cast<const uint4*>(brow + k)) : make_uint4(0u, 0u, 0u, 0u);
+      }
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[r] = fmaf(af[j], wf[j], acc[r]);
+      for (int u = 0; u < 4; ++u) {
+        const int k = k0 + u * 256;
+        if (k >= g.K) break;
+        float wf[8];
+        unpack8(wv[u], wf);
+#pragma unroll
+        for (int r = 0; r < ROWS_PER_GROUP; ++r) {
+          if (r < nr) {
+            float af[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(a + (long long)r * g.lda + k)), af);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[r] = fmaf(af[j], wf[j], acc[r]);
+          }
         }
       }
     }
@@ -78,23 +90,30 @@ __global__ void __launch_bounds__(256) rows_nt_kernel(RowsArgs g) {
   }
 }
 
-// B [K, N]: CTA = 64 output columns; thread = (8 consecutive columns) x (one of 32 K slices, 8 consecutive k per step);
-// slices are summed by shuffles inside a warp and through shared memory across the 8 warps
+// B [K, N]: CTA = CG * 8 output columns; thread = (8 consecutive columns) x (one of 256 / CG K slices, 8 consecutive k per
+// step); slices are summed by shuffles inside a warp and through shared memory across the 8 warps.  CG is chosen so
+// that even N = 768 spreads over 48 CTAs.
+template <int CG>
 __global__ void __launch_bounds__(256) rows_nn_kernel(RowsArgs g) {
-  __shared__ float red[8][ROWS_PER_GROUP * 64];
+  constexpr int COLS = CG * 8, SLICES = 256 / CG;
+  __shared__ float red[8][ROWS_PER_GROUP * COLS];
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  const int cg = t & 7, ks = t >> 3;
+  const int cg = t % CG, ks = t / CG;
   const int r0 = blockIdx.y * ROWS_PER_GROUP;
   const int nr = min(ROWS_PER_GROUP, g.R - r0);
   const __nv_bfloat16* a = g.a + (long long)r0 * g.lda;
-  const int n0 = blockIdx.x * 64 + cg * 8;
+  const int n0 = blockIdx.x * COLS + cg * 8;
   const bool col_ok = n0 < g.N;
   float acc[ROWS_PER_GROUP][8];
 #pragma unroll
   for (int r = 0; r < ROWS_PER_GROUP; ++r)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[r][j] = 0.f;
-  for (int k = ks * 8; k < g.K; k += 256) {
+  for (int k = ks * 8; k < g.K; k += SLICES * 8) {
+    uint4 wv[8];
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk)
+      wv[kk] = col_ok ? __ldg(reinterpret_cast<const uint4*>(g.b + (long long)(k + kk) * g.ldb + n0)) : make_uint4(0u, 0u, 0u, 0u);
     float af[ROWS_PER_GROUP][8];
 #pragma unroll
     for (int r = 0; r < ROWS_PER_GROUP; ++r) {
@@ -107,37 +126,33 @@ __global__ void __launch_bounds__(256) rows_nn_kernel(RowsArgs g) {
 #pragma unroll
     for (int kk = 0; kk < 8; ++kk) {
       float wf[8];
-      if (col_ok) unpack8(__ldg(reinterpret_cast<const uint4*>(g.b + (long long)(k + kk) * g.ldb + n0)), wf);
-      else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) wf[j] = 0.f;
-      }
+      unpack8(wv[kk], wf);
 #pragma unroll
       for (int r = 0; r < ROWS_PER_GROUP; ++r)
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[r][j] = fmaf(af[r][kk], wf[j], acc[r][j]);
     }
   }
-  // lanes cg, cg + 8, cg + 16, cg + 24 of a warp hold four K slices of the same columns
+  // lanes cg, cg + CG, cg + 2 CG, ... of a warp hold different K slices of the same columns
 #pragma unroll
   for (int r = 0; r < ROWS_PER_GROUP; ++r)
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float v = acc[r][j];
-      v += __shfl_xor_sync(0xffffffffu, v, 8);
-      v += __shfl_xor_sync(0xffffffffu, v, 16);
+#pragma unroll
+      for (int o = CG; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
       acc[r][j] = v;
     }
-  if (lane < 8) {
+  if (lane < CG) {
 #pragma unroll
     for (int r = 0; r < ROWS_PER_GROUP; ++r)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) red[warp][r * 64 + cg * 8 + j] = acc[r][j];
+      for (int j = 0; j < 8; ++j) red[warp][r * COLS + cg * 8 + j] = acc[r][j];
   }
   __syncthreads();
-  for (int i = t; i < nr * 64; i += 256) {
-    const int r = i >> 6, c = i & 63;
-    const int n = blockIdx.x * 64 + c;
+  for (int i = t; i < nr * COLS; i += 256) {
+    const int r = i / COLS, c = i - r * COLS;
+    const int n = blockIdx.x * COLS + c;
     if (n >= g.N) continue;
     float v = red[0][i];
 #pragma unroll
@@ -167,13 +182,15 @@ int launch_gemm_rows(const vt_gemm_params* q, int m0, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int groups = (R + ROWS_PER_GROUP - 1) / ROWS_PER_GROUP;
   if (q->b_mn_major) {
-    rows_nn_kernel<<<dim3((q->N + 63) / 64, groups), 256, 0, st>>>(g);
+    if (q->N >= 2048) rows_nn_kernel<8><<<dim3((q->N + 63) / 64, groups), 256, 0, st>>>(g);
+    else if (q->N >= 1024) rows_nn_kernel<4><<<dim3((q->N + 31) / 32, groups), 256, 0, st>>>(g);
+    else rows_nn_kernel<2><<<dim3((q->N + 15) / 16, groups), 256, 0, st>>>(g);
     return check_launch("rows_nn_kernel");
   }
-  int blocks = (q->N + 7) / 8;
+  int blocks = (q->N + NT_WARPS - 1) / NT_WARPS;
   const int cap = sm_count() * 8;
   if (blocks > cap) blocks = cap;
-  rows_nt_kernel<<<dim3(blocks, groups), 256, 0, st>>>(g);
+  rows_nt_kernel<<<dim3(blocks, groups), NT_WARPS * 32, 0, st>>>(g);
   return check_launch("rows_nt_kernel");
 }
 

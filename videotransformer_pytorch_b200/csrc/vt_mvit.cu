@@ -396,9 +396,9 @@ pool_dw_kernel(const float* __restrict__ dpooled, const __nv_bfloat16* __restric
 // [4l, 4l+4) of a head, so one token row of a head is ONE 8-byte load per lane (bf16) or one 16-byte load (fp32) instead
 // of three 2-byte / 4-byte ones, filter taps sit in shared memory as float4 [tap][lane], and every tap of a window is
 // in flight before the first FMA.  Lanes 24..31 carry zeros through the warp reductions.
-//   forward: warp = pooled row (b, h, l)
-//   d(input): warp = (input token, head); the <= 27 covering outputs come from the per-axis tables, nine predicated
-//             loads per valid time plane
+//   d(input): CTA = one (b, t) plane of the input grid, warp = token, looping over the heads; the covering outputs come
+//             from the per-axis tables (uniform branches), tokens without any leave through a zero store
+//   (the forward kernel keeps the first-generation mapping: a 27 x 8-byte-load version measured slower, 1.35 vs 1.08 ms)
 //   d(filter): warp = (pooled row, time tap): 9 taps x 4 channels of accumulators per lane, CTA = 4 row slots x 3 time
 //             taps; the four slots are summed in shared memory in a fixed order (deterministic), one partial row per CTA
 // Needs 8-byte aligned token rows (row / batch strides multiples of 4 elements) — the launchers check.
@@ -427,88 +427,9 @@ __device__ __forceinline__ void stage_taps(float4* sw4, const float* __restrict_
   }
 }
 
-__global__ void __launch_bounds__(ROW_WARPS * 32)
-pool_ln_fwd_v2_kernel(const __nv_bfloat16* __restrict__ in, long long in_bs, long long in_rs,
-                      const float* __restrict__ w, const float* __restrict__ gamma, const float* __restrict__ beta,
-                      float* __restrict__ pooled, __nv_bfloat16* __restrict__ out, float* __restrict__ mean,
-                      float* __restrict__ rstd, PoolDims d, float eps) {
-  __shared__ float4 sw4[27 * PV_LANES];
-  stage_taps(sw4, w);
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool act = lane < PV_LANES;
-  const int cl = act ? lane : 0;                                  // idle lanes shadow lane 0's addresses, contribute zeros
-  const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma) + cl);
-  const float4 b4 = __ldg(reinterpret_cast<const float4*>(beta) + cl);
-  const int Lo1 = 1 + d.To * d.Ho * d.Wo;
-  const int rows = d.B * d.H * Lo1;                               // < 2^31, checked by the launcher
-  for (int r = blockIdx.x * ROW_WARPS + warp; r < rows; r += gridDim.x * ROW_WARPS) {
-    const int bh = r / Lo1, l = r - bh * Lo1;
-    const int b = bh / d.H, h = bh - b * d.H;
-    const __nv_bfloat16* base = in + (long long)b * in_bs + (long long)h * PV_HD + 4 * cl;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    if (l == 0) {
-      bf16x4_to_f(__ldg(reinterpret_cast<const uint2*>(base)), acc);
-    } else {
-      const int o = l - 1;
-      const int o2 = o / d.Wo;
-      const int ow = o - o2 * d.Wo, ot = o2 / d.Ho, oh = o2 - ot * d.Ho;
-      long long off[9];
-      bool ok[9];
-#pragma unroll
-      for (int dh = 0; dh < 3; ++dh)
-#pragma unroll
-        for (int dw = 0; dw < 3; ++dw) {
-          const int hi = oh * d.sh - 1 + dh, wi = ow * d.sw - 1 + dw;
-          ok[dh * 3 + dw] = hi >= 0 && hi < d.Hin && wi >= 0 && wi < d.Win;
-          off[dh * 3 + dw] = ((long long)min(max(hi, 0), d.Hin - 1) * d.Win + min(max(wi, 0), d.Win - 1)) * in_rs;
-        }
-      uint2 x[27];
-      bool tok[3];
-#pragma unroll
-      for (int dt = 0; dt < 3; ++dt) {
-        const int ti = ot * d.st - 1 + dt;
-        tok[dt] = ti >= 0 && ti < d.T;
-        const __nv_bfloat16* plane = base + (1 + (long long)min(max(ti, 0), d.T - 1) * d.Hin * d.Win) * in_rs;
-#pragma unroll
-        for (int k = 0; k < 9; ++k) x[dt * 9 + k] = __ldg(reinterpret_cast<const uint2*>(plane + off[k]));
-      }
-#pragma unroll
-      for (int dt = 0; dt < 3; ++dt)
-#pragma unroll
-        for (int k = 0; k < 9; ++k) {
-          const float4 f = sw4[(dt * 9 + k) * PV_LANES + cl];
-          float xv[4];
-          bf16x4_to_f(x[dt * 9 + k], xv);
-          const float m = tok[dt] && ok[k] ? 1.f : 0.f;
-          acc[0] = fmaf(xv[0] * m, f.x, acc[0]);
-          acc[1] = fmaf(xv[1] * m, f.y, acc[1]);
-          acc[2] = fmaf(xv[2] * m, f.z, acc[2]);
-          acc[3] = fmaf(xv[3] * m, f.w, acc[3]);
-        }
-    }
-    if (!act) acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
-    const float mu = warp_sum(acc[0] + acc[1] + acc[2] + acc[3]) * (1.0f / PV_HD);
-    float ss = 0.f;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float c = acc[j] - mu;
-      ss += c * c;
-    }
-    const float rs = rsqrtf(warp_sum(act ? ss : 0.f) * (1.0f / PV_HD) + eps);
-    if (lane == 0) {
-      mean[r] = mu;
-      rstd[r] = rs;
-    }
-    if (act) {
-      *reinterpret_cast<float4*>(pooled + (long long)r * PV_HD + 4 * lane) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-      const float y[4] = {(acc[0] - mu) * rs * g4.x + b4.x, (acc[1] - mu) * rs * g4.y + b4.y, (acc[2] - mu) * rs * g4.z + b4.z,
-                          (acc[3] - mu) * rs * g4.w + b4.w};
-      *reinterpret_cast<uint2*>(out + (long long)r * PV_HD + 4 * lane) = f_to_bf16x4(y);
-    }
-  }
-}
-
+// blockIdx.y = (b, ti) plane of the input grid (one extra y for the B cls tokens): the time taps are decoded once per CTA,
+// a token costs one division, and tokens no output window covers (most of them at strides 4 and 8) leave through a
+// zero store without touching the gradient
 __global__ void __launch_bounds__(ROW_WARPS * 32)
 pool_din_v2_kernel(const float* __restrict__ dpooled, const float* __restrict__ w, __nv_bfloat16* __restrict__ din,
                    long long din_bs, long long din_rs, PoolDims d) {
@@ -531,49 +452,65 @@ pool_din_v2_kernel(const float* __restrict__ dpooled, const float* __restrict__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool act = lane < PV_LANES;
   const int cl = act ? lane : 0;
-  const int L1 = 1 + d.T * d.Hin * d.Win;
   const int Lo1 = 1 + d.To * d.Ho * d.Wo;
-  const long long items = (long long)d.B * L1 * d.H;
-  for (long long it = (long long)blockIdx.x * ROW_WARPS + warp; it < items; it += (long long)gridDim.x * ROW_WARPS) {
-    const int tok = (int)(it / d.H), h = (int)(it - (long long)tok * d.H);
-    const int b = tok / L1, n = tok - b * L1;
-    const float* dp = dpooled + ((long long)b * d.H + h) * Lo1 * PV_HD + 4 * cl;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    if (n == 0) {
-      const float4 g = __ldg(reinterpret_cast<const float4*>(dp));
-      acc[0] = g.x, acc[1] = g.y, acc[2] = g.z, acc[3] = g.w;
-    } else {
-      const int idx = n - 1;
-      const int t2 = idx / d.Win;
-      const int wi = idx - t2 * d.Win, ti = t2 / d.Hin, hi = t2 - ti * d.Hin;
-      int rowoff[9];                                 // (oh * Wo + ow) of the output reached through (dh, dw), -1 = none
+  const int planes = d.B * d.T;
+  if ((int)blockIdx.y == planes) {                 // cls tokens: straight copy of the pooled cls gradient
+    for (int it = blockIdx.x * ROW_WARPS + warp; it < d.B * d.H; it += gridDim.x * ROW_WARPS) {
+      const int b = it / d.H, h = it - b * d.H;
+      const float4 g = __ldg(reinterpret_cast<const float4*>(dpooled + (long long)it * Lo1 * PV_HD + 4 * cl));
+      const float v[4] = {g.x, g.y, g.z, g.w};
+      if (act) *reinterpret_cast<uint2*>(din + (long long)b * din_bs + h * PV_HD + 4 * lane) = f_to_bf16x4(v);
+    }
+    return;
+  }
+  const int b = blockIdx.y / d.T, ti = blockIdx.y - b * d.T;
+  int ot3[3];
 #pragma unroll
-      for (int dh = 0; dh < 3; ++dh)
+  for (int k = 0; k < 3; ++k) ot3[k] = tab[0][k][ti];
+  const bool t_any = ot3[0] >= 0 || ot3[1] >= 0 || ot3[2] >= 0;
+  const int HW = d.Hin * d.Win;
+  const float zero4[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int idx = blockIdx.x * ROW_WARPS + warp; idx < HW; idx += gridDim.x * ROW_WARPS) {
+    const int hi = idx / d.Win, wi = idx - hi * d.Win;
+    __nv_bfloat16* dst = din + (long long)b * din_bs + (1 + (long long)ti * HW + idx) * din_rs + 4 * lane;
+    int oh3[3], ow3[3];
 #pragma unroll
-        for (int dw = 0; dw < 3; ++dw) {
-          const int oh = tab[1][dh][hi], ow = tab[2][dw][wi];
-          rowoff[dh * 3 + dw] = oh >= 0 && ow >= 0 ? oh * d.Wo + ow : -1;
-        }
+    for (int k = 0; k < 3; ++k) {
+      oh3[k] = tab[1][k][hi];
+      ow3[k] = tab[2][k][wi];
+    }
+    const bool any = t_any && (oh3[0] >= 0 || oh3[1] >= 0 || oh3[2] >= 0) && (ow3[0] >= 0 || ow3[1] >= 0 || ow3[2] >= 0);
+    if (!any) {                                    // warp-uniform
+      if (act)
+        for (int h = 0; h < d.H; ++h) *reinterpret_cast<uint2*>(dst + h * PV_HD) = f_to_bf16x4(zero4);
+      continue;
+    }
+    for (int h = 0; h < d.H; ++h) {
+      const float* dp = dpooled + (((long long)b * d.H + h) * Lo1 + 1) * PV_HD + 4 * cl;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int dt = 0; dt < 3; ++dt) {
-        const int ot = tab[0][dt][ti];
-        if (ot < 0) continue;                          // warp-uniform
-        const float* plane = dp + (1 + (long long)ot * d.Ho * d.Wo) * PV_HD;
-        float4 g[9];
+        if (ot3[dt] < 0) continue;                 // warp-uniform
 #pragma unroll
-        for (int k = 0; k < 9; ++k)
-          g[k] = rowoff[k] >= 0 ? __ldg(reinterpret_cast<const float4*>(plane + (long long)rowoff[k] * PV_HD)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int dh = 0; dh < 3; ++dh) {
+          if (oh3[dh] < 0) continue;               // warp-uniform
+          const float* rowp = dp + (long long)(ot3[dt] * d.Ho + oh3[dh]) * d.Wo * PV_HD;
+          float4 g[3];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) {
-          const float4 f = sw4[(dt * 9 + k) * PV_LANES + cl];
-          acc[0] = fmaf(g[k].x, f.x, acc[0]);
-          acc[1] = fmaf(g[k].y, f.y, acc[1]);
-          acc[2] = fmaf(g[k].z, f.z, acc[2]);
-          acc[3] = fmaf(g[k].w, f.w, acc[3]);
+          for (int dw = 0; dw < 3; ++dw)
+            g[dw] = ow3[dw] >= 0 ? __ldg(reinterpret_cast<const float4*>(rowp + (long long)ow3[dw] * PV_HD)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int dw = 0; dw < 3; ++dw) {
+            const float4 f = sw4[((dt * 3 + dh) * 3 + dw) * PV_LANES + cl];
+            acc[0] = fmaf(g[dw].x, f.x, acc[0]);
+            acc[1] = fmaf(g[dw].y, f.y, acc[1]);
+            acc[2] = fmaf(g[dw].z, f.z, acc[2]);
+            acc[3] = fmaf(g[dw].w, f.w, acc[3]);
+          }
         }
       }
+      if (act) *reinterpret_cast<uint2*>(dst + h * PV_HD) = f_to_bf16x4(acc);
     }
-    if (act) *reinterpret_cast<uint2*>(din + (long long)b * din_bs + (long long)n * din_rs + h * PV_HD + 4 * lane) = f_to_bf16x4(acc);
   }
 }
 
@@ -1295,12 +1232,6 @@ extern "C" int vt_pool_fwd(const vt_pool_fwd_params* p, void* stream) {
   const PoolDims d{p->B, p->H, p->T, p->Hin, p->Win, p->st, p->sh, p->sw, p->To, p->Ho, p->Wo};
   const long long rows = (long long)p->B * p->H * (1 + (long long)p->To * p->Ho * p->Wo);
   VT_REQUIRE(rows < 0x7fffffffll, "vt_pool_fwd: too many rows");
-  if (pool_v2(p->in, p->in_bs, p->in_rs)) {
-    pool_ln_fwd_v2_kernel<<<row_blocks(rows, 8), ROW_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16*>(p->in), p->in_bs, p->in_rs, p->w, p->gamma, p->beta, p->pooled,
-        static_cast<__nv_bfloat16*>(p->out), p->mean, p->rstd, d, p->eps);
-    return check_launch("pool_ln_fwd_v2_kernel");
-  }
   pool_ln_fwd_kernel<3><<<row_blocks(rows, 8), ROW_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(p->in), p->in_bs, p->in_rs, p->w, p->gamma, p->beta, p->pooled,
       static_cast<__nv_bfloat16*>(p->out), p->mean, p->rstd, d, p->eps);
@@ -1361,8 +1292,9 @@ extern "C" int vt_pool_bwd(const vt_pool_bwd_params* p, void* stream) {
   VT_REQUIRE(tokens_in < 0x7fffffffll, "vt_pool_bwd: too many tokens");
   const bool v2 = pool_v2(p->in, p->in_bs, p->in_rs) && pool_v2(p->din, p->din_bs, p->din_rs);
   if (v2) {
-    pool_din_v2_kernel<<<row_blocks(tokens_in * p->H, 8), ROW_WARPS * 32, 0, st>>>(dpooled, p->w, static_cast<__nv_bfloat16*>(p->din),
-                                                                                   p->din_bs, p->din_rs, d);
+    const int hw = p->Hin * p->Win;
+    const dim3 dgrid((hw + ROW_WARPS * 4 - 1) / (ROW_WARPS * 4), p->B * p->T + 1);      // ~4 tokens per warp; + 1: the cls tokens
+    pool_din_v2_kernel<<<dgrid, ROW_WARPS * 32, 0, st>>>(dpooled, p->w, static_cast<__nv_bfloat16*>(p->din), p->din_bs, p->din_rs, d);
     rc = check_launch("pool_din_v2_kernel");
   } else {
     pool_din_kernel<3><<<row_blocks(tokens_in, 8), ROW_WARPS * 32, 0, st>>>(dpooled, p->w, static_cast<__nv_bfloat16*>(p->din),
