@@ -92,8 +92,10 @@ typedef struct {
    * outer * map_special_stride (dropped when map_special_base < 0).  Every other row reads its addend from / writes its
    * result to element offset  map_base + (outer % map_tcount) * map_stride_t + (inner - map_skip) * map_stride_p +
    * (outer / map_tcount) * map_stride_b  of aux / out.  With it the epilogue moves whole 32 x 32 boxes by TMA through a
-   * 4-D tensor map (reference einops: transformer.py:250, :279-280, :352-356, :375-377) instead of per-thread rows; the
-   * out_row / aux_row arrays, when also given, must describe the same mapping (they serve the generic epilogue). */
+   * tensor map (col, row in sample, sample) of the token stream (reference einops: transformer.py:250, :279-280, :352-356,
+   * :375-377) instead of per-thread rows; the out_row / aux_row arrays, when also given, must describe the same mapping
+   * (they serve the generic epilogue, which also covers map_tcount > 1: the element-strided boxes that case needs fault
+   * on hardware and stay switched off). */
   int32_t map_period, map_skip, map_tcount;
   int32_t force_tail;      /* 0 = heuristic, 1 = never cut the partial last row of tiles into narrow units, 2 = prefer to */
   int64_t map_stride_t, map_stride_p, map_stride_b, map_base;

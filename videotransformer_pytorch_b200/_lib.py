@@ -279,7 +279,7 @@ class CudaKernels:
              aux=None, out_row=None, aux_row=None, row_scale=None, out_rows=None, split_ok=False,
              force_splits=0, force_bn=0, force_cluster=0, debug=None, row_map=None, force_tail=0, tag=None):
         """row_map: affine description of out_row / aux_row (ops.affine_row_maps) for the fp32 residual epilogue — lets the
-        kernel move 32 x 32 boxes by TMA through a 4-D tensor map instead of per-thread rows.  tag: role label of the launch
+        kernel move 32 x 32 boxes by TMA through a tensor map of the token stream instead of per-thread rows.  tag: role label of the launch
         ('qkv', 'proj', ...) for profilers that wrap this method (bench.py); ignored here."""
         lib = load_library()
         _rows2d(_req(a, torch.bfloat16, 'gemm.a'), 'gemm.a')
