@@ -157,6 +157,14 @@ class EmuKernels:
         zz = self._up(z)
         return self._h(0.5 * zz * (1 + torch.erf(zz / math.sqrt(2.0))))
 
+    def gather_cast_colsum(self, src2d, in_row=None, row_scale=None, rows=None):
+        out = self.gather_cast(src2d, in_row=in_row, row_scale=row_scale, rows=rows)
+        return out, self.colsum(out)
+
+    def dgelu_colsum(self, dh, z):
+        out = self.dgelu(dh, z)
+        return out, self.colsum(out)
+
     def dgelu(self, dh, z):
         zz = self._up(z)
         cdf = 0.5 * (1 + torch.erf(zz / math.sqrt(2.0)))

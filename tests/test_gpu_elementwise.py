@@ -111,3 +111,34 @@ def test_im2col_u8_normalised():
         assert got.shape == ref.shape
         assert float((got.float().cpu() - ref).abs().max()) < 2e-2          # bf16 rounding of values in [-2.2, 2.7]
         assert float((got.float().cpu() - ref.bfloat16().float()).abs().max()) < 1.6e-2
+
+
+@pytest.mark.parametrize('rows,D,mapped', [(12544, 768, True), (12608, 768, True), (12552, 768, False), (37, 1024, False),
+                                           (1000, 64, True), (5, 8, False)])
+def test_gather_cast_with_column_sums(rows, D, mapped):
+    """gather_cast + colsum in one kernel: same bf16 rows as the two-kernel form, column sums of exactly those rows."""
+    g = torch.Generator().manual_seed(3)
+    src = torch.randn(rows + 50, D, generator=g).cuda()
+    in_row = scale = None
+    if mapped:
+        in_row = torch.randint(-1, rows + 50, (rows,), generator=g, dtype=torch.int32).cuda()
+        scale = torch.rand(rows, generator=g).cuda()
+    ref = K().gather_cast(src, in_row=in_row, row_scale=scale, rows=rows)
+    for _ in range(2):                                    # twice: the arrival counter must be left at zero
+        out, cs = K().gather_cast_colsum(src, in_row=in_row, row_scale=scale, rows=rows)
+        assert torch.equal(out, ref)
+        exp = ref.double().sum(0)
+        assert float((cs.double() - exp).abs().max()) <= 1e-4 * max(1.0, float(exp.abs().max()))
+
+
+@pytest.mark.parametrize('M,N', [(12552, 3072), (100, 256), (3, 8192), (777, 1536)])
+def test_gelu_backward_with_column_sums(M, N):
+    g = torch.Generator().manual_seed(4)
+    dh = torch.randn(M, N, generator=g).bfloat16().cuda()
+    z = (torch.randn(M, N, generator=g) * 2).bfloat16().cuda()
+    ref = K().dgelu(dh, z)
+    for _ in range(2):
+        out, cs = K().dgelu_colsum(dh, z)
+        assert torch.equal(out, ref)
+        exp = ref.double().sum(0)
+        assert float((cs.double() - exp).abs().max()) <= 1e-4 * max(1.0, float(exp.abs().max()))

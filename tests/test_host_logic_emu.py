@@ -49,8 +49,11 @@ def test_timesformer_eval_tokens_attention(golden, emu, name):
     assert rel_err(attn, g.out['last_attn']) < 2e-5
 
 
+@pytest.mark.parametrize('fused_colsum', [False, True], ids=['colsum-pass', 'colsum-from-producers'])
 @pytest.mark.parametrize('name', ['timesformer_tiny', 'timesformer_hd64'])
-def test_timesformer_train_forward_backward(golden, emu, name):
+def test_timesformer_train_forward_backward(golden, emu, name, fused_colsum, monkeypatch):
+    from videotransformer_pytorch_b200 import ops
+    monkeypatch.setattr(ops, 'FUSED_COLSUM', fused_colsum)       # bias gradients from the dY producers or a separate pass
     g = golden(name)
     m = build_ts(g).train()
     x = g.x.clone().requires_grad_(True)

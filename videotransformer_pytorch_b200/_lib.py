@@ -69,6 +69,17 @@ class GeluParams(C.Structure):
     _fields_ = [('z', c_vp), ('dh', c_vp), ('out', c_vp), ('n', c_i64)]
 
 
+class GatherCastColsumParams(C.Structure):
+    _fields_ = [('src', c_vp), ('lds', c_i64), ('in_row', c_vp), ('row_scale', c_vp), ('dst', c_vp),
+                ('rows', c_i32), ('D', c_i32), ('colsum', c_vp), ('workspace', c_vp), ('counter', c_vp),
+                ('workspace_rows', c_i32)]
+
+
+class GeluBwdColsumParams(C.Structure):
+    _fields_ = [('z', c_vp), ('dh', c_vp), ('out', c_vp), ('M', c_i32), ('N', c_i32), ('colsum', c_vp),
+                ('workspace', c_vp), ('counter', c_vp), ('workspace_rows', c_i32)]
+
+
 class AttnFwdParams(C.Structure):
     _fields_ = [('qkv', c_vp), ('ctx', c_vp), ('lse', c_vp), ('probs', c_vp),
                 ('Bp', c_i32), ('N', c_i32), ('H', c_i32), ('hd', c_i32), ('scale', c_f32), ('impl', c_i32)]
@@ -200,6 +211,7 @@ class Im2colU8MixParams(C.Structure):
 
 EXPORTS = ['vt_version', 'vt_last_error', 'vt_sm_count', 'vt_set_reserved_sms', 'vt_launch_count', 'vt_gemm', 'vt_layernorm_fwd', 'vt_ln_bwd_blocks',
            'vt_layernorm_bwd', 'vt_reduce_rows', 'vt_colsum_chunks', 'vt_colsum_bf16', 'vt_cast_f32_bf16',
+           'vt_gather_cast_colsum_blocks', 'vt_gather_cast_colsum_bf16', 'vt_gelu_bwd_colsum_blocks', 'vt_gelu_bwd_colsum_bf16',
            'vt_gather_cast_bf16', 'vt_gelu_fwd_bf16', 'vt_gelu_bwd_bf16', 'vt_attn_fwd', 'vt_attn_bwd', 'vt_debug_buffer', 'vt_im2col_bf16', 'vt_im2col_u8_bf16', 'vt_col2im_f32', 'vt_hog',
            'vt_pool_fwd', 'vt_pool_bwd_scratch', 'vt_pool_bwd', 'vt_xattn_fwd', 'vt_xattn_bwd', 'vt_maxpool_fwd',
            'vt_maxpool_bwd', 'vt_im2col3d_bf16', 'vt_mvit_tokens_fwd', 'vt_mvit_tokens_bwd', 'vt_mse_blocks',
@@ -420,6 +432,58 @@ class CudaKernels:
         p.dst, p.rows, p.D = out.data_ptr(), rows, D
         _check(lib.vt_gather_cast_bf16(C.byref(p), _stream()), 'vt_gather_cast_bf16')
         return out
+
+    def _fused_counter(self, device):
+        """One zeroed int32 per (device, stream) for the producer + column-sum kernels (they leave it zero)."""
+        key = ('fused', device.index, torch.cuda.current_stream(device).cuda_stream)
+        cnt = self._counters.get(key)
+        if cnt is None:
+            cnt = self._counters[key] = torch.zeros(4, dtype=torch.int32, device=device)
+        return cnt
+
+    def gather_cast_colsum(self, src2d, in_row=None, row_scale=None, rows=None):
+        """gather_cast + colsum of its output in one pass -> (bf16 [rows, D], fp32 [D]); D <= 1024, else two kernels."""
+        lib = load_library()
+        _rows2d(_req(src2d, torch.float32, 'gather_cast.src'), 'gather_cast.src')
+        rows = src2d.shape[0] if rows is None else rows
+        D = src2d.shape[1]
+        if D > 1024 or D % 8:
+            out = self.gather_cast(src2d, in_row=in_row, row_scale=row_scale, rows=rows)
+            return out, self.colsum(out)
+        dev = src2d.device
+        out = torch.empty((rows, D), dtype=torch.bfloat16, device=dev)
+        cs = torch.empty(D, dtype=torch.float32, device=dev)
+        nb = lib.vt_gather_cast_colsum_blocks(rows)
+        ws = torch.empty((nb, D), dtype=torch.float32, device=dev)
+        p = GatherCastColsumParams()
+        p.src, p.lds = src2d.data_ptr(), src2d.stride(0)
+        p.in_row, p.row_scale = _ptr(in_row), _ptr(row_scale)
+        p.dst, p.rows, p.D = out.data_ptr(), rows, D
+        p.colsum, p.workspace, p.counter, p.workspace_rows = cs.data_ptr(), ws.data_ptr(), self._fused_counter(dev).data_ptr(), nb
+        _check(lib.vt_gather_cast_colsum_bf16(C.byref(p), _stream()), 'vt_gather_cast_colsum_bf16')
+        return out, cs
+
+    def dgelu_colsum(self, dh, z):
+        """dz = dh * gelu'(z) and the column sums of dz in one pass -> (bf16 [M, N], fp32 [N])."""
+        lib = load_library()
+        for t, n in ((dh, 'dh'), (z, 'z')):
+            _req(t, torch.bfloat16, 'dgelu.' + n)
+            if not t.is_contiguous() or t.dim() != 2:
+                raise RuntimeError(f'dgelu_colsum: {n} must be a contiguous matrix')
+        M, N = z.shape
+        if N % 256 or N > 8192:
+            out = self.dgelu(dh, z)
+            return out, self.colsum(out)
+        dev = z.device
+        out = torch.empty_like(z)
+        cs = torch.empty(N, dtype=torch.float32, device=dev)
+        nb = lib.vt_gelu_bwd_colsum_blocks(M)
+        ws = torch.empty((nb, N), dtype=torch.float32, device=dev)
+        p = GeluBwdColsumParams()
+        p.z, p.dh, p.out, p.M, p.N = z.data_ptr(), dh.data_ptr(), out.data_ptr(), M, N
+        p.colsum, p.workspace, p.counter, p.workspace_rows = cs.data_ptr(), ws.data_ptr(), self._fused_counter(dev)[1:].data_ptr(), nb
+        _check(lib.vt_gelu_bwd_colsum_bf16(C.byref(p), _stream()), 'vt_gelu_bwd_colsum_bf16')
+        return out, cs
 
     def gelu(self, z):
         lib = load_library()

@@ -350,6 +350,142 @@ __global__ void gather_cast_kernel(const float* __restrict__ src, long long lds,
 }
 
 // ------------------------------------------------------------------------------------------------
+// Producer kernels that also emit the column sums of what they write (the bias gradient of the layer whose dY they
+// produce): the separate column-sum pass re-read 19 - 77 MB per launch at ~1.2 - 3.7 TB/s (profiles/r2_*), 4 of the 7 per
+// block disappear this way.  Sums are taken over the bf16-rounded values, as the separate pass does.  Per-CTA partial rows,
+// summed by the last CTA to finish in CTA order (deterministic).
+// ------------------------------------------------------------------------------------------------
+constexpr int GCC_CH = 4;         // 8-column pieces per lane: D <= 1024
+
+__device__ __forceinline__ bool last_cta_arrives(int* counter) {
+  __shared__ int is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int done = atomicAdd(counter, 1);
+    is_last = (done == (int)gridDim.x - 1);
+    if (is_last) *counter = 0;      // self-cleaning for the next call
+  }
+  __syncthreads();
+  if (is_last) __threadfence();
+  return is_last != 0;
+}
+
+__global__ void __launch_bounds__(256)
+gather_cast_colsum_kernel(const float* __restrict__ src, long long lds, const int* __restrict__ in_row,
+                          const float* __restrict__ row_scale, __nv_bfloat16* __restrict__ dst, int rows, int D8,
+                          float* __restrict__ ws, float* __restrict__ out, int* __restrict__ counter) {
+  extern __shared__ float sh_gcc[];            // [8 warps][D]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int D = D8 * 8;
+  float acc[GCC_CH][8];
+#pragma unroll
+  for (int c = 0; c < GCC_CH; ++c)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[c][j] = 0.f;
+  for (int m = blockIdx.x * 8 + warp; m < rows; m += gridDim.x * 8) {
+    const int s = in_row ? in_row[m] : m;
+    const float sc = row_scale ? row_scale[m] : 1.0f;
+    uint4* o = reinterpret_cast<uint4*>(dst + (long long)m * D);
+    if (s < 0) {
+      for (int i = lane; i < D8; i += 32) o[i] = make_uint4(0, 0, 0, 0);
+      continue;
+    }
+    const float4* r = reinterpret_cast<const float4*>(src + (long long)s * lds);
+    float4 a[GCC_CH], b[GCC_CH];
+#pragma unroll
+    for (int c = 0; c < GCC_CH; ++c) {
+      const int i = lane + 32 * c;
+      if (i < D8) { a[c] = r[2 * i]; b[c] = r[2 * i + 1]; }
+    }
+#pragma unroll
+    for (int c = 0; c < GCC_CH; ++c) {
+      const int i = lane + 32 * c;
+      if (i < D8) {
+        uint4 v;
+        v.x = pack_bf16x2(sc * a[c].x, sc * a[c].y); v.y = pack_bf16x2(sc * a[c].z, sc * a[c].w);
+        v.z = pack_bf16x2(sc * b[c].x, sc * b[c].y); v.w = pack_bf16x2(sc * b[c].z, sc * b[c].w);
+        o[i] = v;
+        const float2 p0 = unpack_bf16x2(v.x), p1 = unpack_bf16x2(v.y), p2 = unpack_bf16x2(v.z), p3 = unpack_bf16x2(v.w);
+        acc[c][0] += p0.x; acc[c][1] += p0.y; acc[c][2] += p1.x; acc[c][3] += p1.y;
+        acc[c][4] += p2.x; acc[c][5] += p2.y; acc[c][6] += p3.x; acc[c][7] += p3.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < GCC_CH; ++c) {
+    const int i = lane + 32 * c;
+    if (i < D8) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sh_gcc[warp * D + i * 8 + j] = acc[c][j];
+    }
+  }
+  __syncthreads();
+  for (int col = threadIdx.x; col < D; col += 256) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sh_gcc[w * D + col];
+    ws[(long long)blockIdx.x * D + col] = t;
+  }
+  if (!last_cta_arrives(counter)) return;
+  for (int c4 = threadIdx.x; c4 < D / 4; c4 += 256) {
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < (int)gridDim.x; ++k) {
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(ws + (long long)k * D) + c4);
+      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+    }
+    reinterpret_cast<float4*>(out)[c4] = t;
+  }
+}
+
+// dz = dh * gelu'(z) with the column sums of dz: blockDim = N / 8 (thread = 8 columns of every row the CTA walks)
+constexpr int GBC_UNROLL = 2;
+__global__ void __launch_bounds__(1024)
+gelu_bwd_colsum_kernel(const uint4* __restrict__ dh, const uint4* __restrict__ z, uint4* __restrict__ dz, int M, int N8,
+                       float* __restrict__ ws, float* __restrict__ out, int* __restrict__ counter) {
+  const int c8 = threadIdx.x;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int r0 = blockIdx.x * GBC_UNROLL; r0 < M; r0 += gridDim.x * GBC_UNROLL) {
+    uint4 g[GBC_UNROLL], v[GBC_UNROLL];
+#pragma unroll
+    for (int u = 0; u < GBC_UNROLL; ++u) {
+      const int r = min(r0 + u, M - 1);
+      g[u] = dh[(long long)r * N8 + c8];
+      v[u] = z[(long long)r * N8 + c8];
+    }
+#pragma unroll
+    for (int u = 0; u < GBC_UNROLL; ++u) {
+      if (r0 + u >= M) break;
+      const uint32_t gw[4] = {g[u].x, g[u].y, g[u].z, g[u].w}, zw[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+      uint32_t o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 a = unpack_bf16x2(gw[k]), f = unpack_bf16x2(zw[k]);
+        o[k] = pack_bf16x2(a.x * dgelu_fast(f.x), a.y * dgelu_fast(f.y));
+        const float2 q = unpack_bf16x2(o[k]);
+        acc[2 * k] += q.x; acc[2 * k + 1] += q.y;
+      }
+      dz[(long long)(r0 + u) * N8 + c8] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+  float4* wrow = reinterpret_cast<float4*>(ws + (long long)blockIdx.x * N8 * 8) + 2 * c8;
+  wrow[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  wrow[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  if (!last_cta_arrives(counter)) return;
+  float4 t0 = make_float4(0.f, 0.f, 0.f, 0.f), t1 = t0;
+  for (int k = 0; k < (int)gridDim.x; ++k) {
+    const float4* prow = reinterpret_cast<const float4*>(ws + (long long)k * N8 * 8) + 2 * c8;
+    const float4 a = __ldcg(prow), b = __ldcg(prow + 1);
+    t0.x += a.x; t0.y += a.y; t0.z += a.z; t0.w += a.w;
+    t1.x += b.x; t1.y += b.y; t1.z += b.z; t1.w += b.w;
+  }
+  reinterpret_cast<float4*>(out)[2 * c8] = t0;
+  reinterpret_cast<float4*>(out)[2 * c8 + 1] = t1;
+}
+
+// ------------------------------------------------------------------------------------------------
 // column sums of a bf16 matrix: CTA = 64 columns x one row chunk; 256 threads = 8 row lanes x 32 column pairs
 // ------------------------------------------------------------------------------------------------
 constexpr int COLSUM_ROWS = 512;  // rows per chunk
@@ -763,4 +899,36 @@ extern "C" int vt_gelu_bwd_bf16(const vt_gelu_params* p, void* stream) {
   gelu_bwd_kernel<<<grid_for(n8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(p->dh), static_cast<const uint4*>(p->z), static_cast<uint4*>(p->out), n8);
   return check_launch("gelu_bwd_kernel");
+}
+
+// partial rows of the fused producer + column-sum kernels (one per CTA)
+static int fused_colsum_blocks(int rows_per_step, int rows, int per_sm) {
+  long long b = ((long long)rows + rows_per_step - 1) / rows_per_step;
+  const long long cap = (long long)sm_count() * per_sm;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+extern "C" int vt_gather_cast_colsum_blocks(int32_t rows) { return fused_colsum_blocks(8, rows, 2); }
+extern "C" int vt_gelu_bwd_colsum_blocks(int32_t M) { return fused_colsum_blocks(GBC_UNROLL, M, 4); }
+
+extern "C" int vt_gather_cast_colsum_bf16(const vt_gather_cast_colsum_params* p, void* stream) {
+  VT_REQUIRE(p && p->src && p->dst && p->colsum && p->workspace && p->counter && p->rows > 0, "vt_gather_cast_colsum_bf16: bad params");
+  VT_REQUIRE(p->D % 8 == 0 && p->lds % 4 == 0 && p->D <= GCC_CH * 256, "vt_gather_cast_colsum_bf16: D %% 8, lds %% 4 and D <= %d required", GCC_CH * 256);
+  const int blocks = vt_gather_cast_colsum_blocks(p->rows);
+  VT_REQUIRE(p->workspace_rows >= blocks, "vt_gather_cast_colsum_bf16: workspace holds %d partial rows, %d needed", p->workspace_rows, blocks);
+  gather_cast_colsum_kernel<<<blocks, 256, 8 * p->D * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+      p->src, p->lds, p->in_row, p->row_scale, static_cast<__nv_bfloat16*>(p->dst), p->rows, p->D / 8, p->workspace, p->colsum, p->counter);
+  return check_launch("gather_cast_colsum_kernel");
+}
+
+extern "C" int vt_gelu_bwd_colsum_bf16(const vt_gelu_bwd_colsum_params* p, void* stream) {
+  VT_REQUIRE(p && p->z && p->dh && p->out && p->colsum && p->workspace && p->counter && p->M > 0 && p->N > 0, "vt_gelu_bwd_colsum_bf16: bad params");
+  VT_REQUIRE(p->N % 256 == 0 && p->N <= 8192, "vt_gelu_bwd_colsum_bf16: N must be a multiple of 256, at most 8192 (got %d)", p->N);
+  const int blocks = vt_gelu_bwd_colsum_blocks(p->M);
+  VT_REQUIRE(p->workspace_rows >= blocks, "vt_gelu_bwd_colsum_bf16: workspace holds %d partial rows, %d needed", p->workspace_rows, blocks);
+  gelu_bwd_colsum_kernel<<<blocks, p->N / 8, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(p->dh), static_cast<const uint4*>(p->z), static_cast<uint4*>(p->out), p->M, p->N / 8, p->workspace, p->colsum,
+      p->counter);
+  return check_launch("gelu_bwd_colsum_kernel");
 }

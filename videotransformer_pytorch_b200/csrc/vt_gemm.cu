@@ -15,7 +15,7 @@ namespace vt {
 // RES: instantiation for the fp32 residual epilogue on TMA (epilogue_tile_tma_res): 8 KiB of staging per epilogue warp
 // instead of 4.1 KiB, paid for with one pipeline stage where shared memory is full.
 // compiled defaults of the round-2 paths (environment VT_TMA_RES / VT_TAIL_UNITS / VT_TMA_GELU / VT_TMA_DGELU = 0 | 1 override)
-constexpr bool VT_DEFAULT_TMA_RES = false;
+constexpr bool VT_DEFAULT_TMA_RES = true;
 constexpr bool VT_DEFAULT_TMA_RES_SPATIAL = false;
 constexpr bool VT_DEFAULT_TAIL_UNITS = false;
 constexpr bool VT_DEFAULT_TMA_GELU = false;
@@ -591,11 +591,14 @@ int launch_gemm_rows(const vt_gemm_params* q, int m0, void* stream);   // vt_gem
 // M a few rows past a multiple of 128: tensor-core kernel on the full row tiles, CUDA-core dot products for the rest
 // (vt_gemm_rows.cu).  Plain row-major calls only; anything forced by a test goes through the one-kernel path.
 #ifndef VT_DEFAULT_ROWS_SPLIT
-#define VT_DEFAULT_ROWS_SPLIT false
+#define VT_DEFAULT_ROWS_SPLIT true
 #endif
 static int rows_split_point(const vt_gemm_params* q) {
   const int r = q->M % vt::BM;
   if (r == 0 || r > 16 || q->M < 8 * vt::BM) return 0;
+  // measured (tools/rows_probe.py): the extra launch costs ~10 us, so the split only pays where the partial row of tiles
+  // costs a long extra round — few n-tiles, long K (FC2 and the FC1 data gradient: 82 -> 78 us, 73 -> 62 us)
+  if (q->N > 1024 || q->K < 2048) return 0;
   if (!vt::feature_on("VT_ROWS_SPLIT", VT_DEFAULT_ROWS_SPLIT)) return 0;
   if (q->a_mn_major || (q->epilogue != VT_EPI_BF16 && q->epilogue != VT_EPI_F32)) return 0;
   if (q->out_row || q->aux_row || q->map_period > 0 || q->debug || q->force_splits || q->force_bn || q->force_cluster || q->force_tail) return 0;

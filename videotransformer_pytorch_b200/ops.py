@@ -41,6 +41,9 @@ import os as _os
 FUSED_GELU_FWD = _os.environ.get('VT_FUSED_GELU', '0') == '1'
 FUSED_DGELU_BWD = _os.environ.get('VT_TMA_DGELU', '0') == '1'      # dGELU epilogue of the FC2 data gradient on TMA
 FUSED_GELU_EPILOGUE = False
+# bias gradients from the kernels that produce dY (gather_cast / dgelu with column sums) instead of a separate pass;
+# VT_FUSED_COLSUM=0/1 overrides
+FUSED_COLSUM = _os.environ.get('VT_FUSED_COLSUM', '0') == '1'
 
 
 def set_mask_arena(arena):
@@ -173,6 +176,14 @@ def _streaming_attn_bwd(k, qkv, cx, dcx, lse, Bp, N, H, hd):
     return dqkv
 
 
+def _cast_with_colsum(k, src2d, in_row=None, row_scale=None, rows=None):
+    """dY in bf16 (gathered / scaled rows of the fp32 gradient stream) and its column sums = the bias gradient."""
+    if FUSED_COLSUM:
+        return k.gather_cast_colsum(src2d, in_row=in_row, row_scale=row_scale, rows=rows)
+    g = k.gather_cast(src2d, in_row=in_row, row_scale=row_scale, rows=rows)
+    return g, k.colsum(g)
+
+
 def _mul_opt(a, b):
     if a is None:
         return b
@@ -219,9 +230,8 @@ class TemporalAttnFn(torch.autograd.Function):
         dy = dy.contiguous()
         dy2 = dy.view(B * S, D)
         x2 = x.reshape(B * S, D)
-        g = k.gather_cast(dy2, in_row=maps['temporal'], rows=Mt)
+        g, d_fc_b = _cast_with_colsum(k, dy2, in_row=maps['temporal'], rows=Mt)
         d_fc_w = _wgrad(g, a, D, D, Mt, wptr=ctx.wptrs[2])
-        d_fc_b = k.colsum(g)
         da = _dgrad(g, fc_wh, Mt, D, D, epi='bf16', row_scale=dp)
         d_proj_w = _wgrad(da, cx, D, D, Mt, tag='proj', wptr=ctx.wptrs[1])
         d_proj_b = k.colsum(da)
@@ -275,9 +285,8 @@ class SpatialAttnFn(torch.autograd.Function):
         dy = dy.contiguous()
         dy2 = dy.view(R, D)
         x2 = x.reshape(R, D)
-        g = k.gather_cast(dy2, in_row=maps['sp_in'], row_scale=_mul_opt(dp, maps['sp_cls_scale']), rows=Ms)
+        g, d_proj_b = _cast_with_colsum(k, dy2, in_row=maps['sp_in'], row_scale=_mul_opt(dp, maps['sp_cls_scale']), rows=Ms)
         d_proj_w = _wgrad(g, cx, D, D, Ms, tag='proj', wptr=ctx.wptrs[1])
-        d_proj_b = k.colsum(g)
         dcx = _dgrad(g, proj_wh, Ms, D, D, epi='bf16', tag='proj')
         dqkv = k.attn_bwd(qkv, cx, dcx, lse, B * T, P + 1, H, hd, hd ** -0.5)
         d_qkv_w = _wgrad(dqkv, xn, 3 * D, D, Ms, tag='qkv', wptr=ctx.wptrs[0])
@@ -328,9 +337,8 @@ class JointAttnFn(torch.autograd.Function):
         dy = dy.contiguous()
         dy2 = dy.view(M, D)
         x2 = x.reshape(M, D)
-        g = k.gather_cast(dy2, row_scale=dp)
+        g, d_proj_b = _cast_with_colsum(k, dy2, row_scale=dp)
         d_proj_w = _wgrad(g, cx, D, D, M, tag='proj', wptr=ctx.wptrs[1])
-        d_proj_b = k.colsum(g)
         dcx = _dgrad(g, proj_wh, M, D, D, epi='bf16', tag='proj')
         if N <= ATTN_SINGLE_PASS_MAX:
             dqkv = k.attn_bwd(qkv, cx, dcx, lse, Bp, N, H, hd, hd ** -0.5)
@@ -377,15 +385,19 @@ class FFNFn(torch.autograd.Function):
         dy = dy.contiguous()
         dy2 = dy.view(M, D)
         x2 = x.reshape(M, D)
-        g = k.gather_cast(dy2, row_scale=dp)
+        g, d_b2 = _cast_with_colsum(k, dy2, row_scale=dp)
         d_w2 = _wgrad(g, h, D, Dh, M, wptr=ctx.wptrs[1])
-        d_b2 = k.colsum(g)
+        d_b1 = None
         if FUSED_GELU_EPILOGUE or FUSED_DGELU_BWD:
             dz = _dgrad(g, w2h, M, Dh, D, epi='dgelu', aux=z)
         else:
-            dz = k.dgelu(_dgrad(g, w2h, M, Dh, D, epi='bf16'), z)
+            if FUSED_COLSUM:
+                dz, d_b1 = k.dgelu_colsum(_dgrad(g, w2h, M, Dh, D, epi='bf16'), z)
+            else:
+                dz = k.dgelu(_dgrad(g, w2h, M, Dh, D, epi='bf16'), z)
         d_w1 = _wgrad(dz, xn, Dh, D, M, wptr=ctx.wptrs[0])
-        d_b1 = k.colsum(dz)
+        if d_b1 is None:
+            d_b1 = k.colsum(dz)
         dxn = _dgrad(dz, w1h, M, D, Dh, epi='bf16')
         dx = torch.empty_like(x)
         _, _, d_ln_w, d_ln_b = k.ln_bwd(dxn, x2, mean, rstd, ln_w, dres=dy2, dx=dx.view(M, D))
@@ -459,9 +471,8 @@ class PatchTokensFn(torch.autograd.Function):
             maps = token_maps(B, Tp, P, str(dout.device))
         else:
             maps = frame_maps(B * Tp, P, str(dout.device))
-        g = k.gather_cast(d2, in_row=maps['emb_out'], rows=M)
+        g, db = _cast_with_colsum(k, d2, in_row=maps['emb_out'], rows=M)
         dw = _wgrad(g, cols, D, Kc, M).view(wshape)
-        db = k.colsum(g)
         dcls = dout[:, 0].sum(dim=0)
         if mode == 'timesformer':
             dtab = dout[:, 1:].sum(dim=0).view(P, Tp, D)
