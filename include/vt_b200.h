@@ -174,13 +174,12 @@ int vt_gelu_bwd_bf16(const vt_gelu_params* p, void* stream);
 /* The two producers of a layer's dY that also emit its column sums (= the bias gradient autograd's sum over tokens gives
  * nn.Linear, transformer.py:175 / :267 / :505 / :501): vt_gather_cast_bf16 + vt_colsum_bf16, and vt_gelu_bwd_bf16 +
  * vt_colsum_bf16, in one pass each.  colsum fp32 [D] / [N]; workspace fp32 [workspace_rows, D] with workspace_rows >=
- * vt_*_blocks(rows); counter: one int32, zero before the first call (the kernels leave it zero).  Sums are over the
- * bf16-rounded outputs, in a fixed order. */
+ * vt_*_blocks(rows).  Sums are over the bf16-rounded outputs, in a fixed order. */
 typedef struct { const float* src; int64_t lds; const int32_t* in_row; const float* row_scale; void* dst; int32_t rows, D;
-                 float* colsum; float* workspace; int32_t* counter; int32_t workspace_rows; } vt_gather_cast_colsum_params;
+                 float* colsum; float* workspace; int32_t workspace_rows; } vt_gather_cast_colsum_params;
 int vt_gather_cast_colsum_blocks(int32_t rows);
 int vt_gather_cast_colsum_bf16(const vt_gather_cast_colsum_params* p, void* stream);
-typedef struct { const void* z; const void* dh; void* out; int32_t M, N; float* colsum; float* workspace; int32_t* counter;
+typedef struct { const void* z; const void* dh; void* out; int32_t M, N; float* colsum; float* workspace;
                  int32_t workspace_rows; } vt_gelu_bwd_colsum_params;
 int vt_gelu_bwd_colsum_blocks(int32_t M);
 int vt_gelu_bwd_colsum_bf16(const vt_gelu_bwd_colsum_params* p, void* stream);

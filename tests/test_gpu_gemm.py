@@ -200,7 +200,7 @@ def test_gemm_pair_kernel_epilogues(epi):
         assert rel(out, r * zz.grad) < 4e-3
 
 
-# ---- round 2: fp32 residual epilogue on TMA (affine row maps through a 4-D tensor map) and narrow tail units -------------
+# ---- round 2: fp32 residual epilogue on TMA (affine row maps through a tensor map of the token stream), narrow tail units ---
 def _ops():
     from videotransformer_pytorch_b200 import ops
     return ops
@@ -231,8 +231,9 @@ def test_residual_epilogue_tma_plain_rows(M, N, Kd, bn, cluster, monkeypatch):
 @pytest.mark.parametrize('cluster', [1, 3], ids=['single-cta', 'cta-pair'])
 @pytest.mark.parametrize('B,T,P,D', [(2, 8, 196, 768), (3, 4, 9, 128), (1, 2, 50, 256), (2, 8, 196, 96)])
 def test_residual_epilogue_tma_temporal_and_spatial_maps(B, T, P, D, cluster, monkeypatch):
-    """The divided space-time scatters as 4-D TMA boxes (temporal '(b p) t', spatial '(b t) (1+p)' with the per-frame cls
-    replicas going to side rows) against the same GEMM driven by the out_row / aux_row arrays (generic epilogue)."""
+    """The divided space-time scatters as TMA boxes (temporal '(b p) t', spatial '(b t) (1+p)' with the per-frame cls
+    replicas going to side rows; 32-row groups that straddle a period go row by row) against the same GEMM driven by the
+    out_row / aux_row arrays alone (generic epilogue)."""
     ops = _ops()
     maps = ops.token_maps(B, T, P, 'cuda:0')
     aff = ops.affine_row_maps(B, T, P, D)
@@ -247,6 +248,7 @@ def test_residual_epilogue_tma_temporal_and_spatial_maps(B, T, P, D, cluster, mo
         rs = mk((Mrows,), 44)
         got = torch.full((out_rows, D), -7.0, device='cuda')
         monkeypatch.setenv('VT_TMA_RES', '1')
+        monkeypatch.setenv('VT_TMA_RES_SPATIAL', '1')
         K().gemm(a, w, Mrows, D, Kd, epi='f32', bias=bias, row_scale=rs, aux=x2, aux_row=aux_row, out=got, out_row=out_row,
                  row_map=aff[name], force_cluster=cluster)
         monkeypatch.setenv('VT_TMA_RES', '0')

@@ -605,33 +605,62 @@ def test_residual_epilogue_segments_cover_every_row_once(B, T, P, kind):
     def view3(buf):
         return torch.as_strided(buf.reshape(-1), (bc, pc * tcount, D), (aff['stride_b'], row_stride, 1), aff['base'])
     x3 = view3(x if kind == 'temporal' else torch.cat([x, torch.zeros(B * T, D)]))
+    n_outer = M // period
+    n_direct = n_tma = 0
     for m0 in range(0, (M + 127) // 128 * 128, 32):
         outer0, inner0 = m0 // period, m0 % period
-        two = inner0 + 32 > period
-        segs = []
-        for sg in range(2 if two else 1):
+        seg, live = [], []
+        for sg in range(2):
             outer = outer0 + sg
             seg_t, seg_p, seg_b = outer % tcount, inner0 - sg * period - skip, outer // tcount
-            segs.append((seg_p * tcount + seg_t, seg_b))        # the kernel's box coordinates
-        boxes = [_tma_box(x3, c_row, c_b, tcount) for c_row, c_b in segs]
+            seg.append((seg_p, seg_t, seg_b))
+            live.append(outer < n_outer and seg_p + 31 >= 0 and seg_p < pc and (sg == 0 or inner0 + 32 > period))
+        if not (live[0] or live[1]):
+            continue
+        only = 0 if live[0] else 1
+        direct = (live[0] and live[1]) or seg[only][0] < 0
+        if direct:                                          # thread = row, addresses from the index arrays
+            n_direct += 1
+            for lane in range(32):
+                row = m0 + lane
+                if row >= M:
+                    continue
+                my_seg = 1 if inner0 + lane >= period else 0
+                my_inner = inner0 + lane - my_seg * period
+                if my_inner < skip:
+                    dst = (aff['special_base'] + (outer0 + my_seg) * aff['special_stride']) // D
+                    got[dst] = acc[row]
+                    writes[dst] += 1
+                    continue
+                o, a = int(out_row[row]), int(aux_row[row])
+                if o >= 0:
+                    got[o] = acc[row] + (x[a] if a >= 0 else 0)
+                    writes[o] += 1
+            continue
+        n_tma += 1
+        seg_p, seg_t, seg_b = seg[only]
+        assert seg_p >= 0                                   # TMA boxes never start outside the tensor
+        box, valid, where = _tma_box(x3, seg_p * tcount + seg_t, seg_b, tcount)
         result = torch.zeros(32, D)
         for lane in range(32):
             row = m0 + lane
             my_seg = 1 if inner0 + lane >= period else 0
             my_inner = inner0 + lane - my_seg * period
-            aux = boxes[my_seg][0][lane] if my_seg < len(boxes) else torch.zeros(D)
-            val = (acc[row] if row < M else torch.zeros(D)) + aux
+            val = (acc[row] if row < M else torch.zeros(D)) + box[lane]
             result[lane] = val
-            if row < M and my_inner < skip:                   # special row: plain store to the side rows
+            if row < M and my_inner < skip:                   # next period's special row at the tail of the box
+                assert not valid[lane]
                 dst = (aff['special_base'] + (outer0 + my_seg) * aff['special_stride']) // D
                 got[dst] = val
                 writes[dst] += 1
-        for (c_row, c_b), (_, valid, where) in zip(segs, boxes):  # TMA stores clip exactly like the loads
-            for lane in range(32):
-                if valid[lane]:
-                    off = aff['base'] + where[lane] * row_stride + c_b * aff['stride_b']
-                    got[off // D] = result[lane]
-                    writes[off // D] += 1
+        for lane in range(32):                                # the TMA store clips exactly like the load
+            if valid[lane]:
+                off = aff['base'] + where[lane] * row_stride + seg_b * aff['stride_b']
+                if m0 + lane < M:
+                    assert int(out_row[m0 + lane]) == off // D
+                got[off // D] = result[lane]
+                writes[off // D] += 1
+    assert n_tma > 0
     exp = torch.full((rows_total, D), float('nan'))
     add = x[aux_row.long().clamp(min=0)] * (aux_row >= 0)[:, None]
     exp[out_row.long()] = acc + add

@@ -71,13 +71,12 @@ class GeluParams(C.Structure):
 
 class GatherCastColsumParams(C.Structure):
     _fields_ = [('src', c_vp), ('lds', c_i64), ('in_row', c_vp), ('row_scale', c_vp), ('dst', c_vp),
-                ('rows', c_i32), ('D', c_i32), ('colsum', c_vp), ('workspace', c_vp), ('counter', c_vp),
-                ('workspace_rows', c_i32)]
+                ('rows', c_i32), ('D', c_i32), ('colsum', c_vp), ('workspace', c_vp), ('workspace_rows', c_i32)]
 
 
 class GeluBwdColsumParams(C.Structure):
     _fields_ = [('z', c_vp), ('dh', c_vp), ('out', c_vp), ('M', c_i32), ('N', c_i32), ('colsum', c_vp),
-                ('workspace', c_vp), ('counter', c_vp), ('workspace_rows', c_i32)]
+                ('workspace', c_vp), ('workspace_rows', c_i32)]
 
 
 class AttnFwdParams(C.Structure):
@@ -433,14 +432,6 @@ class CudaKernels:
         _check(lib.vt_gather_cast_bf16(C.byref(p), _stream()), 'vt_gather_cast_bf16')
         return out
 
-    def _fused_counter(self, device):
-        """One zeroed int32 per (device, stream) for the producer + column-sum kernels (they leave it zero)."""
-        key = ('fused', device.index, torch.cuda.current_stream(device).cuda_stream)
-        cnt = self._counters.get(key)
-        if cnt is None:
-            cnt = self._counters[key] = torch.zeros(4, dtype=torch.int32, device=device)
-        return cnt
-
     def gather_cast_colsum(self, src2d, in_row=None, row_scale=None, rows=None):
         """gather_cast + colsum of its output in one pass -> (bf16 [rows, D], fp32 [D]); D <= 1024, else two kernels."""
         lib = load_library()
@@ -459,7 +450,7 @@ class CudaKernels:
         p.src, p.lds = src2d.data_ptr(), src2d.stride(0)
         p.in_row, p.row_scale = _ptr(in_row), _ptr(row_scale)
         p.dst, p.rows, p.D = out.data_ptr(), rows, D
-        p.colsum, p.workspace, p.counter, p.workspace_rows = cs.data_ptr(), ws.data_ptr(), self._fused_counter(dev).data_ptr(), nb
+        p.colsum, p.workspace, p.workspace_rows = cs.data_ptr(), ws.data_ptr(), nb
         _check(lib.vt_gather_cast_colsum_bf16(C.byref(p), _stream()), 'vt_gather_cast_colsum_bf16')
         return out, cs
 
@@ -481,7 +472,7 @@ class CudaKernels:
         ws = torch.empty((nb, N), dtype=torch.float32, device=dev)
         p = GeluBwdColsumParams()
         p.z, p.dh, p.out, p.M, p.N = z.data_ptr(), dh.data_ptr(), out.data_ptr(), M, N
-        p.colsum, p.workspace, p.counter, p.workspace_rows = cs.data_ptr(), ws.data_ptr(), self._fused_counter(dev)[1:].data_ptr(), nb
+        p.colsum, p.workspace, p.workspace_rows = cs.data_ptr(), ws.data_ptr(), nb
         _check(lib.vt_gelu_bwd_colsum_bf16(C.byref(p), _stream()), 'vt_gelu_bwd_colsum_bf16')
         return out, cs
 

@@ -353,28 +353,15 @@ __global__ void gather_cast_kernel(const float* __restrict__ src, long long lds,
 // Producer kernels that also emit the column sums of what they write (the bias gradient of the layer whose dY they
 // produce): the separate column-sum pass re-read 19 - 77 MB per launch at ~1.2 - 3.7 TB/s (profiles/r2_*), 4 of the 7 per
 // block disappear this way.  Sums are taken over the bf16-rounded values, as the separate pass does.  Per-CTA partial rows,
-// summed by the last CTA to finish in CTA order (deterministic).
+// summed by reduce_rows in CTA order (deterministic) — a last-CTA-finishes pass inside the kernel pulled the 1 - 7 MB of
+// partials through ONE SM (171 us for the dGELU case).
 // ------------------------------------------------------------------------------------------------
 constexpr int GCC_CH = 4;         // 8-column pieces per lane: D <= 1024
-
-__device__ __forceinline__ bool last_cta_arrives(int* counter) {
-  __shared__ int is_last;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const int done = atomicAdd(counter, 1);
-    is_last = (done == (int)gridDim.x - 1);
-    if (is_last) *counter = 0;      // self-cleaning for the next call
-  }
-  __syncthreads();
-  if (is_last) __threadfence();
-  return is_last != 0;
-}
 
 __global__ void __launch_bounds__(256)
 gather_cast_colsum_kernel(const float* __restrict__ src, long long lds, const int* __restrict__ in_row,
                           const float* __restrict__ row_scale, __nv_bfloat16* __restrict__ dst, int rows, int D8,
-                          float* __restrict__ ws, float* __restrict__ out, int* __restrict__ counter) {
+                          float* __restrict__ ws) {
   extern __shared__ float sh_gcc[];            // [8 warps][D]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int D = D8 * 8;
@@ -427,22 +414,13 @@ gather_cast_colsum_kernel(const float* __restrict__ src, long long lds, const in
     for (int w = 0; w < 8; ++w) t += sh_gcc[w * D + col];
     ws[(long long)blockIdx.x * D + col] = t;
   }
-  if (!last_cta_arrives(counter)) return;
-  for (int c4 = threadIdx.x; c4 < D / 4; c4 += 256) {
-    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int k = 0; k < (int)gridDim.x; ++k) {
-      const float4 v = __ldcg(reinterpret_cast<const float4*>(ws + (long long)k * D) + c4);
-      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
-    }
-    reinterpret_cast<float4*>(out)[c4] = t;
-  }
 }
 
 // dz = dh * gelu'(z) with the column sums of dz: blockDim = N / 8 (thread = 8 columns of every row the CTA walks)
 constexpr int GBC_UNROLL = 2;
 __global__ void __launch_bounds__(1024)
 gelu_bwd_colsum_kernel(const uint4* __restrict__ dh, const uint4* __restrict__ z, uint4* __restrict__ dz, int M, int N8,
-                       float* __restrict__ ws, float* __restrict__ out, int* __restrict__ counter) {
+                       float* __restrict__ ws) {
   const int c8 = threadIdx.x;
   float acc[8];
 #pragma unroll
@@ -473,16 +451,6 @@ gelu_bwd_colsum_kernel(const uint4* __restrict__ dh, const uint4* __restrict__ z
   float4* wrow = reinterpret_cast<float4*>(ws + (long long)blockIdx.x * N8 * 8) + 2 * c8;
   wrow[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
   wrow[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
-  if (!last_cta_arrives(counter)) return;
-  float4 t0 = make_float4(0.f, 0.f, 0.f, 0.f), t1 = t0;
-  for (int k = 0; k < (int)gridDim.x; ++k) {
-    const float4* prow = reinterpret_cast<const float4*>(ws + (long long)k * N8 * 8) + 2 * c8;
-    const float4 a = __ldcg(prow), b = __ldcg(prow + 1);
-    t0.x += a.x; t0.y += a.y; t0.z += a.z; t0.w += a.w;
-    t1.x += b.x; t1.y += b.y; t1.z += b.z; t1.w += b.w;
-  }
-  reinterpret_cast<float4*>(out)[2 * c8] = t0;
-  reinterpret_cast<float4*>(out)[2 * c8 + 1] = t1;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -830,9 +798,10 @@ extern "C" int vt_gather_cast_bf16(const vt_gather_cast_params* p, void* stream)
   return check_launch("gather_cast_kernel");
 }
 
+namespace vt { int launch_reduce_rows(const float*, float*, long long, int, long long, int, float, cudaStream_t); }
+
 extern "C" int vt_colsum_chunks(int32_t M) { return (M + COLSUM_WROWS - 1) / COLSUM_WROWS; }   // rows of the partial-sum workspace
 
-namespace vt { int launch_reduce_rows(const float*, float*, long long, int, long long, int, float, cudaStream_t); }
 
 extern "C" int vt_colsum_bf16(const vt_colsum_params* p, void* stream) {
   VT_REQUIRE(p && p->in && p->out && p->workspace && p->M > 0 && p->N > 0, "vt_colsum_bf16: bad params");
@@ -913,22 +882,25 @@ extern "C" int vt_gather_cast_colsum_blocks(int32_t rows) { return fused_colsum_
 extern "C" int vt_gelu_bwd_colsum_blocks(int32_t M) { return fused_colsum_blocks(GBC_UNROLL, M, 4); }
 
 extern "C" int vt_gather_cast_colsum_bf16(const vt_gather_cast_colsum_params* p, void* stream) {
-  VT_REQUIRE(p && p->src && p->dst && p->colsum && p->workspace && p->counter && p->rows > 0, "vt_gather_cast_colsum_bf16: bad params");
+  VT_REQUIRE(p && p->src && p->dst && p->colsum && p->workspace && p->rows > 0, "vt_gather_cast_colsum_bf16: bad params");
   VT_REQUIRE(p->D % 8 == 0 && p->lds % 4 == 0 && p->D <= GCC_CH * 256, "vt_gather_cast_colsum_bf16: D %% 8, lds %% 4 and D <= %d required", GCC_CH * 256);
   const int blocks = vt_gather_cast_colsum_blocks(p->rows);
   VT_REQUIRE(p->workspace_rows >= blocks, "vt_gather_cast_colsum_bf16: workspace holds %d partial rows, %d needed", p->workspace_rows, blocks);
   gather_cast_colsum_kernel<<<blocks, 256, 8 * p->D * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
-      p->src, p->lds, p->in_row, p->row_scale, static_cast<__nv_bfloat16*>(p->dst), p->rows, p->D / 8, p->workspace, p->colsum, p->counter);
-  return check_launch("gather_cast_colsum_kernel");
+      p->src, p->lds, p->in_row, p->row_scale, static_cast<__nv_bfloat16*>(p->dst), p->rows, p->D / 8, p->workspace);
+  const int rc = check_launch("gather_cast_colsum_kernel");
+  if (rc) return rc;
+  return launch_reduce_rows(p->workspace, p->colsum, p->D, blocks, p->D, 0, 1.0f, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int vt_gelu_bwd_colsum_bf16(const vt_gelu_bwd_colsum_params* p, void* stream) {
-  VT_REQUIRE(p && p->z && p->dh && p->out && p->colsum && p->workspace && p->counter && p->M > 0 && p->N > 0, "vt_gelu_bwd_colsum_bf16: bad params");
+  VT_REQUIRE(p && p->z && p->dh && p->out && p->colsum && p->workspace && p->M > 0 && p->N > 0, "vt_gelu_bwd_colsum_bf16: bad params");
   VT_REQUIRE(p->N % 256 == 0 && p->N <= 8192, "vt_gelu_bwd_colsum_bf16: N must be a multiple of 256, at most 8192 (got %d)", p->N);
   const int blocks = vt_gelu_bwd_colsum_blocks(p->M);
   VT_REQUIRE(p->workspace_rows >= blocks, "vt_gelu_bwd_colsum_bf16: workspace holds %d partial rows, %d needed", p->workspace_rows, blocks);
   gelu_bwd_colsum_kernel<<<blocks, p->N / 8, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const uint4*>(p->dh), static_cast<const uint4*>(p->z), static_cast<uint4*>(p->out), p->M, p->N / 8, p->workspace, p->colsum,
-      p->counter);
-  return check_launch("gelu_bwd_colsum_kernel");
+      static_cast<const uint4*>(p->dh), static_cast<const uint4*>(p->z), static_cast<uint4*>(p->out), p->M, p->N / 8, p->workspace);
+  const int rc = check_launch("gelu_bwd_colsum_kernel");
+  if (rc) return rc;
+  return launch_reduce_rows(p->workspace, p->colsum, p->N, blocks, p->N, 0, 1.0f, static_cast<cudaStream_t>(stream));
 }

@@ -298,6 +298,8 @@ bool res_tma_applicable(const vt_gemm_params* q) {
       if (!feature_on("VT_TMA_RES_SPATIAL", VT_DEFAULT_TMA_RES_SPATIAL)) return false;
       if (q->map_tcount > 8 || q->map_stride_p != (long long)q->map_tcount * q->map_stride_t) return false;
     }
+    // groups of 32 rows that straddle a period boundary or start on a special row are written row by row from the index arrays
+    if ((q->map_period % 32 != 0 || q->map_skip > 0) && !(q->out_row && q->aux_row)) return false;
     return q->map_period >= 32 && q->map_tcount >= 1 && q->M % q->map_period == 0;
   }
   return !q->out_row && !q->aux_row && q->ldo % 4 == 0 && q->ldaux % 4 == 0;

@@ -384,34 +384,36 @@ __device__ __forceinline__ void epilogue_tile_tma_res(const GemmDev& p, const CU
     seg_p[sgm] = inner0 - sgm * p.map_period - p.map_skip;
     live[sgm] = outer < n_outer && seg_p[sgm] + 31 >= 0 && seg_p[sgm] < pcount && (sgm == 0 || inner0 + 32 > p.map_period);
   }
-  const bool two = live[0] && live[1];
-  const int only = live[0] ? 0 : 1;                    // the segment served in single-segment mode
   const bool any = live[0] || live[1];
+  const int only = live[0] ? 0 : 1;                    // the segment served by TMA
+  // TMA moves the group's box only when it is ONE segment that starts inside the tensor (rows past the end are clipped by
+  // the unit — proven on hardware).  Groups that straddle a period boundary, or start on a special row (negative start
+  // coordinate), go row by row: thread = row, 128 contiguous bytes per chunk, addresses from the out_row / aux_row arrays.
+  // (Boxes with negative start coordinates raised "illegal instruction" at the store on the B200, with rank-3 and rank-4 maps.)
+  const bool direct = any && ((live[0] && live[1]) || seg_p[only] < 0);
   // this lane's row: which segment, special?
   const int my_seg = (inner0 + lane >= p.map_period) ? 1 : 0;
   const int my_inner = inner0 + lane - my_seg * p.map_period;
   const bool special = row < p.M && my_inner < p.map_skip;
   const int nchunks = (bn / 32 - half + 1) / 2;          // chunks c = half, half + 2, ... of this warpgroup
+  auto chunk_cols_ok = [&](int it) { return n_base + (half + 2 * it) * 32 < p.N; };
   // row coordinate of a segment in the (col, row-in-sample, sample) map: rows of one frame sit map_tcount apart (the box
   // walks them through the map's element stride), so segment row p of frame t starts at p * map_tcount + t
-  auto chunk_cols_ok = [&](int it) { return n_base + (half + 2 * it) * 32 < p.N; };
-  auto request = [&](int it, int buf, int sgm) {        // lane 0: residual box of chunk `it`, segment sgm -> buffer buf
+  auto request = [&](int it, int buf) {        // lane 0: residual box of chunk `it` -> buffer buf
     const int n = n_base + (half + 2 * it) * 32;
-    tma_load_3d(slot + buf * 4096, tmX, &aux_bar[buf], n, seg_p[sgm] * p.map_tcount + seg_t[sgm], seg_b[sgm]);
+    tma_load_3d(slot + buf * 4096, tmX, &aux_bar[buf], n, seg_p[only] * p.map_tcount + seg_t[only], seg_b[only]);
   };
-  auto store = [&](const void* src, int n0, int sgm) {
-    tma_store_3d(tmC, src, n0, seg_p[sgm] * p.map_tcount + seg_t[sgm], seg_b[sgm]);
-  };
-  // Single-segment groups: chunk `it` lives in buffer it & 1 and chunk it + 1 is prefetched into the other buffer.
-  // Groups with two live segments use both buffers for one chunk (segment k -> buffer k), without prefetch.
-  if (lane == 0 && any) {
-    if (!two) {
-      if (nchunks > 0 && chunk_cols_ok(0)) { mbar_arrive_expect_tx(&aux_bar[0], 4096); request(0, 0, only); }
-      if (nchunks > 1 && chunk_cols_ok(1)) { mbar_arrive_expect_tx(&aux_bar[1], 4096); request(1, 1, only); }
-    } else if (nchunks > 0 && chunk_cols_ok(0)) {
-      mbar_arrive_expect_tx(&aux_bar[0], 4096); request(0, 0, 0);
-      mbar_arrive_expect_tx(&aux_bar[1], 4096); request(0, 1, 1);
-    }
+  // chunk `it` lives in buffer it & 1 and chunk it + 1 is prefetched into the other buffer
+  if (lane == 0 && any && !direct) {
+    if (nchunks > 0 && chunk_cols_ok(0)) { mbar_arrive_expect_tx(&aux_bar[0], 4096); request(0, 0); }
+    if (nchunks > 1 && chunk_cols_ok(1)) { mbar_arrive_expect_tx(&aux_bar[1], 4096); request(1, 1); }
+  }
+  long long o_off = -1, a_off = -1;             // direct mode: this lane's output / addend row (element offsets), -1 = none
+  if (direct && row < p.M && !special) {
+    const int orow = p.out_row ? p.out_row[row] : row;
+    const int arow = p.aux_row ? p.aux_row[row] : row;
+    if (orow >= 0) o_off = (long long)orow * p.ldo;
+    if (arow >= 0) a_off = (long long)arow * p.ldaux;
   }
   mbar_wait(tfull, ph);
   tc_fence_after();
@@ -431,58 +433,62 @@ __device__ __forceinline__ void epilogue_tile_tma_res(const GemmDev& p, const CU
     uint32_t r[32];
     tmem_ld32(t_base + c * 32, r);
     tmem_ld_wait();
-    const int cur = two ? 0 : (it & 1);
-    // residual box(es) of this chunk have landed
-    if (!two) {
-      if (cur == 0) { mbar_wait(&aux_bar[0], aux_use[0] & 1); ++aux_use[0]; }
-      else { mbar_wait(&aux_bar[1], aux_use[1] & 1); ++aux_use[1]; }
-    } else {
-      mbar_wait(&aux_bar[0], aux_use[0] & 1);
-      mbar_wait(&aux_bar[1], aux_use[1] & 1);
-      ++aux_use[0]; ++aux_use[1];
+    if (direct) {
+      float4 v[8];
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a_off >= 0) a = *reinterpret_cast<const float4*>(static_cast<const float*>(p.aux) + a_off + n0 + 4 * g);
+        v[g].x = fmaf(s, __uint_as_float(r[4 * g + 0]) + b[g].x, a.x);
+        v[g].y = fmaf(s, __uint_as_float(r[4 * g + 1]) + b[g].y, a.y);
+        v[g].z = fmaf(s, __uint_as_float(r[4 * g + 2]) + b[g].z, a.z);
+        v[g].w = fmaf(s, __uint_as_float(r[4 * g + 3]) + b[g].w, a.w);
+      }
+      float* dst = nullptr;
+      if (special) {
+        if (p.special_out) dst = p.special_out + (long long)(outer0 + my_seg) * p.special_ld + n0;
+      } else if (o_off >= 0) {
+        dst = static_cast<float*>(p.out) + o_off + n0;
+      }
+      if (dst) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g) *reinterpret_cast<float4*>(dst + 4 * g) = v[g];
+      }
+      continue;
     }
-    uint8_t* out_buf = slot + cur * 4096;                                  // result box (segment-0 buffer when two)
-    // where this row's residual landed; rows of a segment that is not live (beyond M, or special) have none
-    const bool have_aux = two || my_seg == only;
-    const uint8_t* my_aux = slot + (two ? my_seg : cur) * 4096;
+    const int cur = it & 1;
+    // residual box of this chunk has landed
+    if (cur == 0) { mbar_wait(&aux_bar[0], aux_use[0] & 1); ++aux_use[0]; }
+    else { mbar_wait(&aux_bar[1], aux_use[1] & 1); ++aux_use[1]; }
+    uint8_t* buf = slot + cur * 4096;
     float4 v[8];
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
-      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (have_aux) a = *reinterpret_cast<const float4*>(my_aux + lane * 128 + ((g ^ (lane & 7)) << 4));    // SWIZZLE_128B
+      const float4 a = *reinterpret_cast<const float4*>(buf + lane * 128 + ((g ^ (lane & 7)) << 4));    // SWIZZLE_128B
       v[g].x = fmaf(s, __uint_as_float(r[4 * g + 0]) + b[g].x, a.x);
       v[g].y = fmaf(s, __uint_as_float(r[4 * g + 1]) + b[g].y, a.y);
       v[g].z = fmaf(s, __uint_as_float(r[4 * g + 2]) + b[g].z, a.z);
       v[g].w = fmaf(s, __uint_as_float(r[4 * g + 3]) + b[g].w, a.w);
     }
-    if (special) {
-      // replicated-cls rows have no residual (their box row was clipped to zeros) and go to the side buffer
-      if (p.special_out) {
-        float* dst = p.special_out + (long long)(outer0 + my_seg) * p.special_ld + n0;
+    if (special && p.special_out) {
+      // the next period's special row at the tail of the box: its box row was clipped to zeros by the load and will be
+      // clipped again by the store; the value goes to the side rows
+      float* dst = p.special_out + (long long)(outer0 + my_seg) * p.special_ld + n0;
 #pragma unroll
-        for (int g = 0; g < 8; ++g) *reinterpret_cast<float4*>(dst + 4 * g) = v[g];
-      }
+      for (int g = 0; g < 8; ++g) *reinterpret_cast<float4*>(dst + 4 * g) = v[g];
     }
-    __syncwarp();      // every lane has read its residual (possibly from the other buffer) before the box is overwritten
 #pragma unroll
-    for (int g = 0; g < 8; ++g) *reinterpret_cast<float4*>(out_buf + lane * 128 + ((g ^ (lane & 7)) << 4)) = v[g];
+    for (int g = 0; g < 8; ++g) *reinterpret_cast<float4*>(buf + lane * 128 + ((g ^ (lane & 7)) << 4)) = v[g];
     fence_proxy_async();
     __syncwarp();
     if (lane == 0) {
-      if (two) { store(out_buf, n0, 0); store(out_buf, n0, 1); }
-      else store(out_buf, n0, only);
+      tma_store_3d(tmC, buf, n0, seg_p[only] * p.map_tcount + seg_t[only], seg_b[only]);
       bulk_commit();
       // refill: the buffer just stored from must have been read out by its store first
-      if (!two) {
-        if (it + 2 < nchunks && chunk_cols_ok(it + 2)) {
-          bulk_wait_read<0>();
-          mbar_arrive_expect_tx(&aux_bar[cur], 4096);
-          request(it + 2, cur, only);
-        }
-      } else if (it + 1 < nchunks && chunk_cols_ok(it + 1)) {
+      if (it + 2 < nchunks && chunk_cols_ok(it + 2)) {
         bulk_wait_read<0>();
-        mbar_arrive_expect_tx(&aux_bar[0], 4096); request(it + 1, 0, 0);
-        mbar_arrive_expect_tx(&aux_bar[1], 4096); request(it + 1, 1, 1);
+        mbar_arrive_expect_tx(&aux_bar[cur], 4096);
+        request(it + 2, cur);
       }
     }
     __syncwarp();

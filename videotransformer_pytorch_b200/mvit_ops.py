@@ -16,7 +16,8 @@ from __future__ import annotations
 import torch
 
 from . import _lib
-from .ops import _dgrad, _wgrad
+from . import ops as _ops
+from .ops import _cast_with_colsum, _dgrad, _wgrad
 
 
 def K():
@@ -136,9 +137,8 @@ class PoolAttnFn(torch.autograd.Function):
         Nq = dy.shape[1]
         Mq = B * Nq
         dy2 = dy.view(Mq, d)
-        g = k.gather_cast(dy2)
+        g, d_pb = _cast_with_colsum(k, dy2)
         d_pw = _wgrad(g, o.view(Mq, d), d, d, Mq)
-        d_pb = k.colsum(g)
         do = _dgrad(g, proj_wh, Mq, d, d, epi='bf16')
         sq, sk, sv = _slots(qkv, B, N1, d)
         dqkv = torch.empty_like(qkv)                      # every element is written by the kernels below
@@ -201,12 +201,14 @@ class MlpFn(torch.autograd.Function):
         Dh, do = w1h.shape[0], w2h.shape[0]
         dy = dy.contiguous()
         dy2 = dy.view(M, do)
-        g = k.gather_cast(dy2)
+        g, d_b2 = _cast_with_colsum(k, dy2)
         d_w2 = _wgrad(g, h, do, Dh, M)
-        d_b2 = k.colsum(g)
-        dz = k.dgelu(_dgrad(g, w2h, M, Dh, do, epi='bf16'), z)
+        if _ops.FUSED_COLSUM:
+            dz, d_b1 = k.dgelu_colsum(_dgrad(g, w2h, M, Dh, do, epi='bf16'), z)
+        else:
+            dz = k.dgelu(_dgrad(g, w2h, M, Dh, do, epi='bf16'), z)
+            d_b1 = k.colsum(dz)
         d_w1 = _wgrad(dz, xn, Dh, d, M)
-        d_b1 = k.colsum(dz)
         dx = torch.empty_like(x)
         d_pjw = d_pjb = None
         if ctx.has_proj:
