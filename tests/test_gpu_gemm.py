@@ -206,7 +206,6 @@ def _ops():
     return ops
 
 
-@pytest.mark.experimental
 @pytest.mark.parametrize('cluster', [1, 3], ids=['single-cta', 'cta-pair'])
 @pytest.mark.parametrize('bn', [0, 128, 192, 256])
 @pytest.mark.parametrize('M,N,Kd', [(1000, 768, 256), (12552, 768, 768), (130, 96, 192), (4096, 256, 64)])
@@ -227,7 +226,6 @@ def test_residual_epilogue_tma_plain_rows(M, N, Kd, bn, cluster, monkeypatch):
     assert rel(out, old) < 1e-6
 
 
-@pytest.mark.experimental
 @pytest.mark.parametrize('cluster', [1, 3], ids=['single-cta', 'cta-pair'])
 @pytest.mark.parametrize('B,T,P,D', [(2, 8, 196, 768), (3, 4, 9, 128), (1, 2, 50, 256), (2, 8, 196, 96)])
 def test_residual_epilogue_tma_temporal_and_spatial_maps(B, T, P, D, cluster, monkeypatch):
@@ -331,7 +329,6 @@ def test_remainder_rows_split(M, N, Kd, form, monkeypatch):
     assert rel(got[m0:], one[m0:]) < (2e-5 if f32 else 8e-3)
 
 
-@pytest.mark.experimental
 @pytest.mark.parametrize('cluster', [1, 3], ids=['single-cta', 'cta-pair'])
 @pytest.mark.parametrize('M,N,Kd', [(12552, 3072, 768), (1000, 512, 128), (130, 96, 64)])
 def test_gelu_and_dgelu_epilogues_on_tma(M, N, Kd, cluster, monkeypatch):

@@ -746,8 +746,8 @@ class CudaKernels:
             raise RuntimeError('pool_bwd: problem too large')
         scratch = torch.empty(need, dtype=torch.float32, device=dev)
         dw = torch.empty((hd, 27), dtype=torch.float32, device=dev)
-        dgamma = torch.empty(hd, dtype=torch.float32, device=dev)
-        dbeta = torch.empty(hd, dtype=torch.float32, device=dev)
+        gb = torch.empty((2, hd), dtype=torch.float32, device=dev)      # adjacent: the library sums both with one launch
+        dgamma, dbeta = gb[0], gb[1]
         p = PoolBwdParams()
         p.dout, p.dout_fp32 = dout.data_ptr(), int(dout.dtype == torch.float32)
         p.pooled, p.mean, p.rstd, p.gamma = pooled.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr()

@@ -16,7 +16,7 @@ namespace vt {
 // instead of 4.1 KiB, paid for with one pipeline stage where shared memory is full.
 // compiled defaults of the round-2 paths (environment VT_TMA_RES / VT_TAIL_UNITS / VT_TMA_GELU / VT_TMA_DGELU = 0 | 1 override)
 constexpr bool VT_DEFAULT_TMA_RES = true;
-constexpr bool VT_DEFAULT_TMA_RES_SPATIAL = false;
+constexpr bool VT_DEFAULT_TMA_RES_SPATIAL = true;
 constexpr bool VT_DEFAULT_TAIL_UNITS = false;
 constexpr bool VT_DEFAULT_TMA_GELU = false;
 constexpr bool VT_DEFAULT_TMA_DGELU = false;

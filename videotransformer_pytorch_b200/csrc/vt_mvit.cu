@@ -396,8 +396,8 @@ pool_dw_kernel(const float* __restrict__ dpooled, const __nv_bfloat16* __restric
 // [4l, 4l+4) of a head, so one token row of a head is ONE 8-byte load per lane (bf16) or one 16-byte load (fp32) instead
 // of three 2-byte / 4-byte ones, filter taps sit in shared memory as float4 [tap][lane], and every tap of a window is
 // in flight before the first FMA.  Lanes 24..31 carry zeros through the warp reductions.
-//   d(input): CTA = one (b, t) plane of the input grid, warp = token, looping over the heads; the covering outputs come
-//             from the per-axis tables (uniform branches), tokens without any leave through a zero store
+//   d(input): CTA = one (b, t) plane of the input grid and one head, warp = token; the covering outputs come from the
+//             per-axis tables, the nine taps of a time plane are in flight together, tokens without any store zeros
 //   (the forward kernel keeps the first-generation mapping: a 27 x 8-byte-load version measured slower, 1.35 vs 1.08 ms)
 //   d(filter): warp = (pooled row, time tap): 9 taps x 4 channels of accumulators per lane, CTA = 4 row slots x 3 time
 //             taps; the four slots are summed in shared memory in a fixed order (deterministic), one partial row per CTA
@@ -454,10 +454,10 @@ pool_din_v2_kernel(const float* __restrict__ dpooled, const float* __restrict__ 
   const int cl = act ? lane : 0;
   const int Lo1 = 1 + d.To * d.Ho * d.Wo;
   const int planes = d.B * d.T;
+  const int h = blockIdx.z;                        // one head per CTA: 4 - 8x more warps in flight than looping over the heads
   if ((int)blockIdx.y == planes) {                 // cls tokens: straight copy of the pooled cls gradient
-    for (int it = blockIdx.x * ROW_WARPS + warp; it < d.B * d.H; it += gridDim.x * ROW_WARPS) {
-      const int b = it / d.H, h = it - b * d.H;
-      const float4 g = __ldg(reinterpret_cast<const float4*>(dpooled + (long long)it * Lo1 * PV_HD + 4 * cl));
+    for (int b = blockIdx.x * ROW_WARPS + warp; b < d.B; b += gridDim.x * ROW_WARPS) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(dpooled + ((long long)b * d.H + h) * Lo1 * PV_HD + 4 * cl));
       const float v[4] = {g.x, g.y, g.z, g.w};
       if (act) *reinterpret_cast<uint2*>(din + (long long)b * din_bs + h * PV_HD + 4 * lane) = f_to_bf16x4(v);
     }
@@ -469,48 +469,42 @@ pool_din_v2_kernel(const float* __restrict__ dpooled, const float* __restrict__ 
   for (int k = 0; k < 3; ++k) ot3[k] = tab[0][k][ti];
   const bool t_any = ot3[0] >= 0 || ot3[1] >= 0 || ot3[2] >= 0;
   const int HW = d.Hin * d.Win;
-  const float zero4[4] = {0.f, 0.f, 0.f, 0.f};
+  const float* dp = dpooled + (((long long)b * d.H + h) * Lo1 + 1) * PV_HD + 4 * cl;
   for (int idx = blockIdx.x * ROW_WARPS + warp; idx < HW; idx += gridDim.x * ROW_WARPS) {
     const int hi = idx / d.Win, wi = idx - hi * d.Win;
-    __nv_bfloat16* dst = din + (long long)b * din_bs + (1 + (long long)ti * HW + idx) * din_rs + 4 * lane;
-    int oh3[3], ow3[3];
+    __nv_bfloat16* dst = din + (long long)b * din_bs + (1 + (long long)ti * HW + idx) * din_rs + h * PV_HD + 4 * lane;
+    int rowoff[9];                                 // (oh * Wo + ow) of the output reached through (dh, dw), -1 = none
+    bool any = false;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      oh3[k] = tab[1][k][hi];
-      ow3[k] = tab[2][k][wi];
-    }
-    const bool any = t_any && (oh3[0] >= 0 || oh3[1] >= 0 || oh3[2] >= 0) && (ow3[0] >= 0 || ow3[1] >= 0 || ow3[2] >= 0);
-    if (!any) {                                    // warp-uniform
-      if (act)
-        for (int h = 0; h < d.H; ++h) *reinterpret_cast<uint2*>(dst + h * PV_HD) = f_to_bf16x4(zero4);
-      continue;
-    }
-    for (int h = 0; h < d.H; ++h) {
-      const float* dp = dpooled + (((long long)b * d.H + h) * Lo1 + 1) * PV_HD + 4 * cl;
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int dh = 0; dh < 3; ++dh)
+#pragma unroll
+      for (int dw = 0; dw < 3; ++dw) {
+        const int oh = tab[1][dh][hi], ow = tab[2][dw][wi];
+        rowoff[dh * 3 + dw] = oh >= 0 && ow >= 0 ? oh * d.Wo + ow : -1;
+        any = any || (oh >= 0 && ow >= 0);
+      }
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (any && t_any) {                            // warp-uniform
 #pragma unroll
       for (int dt = 0; dt < 3; ++dt) {
         if (ot3[dt] < 0) continue;                 // warp-uniform
+        const float* plane = dp + (long long)ot3[dt] * d.Ho * d.Wo * PV_HD;
+        float4 g[9];                               // the nine taps of the plane in flight together; absent ones predicated off
 #pragma unroll
-        for (int dh = 0; dh < 3; ++dh) {
-          if (oh3[dh] < 0) continue;               // warp-uniform
-          const float* rowp = dp + (long long)(ot3[dt] * d.Ho + oh3[dh]) * d.Wo * PV_HD;
-          float4 g[3];
+        for (int k = 0; k < 9; ++k)
+          g[k] = rowoff[k] >= 0 ? __ldg(reinterpret_cast<const float4*>(plane + (long long)rowoff[k] * PV_HD)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-          for (int dw = 0; dw < 3; ++dw)
-            g[dw] = ow3[dw] >= 0 ? __ldg(reinterpret_cast<const float4*>(rowp + (long long)ow3[dw] * PV_HD)) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-          for (int dw = 0; dw < 3; ++dw) {
-            const float4 f = sw4[((dt * 3 + dh) * 3 + dw) * PV_LANES + cl];
-            acc[0] = fmaf(g[dw].x, f.x, acc[0]);
-            acc[1] = fmaf(g[dw].y, f.y, acc[1]);
-            acc[2] = fmaf(g[dw].z, f.z, acc[2]);
-            acc[3] = fmaf(g[dw].w, f.w, acc[3]);
-          }
+        for (int k = 0; k < 9; ++k) {
+          if (rowoff[k] < 0) continue;             // warp-uniform
+          const float4 f = sw4[(dt * 9 + k) * PV_LANES + cl];
+          acc[0] = fmaf(g[k].x, f.x, acc[0]);
+          acc[1] = fmaf(g[k].y, f.y, acc[1]);
+          acc[2] = fmaf(g[k].z, f.z, acc[2]);
+          acc[3] = fmaf(g[k].w, f.w, acc[3]);
         }
       }
-      if (act) *reinterpret_cast<uint2*>(dst + h * PV_HD) = f_to_bf16x4(acc);
     }
+    if (act) *reinterpret_cast<uint2*>(dst) = f_to_bf16x4(acc);        // zeros when no output window covers the token
   }
 }
 
@@ -1277,13 +1271,18 @@ extern "C" int vt_pool_bwd(const vt_pool_bwd_params* p, void* stream) {
   int rc = check_launch("ln_small_bwd_kernel(pool)");
   if (rc) return rc;
   {
-    // dgamma and dbeta live in two separate buffers: reduce each half of the [blocks, 2, hd] partials
-    vt_reduce_params r{ln_part, p->dgamma, 2ll * hd, ln_blocks_n, hd, 0, 1.0f};
-    rc = vt_reduce_rows(&r, stream);
-    if (rc) return rc;
-    vt_reduce_params r2{ln_part + hd, p->dbeta, 2ll * hd, ln_blocks_n, hd, 0, 1.0f};
-    rc = vt_reduce_rows(&r2, stream);
-    if (rc) return rc;
+    if (p->dbeta == p->dgamma + hd) {        // adjacent outputs ([2, hd], what the Python wrapper allocates): one launch
+      vt_reduce_params r{ln_part, p->dgamma, 2ll * hd, ln_blocks_n, 2ll * hd, 0, 1.0f};
+      rc = vt_reduce_rows(&r, stream);
+      if (rc) return rc;
+    } else {                                 // separate buffers: reduce each half of the [blocks, 2, hd] partials
+      vt_reduce_params r{ln_part, p->dgamma, 2ll * hd, ln_blocks_n, hd, 0, 1.0f};
+      rc = vt_reduce_rows(&r, stream);
+      if (rc) return rc;
+      vt_reduce_params r2{ln_part + hd, p->dbeta, 2ll * hd, ln_blocks_n, hd, 0, 1.0f};
+      rc = vt_reduce_rows(&r2, stream);
+      if (rc) return rc;
+    }
   }
   // 2. gradient w.r.t. the input tokens
   VT_REQUIRE(p->T <= POOL_MAX_DIM && p->Hin <= POOL_MAX_DIM && p->Win <= POOL_MAX_DIM, "vt_pool_bwd: token grid %dx%dx%d exceeds %d per axis",
@@ -1293,7 +1292,7 @@ extern "C" int vt_pool_bwd(const vt_pool_bwd_params* p, void* stream) {
   const bool v2 = pool_v2(p->in, p->in_bs, p->in_rs) && pool_v2(p->din, p->din_bs, p->din_rs);
   if (v2) {
     const int hw = p->Hin * p->Win;
-    const dim3 dgrid((hw + ROW_WARPS * 4 - 1) / (ROW_WARPS * 4), p->B * p->T + 1);      // ~4 tokens per warp; + 1: the cls tokens
+    const dim3 dgrid((hw + ROW_WARPS * 4 - 1) / (ROW_WARPS * 4), p->B * p->T + 1, p->H);   // ~4 tokens per warp; y + 1: the cls tokens
     pool_din_v2_kernel<<<dgrid, ROW_WARPS * 32, 0, st>>>(dpooled, p->w, static_cast<__nv_bfloat16*>(p->din), p->din_bs, p->din_rs, d);
     rc = check_launch("pool_din_v2_kernel");
   } else {

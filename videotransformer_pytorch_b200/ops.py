@@ -43,7 +43,7 @@ FUSED_DGELU_BWD = _os.environ.get('VT_TMA_DGELU', '0') == '1'      # dGELU epilo
 FUSED_GELU_EPILOGUE = False
 # bias gradients from the kernels that produce dY (gather_cast / dgelu with column sums) instead of a separate pass;
 # VT_FUSED_COLSUM=0/1 overrides
-FUSED_COLSUM = _os.environ.get('VT_FUSED_COLSUM', '0') == '1'
+FUSED_COLSUM = _os.environ.get('VT_FUSED_COLSUM', '1') == '1'
 
 
 def set_mask_arena(arena):
