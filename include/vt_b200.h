@@ -100,6 +100,8 @@ typedef struct {
   int32_t force_tail;      /* 0 = heuristic, 1 = never cut the partial last row of tiles into narrow units, 2 = prefer to */
   int64_t map_stride_t, map_stride_p, map_stride_b, map_base;
   int64_t map_special_base, map_special_stride;
+  const float* bias2;      /* VT_EPI_F32 with aux only: out = s(m) * (acc + bias[n]) + bias2[n] + aux — the bias of a second
+                              linear layer folded into this GEMM (temporal_fc after proj, transformer.py:264-267) */
 } vt_gemm_params;
 
 int vt_gemm(const vt_gemm_params* p, void* stream);
@@ -176,7 +178,9 @@ int vt_gelu_bwd_bf16(const vt_gelu_params* p, void* stream);
  * vt_colsum_bf16, in one pass each.  colsum fp32 [D] / [N]; workspace fp32 [workspace_rows, D] with workspace_rows >=
  * vt_*_blocks(rows).  Sums are over the bf16-rounded outputs, in a fixed order. */
 typedef struct { const float* src; int64_t lds; const int32_t* in_row; const float* row_scale; void* dst; int32_t rows, D;
-                 float* colsum; float* workspace; int32_t workspace_rows; } vt_gather_cast_colsum_params;
+                 float* colsum; float* workspace; int32_t workspace_rows;
+                 int32_t unscaled_sums;   /* 1: colsum is [2, D] — row 1 = sums of the rows before row_scale; workspace [rows, 2 D] */
+               } vt_gather_cast_colsum_params;
 int vt_gather_cast_colsum_blocks(int32_t rows);
 int vt_gather_cast_colsum_bf16(const vt_gather_cast_colsum_params* p, void* stream);
 typedef struct { const void* z; const void* dh; void* out; int32_t M, N; float* colsum; float* workspace;

@@ -35,7 +35,7 @@ class EmuKernels:
     def _idx(self, t):
         return t.to(torch.int64)
 
-    def gemm(self, a, b, M, N, Kdim, *, a_mn=False, b_mn=False, epi='bf16', bias=None, out=None, out2=None,
+    def gemm(self, a, b, M, N, Kdim, *, a_mn=False, b_mn=False, epi='bf16', bias=None, bias2=None, out=None, out2=None,
              aux=None, out_row=None, aux_row=None, row_scale=None, out_rows=None, split_ok=False,
              force_splits=0, force_bn=0, force_cluster=0, debug=None, row_map=None, force_tail=0, tag=None):
         self.calls.append(('gemm', M, N, Kdim, a_mn, b_mn, epi))
@@ -72,6 +72,9 @@ class EmuKernels:
             return self._h(acc * (cdf + z * pdf))
         if row_scale is not None:
             acc = acc * self._up(row_scale)[:, None]
+        if bias2 is not None:
+            assert epi == 'f32' and aux is not None
+            acc = acc + self._up(bias2)
         if epi == 'f32' and aux is not None:
             if aux_row is not None:
                 ar = self._idx(aux_row)
@@ -157,8 +160,10 @@ class EmuKernels:
         zz = self._up(z)
         return self._h(0.5 * zz * (1 + torch.erf(zz / math.sqrt(2.0))))
 
-    def gather_cast_colsum(self, src2d, in_row=None, row_scale=None, rows=None):
+    def gather_cast_colsum(self, src2d, in_row=None, row_scale=None, rows=None, unscaled_sums=False):
         out = self.gather_cast(src2d, in_row=in_row, row_scale=row_scale, rows=rows)
+        if unscaled_sums:
+            return out, self.colsum(out), self.colsum(self.gather_cast(src2d, in_row=in_row, rows=rows))
         return out, self.colsum(out)
 
     def dgelu_colsum(self, dh, z):

@@ -354,3 +354,16 @@ def test_gelu_and_dgelu_epilogues_on_tma(M, N, Kd, cluster, monkeypatch):
     torch.nn.functional.gelu(zz).sum().backward()
     assert rel(d1, (g.float() @ w.float()) * zz.grad) < 4e-3
     assert torch.equal(d0, d1)
+
+
+@pytest.mark.parametrize('res', ['0', '1'], ids=['generic-epilogue', 'tma-residual'])
+@pytest.mark.parametrize('M,N,Kd', [(12544, 768, 768), (1000, 256, 64), (12552, 768, 3072)])
+def test_second_bias_after_row_scale(M, N, Kd, res, monkeypatch):
+    """out = s(m) (A B^T + bias) + bias2 + aux: the bias of a second linear layer folded into the GEMM (merged proj +
+    temporal_fc), through the generic, the TMA-residual and the remainder-row paths."""
+    monkeypatch.setenv('VT_TMA_RES', res)
+    a, b = mk((M, Kd), 70).bfloat16(), mk((N, Kd), 71).bfloat16()
+    bias, bias2, rs, aux = mk((N,), 72), mk((N,), 73), mk((M,), 74), mk((M, N), 75)
+    out = K().gemm(a, b, M, N, Kd, epi='f32', bias=bias, bias2=bias2, row_scale=rs, aux=aux)
+    r = (ref_mm(a, b, False, False) + bias) * rs[:, None] + bias2 + aux
+    assert rel(out, r) < 1e-5

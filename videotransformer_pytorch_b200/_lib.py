@@ -31,7 +31,7 @@ class GemmParams(C.Structure):
                 ('force_splits', c_i32), ('force_bn', c_i32), ('force_cluster', c_i32), ('debug', c_vp),
                 ('map_period', c_i32), ('map_skip', c_i32), ('map_tcount', c_i32), ('force_tail', c_i32),
                 ('map_stride_t', c_i64), ('map_stride_p', c_i64), ('map_stride_b', c_i64), ('map_base', c_i64),
-                ('map_special_base', c_i64), ('map_special_stride', c_i64)]
+                ('map_special_base', c_i64), ('map_special_stride', c_i64), ('bias2', c_vp)]
 
 
 class LnFwdParams(C.Structure):
@@ -71,7 +71,8 @@ class GeluParams(C.Structure):
 
 class GatherCastColsumParams(C.Structure):
     _fields_ = [('src', c_vp), ('lds', c_i64), ('in_row', c_vp), ('row_scale', c_vp), ('dst', c_vp),
-                ('rows', c_i32), ('D', c_i32), ('colsum', c_vp), ('workspace', c_vp), ('workspace_rows', c_i32)]
+                ('rows', c_i32), ('D', c_i32), ('colsum', c_vp), ('workspace', c_vp), ('workspace_rows', c_i32),
+                ('unscaled_sums', c_i32)]
 
 
 class GeluBwdColsumParams(C.Structure):
@@ -286,7 +287,7 @@ class CudaKernels:
         return ws
 
     # -- GEMM ---------------------------------------------------------------------------------
-    def gemm(self, a, b, M, N, Kdim, *, a_mn=False, b_mn=False, epi='bf16', bias=None, out=None, out2=None,
+    def gemm(self, a, b, M, N, Kdim, *, a_mn=False, b_mn=False, epi='bf16', bias=None, bias2=None, out=None, out2=None,
              aux=None, out_row=None, aux_row=None, row_scale=None, out_rows=None, split_ok=False,
              force_splits=0, force_bn=0, force_cluster=0, debug=None, row_map=None, force_tail=0, tag=None):
         """row_map: affine description of out_row / aux_row (ops.affine_row_maps) for the fp32 residual epilogue — lets the
@@ -312,6 +313,8 @@ class CudaKernels:
         p.a_mn_major, p.b_mn_major = int(a_mn), int(b_mn)
         p.epilogue = EPI[epi]
         p.bias = _ptr(None if bias is None else _req(bias, torch.float32, 'gemm.bias'))
+        if bias2 is not None:                  # fp32 epilogue with aux only: added after the row scale
+            p.bias2 = _req(bias2, torch.float32, 'gemm.bias2').data_ptr()
         p.out, p.ldo = out.data_ptr(), out.stride(0)
         if out2 is not None:
             p.out2, p.ldo2 = out2.data_ptr(), out2.stride(0)
@@ -432,27 +435,31 @@ class CudaKernels:
         _check(lib.vt_gather_cast_bf16(C.byref(p), _stream()), 'vt_gather_cast_bf16')
         return out
 
-    def gather_cast_colsum(self, src2d, in_row=None, row_scale=None, rows=None):
-        """gather_cast + colsum of its output in one pass -> (bf16 [rows, D], fp32 [D]); D <= 1024, else two kernels."""
+    def gather_cast_colsum(self, src2d, in_row=None, row_scale=None, rows=None, unscaled_sums=False):
+        """gather_cast + colsum of its output in one pass -> (bf16 [rows, D], fp32 [D]); with unscaled_sums a third result:
+        the column sums of the same rows before row_scale.  D <= 1024, else separate kernels."""
         lib = load_library()
         _rows2d(_req(src2d, torch.float32, 'gather_cast.src'), 'gather_cast.src')
         rows = src2d.shape[0] if rows is None else rows
         D = src2d.shape[1]
         if D > 1024 or D % 8:
             out = self.gather_cast(src2d, in_row=in_row, row_scale=row_scale, rows=rows)
+            if unscaled_sums:
+                return out, self.colsum(out), self.colsum(self.gather_cast(src2d, in_row=in_row, rows=rows))
             return out, self.colsum(out)
         dev = src2d.device
         out = torch.empty((rows, D), dtype=torch.bfloat16, device=dev)
-        cs = torch.empty(D, dtype=torch.float32, device=dev)
+        nsum = 2 if unscaled_sums else 1
+        cs = torch.empty((nsum, D), dtype=torch.float32, device=dev)
         nb = lib.vt_gather_cast_colsum_blocks(rows)
-        ws = torch.empty((nb, D), dtype=torch.float32, device=dev)
+        ws = torch.empty((nb, nsum * D), dtype=torch.float32, device=dev)
         p = GatherCastColsumParams()
         p.src, p.lds = src2d.data_ptr(), src2d.stride(0)
         p.in_row, p.row_scale = _ptr(in_row), _ptr(row_scale)
         p.dst, p.rows, p.D = out.data_ptr(), rows, D
-        p.colsum, p.workspace, p.workspace_rows = cs.data_ptr(), ws.data_ptr(), nb
+        p.colsum, p.workspace, p.workspace_rows, p.unscaled_sums = cs.data_ptr(), ws.data_ptr(), nb, int(unscaled_sums)
         _check(lib.vt_gather_cast_colsum_bf16(C.byref(p), _stream()), 'vt_gather_cast_colsum_bf16')
-        return out, cs
+        return (out, cs[0], cs[1]) if unscaled_sums else (out, cs[0])
 
     def dgelu_colsum(self, dh, z):
         """dz = dh * gelu'(z) and the column sums of dz in one pass -> (bf16 [M, N], fp32 [N])."""

@@ -358,6 +358,9 @@ __global__ void gather_cast_kernel(const float* __restrict__ src, long long lds,
 // ------------------------------------------------------------------------------------------------
 constexpr int GCC_CH = 4;         // 8-column pieces per lane: D <= 1024
 
+// DUAL: a second set of sums over the rows *before* the row scale (bf16-rounded as well) — the bias gradient of a layer
+// that sits behind DropPath when the scaled rows feed the layer in front of it (merged proj + temporal_fc)
+template <bool DUAL>
 __global__ void __launch_bounds__(256)
 gather_cast_colsum_kernel(const float* __restrict__ src, long long lds, const int* __restrict__ in_row,
                           const float* __restrict__ row_scale, __nv_bfloat16* __restrict__ dst, int rows, int D8,
@@ -365,11 +368,14 @@ gather_cast_colsum_kernel(const float* __restrict__ src, long long lds, const in
   extern __shared__ float sh_gcc[];            // [8 warps][D]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int D = D8 * 8;
-  float acc[GCC_CH][8];
+  float acc[GCC_CH][8], acc2[DUAL ? GCC_CH : 1][8];
 #pragma unroll
   for (int c = 0; c < GCC_CH; ++c)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[c][j] = 0.f;
+    for (int j = 0; j < 8; ++j) {
+      acc[c][j] = 0.f;
+      if (DUAL) acc2[c][j] = 0.f;
+    }
   for (int m = blockIdx.x * 8 + warp; m < rows; m += gridDim.x * 8) {
     const int s = in_row ? in_row[m] : m;
     const float sc = row_scale ? row_scale[m] : 1.0f;
@@ -396,23 +402,34 @@ gather_cast_colsum_kernel(const float* __restrict__ src, long long lds, const in
         const float2 p0 = unpack_bf16x2(v.x), p1 = unpack_bf16x2(v.y), p2 = unpack_bf16x2(v.z), p3 = unpack_bf16x2(v.w);
         acc[c][0] += p0.x; acc[c][1] += p0.y; acc[c][2] += p1.x; acc[c][3] += p1.y;
         acc[c][4] += p2.x; acc[c][5] += p2.y; acc[c][6] += p3.x; acc[c][7] += p3.y;
+        if (DUAL) {
+          const float2 q0 = unpack_bf16x2(pack_bf16x2(a[c].x, a[c].y)), q1 = unpack_bf16x2(pack_bf16x2(a[c].z, a[c].w));
+          const float2 q2 = unpack_bf16x2(pack_bf16x2(b[c].x, b[c].y)), q3 = unpack_bf16x2(pack_bf16x2(b[c].z, b[c].w));
+          acc2[c][0] += q0.x; acc2[c][1] += q0.y; acc2[c][2] += q1.x; acc2[c][3] += q1.y;
+          acc2[c][4] += q2.x; acc2[c][5] += q2.y; acc2[c][6] += q3.x; acc2[c][7] += q3.y;
+        }
       }
     }
   }
+  const int W = DUAL ? 2 * D : D;              // columns of a partial row
+#pragma unroll 1
+  for (int pass = 0; pass < (DUAL ? 2 : 1); ++pass) {
+    __syncthreads();
 #pragma unroll
-  for (int c = 0; c < GCC_CH; ++c) {
-    const int i = lane + 32 * c;
-    if (i < D8) {
+    for (int c = 0; c < GCC_CH; ++c) {
+      const int i = lane + 32 * c;
+      if (i < D8) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) sh_gcc[warp * D + i * 8 + j] = acc[c][j];
+        for (int j = 0; j < 8; ++j) sh_gcc[warp * D + i * 8 + j] = pass == 0 ? acc[c][j] : acc2[c][j];
+      }
     }
-  }
-  __syncthreads();
-  for (int col = threadIdx.x; col < D; col += 256) {
-    float t = 0.f;
+    __syncthreads();
+    for (int col = threadIdx.x; col < D; col += 256) {
+      float t = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) t += sh_gcc[w * D + col];
-    ws[(long long)blockIdx.x * D + col] = t;
+      for (int w = 0; w < 8; ++w) t += sh_gcc[w * D + col];
+      ws[(long long)blockIdx.x * W + pass * D + col] = t;
+    }
   }
 }
 
@@ -886,11 +903,16 @@ extern "C" int vt_gather_cast_colsum_bf16(const vt_gather_cast_colsum_params* p,
   VT_REQUIRE(p->D % 8 == 0 && p->lds % 4 == 0 && p->D <= GCC_CH * 256, "vt_gather_cast_colsum_bf16: D %% 8, lds %% 4 and D <= %d required", GCC_CH * 256);
   const int blocks = vt_gather_cast_colsum_blocks(p->rows);
   VT_REQUIRE(p->workspace_rows >= blocks, "vt_gather_cast_colsum_bf16: workspace holds %d partial rows, %d needed", p->workspace_rows, blocks);
-  gather_cast_colsum_kernel<<<blocks, 256, 8 * p->D * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
-      p->src, p->lds, p->in_row, p->row_scale, static_cast<__nv_bfloat16*>(p->dst), p->rows, p->D / 8, p->workspace);
+  const int W = p->unscaled_sums ? 2 * p->D : p->D;     // colsum then holds [scaled sums | sums before the row scale]
+  if (p->unscaled_sums)
+    gather_cast_colsum_kernel<true><<<blocks, 256, 8 * p->D * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+        p->src, p->lds, p->in_row, p->row_scale, static_cast<__nv_bfloat16*>(p->dst), p->rows, p->D / 8, p->workspace);
+  else
+    gather_cast_colsum_kernel<false><<<blocks, 256, 8 * p->D * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+        p->src, p->lds, p->in_row, p->row_scale, static_cast<__nv_bfloat16*>(p->dst), p->rows, p->D / 8, p->workspace);
   const int rc = check_launch("gather_cast_colsum_kernel");
   if (rc) return rc;
-  return launch_reduce_rows(p->workspace, p->colsum, p->D, blocks, p->D, 0, 1.0f, static_cast<cudaStream_t>(stream));
+  return launch_reduce_rows(p->workspace, p->colsum, W, blocks, W, 0, 1.0f, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int vt_gelu_bwd_colsum_bf16(const vt_gelu_bwd_colsum_params* p, void* stream) {

@@ -640,6 +640,8 @@ static int gemm_dispatch(const vt_gemm_params* q, void* stream) {
              "vt_gemm: out must be 16B aligned with 16B-multiple row pitch");
   if (q->aux) VT_REQUIRE((reinterpret_cast<uintptr_t>(q->aux) & 15) == 0 && (q->ldaux * esz) % 16 == 0, "vt_gemm: aux misaligned");
   if (q->bias) VT_REQUIRE((reinterpret_cast<uintptr_t>(q->bias) & 15) == 0, "vt_gemm: bias misaligned");
+  if (q->bias2) VT_REQUIRE(q->epilogue == VT_EPI_F32 && q->aux && (reinterpret_cast<uintptr_t>(q->bias2) & 15) == 0,
+                           "vt_gemm: bias2 needs the fp32 epilogue with an addend, 16-byte aligned");
 
   GemmDev d;
   d.M = q->M; d.N = q->N; d.K = q->K;
@@ -647,6 +649,7 @@ static int gemm_dispatch(const vt_gemm_params* q, void* stream) {
   d.b_mn = q->b_mn_major ? 1 : 0;
   d.epi = q->epilogue;
   d.bias = q->bias;
+  d.bias2 = q->bias2;
   d.out = q->out; d.out2 = q->out2; d.aux = q->aux;
   d.ldo = q->ldo; d.ldo2 = q->ldo2; d.ldaux = q->ldaux;
   d.out_row = q->out_row; d.aux_row = q->aux_row; d.row_scale = q->row_scale;

@@ -19,6 +19,7 @@ struct GemmDev {
   int num_mp;   // macro row-tiles: ceil(num_m / cluster size)
   int a_mn, b_mn, epi;
   const float* bias;
+  const float* bias2;      // VT_EPI_F32 with aux only: second bias, added after the row scale (unscaled)
   void* out;
   void* out2;
   const void* aux;
@@ -148,6 +149,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, float* stg, uint
         const float s = rs[it];
         v.x = fmaf(s, v.x, __uint_as_float(cur[it].x)); v.y = fmaf(s, v.y, __uint_as_float(cur[it].y));
         v.z = fmaf(s, v.z, __uint_as_float(cur[it].z)); v.w = fmaf(s, v.w, __uint_as_float(cur[it].w));
+        if (p.bias2) {
+          const float4 b2 = __ldg(reinterpret_cast<const float4*>(p.bias2 + n));
+          v.x += b2.x; v.y += b2.y; v.z += b2.z; v.w += b2.w;
+        }
         *reinterpret_cast<float4*>(static_cast<float*>(p.out) + (long long)split * p.split_stride + o * p.ldo + n) = v;
       } else if (p.epi == VT_EPI_GELU) {
         uint2 z, h;
@@ -439,6 +444,10 @@ __device__ __forceinline__ void epilogue_tile_tma_res(const GemmDev& p, const CU
       for (int g = 0; g < 8; ++g) {
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
         if (a_off >= 0) a = *reinterpret_cast<const float4*>(static_cast<const float*>(p.aux) + a_off + n0 + 4 * g);
+        if (p.bias2) {
+          const float4 b2 = __ldg(reinterpret_cast<const float4*>(p.bias2 + n0) + g);
+          a.x += b2.x; a.y += b2.y; a.z += b2.z; a.w += b2.w;
+        }
         v[g].x = fmaf(s, __uint_as_float(r[4 * g + 0]) + b[g].x, a.x);
         v[g].y = fmaf(s, __uint_as_float(r[4 * g + 1]) + b[g].y, a.y);
         v[g].z = fmaf(s, __uint_as_float(r[4 * g + 2]) + b[g].z, a.z);
@@ -464,7 +473,11 @@ __device__ __forceinline__ void epilogue_tile_tma_res(const GemmDev& p, const CU
     float4 v[8];
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
-      const float4 a = *reinterpret_cast<const float4*>(buf + lane * 128 + ((g ^ (lane & 7)) << 4));    // SWIZZLE_128B
+      float4 a = *reinterpret_cast<const float4*>(buf + lane * 128 + ((g ^ (lane & 7)) << 4));    // SWIZZLE_128B
+      if (p.bias2) {
+        const float4 b2 = __ldg(reinterpret_cast<const float4*>(p.bias2 + n0) + g);
+        a.x += b2.x; a.y += b2.y; a.z += b2.z; a.w += b2.w;
+      }
       v[g].x = fmaf(s, __uint_as_float(r[4 * g + 0]) + b[g].x, a.x);
       v[g].y = fmaf(s, __uint_as_float(r[4 * g + 1]) + b[g].y, a.y);
       v[g].z = fmaf(s, __uint_as_float(r[4 * g + 2]) + b[g].z, a.z);

@@ -15,6 +15,7 @@ struct RowsArgs {
   long long lda, ldb;
   int R, N, K;
   const float* bias;        // [N] or null
+  const float* bias2;       // [N] or null: added unscaled (fp32 out with aux)
   const float* row_scale;   // [R] or null
   const float* aux;         // [R, N] fp32 (ldaux) or null
   long long ldaux;
@@ -37,6 +38,7 @@ __device__ __forceinline__ void rows_store(const RowsArgs& g, int r, int n, floa
   float v = s * (acc + (g.bias ? g.bias[n] : 0.f));
   if (g.f32_out) {
     if (g.aux) v += g.aux[(long long)r * g.ldaux + n];
+    if (g.bias2) v += g.bias2[n];
     static_cast<float*>(g.out)[(long long)r * g.ldo + n] = v;
   } else {
     static_cast<__nv_bfloat16*>(g.out)[(long long)r * g.ldo + n] = __float2bfloat16_rn(v);
@@ -172,6 +174,7 @@ int launch_gemm_rows(const vt_gemm_params* q, int m0, void* stream) {
   g.lda = q->lda; g.ldb = q->ldb;
   g.R = R; g.N = q->N; g.K = q->K;
   g.bias = q->bias;
+  g.bias2 = q->bias2;
   g.row_scale = q->row_scale ? q->row_scale + m0 : nullptr;
   g.aux = (f32 && q->aux) ? static_cast<const float*>(q->aux) + (long long)m0 * q->ldaux : nullptr;
   g.ldaux = q->ldaux;

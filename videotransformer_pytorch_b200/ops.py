@@ -44,6 +44,9 @@ FUSED_GELU_EPILOGUE = False
 # bias gradients from the kernels that produce dY (gather_cast / dgelu with column sums) instead of a separate pass;
 # VT_FUSED_COLSUM=0/1 overrides
 FUSED_COLSUM = _os.environ.get('VT_FUSED_COLSUM', '1') == '1'
+# temporal_fc(DropPath(proj(.))) as ONE token GEMM with the product weight W_fc W_proj (two 768^3 GEMMs per step instead of
+# two 12544 x 768 x 768 ones forward, and the same saving twice in backward); VT_MERGE_TEMPORAL_FC=0/1 overrides
+MERGE_TEMPORAL_FC = _os.environ.get('VT_MERGE_TEMPORAL_FC', '0') == '1'
 
 
 def set_mask_arena(arena):
@@ -150,6 +153,16 @@ def _wgrad(dout, act, n_out, k_in, m_tok, tag=None, wptr=None):
     return K().gemm(dout, act, n_out, k_in, m_tok, a_mn=True, b_mn=True, epi='f32', split_ok=True, tag=tag, out=out)
 
 
+def _grad_dest(wptr, n_out, k_in):
+    """The DDP bucket slice registered for the parameter at wptr (GRAD_DEST), as an [n_out, k_in] view, or None."""
+    if GRAD_DEST is None or wptr is None:
+        return None
+    dest = GRAD_DEST.get(wptr)
+    if dest is not None and dest.numel() == n_out * k_in and dest.is_contiguous():
+        return dest.view(n_out, k_in)
+    return None
+
+
 def _dgrad(dout, w, m_tok, k_in, n_out, **kw):
     """dX[m_tok, k_in] = dout[m_tok, n_out] @ W[n_out, k_in]  (W read MN-major)."""
     return K().gemm(dout, w, m_tok, k_in, n_out, b_mn=True, **kw)
@@ -208,13 +221,24 @@ class TemporalAttnFn(torch.autograd.Function):
         qkv = k.gemm(xn, qkv_wh, Mt, 3 * D, D, bias=qkv_b, epi='bf16', tag='qkv')
         hd = D // H
         cx, lse, _ = k.attn_fwd(qkv, B * P, T, H, hd, hd ** -0.5)
-        a = k.gemm(cx, proj_wh, Mt, D, D, bias=proj_b, epi='bf16', row_scale=dp, tag='proj')
         y = torch.empty_like(x)
         y2 = y.view(B * S, D)
-        k.gemm(a, fc_wh, Mt, D, D, bias=fc_b, epi='f32', aux=x2, aux_row=maps['temporal'], out=y2,
-               out_row=maps['temporal'], row_map=affine_row_maps(B, T, P, D)['temporal'])
+        ctx.merged = MERGE_TEMPORAL_FC
+        if ctx.merged:
+            # y = s (W_f (W_p c + b_p)) + b_f + x = s (W_c c + b_c) + b_f + x,  W_c = W_f W_p,  b_c = W_f b_p
+            # (transformer.py:261-267: two nn.Linear with only DropPath's per-sample scale between them)
+            wc = k.gemm(fc_wh, proj_wh, D, D, D, b_mn=True, epi='bf16')
+            bc = torch.mv(fc_w.detach().float(), proj_b.detach().float())
+            k.gemm(cx, wc, Mt, D, D, bias=bc, bias2=fc_b, epi='f32', aux=x2, aux_row=maps['temporal'], out=y2,
+                   out_row=maps['temporal'], row_scale=dp, row_map=affine_row_maps(B, T, P, D)['temporal'], tag='proj')
+            a = wc
+        else:
+            a = k.gemm(cx, proj_wh, Mt, D, D, bias=proj_b, epi='bf16', row_scale=dp, tag='proj')
+            k.gemm(a, fc_wh, Mt, D, D, bias=fc_b, epi='f32', aux=x2, aux_row=maps['temporal'], out=y2,
+                   out_row=maps['temporal'], row_map=affine_row_maps(B, T, P, D)['temporal'])
         y[:, 0] = x[:, 0]
-        ctx.save_for_backward(x, ln_w, mean, rstd, xn, qkv, cx, lse, a, qkv_wh, proj_wh, fc_wh, dp)
+        ctx.save_for_backward(x, ln_w, mean, rstd, xn, qkv, cx, lse, a, qkv_wh, proj_wh, fc_wh, dp,
+                              fc_w if ctx.merged else None, proj_b if ctx.merged else None)
         ctx.geom = (B, S, D, T, H, P)
         ctx.wptrs = (qkv_w.data_ptr(), proj_w.data_ptr(), fc_w.data_ptr())
         return y
@@ -222,7 +246,7 @@ class TemporalAttnFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         k = K()
-        x, ln_w, mean, rstd, xn, qkv, cx, lse, a, qkv_wh, proj_wh, fc_wh, dp = ctx.saved_tensors
+        x, ln_w, mean, rstd, xn, qkv, cx, lse, a, qkv_wh, proj_wh, fc_wh, dp, fc_w, proj_b = ctx.saved_tensors
         B, S, D, T, H, P = ctx.geom
         maps = token_maps(B, T, P, str(x.device))
         hd = D // H
@@ -230,12 +254,33 @@ class TemporalAttnFn(torch.autograd.Function):
         dy = dy.contiguous()
         dy2 = dy.view(B * S, D)
         x2 = x.reshape(B * S, D)
-        g, d_fc_b = _cast_with_colsum(k, dy2, in_row=maps['temporal'], rows=Mt)
-        d_fc_w = _wgrad(g, a, D, D, Mt, wptr=ctx.wptrs[2])
-        da = _dgrad(g, fc_wh, Mt, D, D, epi='bf16', row_scale=dp)
-        d_proj_w = _wgrad(da, cx, D, D, Mt, tag='proj', wptr=ctx.wptrs[1])
-        d_proj_b = k.colsum(da)
-        dcx = _dgrad(da, proj_wh, Mt, D, D, epi='bf16', tag='proj')
+        if ctx.merged:
+            # gs = s * dY rows;  v = colsum(gs);  G = gs^T c
+            # dc = gs W_c;  dW_f = G W_p^T + v b_p^T;  db_f = colsum(dY);  dW_p = W_f^T G;  db_p = W_f^T v
+            wc = a
+            if dp is None:
+                gs, v = _cast_with_colsum(k, dy2, in_row=maps['temporal'], rows=Mt)
+                d_fc_b = v
+            elif FUSED_COLSUM:
+                gs, v, d_fc_b = k.gather_cast_colsum(dy2, in_row=maps['temporal'], row_scale=dp, rows=Mt, unscaled_sums=True)
+            else:
+                gs = k.gather_cast(dy2, in_row=maps['temporal'], row_scale=dp, rows=Mt)
+                v = k.colsum(gs)
+                d_fc_b = k.colsum(k.gather_cast(dy2, in_row=maps['temporal'], rows=Mt))
+            dcx = _dgrad(gs, wc, Mt, D, D, epi='bf16', tag='proj')
+            G = k.gemm(gs, cx, D, D, Mt, a_mn=True, b_mn=True, epi='f32', split_ok=True, tag='proj')
+            Gh = k.cast_bf16(G)
+            d_fc_w = k.gemm(Gh, proj_wh, D, D, D, epi='f32', out=_grad_dest(ctx.wptrs[2], D, D))
+            d_fc_w.addr_(v, proj_b.detach().float())
+            d_proj_w = k.gemm(fc_wh, Gh, D, D, D, a_mn=True, b_mn=True, epi='f32', out=_grad_dest(ctx.wptrs[1], D, D))
+            d_proj_b = torch.mv(fc_w.detach().float().t(), v)
+        else:
+            g, d_fc_b = _cast_with_colsum(k, dy2, in_row=maps['temporal'], rows=Mt)
+            d_fc_w = _wgrad(g, a, D, D, Mt, wptr=ctx.wptrs[2])
+            da = _dgrad(g, fc_wh, Mt, D, D, epi='bf16', row_scale=dp)
+            d_proj_w = _wgrad(da, cx, D, D, Mt, tag='proj', wptr=ctx.wptrs[1])
+            d_proj_b = k.colsum(da)
+            dcx = _dgrad(da, proj_wh, Mt, D, D, epi='bf16', tag='proj')
         dqkv = k.attn_bwd(qkv, cx, dcx, lse, B * P, T, H, hd, hd ** -0.5)
         d_qkv_w = _wgrad(dqkv, xn, 3 * D, D, Mt, tag='qkv', wptr=ctx.wptrs[0])
         d_qkv_b = k.colsum(dqkv)
