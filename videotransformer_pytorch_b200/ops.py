@@ -46,7 +46,7 @@ FUSED_GELU_EPILOGUE = False
 FUSED_COLSUM = _os.environ.get('VT_FUSED_COLSUM', '1') == '1'
 # temporal_fc(DropPath(proj(.))) as ONE token GEMM with the product weight W_fc W_proj (two 768^3 GEMMs per step instead of
 # two 12544 x 768 x 768 ones forward, and the same saving twice in backward); VT_MERGE_TEMPORAL_FC=0/1 overrides
-MERGE_TEMPORAL_FC = _os.environ.get('VT_MERGE_TEMPORAL_FC', '0') == '1'
+MERGE_TEMPORAL_FC = _os.environ.get('VT_MERGE_TEMPORAL_FC', '1') == '1'
 
 
 def set_mask_arena(arena):
