@@ -142,3 +142,21 @@ def test_gelu_backward_with_column_sums(M, N):
         assert torch.equal(out, ref)
         exp = ref.double().sum(0)
         assert float((cs.double() - exp).abs().max()) <= 1e-4 * max(1.0, float(exp.abs().max()))
+
+
+@pytest.mark.parametrize('S,n,stride', [(296, 768, 768), (33, 8, 8), (592, 3072, 3072), (1000, 4, 12), (5, 256, 256), (64, 192, 384)])
+def test_reduce_rows_tall_and_flat(S, n, stride):
+    """out[j] (+)= scale * sum_s in[s * stride + j]: the partial-row sums behind split-K, LayerNorm dgamma / dbeta and the
+    producer column sums (tall kernel for S >= 32, flat otherwise)."""
+    import ctypes as C
+    from videotransformer_pytorch_b200 import _lib
+    lib = _lib.load_library()
+    g = torch.Generator().manual_seed(9)
+    src = torch.randn(S, stride, generator=g).cuda()
+    for accumulate in (0, 1):
+        out = torch.full((n,), 3.0, device='cuda')
+        r = _lib.ReduceParams()
+        r.inp, r.out, r.stride, r.S, r.n, r.accumulate, r.scale = src.data_ptr(), out.data_ptr(), stride, S, n, accumulate, 0.5
+        assert lib.vt_reduce_rows(C.byref(r), C.c_void_p(torch.cuda.current_stream().cuda_stream)) == 0
+        exp = 0.5 * src[:, :n].double().sum(0) + (3.0 if accumulate else 0.0)
+        assert float((out.double() - exp).abs().max()) < 1e-4

@@ -440,22 +440,32 @@ __global__ void reduce_rows_kernel(const float* __restrict__ in, float* __restri
   }
 }
 
-// Tall reductions (many partial rows, few columns — LayerNorm dgamma/dbeta partials): 16 column quads x 16 row
-// lanes per CTA, rows strided over the row lanes, then a shared-memory tree.  Deterministic.
-__global__ void __launch_bounds__(256)
+// Tall reductions (many partial rows, few columns — LayerNorm dgamma/dbeta partials, the per-CTA column sums of the
+// producer kernels): 4 column quads x 64 row lanes per CTA, rows strided over the row lanes, then a shared-memory sum in
+// lane order.  Deterministic.  (16 quads x 16 lanes gave 12 CTAs walking 19 - 37 dependent rows each for n = 768.)
+constexpr int RT_QUADS = 4, RT_LANES = 64;
+__global__ void __launch_bounds__(RT_QUADS * RT_LANES)
 reduce_rows_tall_kernel(const float* __restrict__ in, float* __restrict__ out, long long stride, int S, long long n4,
                         int accumulate, float scale) {
-  const int cq = threadIdx.x & 15, rl = threadIdx.x >> 4;
-  const long long i = blockIdx.x * 16LL + cq;
+  const int cq = threadIdx.x % RT_QUADS, rl = threadIdx.x / RT_QUADS;
+  const long long i = blockIdx.x * (long long)RT_QUADS + cq;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if (i < n4) {
-    for (int s = rl; s < S; s += 16) {
+    for (int s = rl; s < S; s += RT_LANES) {
       const float4 v = *reinterpret_cast<const float4*>(in + (long long)s * stride + i * 4);
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
   }
-  __shared__ float4 sh[16][16];
+  __shared__ float4 sh[RT_LANES][RT_QUADS];
   sh[rl][cq] = acc;
+  __syncthreads();
+  // 16 threads per quad: thread j sums lanes j, j + 16, j + 32, j + 48; then lane 0 of the quad adds the 16 in order
+  if (rl < 16) {
+    float4 a = sh[rl][cq];
+#pragma unroll
+    for (int r = rl + 16; r < RT_LANES; r += 16) { a.x += sh[r][cq].x; a.y += sh[r][cq].y; a.z += sh[r][cq].z; a.w += sh[r][cq].w; }
+    sh[rl][cq] = a;
+  }
   __syncthreads();
   if (rl == 0 && i < n4) {
     float4 a = sh[0][cq];
@@ -473,7 +483,7 @@ int launch_reduce_rows(const float* in, float* out, long long stride, int S, lon
   VT_REQUIRE(n % 4 == 0 && stride % 4 == 0, "vt_reduce_rows: n and stride must be multiples of 4");
   const long long n4 = n / 4;
   if (S >= 32 && n4 <= 16 * 4096) {
-    reduce_rows_tall_kernel<<<(int)((n4 + 15) / 16), 256, 0, st>>>(in, out, stride, S, n4, accumulate, scale);
+    reduce_rows_tall_kernel<<<(int)((n4 + RT_QUADS - 1) / RT_QUADS), RT_QUADS * RT_LANES, 0, st>>>(in, out, stride, S, n4, accumulate, scale);
     return check_launch("reduce_rows_tall_kernel");
   }
   int blocks = (int)((n4 + 255) / 256);
