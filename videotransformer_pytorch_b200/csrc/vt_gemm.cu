@@ -17,7 +17,7 @@ namespace vt {
 // compiled defaults of the round-2 paths (environment VT_TMA_RES / VT_TAIL_UNITS / VT_TMA_GELU / VT_TMA_DGELU = 0 | 1 override)
 constexpr bool VT_DEFAULT_TMA_RES = true;
 constexpr bool VT_DEFAULT_TMA_RES_SPATIAL = true;
-constexpr bool VT_DEFAULT_TAIL_UNITS = false;
+constexpr bool VT_DEFAULT_TAIL_UNITS = true;    // MViT step 21.32 -> 21.02 ms (every GEMM there is 8 rows past a tile); neutral elsewhere
 constexpr bool VT_DEFAULT_TMA_GELU = false;
 constexpr bool VT_DEFAULT_TMA_DGELU = false;
 bool tail_units_enabled() { return feature_on("VT_TAIL_UNITS", VT_DEFAULT_TAIL_UNITS); }
