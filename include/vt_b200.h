@@ -102,6 +102,8 @@ typedef struct {
   int64_t map_special_base, map_special_stride;
   const float* bias2;      /* VT_EPI_F32 with aux only: out = s(m) * (acc + bias[n]) + bias2[n] + aux — the bias of a second
                               linear layer folded into this GEMM (temporal_fc after proj, transformer.py:264-267) */
+  int32_t out_zeroed;      /* split-K accumulates into `out` by TMA reduce-add and normally zeroes it first; 1 = the caller
+                              already did (a gradient arena / DDP bucket zeroed once per step) */
 } vt_gemm_params;
 
 int vt_gemm(const vt_gemm_params* p, void* stream);

@@ -367,3 +367,17 @@ def test_second_bias_after_row_scale(M, N, Kd, res, monkeypatch):
     out = K().gemm(a, b, M, N, Kd, epi='f32', bias=bias, bias2=bias2, row_scale=rs, aux=aux)
     r = (ref_mm(a, b, False, False) + bias) * rs[:, None] + bias2 + aux
     assert rel(out, r) < 1e-5
+
+
+@pytest.mark.parametrize('M,N,Kd', [(768, 768, 12544), (2304, 768, 12608), (96, 448, 20000)])
+def test_split_k_into_a_prezeroed_output(M, N, Kd):
+    """Weight-gradient form (both operands MN-major, split-K by TMA reduce-add): with out_zeroed the library skips its own
+    memset and accumulates into what the caller zeroed (gradient arena / DDP bucket); without it stale contents are harmless."""
+    a, b = mk((Kd, M), 80).bfloat16(), mk((Kd, N), 81).bfloat16()
+    r = a.float().t() @ b.float()
+    stale = torch.full((M, N), 9.0, device='cuda')
+    K().gemm(a, b, M, N, Kd, a_mn=True, b_mn=True, epi='f32', split_ok=True, out=stale)
+    assert rel(stale, r) < 1e-5
+    zeroed = torch.zeros((M, N), device='cuda')
+    K().gemm(a, b, M, N, Kd, a_mn=True, b_mn=True, epi='f32', split_ok=True, out=zeroed, out_zeroed=True)
+    assert rel(zeroed, r) < 1e-5

@@ -31,7 +31,7 @@ class GemmParams(C.Structure):
                 ('force_splits', c_i32), ('force_bn', c_i32), ('force_cluster', c_i32), ('debug', c_vp),
                 ('map_period', c_i32), ('map_skip', c_i32), ('map_tcount', c_i32), ('force_tail', c_i32),
                 ('map_stride_t', c_i64), ('map_stride_p', c_i64), ('map_stride_b', c_i64), ('map_base', c_i64),
-                ('map_special_base', c_i64), ('map_special_stride', c_i64), ('bias2', c_vp)]
+                ('map_special_base', c_i64), ('map_special_stride', c_i64), ('bias2', c_vp), ('out_zeroed', c_i32)]
 
 
 class LnFwdParams(C.Structure):
@@ -289,7 +289,7 @@ class CudaKernels:
     # -- GEMM ---------------------------------------------------------------------------------
     def gemm(self, a, b, M, N, Kdim, *, a_mn=False, b_mn=False, epi='bf16', bias=None, bias2=None, out=None, out2=None,
              aux=None, out_row=None, aux_row=None, row_scale=None, out_rows=None, split_ok=False,
-             force_splits=0, force_bn=0, force_cluster=0, debug=None, row_map=None, force_tail=0, tag=None):
+             force_splits=0, force_bn=0, force_cluster=0, debug=None, row_map=None, force_tail=0, tag=None, out_zeroed=False):
         """row_map: affine description of out_row / aux_row (ops.affine_row_maps) for the fp32 residual epilogue — lets the
         kernel move 32 x 32 boxes by TMA through a tensor map of the token stream instead of per-thread rows.  tag: role label of the launch
         ('qkv', 'proj', ...) for profilers that wrap this method (bench.py); ignored here."""
@@ -338,6 +338,7 @@ class CudaKernels:
             p.workspace, p.workspace_bytes = ws.data_ptr(), ws.numel() * 4
         p.force_splits, p.force_bn, p.force_cluster = force_splits, force_bn, force_cluster
         p.force_tail = force_tail
+        p.out_zeroed = int(bool(out_zeroed) and out is not None)
         p.debug = _ptr(debug)
         p.map_special_base = -1
         if row_map is not None:

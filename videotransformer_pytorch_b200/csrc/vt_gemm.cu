@@ -540,7 +540,7 @@ static int launch_gemm(const vt_gemm_params* q, GemmDev& d, cudaStream_t st) {
   const bool in_place = splits > 1 && splitk_in_place(q);
   d.split_stride = 0;
   if (in_place) {
-    rc = splitk_zero(q, st);
+    rc = q->out_zeroed ? 0 : splitk_zero(q, st);
     if (rc) return rc;
   } else if (splits > 1) {
     d.out = q->workspace;

@@ -140,18 +140,23 @@ class GradientBuckets:
             self._arrived[bi] = []
             self._launch(bi)
 
-    def backward_into_buckets(self, loss, params):
+    def backward_into_buckets(self, loss, params, zero_first=False):
         """Backward of `loss` with the gradients landing in the flat buckets and every bucket's all-reduce issued as soon as
         it is complete (the body of a captured data-parallel step, graph.GraphedTrainStep; also usable eagerly after
         zero_grad()).  Uses torch.autograd.grad, so nothing is ACCUMULATED: weight-gradient GEMMs may therefore write
-        directly into their bucket slice (ops.GRAD_DEST), other gradients are copied in by grad_ready()."""
+        directly into their bucket slice (ops.GRAD_DEST), other gradients are copied in by grad_ready().
+        zero_first: zero the buckets here (16 memsets, part of a captured step) and let the split-K weight-gradient GEMMs
+        skip their own per-output memsets (73 per TimeSformer-B step)."""
         from . import ops
         params = list(params)
         self._pending = [len(ps) for ps in self._bucket_params]
         self._arrived = [[] for _ in self._bucket_params]
         handles = [p.register_hook(lambda g, p=p: self.grad_ready(p, g)) for p in params]
         if self.direct_wgrad:
-            ops.set_grad_destinations({p.data_ptr(): v for p, v in self._view.items()})
+            if zero_first:
+                for b in self.buckets:
+                    b.zero_()
+            ops.set_grad_destinations({p.data_ptr(): v for p, v in self._view.items()}, zeroed=zero_first)
         try:
             grads = torch.autograd.grad(loss, params)
         finally:
