@@ -175,6 +175,14 @@ typedef struct { const void* z; const void* dh; void* out; int64_t n; } vt_gelu_
 int vt_gelu_fwd_bf16(const vt_gelu_params* p, void* stream);
 int vt_gelu_bwd_bf16(const vt_gelu_params* p, void* stream);
 
+/* cls rows of the divided space-time blocks in one launch:  dst[b, :] = src[b, :] + scale * sum_t extra[b, t, :]
+ * (extra NULL: row copy).  src / dst: fp32 rows b * stride apart; extra: fp32 [B, T, D] with batch stride extra_bs.
+ * Replaces the cls passthrough of the temporal block and `cls + mean_t(cls replicas)` of the spatial block
+ * (transformer.py:282-283, :371-377) and their adjoints. */
+typedef struct { const float* src; int64_t src_stride; const float* extra; int64_t extra_bs; int32_t T; float scale;
+                 float* dst; int64_t dst_stride; int32_t B, D; } vt_cls_rows_params;
+int vt_cls_rows(const vt_cls_rows_params* p, void* stream);
+
 /* The two producers of a layer's dY that also emit its column sums (= the bias gradient autograd's sum over tokens gives
  * nn.Linear, transformer.py:175 / :267 / :505 / :501): vt_gather_cast_bf16 + vt_colsum_bf16, and vt_gelu_bwd_bf16 +
  * vt_colsum_bf16, in one pass each.  colsum fp32 [D] / [N]; workspace fp32 [workspace_rows, D] with workspace_rows >=

@@ -160,6 +160,13 @@ class EmuKernels:
         zz = self._up(z)
         return self._h(0.5 * zz * (1 + torch.erf(zz / math.sqrt(2.0))))
 
+    def cls_rows(self, dst, src, extra=None, scale=1.0):
+        v = self._up(src)
+        if extra is not None:
+            v = v + scale * self._up(extra).sum(dim=1)
+        dst.copy_(v.to(dst.dtype))
+        return dst
+
     def gather_cast_colsum(self, src2d, in_row=None, row_scale=None, rows=None, unscaled_sums=False):
         out = self.gather_cast(src2d, in_row=in_row, row_scale=row_scale, rows=rows)
         if unscaled_sums:

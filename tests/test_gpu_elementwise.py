@@ -160,3 +160,16 @@ def test_reduce_rows_tall_and_flat(S, n, stride):
         assert lib.vt_reduce_rows(C.byref(r), C.c_void_p(torch.cuda.current_stream().cuda_stream)) == 0
         exp = 0.5 * src[:, :n].double().sum(0) + (3.0 if accumulate else 0.0)
         assert float((out.double() - exp).abs().max()) < 1e-4
+
+
+@pytest.mark.parametrize('B,T,D,S', [(8, 8, 768, 1569), (3, 4, 128, 37), (1, 2, 32, 9)])
+def test_cls_rows(B, T, D, S):
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(B, S, D, generator=g).cuda()
+    extra = torch.randn(B, T, D, generator=g).cuda()
+    y = torch.full((B, S, D), 5.0, device='cuda')
+    K().cls_rows(y[:, 0], x[:, 0])
+    assert torch.equal(y[:, 0], x[:, 0]) and bool((y[:, 1:] == 5.0).all())
+    K().cls_rows(y[:, 0], x[:, 0], extra=extra, scale=1.0 / T)
+    assert float((y[:, 0] - (x[:, 0] + extra.mean(dim=1))).abs().max()) < 1e-5
+    assert bool((y[:, 1:] == 5.0).all())

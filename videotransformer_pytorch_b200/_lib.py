@@ -69,6 +69,11 @@ class GeluParams(C.Structure):
     _fields_ = [('z', c_vp), ('dh', c_vp), ('out', c_vp), ('n', c_i64)]
 
 
+class ClsRowsParams(C.Structure):
+    _fields_ = [('src', c_vp), ('src_stride', c_i64), ('extra', c_vp), ('extra_bs', c_i64), ('T', c_i32), ('scale', c_f32),
+                ('dst', c_vp), ('dst_stride', c_i64), ('B', c_i32), ('D', c_i32)]
+
+
 class GatherCastColsumParams(C.Structure):
     _fields_ = [('src', c_vp), ('lds', c_i64), ('in_row', c_vp), ('row_scale', c_vp), ('dst', c_vp),
                 ('rows', c_i32), ('D', c_i32), ('colsum', c_vp), ('workspace', c_vp), ('workspace_rows', c_i32),
@@ -211,7 +216,7 @@ class Im2colU8MixParams(C.Structure):
 
 EXPORTS = ['vt_version', 'vt_last_error', 'vt_sm_count', 'vt_set_reserved_sms', 'vt_launch_count', 'vt_gemm', 'vt_layernorm_fwd', 'vt_ln_bwd_blocks',
            'vt_layernorm_bwd', 'vt_reduce_rows', 'vt_colsum_chunks', 'vt_colsum_bf16', 'vt_cast_f32_bf16',
-           'vt_gather_cast_colsum_blocks', 'vt_gather_cast_colsum_bf16', 'vt_gelu_bwd_colsum_blocks', 'vt_gelu_bwd_colsum_bf16',
+           'vt_cls_rows', 'vt_gather_cast_colsum_blocks', 'vt_gather_cast_colsum_bf16', 'vt_gelu_bwd_colsum_blocks', 'vt_gelu_bwd_colsum_bf16',
            'vt_gather_cast_bf16', 'vt_gelu_fwd_bf16', 'vt_gelu_bwd_bf16', 'vt_attn_fwd', 'vt_attn_bwd', 'vt_debug_buffer', 'vt_im2col_bf16', 'vt_im2col_u8_bf16', 'vt_col2im_f32', 'vt_hog',
            'vt_pool_fwd', 'vt_pool_bwd_scratch', 'vt_pool_bwd', 'vt_xattn_fwd', 'vt_xattn_bwd', 'vt_maxpool_fwd',
            'vt_maxpool_bwd', 'vt_im2col3d_bf16', 'vt_mvit_tokens_fwd', 'vt_mvit_tokens_bwd', 'vt_mse_blocks',
@@ -435,6 +440,25 @@ class CudaKernels:
         p.dst, p.rows, p.D = out.data_ptr(), rows, D
         _check(lib.vt_gather_cast_bf16(C.byref(p), _stream()), 'vt_gather_cast_bf16')
         return out
+
+    def cls_rows(self, dst, src, extra=None, scale=1.0):
+        """dst[b, :] = src[b, :] + scale * extra[b].sum(0);  dst / src: fp32 [B, D] row views (unit inner stride), extra: fp32
+        contiguous [B, T, D] or None."""
+        lib = load_library()
+        for t, n in ((dst, 'dst'), (src, 'src')):
+            _req(t, torch.float32, 'cls_rows.' + n)
+            if t.dim() != 2 or t.stride(1) != 1 or t.shape != dst.shape:
+                raise RuntimeError(f'cls_rows.{n}: expected a [B, D] row view with unit inner stride')
+        p = ClsRowsParams()
+        p.src, p.src_stride, p.dst, p.dst_stride = src.data_ptr(), src.stride(0), dst.data_ptr(), dst.stride(0)
+        p.B, p.D, p.scale = dst.shape[0], dst.shape[1], float(scale)
+        if extra is not None:
+            _req(extra, torch.float32, 'cls_rows.extra')
+            if extra.dim() != 3 or not extra.is_contiguous() or extra.shape[0] != p.B or extra.shape[2] != p.D:
+                raise RuntimeError('cls_rows.extra: expected a contiguous [B, T, D] tensor')
+            p.extra, p.extra_bs, p.T = extra.data_ptr(), extra.stride(0), extra.shape[1]
+        _check(lib.vt_cls_rows(C.byref(p), _stream()), 'vt_cls_rows')
+        return dst
 
     def gather_cast_colsum(self, src2d, in_row=None, row_scale=None, rows=None, unscaled_sums=False):
         """gather_cast + colsum of its output in one pass -> (bf16 [rows, D], fp32 [D]); with unscaled_sums a third result:

@@ -363,3 +363,43 @@ extern "C" int vt_im2col_u8_mix_bf16(const vt_im2col_u8_mix_params* p, void* str
       p->pw, total8);
   return check_launch("im2col_u8_mix_kernel");
 }
+
+// ------------------------------------------------------------------------------------------------
+// cls rows of the divided space-time blocks: dst[b, :] = src[b, :] + scale * sum_t extra[b, t, :]
+// (extra == NULL: plain row copy).  One launch for what autograd spells as mean / sum + add + strided copy
+// (transformer.py:282-283 cls passthrough of the temporal block, :371-377 mean over the per-frame cls replicas).
+// ------------------------------------------------------------------------------------------------
+namespace vt {
+__global__ void cls_rows_kernel(const float* __restrict__ src, long long src_stride, const float* __restrict__ extra,
+                                long long extra_bs, int T, float scale, float* __restrict__ dst, long long dst_stride, int B, int D4) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B * D4; i += gridDim.x * blockDim.x) {
+    const int b = i / D4, j = i - b * D4;
+    float4 v = reinterpret_cast<const float4*>(src + (long long)b * src_stride)[j];
+    if (extra) {
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int t = 0; t < T; ++t) {
+        const float4 e = reinterpret_cast<const float4*>(extra + (long long)b * extra_bs + (long long)t * D4 * 4)[j];
+        a.x += e.x; a.y += e.y; a.z += e.z; a.w += e.w;
+      }
+      v.x = fmaf(scale, a.x, v.x); v.y = fmaf(scale, a.y, v.y); v.z = fmaf(scale, a.z, v.z); v.w = fmaf(scale, a.w, v.w);
+    }
+    reinterpret_cast<float4*>(dst + (long long)b * dst_stride)[j] = v;
+  }
+}
+}  // namespace vt
+
+extern "C" int vt_cls_rows(const vt_cls_rows_params* p, void* stream) {
+  using namespace vt;
+  VT_REQUIRE(p && p->src && p->dst && p->B > 0 && p->D > 0, "vt_cls_rows: bad params");
+  VT_REQUIRE(p->D % 4 == 0 && p->src_stride % 4 == 0 && p->dst_stride % 4 == 0 && (!p->extra || (p->extra_bs % 4 == 0 && p->T > 0)),
+             "vt_cls_rows: D and strides must be multiples of 4");
+  VT_REQUIRE(((reinterpret_cast<uintptr_t>(p->src) | reinterpret_cast<uintptr_t>(p->dst) | reinterpret_cast<uintptr_t>(p->extra)) & 15) == 0,
+             "vt_cls_rows: pointers must be 16-byte aligned");
+  const int n = p->B * (p->D / 4);
+  int blocks = (n + 255) / 256;
+  if (blocks > 1024) blocks = 1024;
+  cls_rows_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(p->src, p->src_stride, p->extra, p->extra_bs, p->T, p->scale,
+                                                                        p->dst, p->dst_stride, p->B, p->D / 4);
+  return check_launch("cls_rows_kernel");
+}
+

@@ -238,7 +238,7 @@ class TemporalAttnFn(torch.autograd.Function):
             a = k.gemm(cx, proj_wh, Mt, D, D, bias=proj_b, epi='bf16', row_scale=dp, tag='proj')
             k.gemm(a, fc_wh, Mt, D, D, bias=fc_b, epi='f32', aux=x2, aux_row=maps['temporal'], out=y2,
                    out_row=maps['temporal'], row_map=affine_row_maps(B, T, P, D)['temporal'])
-        y[:, 0] = x[:, 0]
+        k.cls_rows(y[:, 0], x[:, 0])
         ctx.save_for_backward(x, ln_w, mean, rstd, xn, qkv, cx, lse, a, qkv_wh, proj_wh, fc_wh, dp,
                               fc_w if ctx.merged else None, proj_b if ctx.merged else None)
         ctx.geom = (B, S, D, T, H, P)
@@ -290,7 +290,7 @@ class TemporalAttnFn(torch.autograd.Function):
         dx = torch.empty_like(x)
         _, _, d_ln_w, d_ln_b = k.ln_bwd(dxn, x2, mean, rstd, ln_w, in_row=maps['temporal'], out_row=maps['temporal'],
                                         dres=dy2, dx=dx.view(B * S, D))
-        dx[:, 0] = dy[:, 0]
+        k.cls_rows(dx[:, 0], dy[:, 0])
         return (dx, d_ln_w, d_ln_b, d_qkv_w, d_qkv_b, d_proj_w, d_proj_b, d_fc_w, d_fc_b,
                 None, None, None, None, None, None, None)
 
@@ -315,7 +315,7 @@ class SpatialAttnFn(torch.autograd.Function):
         k.gemm(cx, proj_wh, Ms, D, D, bias=proj_b, epi='f32', aux=x2, aux_row=maps['sp_aux'], out=ybig,
                out_row=maps['sp_out'], row_scale=dp, row_map=affine_row_maps(B, T, P, D)['spatial'], tag='proj')
         y = ybig[:R].view(B, S, D)
-        y[:, 0] = x[:, 0] + ybig[R:].view(B, T, D).mean(dim=1)
+        k.cls_rows(y[:, 0], x[:, 0], extra=ybig[R:].view(B, T, D), scale=1.0 / T)
         ctx.save_for_backward(x, ln_w, mean, rstd, xn, qkv, cx, lse, qkv_wh, proj_wh, dp)
         ctx.geom = (B, S, D, T, H, P)
         ctx.wptrs = (qkv_w.data_ptr(), proj_w.data_ptr())
@@ -342,7 +342,7 @@ class SpatialAttnFn(torch.autograd.Function):
         dx = torch.empty_like(x)
         _, aux, d_ln_w, d_ln_b = k.ln_bwd(dxn, x2, mean, rstd, ln_w, in_row=maps['sp_in'], out_row=maps['sp_bwd'],
                                           dres=dy2, dx=dx.view(R, D), n_aux=B * T)
-        dx[:, 0] = dy[:, 0] + aux.view(B, T, D).sum(dim=1)
+        k.cls_rows(dx[:, 0], dy[:, 0], extra=aux.view(B, T, D))
         return dx, d_ln_w, d_ln_b, d_qkv_w, d_qkv_b, d_proj_w, d_proj_b, None, None, None, None, None, None
 
 
