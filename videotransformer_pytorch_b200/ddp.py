@@ -63,13 +63,15 @@ class GradientBuckets:
         self._owner = {}
         self._view = {}
         for bi, ps in enumerate(self._bucket_params):
-            n = sum(p.numel() for p in ps)
+            # every slice starts on a 16-byte boundary (the weight-gradient GEMMs store into them by TMA); the padding
+            # elements stay zero and ride along in the all-reduce
+            n = sum((p.numel() + 3) // 4 * 4 for p in ps)
             flat = torch.zeros(n, dtype=torch.float32, device=self.device)
             off = 0
             for p in ps:
                 p.grad = flat[off:off + p.numel()].view_as(p)
                 self._view[p] = p.grad
-                off += p.numel()
+                off += (p.numel() + 3) // 4 * 4
                 self._owner[p] = bi
                 p.register_post_accumulate_grad_hook(self._hook)
             self.buckets.append(flat)

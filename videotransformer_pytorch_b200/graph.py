@@ -100,11 +100,11 @@ class GraphedTrainStep:
         from . import _lib
         if reducer is None:
             mats = [p for p in self.params if p.dim() >= 2]
-            self._grad_arena = torch.zeros(sum(p.numel() for p in mats), dtype=torch.float32, device=dev)
+            self._grad_arena = torch.zeros(sum((p.numel() + 3) // 4 * 4 for p in mats), dtype=torch.float32, device=dev)
             self._grad_views, off = {}, 0
-            for p in mats:
+            for p in mats:                      # 16-byte aligned slices (TMA stores)
                 self._grad_views[p.data_ptr()] = self._grad_arena[off:off + p.numel()]
-                off += p.numel()
+                off += (p.numel() + 3) // 4 * 4
         self.graph = torch.cuda.CUDAGraph()
         launches_before = _lib.launch_count()
         self._zero(set_to_none=True)

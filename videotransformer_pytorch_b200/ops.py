@@ -160,8 +160,8 @@ def _grad_dest(wptr, n_out, k_in):
     if GRAD_DEST is None or wptr is None:
         return None
     dest = GRAD_DEST.get(wptr)
-    if dest is not None and dest.numel() == n_out * k_in and dest.is_contiguous():
-        return dest.view(n_out, k_in)
+    if dest is not None and dest.numel() == n_out * k_in and dest.is_contiguous() and dest.data_ptr() % 16 == 0 and k_in % 4 == 0:
+        return dest.view(n_out, k_in)          # TMA stores need a 16-byte aligned base and row pitch
     return None
 
 
