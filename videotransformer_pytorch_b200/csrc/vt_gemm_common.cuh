@@ -34,7 +34,8 @@ struct GemmDev {
                            //    boxes TMA-loaded into the staging slot, result TMA-stored (epilogue_tile_tma_res)
   // affine row map of the residual epilogue: GEMM row m -> outer = m / map_period, inner = m % map_period;
   // inner < map_skip: "special" row (replicated cls token), else tensor coordinates
-  // (col, t = outer % map_tcount, p = inner - map_skip, b = outer / map_tcount) of the 4-D out / aux maps
+  // t = outer % map_tcount, p = inner - map_skip, b = outer / map_tcount -> box start (col, p * map_tcount + t, b) in the
+  // (col, row in sample, sample) out / aux maps
   int map_period, map_skip, map_tcount;
   int map_rank;            // 3: tensor maps are (col, row in sample, sample), box {32, 32 * map_tcount, 1} with element stride map_tcount
   float* special_out;      // special rows go to special_out + outer * special_ld (plain per-thread stores), or are dropped
