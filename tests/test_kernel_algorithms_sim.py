@@ -156,6 +156,92 @@ def sim_pool_dw(dpooled, inp, in_bs, in_rs, B, H, thw, stride, rows_per_cta=5, u
     return partials.sum(0).reshape(HD, 27)
 
 
+def sim_pool_din_v2(dpooled, w, B, H, thw, stride):
+    """second generation: CTA = one (b, ti) plane x one head (+ one extra plane index for the cls tokens), warp = token;
+    (dh, dw) -> output row offsets tabulated per token, the nine taps of a valid time plane gathered together."""
+    T, Hin, Win = thw
+    To, Ho, Wo = out_dims(thw, stride)
+    L1, Lo1 = 1 + T * Hin * Win, 1 + To * Ho * Wo
+    tab = np.full((3, 3, 64), -1, dtype=np.int64)
+    for axis, (n_in, s_, n_out) in enumerate(((T, stride[0], To), (Hin, stride[1], Ho), (Win, stride[2], Wo))):
+        for k in range(3):
+            for c in range(n_in):
+                nn = c + 1 - k
+                if nn >= 0 and nn % s_ == 0 and nn // s_ < n_out:
+                    tab[axis, k, c] = nn // s_
+    din = np.zeros((B, L1, H, HD))
+    dp_all = dpooled.reshape(B * H, Lo1, HD)
+    planes = B * T
+    for h in range(H):                                   # blockIdx.z
+        for plane in range(planes + 1):                  # blockIdx.y
+            if plane == planes:
+                for b in range(B):
+                    din[b, 0, h] = dp_all[b * H + h, 0]
+                continue
+            b, ti = plane // T, plane % T
+            ot3 = tab[0, :, ti]
+            t_any = (ot3 >= 0).any()
+            dp = dp_all[b * H + h, 1:]                   # rows after the cls row
+            for idx in range(Hin * Win):                 # warps of the CTA(s) stride over the plane's tokens
+                hi, wi = idx // Win, idx % Win
+                rowoff = np.full(9, -1, dtype=np.int64)
+                for dh in range(3):
+                    for dw in range(3):
+                        oh, ow = tab[1, dh, hi], tab[2, dw, wi]
+                        if oh >= 0 and ow >= 0:
+                            rowoff[dh * 3 + dw] = oh * Wo + ow
+                acc = np.zeros(HD)
+                if (rowoff >= 0).any() and t_any:
+                    for dt in range(3):
+                        if ot3[dt] < 0:
+                            continue
+                        plane_rows = dp[ot3[dt] * Ho * Wo:]
+                        for k in range(9):
+                            if rowoff[k] >= 0:
+                                acc += plane_rows[rowoff[k]] * w[:, dt * 9 + k]
+                din[b, 1 + ti * Hin * Win + idx, h] = acc
+    return din.reshape(B, L1, H * HD)
+
+
+def sim_pool_dw_v2(dpooled, inp, in_bs, in_rs, B, H, thw, stride, rows_per_cta=5, slots=4):
+    """second generation: warp = (pooled row, time tap): 12 warps per CTA = `slots` row slots x 3 time taps; each lane keeps
+    9 taps x 4 channels; the slots are summed in slot order, one partial row per CTA."""
+    T, Hin, Win = thw
+    st, sh, sw = stride
+    To, Ho, Wo = out_dims(thw, stride)
+    Lo = To * Ho * Wo
+    rows = B * H * Lo
+    nblocks = (rows + rows_per_cta - 1) // rows_per_cta
+    partials = np.zeros((nblocks, HD * 27))
+    dp = dpooled.reshape(B * H, Lo + 1, HD)
+    for blk in range(nblocks):
+        r0, r1 = blk * rows_per_cta, min(rows, (blk + 1) * rows_per_cta)
+        red = np.zeros((slots, HD * 27))
+        for slot in range(slots):
+            for dt in range(3):
+                acc = np.zeros((9, HD))
+                for r in range(r0 + slot, r1, slots):
+                    bh, o = r // Lo, r % Lo
+                    b, h = bh // H, bh % H
+                    o2 = o // Wo
+                    ow, ot, oh = o - o2 * Wo, o2 // Ho, o2 % Ho
+                    ti = ot * st - 1 + dt
+                    if ti < 0 or ti >= T:
+                        continue
+                    g = dp[bh, 1 + o]
+                    for dh in range(3):
+                        for dw in range(3):
+                            hi, wi = oh * sh - 1 + dh, ow * sw - 1 + dw
+                            ok = 0 <= hi < Hin and 0 <= wi < Win
+                            hc, wc = min(max(hi, 0), Hin - 1), min(max(wi, 0), Win - 1)
+                            off = b * in_bs + h * HD + (1 + (ti * Hin + hc) * Win + wc) * in_rs
+                            acc[dh * 3 + dw] += (g if ok else 0.0) * inp[off:off + HD]
+                for k in range(9):
+                    red[slot, np.arange(HD) * 27 + dt * 9 + k] = acc[k]
+        partials[blk] = red[0] + red[1] + red[2] + red[3] if slots == 4 else red.sum(0)
+    return partials.sum(0).reshape(HD, 27)
+
+
 @pytest.mark.parametrize('thw,stride,H', [((2, 4, 4), (1, 2, 2), 2), ((3, 5, 6), (1, 4, 4), 1), ((2, 3, 3), (1, 1, 1), 2),
                                           ((2, 8, 8), (1, 8, 8), 1)])
 def test_pool_kernels_index_math(thw, stride, H):
@@ -187,6 +273,9 @@ def test_pool_kernels_index_math(thw, stride, H):
     assert rel(sim_din, din.numpy()) < 1e-12
     sim_dw = sim_pool_dw(dpooled.numpy(), flat[off:], N1 * 3 * d, 3 * d, B, H, thw, stride)
     assert rel(sim_dw, dw.numpy()) < 1e-12
+    # second generation of the two adjoint kernels (csrc/vt_mvit.cu: pool_din_v2_kernel, pool_dw_v2_kernel)
+    assert rel(sim_pool_din_v2(dpooled.numpy(), w.numpy(), B, H, thw, stride), din.numpy()) < 1e-12
+    assert rel(sim_pool_dw_v2(dpooled.numpy(), flat[off:], N1 * 3 * d, 3 * d, B, H, thw, stride), dw.numpy()) < 1e-12
 
 
 # ---- maxpool_fwd_kernel / maxpool_bwd_kernel ---------------------------------------------------------
